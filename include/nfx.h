@@ -1,0 +1,170 @@
+/*
+ * nfx.h -- C ABI of libnfx.so: the B200 (sm_100a) per-nucleus feature pipeline that replaces the
+ * tch/libtorch tensor work of oxabz/nuclei-feature-extraction.
+ *
+ * Boundary: the library replaces the stage triple
+ *     patch_loader -> move_tensors_to_device -> extract_features      (src/main.rs:149-151)
+ * i.e. src/utils.rs:141-224 (batch builder + H2D) and the FeatureSet::compute_features_batched
+ * implementations of src/features/{shape,color,texture}.rs.  The Rust host keeps the CLI, GeoJSON
+ * parsing and the polars writers and binds these symbols through an `extern "C"` block
+ * (INTEGRATION.md shows the shim).  Plain pointers and sizes only; no torch types.
+ *
+ * Threading: one nfx_ctx per (host thread, GPU), like one rayon worker of the reference
+ * (src/utils.rs:215-221).  A context is not thread-safe; different contexts are independent.
+ * Errors: nothing throws or aborts across the boundary; every call returns NFX_OK (0) or a negative
+ * code and nfx_last_error() gives the message (the reference panics instead, src/main.rs:76-89).
+ * There is NO CPU fallback: without a usable sm_100 device every compute call fails.
+ */
+#ifndef NFX_H
+#define NFX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFX_OK               0
+#define NFX_ERR_INVALID     -1   /* bad argument */
+#define NFX_ERR_CUDA        -2   /* CUDA runtime/driver error (message has the CUDA string) */
+#define NFX_ERR_STATE       -3   /* call order: no tile / no polygons / nothing computed yet */
+#define NFX_ERR_UNSUPPORTED -4   /* shape outside what the kernels handle (documented per call) */
+#define NFX_ERR_NOMEM       -5
+
+/* Feature-set selector bits in args::FeatureSet::flat() order (src/args.rs:35-49). */
+#define NFX_FS_GEOMETRY 0x01u    /* ShapeFeatureSet        "geometry"      12 columns (shape.rs:113-128)  */
+#define NFX_FS_COLOR    0x02u    /* ColorFeatureSet        "color"         18 columns (color.rs:80-100)   */
+#define NFX_FS_GLCM     0x04u    /* GlcmFeatureSet         "GLCM"         224 columns (texture.rs:81-157) */
+#define NFX_FS_GLRLM    0x08u    /* GLRLMFeatureSet        "GLRLM"         68 columns (texture.rs:243-301)*/
+#define NFX_FS_GABOR    0x10u    /* GaborFilterFeatureSet  "gabor filter"  96 columns (texture.rs:346-361)*/
+#define NFX_FS_TEXTURE  (NFX_FS_GLCM | NFX_FS_GLRLM | NFX_FS_GABOR)
+#define NFX_FS_ALL      0x1Fu
+
+typedef struct nfx_ctx nfx_ctx;
+
+/* Mirrors the reference's operating-point flags (src/args.rs:93-108). */
+typedef struct nfx_config {
+    int32_t patch_size;   /* -p/--patch-size, default 64. Even, 16..256. */
+    int32_t batch_size;   /* -b/--batch-size, default 100. mean_h couples the nuclei of one chunk
+                             [k*B,(k+1)*B) (src/features/color.rs:50-51, 144-155; src/main.rs:148). */
+    int32_t reserved[6];  /* must be 0 */
+} nfx_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Replaces Device::Cuda(gpus[idx]) selection (src/utils.rs:215-221). cfg may be NULL (defaults). */
+int nfx_create(int device, const nfx_config* cfg, nfx_ctx** out);
+int nfx_destroy(nfx_ctx* ctx);
+/* ctx may be NULL: returns the calling thread's last error from nfx_create / schema calls. */
+const char* nfx_last_error(const nfx_ctx* ctx);
+/* Library/ABI version and the sm arch the kernels were built for ("sm_100a"). */
+const char* nfx_version(void);
+
+/* ---- inputs --------------------------------------------------------------------------------- */
+/* Stage one slide tile in HBM. Replaces load_input_image + the image Mutex (src/main.rs:20-35,
+ * src/utils.rs:146). rgb: HOST pointer, u8 interleaved R,G,B, `h` rows of `row_stride_bytes`
+ * (>= 3*w). (origin_x, origin_y) = slide coordinates of the tile's pixel (0,0); polygon coordinates
+ * are slide coordinates. Pixels outside the tile read as 0, exactly like the reference's zero
+ * padding at image borders (src/utils.rs:174-192). The copy is asynchronous on the context stream
+ * when `rgb` is pinned memory. */
+int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h,
+                    int64_t row_stride_bytes, int64_t origin_x, int64_t origin_y);
+
+/* Stage n polygons (GeoJSON ring 0 of each feature, closing duplicate included, exactly as
+ * `geometry.coordinates[0]` parses to f32: src/geojson.rs:8-24) in CSR form:
+ * poly_xy = [poly_off[n]][2] f32 (x,y) slide coordinates, poly_off = [n+1] vertex offsets.
+ * Replaces the `&[Feature]` chunk handed to patch_loader (src/input.rs:13-30). */
+int nfx_polygons_upload(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* poly_off);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* Launch every kernel for the staged tile + polygons (asynchronous on the context stream):
+ * centroid/centring (utils.rs:54-74), mask rasterisation (utils.rs:152-157), patch gather
+ * (utils.rs:159-192, fused into the consumers through TMA) and the selected feature sets
+ * (shape.rs:16-130, color.rs:10-102, texture.rs:24-168). */
+int nfx_compute(nfx_ctx* ctx, uint32_t feature_mask);
+
+/* Wait for nfx_compute and copy results to HOST memory.
+ * centroids: [n][2] f32 (the key of utils.rs:226-232 is nfx_centroid_key of each row), may be NULL.
+ * features:  [n][nfx_feature_count(mask)] f32 row-major, rows in INPUT order, columns in flat()
+ * order (src/main.rs:76-89). May be NULL. */
+int nfx_download(nfx_ctx* ctx, float* centroids, float* features);
+
+/* nfx_polygons_upload + nfx_compute + nfx_download in one call: the drop-in for
+ * `chunk -> patch_loader -> move_tensors_to_device -> extract_features` (src/main.rs:148-151) over
+ * any number of chunks at once (n need not equal batch_size). */
+int nfx_extract(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* poly_off,
+                uint32_t feature_mask, float* centroids, float* features);
+
+int nfx_sync(nfx_ctx* ctx);
+
+/* ---- trait-level drop-in -------------------------------------------------------------------- */
+/* FeatureSet::compute_features_batched(centroids, polygons, patchs, masks) (src/features/mod.rs:
+ * 12-28) for ONE batch built by the reference's own loader: patchs [n,3,P,P] f32 with values k/255
+ * (utils.rs:172), masks [n,1,P,P] f32 in {0,1}, polygons = CENTRED rings (utils.rs:65-72) in CSR.
+ * `feature_set` is exactly one NFX_FS_* bit. All pointers are HOST pointers.
+ * out: [n][nfx_feature_count(feature_set)] f32. The whole call is one chunk for mean_h. */
+int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t feature_set, int64_t n,
+                                 const float* centroids, const float* poly_xy,
+                                 const int64_t* poly_off, const float* patchs, const float* masks,
+                                 float* out);
+
+/* ---- staged kernels (north-star kernels 1 and 2 on their own) and parity taps ---------------- */
+/* Kernel (1): batched patch gather of the staged polygons' windows from the staged tile into a
+ * device array of u8 patches [n][P][3P] (interleaved RGB), utils.rs:159-192. If out != NULL the
+ * patches are copied to the HOST array out[n][P][P][3]. */
+int nfx_gather_patches(nfx_ctx* ctx, uint8_t* out);
+/* Kernel (2): polygon -> mask rasterisation only (utils.rs:152-157). If out != NULL the masks are
+ * copied to HOST as u8 0/1 out[n][P][P]. */
+int nfx_rasterize(nfx_ctx* ctx, uint8_t* out);
+/* Ellipse masks drawn by the last geometry run (shape.rs:80-87), HOST u8 out[n][P][P]. */
+int nfx_debug_ellipses(nfx_ctx* ctx, uint8_t* out);
+/* Symmetric GLCM COUNTS (C + C^T, before normalisation) of the staged inputs for one
+ * (levels, offset) pair, HOST uint32 out[n][levels][levels] (texture.rs:40-46). */
+int nfx_debug_glcm_counts(nfx_ctx* ctx, int levels, int dy, int dx, uint32_t* out);
+/* Quantised grey levels min(floor(grey*levels), levels-1), HOST u8 out[n][P][P] (texture.rs:36). */
+int nfx_debug_grey_levels(nfx_ctx* ctx, int levels, uint8_t* out);
+
+/* ---- schema (column names of src/features/{shape,color,texture}.rs; set names of src/args.rs) -- */
+int nfx_feature_count(uint32_t feature_mask);
+/* Column `idx` (0-based, WITHOUT the leading "centroid" key column) for the given mask, or NULL. */
+const char* nfx_feature_name(uint32_t feature_mask, int idx);
+/* args::FeatureSet::from_str (src/args.rs:18-32): case-insensitive geometry|color|glcm|glrlm|
+ * gabor|texture|all -> bits. Returns NFX_ERR_INVALID for anything else. */
+int nfx_parse_feature_set(const char* name, uint32_t* bits);
+/* FeatureSet::name() of one bit (shape.rs:132-134, color.rs:104-106, texture.rs:169-171,312-314,
+ * 371-373): "geometry", "color", "GLCM", "GLRLM", "gabor filter". */
+const char* nfx_feature_set_name(uint32_t bit);
+/* centroid_to_key_string (src/utils.rs:226-228): Rust `Display` of both f32, comma separated.
+ * Returns the string length (excluding NUL) or NFX_ERR_INVALID if buf is too small. */
+int nfx_centroid_key(float x, float y, char* buf, int buflen);
+
+/* ---- multi-GPU partition ------------------------------------------------------ */
+/* Contiguous index ranges, one per part, boundaries rounded to multiples of batch_size so that
+ * every reference chunk [k*B,(k+1)*B) (src/main.rs:148) lives on one GPU. bounds: [parts+1]. */
+int nfx_partition(int64_t n, int32_t batch_size, int32_t parts, int64_t* bounds);
+
+/* ---- measurement ----------------------------------------------------------------------------- */
+typedef struct nfx_kernel_time {
+    char    name[48];
+    int64_t launches;
+    double  total_ms;      /* sum of CUDA-event durations of this kernel on the context stream */
+} nfx_kernel_time;
+/* When enabled every kernel launch is bracketed by CUDA events on the context stream. */
+int nfx_profile_enable(nfx_ctx* ctx, int enable);
+int nfx_profile_reset(nfx_ctx* ctx);
+/* Synchronises, then fills up to `max` entries; returns the number of distinct kernels. */
+int nfx_profile_get(nfx_ctx* ctx, nfx_kernel_time* out, int max);
+/* Whole-region timer on the context stream (CUDA events). */
+int nfx_timer_start(nfx_ctx* ctx);
+int nfx_timer_stop(nfx_ctx* ctx, float* elapsed_ms);   /* synchronises on the stop event */
+/* Number of kernel launches issued by this context since creation. */
+int64_t nfx_launch_count(const nfx_ctx* ctx);
+/* Write `bytes` of device memory (> L2) to evict the L2 between timed iterations. */
+int nfx_flush_l2(nfx_ctx* ctx);
+/* Pinned host allocations for H2D/D2H staging by the caller. */
+int nfx_host_alloc(void** p, int64_t bytes);
+int nfx_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFX_H */

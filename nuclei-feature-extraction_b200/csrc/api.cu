@@ -1,0 +1,659 @@
+// api.cu -- the C ABI of include/nfx.h: context, HBM staging, TMA descriptors, launch sequencing,
+// measurement. No torch, no CPU fallback: every compute entry point fails if CUDA fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/nfx.h"
+#include "nfx_host.h"
+#include "nfx_kernels.h"
+
+using namespace nfx;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t need) {
+        if (need <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = need + need / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct ProfRec {
+    cudaEvent_t a, b;
+    int kid;
+};
+
+}  // namespace
+
+struct nfx_ctx {
+    int device = 0;
+    int P = 64, B = 100;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    EncodeTiledFn encode = nullptr;
+
+    // tile
+    DevBuf<uint8_t> tile;
+    int64_t tw = 0, th = 0, tpitch = 0, tox = 0, toy = 0;
+    bool have_tile = false;
+    CUtensorMap map_tile_patch, map_tile_slab;
+
+    // polygons
+    DevBuf<float2> xy;
+    DevBuf<int64_t> off;
+    int64_t n = 0, nverts = 0;
+    int vmax = 0;
+    bool have_poly = false;
+
+    // per nucleus
+    DevBuf<float2> centroid;
+    DevBuf<NucInfo> info;
+    DevBuf<uint32_t> bitmask;
+    DevBuf<float> out;
+    DevBuf<float> hue;
+    DevBuf<uint32_t> ellipse;
+    uint32_t computed_mask = 0;
+    int out_cols = 0;
+    bool have_geom = false;   // centroid/info/bitmask valid for the staged polygons
+
+    // staged patch array (kernel (1) output / trait-level input)
+    DevBuf<uint8_t> patches;
+    int64_t ppitch = 0;
+    CUtensorMap map_pat_patch, map_pat_slab, map_pat_store;
+
+    // scratch
+    DevBuf<uint8_t> scratch8;
+    DevBuf<float> scratchf;
+    DevBuf<uint32_t> scratch32;
+    DevBuf<uint8_t> flush;
+    int* d_bad = nullptr;
+
+    // measurement
+    bool profile = false;
+    std::vector<ProfRec> recs;
+    std::vector<std::string> knames;
+    int64_t launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+namespace {
+
+int fail(nfx_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    g_thread_error = msg;
+    return code;
+}
+int cuda_fail(nfx_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, NFX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);   \
+    } while (0)
+
+int kernel_id(nfx_ctx* c, const char* name) {
+    for (size_t k = 0; k < c->knames.size(); ++k)
+        if (c->knames[k] == name) return (int)k;
+    c->knames.push_back(name);
+    return (int)c->knames.size() - 1;
+}
+
+// Launch wrapper: counts launches and, when profiling, brackets the launch with CUDA events on the
+// context stream (the stream the kernel runs on).
+template <typename F>
+cudaError_t timed(nfx_ctx* c, const char* name, int nlaunch, F&& f) {
+    ProfRec r;
+    const bool prof = c->profile;
+    if (prof) {
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        r.kid = kernel_id(c, name);
+        cudaEventRecord(r.a, c->stream);
+    }
+    cudaError_t e = f();
+    c->launches += nlaunch;
+    if (prof) {
+        cudaEventRecord(r.b, c->stream);
+        c->recs.push_back(r);
+    }
+    return e;
+}
+
+// 2D u8 tensor map: dim0 = bytes per row (width_bytes), dim1 = rows, box = {192 B, box_h rows}.
+int make_map(nfx_ctx* ctx, CUtensorMap* m, void* base, int64_t width_bytes, int64_t rows, int64_t pitch,
+             int box_h) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)width_bytes, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)kPanelBytes, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[160];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (CUresult %d; w=%lld rows=%lld pitch=%lld box_h=%d)",
+                 (int)r, (long long)width_bytes, (long long)rows, (long long)pitch, box_h);
+        return fail(ctx, NFX_ERR_CUDA, b);
+    }
+    return NFX_OK;
+}
+
+int set_device(nfx_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return NFX_OK;
+}
+
+struct Cols {
+    int shape, color, glcm, total;
+};
+Cols columns(uint32_t mask) {
+    Cols c;
+    c.shape = column_offset(mask, NFX_FS_GEOMETRY);
+    c.color = column_offset(mask, NFX_FS_COLOR);
+    c.glcm = column_offset(mask, NFX_FS_GLCM);
+    c.total = nfx_feature_count(mask);
+    return c;
+}
+
+int check_patch_size(nfx_ctx* ctx, uint32_t mask) {
+    if ((mask & NFX_FS_GLCM) && ctx->P > 128)
+        return fail(ctx, NFX_ERR_UNSUPPORTED, "GLCM kernel handles patch_size <= 128 in this build");
+    if (mask & (NFX_FS_GLRLM | NFX_FS_GABOR))
+        return fail(ctx, NFX_ERR_UNSUPPORTED, "GLRLM / Gabor feature sets are not built yet (SURVEY.md 8f-1)");
+    if (mask == 0 || (mask & ~NFX_FS_ALL)) return fail(ctx, NFX_ERR_INVALID, "empty or unknown feature mask");
+    return NFX_OK;
+}
+
+// Geometry pass over the staged polygons: centroid, window, bitmask (+ shape columns).
+int run_geom(nfx_ctx* ctx, bool shape, float* out, int stride, int col, uint32_t* ellipse_bits) {
+    const int64_t n = ctx->n;
+    const int wpr = mask_wpr(ctx->P);
+    CK(ctx->centroid.ensure(n));
+    CK(ctx->info.ensure(n));
+    CK(ctx->bitmask.ensure((size_t)n * ctx->P * wpr));
+    GeomParams g;
+    g.poly_xy = ctx->xy.p;
+    g.poly_off = ctx->off.p;
+    g.n = n;
+    g.P = ctx->P;
+    g.tile_ox = (int)ctx->tox;
+    g.tile_oy = (int)ctx->toy;
+    g.vmax = std::max(ctx->vmax, 1);
+    g.centroid = ctx->centroid.p;
+    g.info = ctx->info.p;
+    g.bitmask = ctx->bitmask.p;
+    g.out = out;
+    g.out_stride = stride;
+    g.col_shape = col;
+    g.ellipse_bits = ellipse_bits;
+    CK(timed(ctx, shape ? "k_geom<raster,shape>" : "k_geom<raster>", 1,
+             [&] { return launch_geom(g, true, shape, ctx->stream); }));
+    ctx->have_geom = true;
+    return NFX_OK;
+}
+
+int run_color(nfx_ctx* ctx, int64_t n, int batch, const CUtensorMap* mp, const CUtensorMap* ms, float* out,
+              int stride, int col) {
+    const int R = hue_slab_rows(ctx->P), slabs = (ctx->P + R - 1) / R;
+    CK(ctx->hue.ensure((size_t)n * slabs * 2));
+    ColorParams c;
+    c.n = n;
+    c.P = ctx->P;
+    c.batch_size = batch;
+    c.info = ctx->info.p;
+    c.bitmask = ctx->bitmask.p;
+    c.out = out;
+    c.out_stride = stride;
+    c.col_color = col;
+    c.hue_partial = ctx->hue.p;
+    c.slabs = slabs;
+    CK(timed(ctx, "k_color", 1, [&] { return launch_color(c, mp, ctx->stream); }));
+    CK(timed(ctx, "k_hue_batch", 1, [&] { return launch_hue_batch(c, ms, R, ctx->stream); }));
+    CK(timed(ctx, "k_hue_finalize", 1, [&] { return launch_hue_finalize(c, ctx->stream); }));
+    return NFX_OK;
+}
+
+int run_glcm(nfx_ctx* ctx, int64_t n, const CUtensorMap* mp, float* out, int stride, int col,
+             uint32_t* dbg_counts, int dl, int ddy, int ddx, uint8_t* dbg_grey) {
+    GlcmParams g;
+    g.n = n;
+    g.P = ctx->P;
+    g.info = ctx->info.p;
+    g.bitmask = ctx->bitmask.p;
+    g.out = out;
+    g.out_stride = stride;
+    g.col_glcm = col;
+    g.dbg_counts = dbg_counts;
+    g.dbg_levels = dl;
+    g.dbg_dy = ddy;
+    g.dbg_dx = ddx;
+    g.dbg_grey = dbg_grey;
+    CK(timed(ctx, "k_glcm", 1, [&] { return launch_glcm(g, mp, ctx->stream); }));
+    return NFX_OK;
+}
+
+int need_inputs(nfx_ctx* ctx, bool tile) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (tile && !ctx->have_tile) return fail(ctx, NFX_ERR_STATE, "no tile staged: call nfx_tile_upload first");
+    if (!ctx->have_poly) return fail(ctx, NFX_ERR_STATE, "no polygons staged: call nfx_polygons_upload first");
+    return NFX_OK;
+}
+
+int make_patch_array(nfx_ctx* ctx, int64_t n) {
+    const int P = ctx->P;
+    ctx->ppitch = ((3 * P + 15) / 16) * 16;
+    CK(ctx->patches.ensure((size_t)n * P * ctx->ppitch));
+    const int R = hue_slab_rows(P);
+    int rc;
+    if ((rc = make_map(ctx, &ctx->map_pat_patch, ctx->patches.p, 3 * P, n * P, ctx->ppitch, P))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_pat_slab, ctx->patches.p, 3 * P, n * P, ctx->ppitch, R))) return rc;
+    return NFX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nfx_last_error(const nfx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_thread_error.c_str(); }
+
+int nfx_create(int device, const nfx_config* cfg, nfx_ctx** out) {
+    if (!out) return fail(nullptr, NFX_ERR_INVALID, "nfx_create: out is NULL");
+    *out = nullptr;
+    int P = 64, B = 100;
+    if (cfg) {
+        if (cfg->patch_size) P = cfg->patch_size;
+        if (cfg->batch_size) B = cfg->batch_size;
+    }
+    if (P < 16 || P > 256 || (P & 3)) return fail(nullptr, NFX_ERR_UNSUPPORTED, "patch_size must be a multiple of 4 in [16,256]");
+    if (B < 1) return fail(nullptr, NFX_ERR_INVALID, "batch_size must be >= 1");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceCount (no CUDA device: there is no CPU fallback)");
+    if (device < 0 || device >= count) return fail(nullptr, NFX_ERR_INVALID, "GPU " + std::to_string(device) + " does not exist");   // args.rs:176-180
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10) return fail(nullptr, NFX_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; device is ") + prop.name);
+    nfx_ctx* ctx = new nfx_ctx();
+    ctx->device = device;
+    ctx->P = P;
+    ctx->B = B;
+    auto bail = [&](int rc) { nfx_destroy(ctx); return rc; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(cuda_fail(nullptr, e, "cudaSetDevice"));
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(nullptr, e, "cudaStreamCreate"));
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) return bail(fail(nullptr, NFX_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver"));
+    ctx->encode = (EncodeTiledFn)fn;
+    if ((e = cudaEventCreate(&ctx->t0)) != cudaSuccess || (e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail(cuda_fail(nullptr, e, "cudaEventCreate"));
+    if ((e = cudaMalloc((void**)&ctx->d_bad, sizeof(int))) != cudaSuccess) return bail(cuda_fail(nullptr, e, "cudaMalloc"));
+    *out = ctx;
+    return NFX_OK;
+}
+
+int nfx_destroy(nfx_ctx* ctx) {
+    if (!ctx) return NFX_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->tile.release(); ctx->xy.release(); ctx->off.release(); ctx->centroid.release(); ctx->info.release();
+    ctx->bitmask.release(); ctx->out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->patches.release();
+    ctx->scratch8.release(); ctx->scratchf.release(); ctx->scratch32.release(); ctx->flush.release();
+    if (ctx->d_bad) cudaFree(ctx->d_bad);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return NFX_OK;
+}
+
+int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h, int64_t row_stride_bytes,
+                    int64_t origin_x, int64_t origin_y) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (!rgb || w <= 0 || h <= 0 || row_stride_bytes < 3 * w) return fail(ctx, NFX_ERR_INVALID, "nfx_tile_upload: bad arguments");
+    if (3 * w >= (1ll << 31) || h >= (1ll << 31)) return fail(ctx, NFX_ERR_UNSUPPORTED, "tile too large for 32-bit TMA coordinates");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    const int64_t pitch = ((3 * w + 15) / 16) * 16;
+    CK(ctx->tile.ensure((size_t)pitch * h + 256));
+    CK(cudaMemcpy2DAsync(ctx->tile.p, pitch, rgb, row_stride_bytes, 3 * w, h, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->tw = w; ctx->th = h; ctx->tpitch = pitch; ctx->tox = origin_x; ctx->toy = origin_y;
+    if ((rc = make_map(ctx, &ctx->map_tile_patch, ctx->tile.p, 3 * w, h, pitch, ctx->P))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_tile_slab, ctx->tile.p, 3 * w, h, pitch, hue_slab_rows(ctx->P)))) return rc;
+    ctx->have_tile = true;
+    ctx->have_geom = false;   // window origins depend on the tile origin
+    return NFX_OK;
+}
+
+int nfx_polygons_upload(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* poly_off) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!poly_xy || !poly_off))) return fail(ctx, NFX_ERR_INVALID, "nfx_polygons_upload: bad arguments");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    int64_t total = 0;
+    int vmax = 0;
+    if (n > 0) {
+        if (poly_off[0] != 0) return fail(ctx, NFX_ERR_INVALID, "poly_off[0] must be 0");
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t v = poly_off[i + 1] - poly_off[i];
+            if (v < 0) return fail(ctx, NFX_ERR_INVALID, "poly_off must be non-decreasing");
+            if (v > 8000) return fail(ctx, NFX_ERR_UNSUPPORTED, "ring longer than 8000 vertices");
+            vmax = std::max<int64_t>(vmax, v);
+        }
+        total = poly_off[n];
+    }
+    CK(ctx->xy.ensure((size_t)total + 1));
+    CK(ctx->off.ensure((size_t)n + 1));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->xy.p, poly_xy, (size_t)total * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->off.p, poly_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->n = n; ctx->nverts = total; ctx->vmax = vmax;
+    ctx->have_poly = true;
+    ctx->have_geom = false;
+    ctx->computed_mask = 0;
+    return NFX_OK;
+}
+
+int nfx_compute(nfx_ctx* ctx, uint32_t mask) {
+    int rc = need_inputs(ctx, true);
+    if (rc) return rc;
+    if ((rc = check_patch_size(ctx, mask))) return rc;
+    if ((rc = set_device(ctx))) return rc;
+    const Cols c = columns(mask);
+    const int64_t n = ctx->n;
+    CK(ctx->out.ensure((size_t)std::max<int64_t>(n, 1) * c.total));
+    ctx->out_cols = c.total;
+    ctx->computed_mask = 0;
+    if (n == 0) { ctx->computed_mask = mask; return NFX_OK; }
+    if ((rc = run_geom(ctx, (mask & NFX_FS_GEOMETRY) != 0, ctx->out.p, c.total, c.shape, nullptr))) return rc;
+    if (mask & NFX_FS_COLOR)
+        if ((rc = run_color(ctx, n, ctx->B, &ctx->map_tile_patch, &ctx->map_tile_slab, ctx->out.p, c.total, c.color))) return rc;
+    if (mask & NFX_FS_GLCM)
+        if ((rc = run_glcm(ctx, n, &ctx->map_tile_patch, ctx->out.p, c.total, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
+    ctx->computed_mask = mask;
+    return NFX_OK;
+}
+
+int nfx_sync(nfx_ctx* ctx) {
+    if (!ctx) return NFX_ERR_INVALID;
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_download(nfx_ctx* ctx, float* centroids, float* features) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (!ctx->computed_mask) return fail(ctx, NFX_ERR_STATE, "nothing computed: call nfx_compute first");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    if (ctx->n > 0) {
+        if (centroids) CK(cudaMemcpyAsync(centroids, ctx->centroid.p, (size_t)ctx->n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        if (features) CK(cudaMemcpyAsync(features, ctx->out.p, (size_t)ctx->n * ctx->out_cols * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_extract(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* poly_off, uint32_t mask,
+                float* centroids, float* features) {
+    int rc = nfx_polygons_upload(ctx, n, poly_xy, poly_off);
+    if (rc) return rc;
+    if ((rc = nfx_compute(ctx, mask))) return rc;
+    return nfx_download(ctx, centroids, features);
+}
+
+int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const float* centroids,
+                                 const float* poly_xy, const int64_t* poly_off, const float* patchs,
+                                 const float* masks, float* out) {
+    if (!ctx) return NFX_ERR_INVALID;
+    (void)centroids;   // only used for the key column, which the host formats (utils.rs:226-232)
+    if (fs != NFX_FS_GEOMETRY && fs != NFX_FS_COLOR && fs != NFX_FS_GLCM && fs != NFX_FS_GLRLM && fs != NFX_FS_GABOR)
+        return fail(ctx, NFX_ERR_INVALID, "feature_set must be exactly one NFX_FS_* bit");
+    int rc = check_patch_size(ctx, fs);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!patchs || !masks || !out))) return fail(ctx, NFX_ERR_INVALID, "nfx_compute_features_batched: bad arguments");
+    if (n == 0) return NFX_OK;
+    if ((rc = set_device(ctx))) return rc;
+    // the asserts of shape.rs:23-47 / color.rs:18-42 become argument checks on the CSR
+    if (fs == NFX_FS_GEOMETRY)
+        if ((rc = nfx_polygons_upload(ctx, n, poly_xy, poly_off))) return rc;   // centred rings
+    const int P = ctx->P, wpr = mask_wpr(P);
+    const size_t plane = (size_t)P * P;
+    CK(ctx->scratchf.ensure((size_t)n * 4 * plane));
+    float* d_patchs = ctx->scratchf.p;
+    float* d_masks = d_patchs + (size_t)n * 3 * plane;
+    CK(cudaMemcpyAsync(d_patchs, patchs, (size_t)n * 3 * plane * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_masks, masks, (size_t)n * plane * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = make_patch_array(ctx, n))) return rc;
+    CK(ctx->info.ensure(n));
+    CK(ctx->centroid.ensure(n));
+    CK(ctx->bitmask.ensure((size_t)n * P * wpr));
+    CK(cudaMemsetAsync(ctx->d_bad, 0, sizeof(int), ctx->stream));
+    CK(timed(ctx, "k_pack_batch", 1, [&] {
+        return launch_pack_batch(n, P, d_patchs, d_masks, ctx->patches.p, ctx->ppitch, ctx->bitmask.p,
+                                 ctx->info.p, ctx->d_bad, ctx->stream);
+    }));
+    const int cols = nfx_feature_count(fs);
+    CK(ctx->out.ensure((size_t)n * cols));
+    if (fs == NFX_FS_GEOMETRY) {
+        GeomParams g;
+        g.poly_xy = ctx->xy.p; g.poly_off = ctx->off.p; g.n = n; g.P = P; g.tile_ox = 0; g.tile_oy = 0;
+        g.vmax = std::max(ctx->vmax, 1); g.centroid = ctx->centroid.p; g.info = ctx->info.p;
+        g.bitmask = ctx->bitmask.p; g.out = ctx->out.p; g.out_stride = cols; g.col_shape = 0; g.ellipse_bits = nullptr;
+        CK(timed(ctx, "k_geom<shape>", 1, [&] { return launch_geom(g, false, true, ctx->stream); }));
+    } else if (fs == NFX_FS_COLOR) {
+        if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_patch, &ctx->map_pat_slab, ctx->out.p, cols, 0))) return rc;
+    } else if (fs == NFX_FS_GLCM) {
+        if ((rc = run_glcm(ctx, n, &ctx->map_pat_patch, ctx->out.p, cols, 0, nullptr, 0, 0, 0, nullptr))) return rc;
+    }
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->out.p, (size_t)n * cols * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_geom = false;
+    ctx->have_poly = false;   // the staged rings were centred ones: force a fresh upload for nfx_compute
+    ctx->computed_mask = 0;
+    if (bad) return fail(ctx, NFX_ERR_UNSUPPORTED, "patchs holds values that are not k/255 (only image-derived batches, utils.rs:172, are supported)");
+    return NFX_OK;
+}
+
+int nfx_rasterize(nfx_ctx* ctx, uint8_t* out) {
+    int rc = need_inputs(ctx, false);
+    if (rc) return rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (ctx->n == 0) return NFX_OK;
+    if ((rc = run_geom(ctx, false, nullptr, 0, -1, nullptr))) return rc;
+    if (out) {
+        const size_t total = (size_t)ctx->n * ctx->P * ctx->P;
+        CK(ctx->scratch8.ensure(total));
+        CK(timed(ctx, "k_expand", 1, [&] { return launch_expand_mask(ctx->n, ctx->P, ctx->bitmask.p, ctx->scratch8.p, ctx->stream); }));
+        CK(cudaMemcpyAsync(out, ctx->scratch8.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_gather_patches(nfx_ctx* ctx, uint8_t* out) {
+    int rc = need_inputs(ctx, true);
+    if (rc) return rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (ctx->n == 0) return NFX_OK;
+    if (!ctx->have_geom)
+        if ((rc = run_geom(ctx, false, nullptr, 0, -1, nullptr))) return rc;
+    if ((rc = make_patch_array(ctx, ctx->n))) return rc;
+    CK(timed(ctx, "k_gather", 1, [&] {
+        return launch_gather(ctx->n, ctx->P, ctx->info.p, &ctx->map_tile_patch, &ctx->map_pat_patch, ctx->stream);
+    }));
+    if (out)
+        CK(cudaMemcpy2DAsync(out, (size_t)3 * ctx->P, ctx->patches.p, ctx->ppitch, (size_t)3 * ctx->P,
+                             (size_t)ctx->n * ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_debug_ellipses(nfx_ctx* ctx, uint8_t* out) {
+    int rc = need_inputs(ctx, false);
+    if (rc) return rc;
+    if (!out) return fail(ctx, NFX_ERR_INVALID, "out is NULL");
+    if ((rc = set_device(ctx))) return rc;
+    if (ctx->n == 0) return NFX_OK;
+    const int wpr = mask_wpr(ctx->P);
+    CK(ctx->ellipse.ensure((size_t)ctx->n * ctx->P * wpr));
+    CK(ctx->scratchf.ensure((size_t)ctx->n * kShapeCols));
+    if ((rc = run_geom(ctx, true, ctx->scratchf.p, kShapeCols, 0, ctx->ellipse.p))) return rc;
+    const size_t total = (size_t)ctx->n * ctx->P * ctx->P;
+    CK(ctx->scratch8.ensure(total));
+    CK(timed(ctx, "k_expand", 1, [&] { return launch_expand_mask(ctx->n, ctx->P, ctx->ellipse.p, ctx->scratch8.p, ctx->stream); }));
+    CK(cudaMemcpyAsync(out, ctx->scratch8.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+
+static int glcm_debug(nfx_ctx* ctx, int levels, int dy, int dx, uint32_t* counts, uint8_t* grey) {
+    int rc = need_inputs(ctx, true);
+    if (rc) return rc;
+    if (levels != 32 && levels != 64 && levels != 128 && levels != 254) return fail(ctx, NFX_ERR_INVALID, "levels must be one of 32, 64, 128, 254 (texture.rs:19)");
+    if ((rc = check_patch_size(ctx, NFX_FS_GLCM))) return rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (ctx->n == 0) return NFX_OK;
+    if (!ctx->have_geom)
+        if ((rc = run_geom(ctx, false, nullptr, 0, -1, nullptr))) return rc;
+    uint32_t* d_counts = nullptr;
+    uint8_t* d_grey = nullptr;
+    if (counts) {
+        const size_t words = (size_t)ctx->n * levels * levels;
+        CK(ctx->scratch32.ensure(words));
+        CK(cudaMemsetAsync(ctx->scratch32.p, 0, words * 4, ctx->stream));
+        d_counts = ctx->scratch32.p;
+    }
+    if (grey) {
+        CK(ctx->scratch8.ensure((size_t)ctx->n * ctx->P * ctx->P));
+        d_grey = ctx->scratch8.p;
+    }
+    if ((rc = run_glcm(ctx, ctx->n, &ctx->map_tile_patch, nullptr, 0, 0, d_counts, levels, dy, dx, d_grey))) return rc;
+    if (counts) CK(cudaMemcpyAsync(counts, d_counts, (size_t)ctx->n * levels * levels * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (grey) CK(cudaMemcpyAsync(grey, d_grey, (size_t)ctx->n * ctx->P * ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_debug_glcm_counts(nfx_ctx* ctx, int levels, int dy, int dx, uint32_t* out) {
+    if (!out) return fail(ctx, NFX_ERR_INVALID, "out is NULL");
+    return glcm_debug(ctx, levels, dy, dx, out, nullptr);
+}
+int nfx_debug_grey_levels(nfx_ctx* ctx, int levels, uint8_t* out) {
+    if (!out) return fail(ctx, NFX_ERR_INVALID, "out is NULL");
+    return glcm_debug(ctx, levels, 0, 1, nullptr, out);
+}
+
+// ---- measurement ------------------------------------------------------------------------------
+int nfx_profile_enable(nfx_ctx* ctx, int enable) {
+    if (!ctx) return NFX_ERR_INVALID;
+    ctx->profile = enable != 0;
+    return NFX_OK;
+}
+int nfx_profile_reset(nfx_ctx* ctx) {
+    if (!ctx) return NFX_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->recs.clear();
+    return NFX_OK;
+}
+int nfx_profile_get(nfx_ctx* ctx, nfx_kernel_time* out, int max) {
+    if (!ctx) return NFX_ERR_INVALID;
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<nfx_kernel_time> acc(ctx->knames.size());
+    for (size_t k = 0; k < acc.size(); ++k) {
+        memset(&acc[k], 0, sizeof acc[k]);
+        snprintf(acc[k].name, sizeof acc[k].name, "%s", ctx->knames[k].c_str());
+    }
+    for (auto& r : ctx->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            acc[r.kid].launches += 1;
+            acc[r.kid].total_ms += ms;
+        }
+    }
+    int cnt = 0;
+    for (auto& a : acc) {
+        if (!a.launches) continue;
+        if (out && cnt < max) out[cnt] = a;
+        ++cnt;
+    }
+    return cnt;
+}
+int nfx_timer_start(nfx_ctx* ctx) {
+    if (!ctx) return NFX_ERR_INVALID;
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->t0, ctx->stream));
+    return NFX_OK;
+}
+int nfx_timer_stop(nfx_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return NFX_ERR_INVALID;
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->t1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->t1));
+    CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return NFX_OK;
+}
+int64_t nfx_launch_count(const nfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int nfx_flush_l2(nfx_ctx* ctx) {
+    if (!ctx) return NFX_ERR_INVALID;
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    const size_t bytes = 256ull << 20;   // > 126 MB L2
+    CK(ctx->flush.ensure(bytes));
+    CK(cudaMemsetAsync(ctx->flush.p, 0x5a, bytes, ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes < 0) return NFX_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+    return NFX_OK;
+}
+int nfx_host_free(void* p) {
+    if (!p) return NFX_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFreeHost");
+    return NFX_OK;
+}
+
+}  // extern "C"

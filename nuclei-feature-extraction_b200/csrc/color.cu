@@ -1,0 +1,427 @@
+// color.cu -- north-star kernels (1) patch gather (fused: one TMA box per nucleus, zero fill at the
+// borders) and (3) masked colour/intensity statistics.
+//
+// Replaces ColorFeatureSet::compute_features_batched (src/features/color.rs:10-102):
+//   hsv_from_rgb / hed_from_rgb   color.rs:45-46   (oracle/SPEC.md B3, B4)
+//   mean_std x3                   color.rs:47-53, 117-134
+//   circular_mean (batch coupled) color.rs:50-51, 144-155  -> k_hue_batch + k_hue_finalize
+// and the gather of src/utils.rs:159-192 (the u8 window goes tile -> shared memory by TMA and is
+// never materialised in HBM, neither as u8 nor as the reference's f32 [N,3,P,P]).
+//
+// k_color   : one CTA per nucleus; masked single-pass sums (exact integers for RGB and V, pivoted
+//             f32 for S, H and HED), warp-shuffle + shared-memory reduction, 17 columns.
+// k_hue_batch: the reference's `h.cos() * mask` broadcasts [N,P,P]*[N,1,P,P] to [N,N,P,P]: mean_h[i]
+//             sums the hue of EVERY patch of the batch under mask i. It factorises into one P x P
+//             image per batch, C[p] = sum_j cos h_j[p], S[p] = sum_j sin h_j[p], followed by masked
+//             sums. One CTA per (batch, row slab): a TMA producer warp streams the slab of each of
+//             the batch's patches through a 4-stage mbarrier ring, 8 consumer warps keep C,S in
+//             registers, then each warp folds the slab under the masks of its share of nuclei.
+// k_hue_finalize: sums slab partials in fixed order (bit-reproducible for any GPU count) + atan2.
+#include <math_constants.h>
+
+#include "nfx_kernels.h"
+
+namespace nfx {
+
+namespace {
+
+constexpr int kColorThreads = 128;
+constexpr int kHueConsumers = 256;               // 8 consumer warps
+constexpr int kHueThreads = kHueConsumers + 32;  // + 1 TMA producer warp
+constexpr int kHueStages = 4;
+constexpr int kHueChunk = 128;                   // nuclei whose NucInfo is staged in smem at a time
+
+// OD(v) = ln(max(v/255, 1e-6)) / ln(1e-6), f32 (SPEC.md B4); filled once per process.
+__device__ float g_od_lut[256];
+
+__global__ void k_init_od_lut() {
+    const int v = threadIdx.x;
+    const float x = fmaxf(__fdiv_rn((float)v, 255.0f), 1e-6f);
+    g_od_lut[v] = __fdiv_rn(logf(x), -13.815510749816895f);
+}
+
+// inv([[0.65,0.70,0.29],[0.07,0.99,0.11],[0.27,0.57,0.78]]) in f32, M[k][c] (oracle HED_FROM_RGB)
+#define HED_M00 1.87798273563385f
+#define HED_M01 -1.0076786279678345f
+#define HED_M02 -0.5561158061027527f
+#define HED_M10 -0.06590805947780609f
+#define HED_M11 1.134730339050293f
+#define HED_M12 -0.135521799325943f
+#define HED_M20 -0.6019073724746704f
+#define HED_M21 -0.48041418194770813f
+#define HED_M22 1.5735880136489868f
+
+__device__ __forceinline__ float u8f(uint32_t v) {   // exact u8 -> f32 without I2F
+    return __uint_as_float(0x4B000000u | v) - 8388608.0f;
+}
+
+struct Px {
+    uint32_t r, g, b;
+};
+__device__ __forceinline__ Px quad_px(uint32_t w0, uint32_t w1, uint32_t w2, int k) {
+    Px p;
+    switch (k) {
+        case 0: p.r = w0 & 0xff; p.g = (w0 >> 8) & 0xff; p.b = (w0 >> 16) & 0xff; break;
+        case 1: p.r = w0 >> 24; p.g = w1 & 0xff; p.b = (w1 >> 8) & 0xff; break;
+        case 2: p.r = (w1 >> 16) & 0xff; p.g = w1 >> 24; p.b = w2 & 0xff; break;
+        default: p.r = (w2 >> 8) & 0xff; p.g = (w2 >> 16) & 0xff; p.b = w2 >> 24; break;
+    }
+    return p;
+}
+
+// hexcone hue in sextants t in [0,6] (SPEC.md B3): H = 60 t. d = max - min > 0 required.
+__device__ __forceinline__ float hue_sextant(const Px& p, uint32_t mx, uint32_t d) {
+    const float rd = __frcp_rn(u8f(d));
+    float t;
+    if (mx == p.r) {
+        t = ((float)((int)p.g - (int)p.b)) * rd;
+        if (t < 0.f) t += 6.0f;
+    } else if (mx == p.g) {
+        t = ((float)((int)p.b - (int)p.r)) * rd + 2.0f;
+    } else {
+        t = ((float)((int)p.r - (int)p.g)) * rd + 4.0f;
+    }
+    return t;
+}
+
+struct HsvHed {
+    float h, s;         // degrees, [0,1]
+    float hed[3];
+    uint32_t mx;        // V * 255
+};
+__device__ __forceinline__ HsvHed convert(const Px& p, const float* lut) {
+    HsvHed o;
+    const uint32_t mx = max(p.r, max(p.g, p.b)), mn = min(p.r, min(p.g, p.b)), d = mx - mn;
+    o.mx = mx;
+    o.s = mx ? __fdividef(u8f(d), u8f(mx)) : 0.f;
+    o.h = d ? 60.0f * hue_sextant(p, mx, d) : 0.f;
+    const float a = lut[p.r], b = lut[p.g], c = lut[p.b];
+    o.hed[0] = fmaxf(0.f, a * HED_M00 + b * HED_M10 + c * HED_M20);
+    o.hed[1] = fmaxf(0.f, a * HED_M01 + b * HED_M11 + c * HED_M21);
+    o.hed[2] = fmaxf(0.f, a * HED_M02 + b * HED_M12 + c * HED_M22);
+    return o;
+}
+
+// Zero the part of the window the reference never copies (NucInfo comment): rare, warp-uniform.
+__device__ __forceinline__ void zero_uncopied(uint8_t* patch, int P, int nvc, int nvr) {
+    if (nvc >= P && nvr >= P) return;
+    for (int k = threadIdx.x; k < P * P; k += blockDim.x) {
+        const int r = k / P, c = k - r * P;
+        if (r >= nvr || c >= nvc) {
+            const int a = patch_addr(P, r, c);
+            patch[a] = 0; patch[a + 1] = 0; patch[a + 2] = 0;
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kColorThreads)
+k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x;
+    const int64_t i = blockIdx.x;
+    uint8_t* patch = smem_raw;
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + patch_smem_bytes(P));
+    float* lut = reinterpret_cast<float*>(rows + P * wpr);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_red[19 * (kColorThreads / 32)];
+    __shared__ int s_box[4];
+
+    const NucInfo inf = p.info[i];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        s_box[0] = P; s_box[1] = -1; s_box[2] = P; s_box[3] = -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
+        tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
+    }
+    // while the window is in flight: mask rows, OD table, bounding box of the mask
+    int rmin = P, rmax = -1;
+    uint32_t colbits[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wpr <= 8 (P <= 256)
+    const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
+    for (int r = tid; r < P; r += kColorThreads) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < wpr) {
+                const uint32_t b = gm[r * wpr + w];
+                rows[r * wpr + w] = b;
+                colbits[w] |= b;
+                any |= b;
+            }
+        }
+        if (any) { rmin = min(rmin, r); rmax = max(rmax, r); }
+    }
+    for (int k = tid; k < 256; k += kColorThreads) lut[k] = g_od_lut[k];
+    int cmin = P, cmax = -1;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < wpr) {
+            const uint32_t b = __reduce_or_sync(0xffffffffu, colbits[w]);
+            if (b) { cmin = min(cmin, 32 * w + __ffs(b) - 1); cmax = max(cmax, 32 * w + 31 - __clz(b)); }
+        }
+    }
+    rmin = warp_min(rmin); rmax = warp_max(rmax);
+    if ((tid & 31) == 0) {
+        atomicMin(&s_box[0], rmin); atomicMax(&s_box[1], rmax);
+        atomicMin(&s_box[2], cmin); atomicMax(&s_box[3], cmax);
+    }
+    __syncthreads();
+    rmin = s_box[0]; rmax = s_box[1]; cmin = s_box[2]; cmax = s_box[3];
+
+    mbar_wait(&bar, 0);
+    zero_uncopied(patch, P, inf.nvc, inf.nvr);
+
+    // pivots (any value of the right magnitude removes the cancellation of the one-pass variance)
+    HsvHed pv;
+    {
+        const int a = patch_addr(P, P / 2, P / 2);
+        Px c = {patch[a], patch[a + 1], patch[a + 2]};
+        pv = convert(c, lut);
+    }
+
+    uint32_t n = 0, sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
+    float s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};   // hed0, hed1, hed2, s, h (pivoted)
+    if (rmax >= rmin) {
+        const int q0 = cmin >> 2, nq = (cmax >> 2) - q0 + 1, items = (rmax - rmin + 1) * nq;
+        for (int it = tid; it < items; it += kColorThreads) {
+            const int r = rmin + it / nq, q = q0 + it % nq;
+            const uint32_t nib = (rows[r * wpr + (q >> 3)] >> ((q & 7) * 4)) & 0xFu;
+            if (!nib) continue;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(patch + patch_addr(P, r, q * 4));
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!((nib >> k) & 1u)) continue;
+                const Px px = quad_px(w0, w1, w2, k);
+                const HsvHed c = convert(px, lut);
+                ++n;
+                sr += px.r; sg += px.g; sb += px.b;
+                srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
+                sv += c.mx; svv += c.mx * c.mx;
+                float d;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { d = c.hed[j] - pv.hed[j]; s1[j] += d; s2[j] = fmaf(d, d, s2[j]); }
+                d = c.s - pv.s; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
+                d = c.h - pv.h; s1[4] += d; s2[4] = fmaf(d, d, s2[4]);
+            }
+        }
+    }
+    double v[19];
+    v[0] = n; v[1] = sr; v[2] = sg; v[3] = sb; v[4] = srr; v[5] = sgg; v[6] = sbb; v[7] = sv; v[8] = svv;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { v[9 + j] = s1[j]; v[14 + j] = s2[j]; }
+    block_sum<19>(v, s_red);
+
+    if (tid == 0) {
+        float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
+        const double K = v[0];
+        auto mean8 = [&](double s) { return (float)(s / K / 255.0); };
+        auto std8 = [&](double s, double ss) {
+            const double m = s / K;
+            return (float)(sqrt(fmax(ss / K - m * m, 0.0)) / 255.0);
+        };
+        auto meanp = [&](int j, float pivot) { return (float)((double)pivot + v[9 + j] / K); };
+        auto stdp = [&](int j) {
+            const double m = v[9 + j] / K;
+            return (float)sqrt(fmax(v[14 + j] / K - m * m, 0.0));
+        };
+        out[0] = mean8(v[1]); out[1] = mean8(v[2]); out[2] = mean8(v[3]);
+        out[3] = std8(v[1], v[4]); out[4] = std8(v[2], v[5]); out[5] = std8(v[3], v[6]);
+        // out[6] = mean_h: k_hue_finalize
+        out[7] = meanp(3, pv.s);
+        out[8] = mean8(v[7]);
+        out[9] = stdp(4);
+        out[10] = stdp(3);
+        out[11] = std8(v[7], v[8]);
+        out[12] = meanp(0, pv.hed[0]); out[13] = meanp(1, pv.hed[1]); out[14] = meanp(2, pv.hed[2]);
+        out[15] = stdp(0); out[16] = stdp(1); out[17] = stdp(2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid = (n_batches, slabs). Dynamic smem: ring[kHueStages][panels*192*R] | Cs[R*P] | Ss[R*P] f32.
+__global__ void __launch_bounds__(kHueThreads)
+k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int np = patch_panels(P);
+    const int stage_bytes = np * kPanelBytes * R;
+    const int64_t b0 = (int64_t)blockIdx.x * p.batch_size;
+    const int nb = (int)min((int64_t)p.batch_size, p.n - b0);
+    const int slab = blockIdx.y, row0 = slab * R;
+    uint8_t* ring = smem_raw;
+    float* Cs = reinterpret_cast<float*>(smem_raw + (size_t)kHueStages * stage_bytes);
+    float* Ss = Cs + R * P;
+    __shared__ __align__(8) uint64_t full[kHueStages], empty[kHueStages];
+    __shared__ NucInfo s_info[kHueChunk];
+
+    if (tid == 0) {
+        for (int s = 0; s < kHueStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kHueConsumers / 32); }
+        mbar_fence_init();
+    }
+    // consumer pixel ownership: one quad (4 px) per consumer thread
+    const int qpr = P >> 2;
+    const int rr = tid / qpr, qc = tid - rr * qpr;
+    const bool owner = (tid < kHueConsumers) && (rr < R) && (row0 + rr < P);
+    float C[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
+    const int c0 = qc * 4;
+    const int soff = (c0 >> 6) * (kPanelBytes * R) + rr * kPanelBytes + (c0 & 63) * 3;
+
+    int it = 0;   // global iteration counter over the batch's nuclei (ring position)
+    for (int base = 0; base < nb; base += kHueChunk) {
+        const int cnt = min(kHueChunk, nb - base);
+        __syncthreads();   // previous chunk fully consumed before s_info is overwritten
+        for (int k = tid; k < cnt; k += kHueThreads) s_info[k] = p.info[b0 + base + k];
+        __syncthreads();
+        if (warp == kHueConsumers / 32) {
+            // ---- TMA producer warp (one elected lane) ----
+            if (lane == 0) {
+                for (int j = 0; j < cnt; ++j) {
+                    const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
+                    if (g >= kHueStages) mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                    const NucInfo inf = s_info[j];
+                    for (int k = 0; k < np; ++k)
+                        tma_load_2d(ring + (size_t)s * stage_bytes + (size_t)k * kPanelBytes * R, &map,
+                                    (inf.left + k * kPanelPx) * 3, inf.top + row0, &full[s]);
+                }
+            }
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
+                mbar_wait(&full[s], ph);
+                uint32_t w0 = 0, w1 = 0, w2 = 0;
+                if (owner) {
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(ring + (size_t)s * stage_bytes + soff);
+                    w0 = wp[0]; w1 = wp[1]; w2 = wp[2];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (owner) {
+                    const NucInfo inf = s_info[j];
+                    const bool rowdead = (row0 + rr) >= inf.nvr;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        Px px = quad_px(w0, w1, w2, k);
+                        if (rowdead || (c0 + k) >= inf.nvc) { px.r = 0; px.g = 0; px.b = 0; }
+                        const uint32_t mx = max(px.r, max(px.g, px.b)), mn = min(px.r, min(px.g, px.b)), d = mx - mn;
+                        float cs = 1.0f, sn = 0.0f;
+                        if (d) {
+                            // h = 60 t degrees = t/6 turns; sin/cos.approx take radians
+                            const float ang = hue_sextant(px, mx, d) * 1.0471975511965976f;
+                            cs = __cosf(ang);
+                            sn = __sinf(ang);
+                        }
+                        C[k] += cs;
+                        S[k] += sn;
+                    }
+                }
+            }
+        }
+        it += cnt;
+    }
+    __syncthreads();
+    if (owner) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c0 + k < P) {
+                Cs[rr * P + c0 + k] = C[k];
+                Ss[rr * P + c0 + k] = S[k];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- masked sums of the slab's (S, C) image under each nucleus' mask ----
+    const int nrows = min(R, P - row0), words = nrows * wpr;
+    for (int i = warp; i < nb; i += kHueThreads / 32) {
+        const uint32_t* gm = p.bitmask + ((b0 + i) * (int64_t)P + row0) * wpr;
+        float ss = 0.f, sc = 0.f;
+        for (int w = lane; w < words; w += 32) {
+            uint32_t bits = gm[w];
+            const int r = w / wpr, cb = (w - r * wpr) * 32;
+            while (bits) {
+                const int c = cb + __ffs(bits) - 1;
+                bits &= bits - 1;
+                ss += Ss[r * P + c];
+                sc += Cs[r * P + c];
+            }
+        }
+        ss = warp_sum(ss);
+        sc = warp_sum(sc);
+        if (lane == 0) {
+            float* hp = p.hue_partial + ((b0 + i) * (int64_t)p.slabs + slab) * 2;
+            hp[0] = ss;
+            hp[1] = sc;
+        }
+    }
+}
+
+__global__ void k_hue_finalize(const ColorParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
+    const float* hp = p.hue_partial + i * (int64_t)p.slabs * 2;
+    float ss = 0.f, sc = 0.f;
+    for (int s = 0; s < p.slabs; ++s) { ss += hp[2 * s]; sc += hp[2 * s + 1]; }
+    // color.rs:154  (atan2(sin, cos).rad2deg + 360) fmod 360 ; empty mask -> 0/0 -> NaN
+    float deg = atan2f(ss, sc) * 57.29577951308232f;
+    deg = fmodf(deg + 360.0f, 360.0f);
+    if (out[0] != out[0]) deg = CUDART_NAN_F;   // mean_r is NaN iff the mask is empty
+    out[6] = deg;
+}
+
+}  // namespace
+
+int hue_slab_rows(int P) { return max(1, min(P, 1024 / P)); }
+int color_smem_bytes(int P) { return patch_smem_bytes(P) + P * mask_wpr(P) * 4 + 256 * 4; }
+
+static bool g_lut_ready[64] = {};
+static cudaError_t ensure_lut(cudaStream_t s) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && g_lut_ready[dev]) return cudaSuccess;
+    k_init_od_lut<<<1, 256, 0, s>>>();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && dev < 64) g_lut_ready[dev] = true;
+    return e;
+}
+
+cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStream_t s) {
+    if (p.n <= 0) return cudaSuccess;
+    cudaError_t e = ensure_lut(s);
+    if (e != cudaSuccess) return e;
+    const int smem = color_smem_bytes(p.P);
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(k_color, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_color<<<(unsigned)p.n, kColorThreads, smem, s>>>(p, *map);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int R, cudaStream_t s) {
+    if (p.n <= 0) return cudaSuccess;
+    const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
+    const int smem = kHueStages * patch_panels(p.P) * kPanelBytes * R + 2 * R * p.P * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_hue_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((unsigned)nbatch, (unsigned)p.slabs);
+    k_hue_batch<<<grid, kHueThreads, smem, s>>>(p, *map_slab, R);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hue_finalize(const ColorParams& p, cudaStream_t s) {
+    if (p.n <= 0) return cudaSuccess;
+    k_hue_finalize<<<(unsigned)((p.n + 255) / 256), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace nfx

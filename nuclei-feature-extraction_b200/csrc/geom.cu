@@ -1,0 +1,330 @@
+// geom.cu -- north-star kernels (2) polygon-to-mask rasterisation and (4) shape descriptors.
+//
+// One CTA (64 threads) per nucleus. Replaces, per nucleus:
+//   preprocess_polygon                       src/utils.rs:54-74     (sequential f32 centroid, centring)
+//   tch_utils::shapes::polygon               src/utils.rs:152-157   (oracle/SPEC.md B1, bit-exact)
+//   patch window origin                      src/utils.rs:159-162   (f32, trunc toward zero)
+//   center_of_mass / covariance / linalg_eig src/features/shape.rs:141-226 (closed-form slanv2)
+//   tch_utils::shapes::ellipse + deviation   src/features/shape.rs:80-87, 209-217 (SPEC.md B2)
+//   geometric_features::* and convex hull    src/features/shape.rs:89-97  (SPEC.md B7, B8)
+//
+// Rasterisation is edge-parallel scanline: each thread takes one polygon edge, walks only the rows
+// that edge spans, evaluates the crossing abscissa X with exactly the float64 operations of the
+// per-pixel rule, and XORs the prefix mask {c : c - P/2 < X} into the row's bit words. The result is
+// identical to evaluating the even-odd rule at every pixel, at O(perimeter) instead of O(P*P*V) cost.
+#include <math_constants.h>
+
+#include "nfx_kernels.h"
+
+namespace nfx {
+
+namespace {
+
+constexpr int kGeomThreads = 64;
+
+// first index k in [0,P] such that (k - P/2) >= v   (exact; v may be any double)
+__device__ __forceinline__ int first_index_geq(double v, int P) {
+    if (!(v == v)) return P;
+    const double half = 0.5 * (double)P;
+    const double t = v + half;
+    int k = (t <= 0.0) ? 0 : (t >= (double)P ? P : (int)ceil(t));
+    while (k > 0 && ((double)(k - 1) - half) >= v) --k;
+    while (k < P && ((double)k - half) < v) ++k;
+    return k;
+}
+
+__device__ __forceinline__ uint32_t prefix_bits(int nbits) {   // nbits clamped to [0,32]
+    return nbits >= 32 ? 0xffffffffu : (nbits <= 0 ? 0u : ((1u << nbits) - 1u));
+}
+
+// SPEC.md B2, one IEEE operation at a time.
+__device__ __forceinline__ bool ellipse_inside(double x, double y, double cx, double cy, double cs,
+                                               double sn, double a, double b) {
+    const double dx = __dsub_rn(x, cx), dy = __dsub_rn(y, cy);
+    const double xr = __dadd_rn(__dmul_rn(dx, cs), __dmul_rn(dy, sn));
+    const double yr = __dsub_rn(__dmul_rn(dy, cs), __dmul_rn(dx, sn));
+    const double u = __ddiv_rn(xr, a), v = __ddiv_rn(yr, b);
+    const double val = __dadd_rn(__dmul_rn(u, u), __dmul_rn(v, v));
+    return val <= 1.0;
+}
+
+__device__ __forceinline__ double cross3(float2 o, float2 a, float2 b) {
+    return ((double)a.x - (double)o.x) * ((double)b.y - (double)o.y) -
+           ((double)a.y - (double)o.y) * ((double)b.x - (double)o.x);
+}
+
+template <bool RASTER, bool SHAPE>
+__global__ void __launch_bounds__(kGeomThreads) k_geom(const GeomParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x;
+    const int64_t i = blockIdx.x;
+    const int64_t o0 = p.poly_off[i];
+    const int V = (int)(p.poly_off[i + 1] - o0);
+
+    // shared layout: rows[P*wpr] u32 | pts[vmax] float2 | sorted[vmax] float2 | stk[2*vmax] int
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw);
+    float2* pts = reinterpret_cast<float2*>(rows + ((P * wpr + 1) & ~1));
+    float2* sorted = pts + p.vmax;
+    int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? p.vmax : 0));
+    __shared__ double s_red[16];
+    __shared__ float s_c[2];
+    __shared__ int s_hull[2];
+
+    for (int k = tid; k < V; k += kGeomThreads) pts[k] = p.poly_xy[o0 + k];
+    if (RASTER)
+        for (int k = tid; k < P * wpr; k += kGeomThreads) rows[k] = 0u;
+    else
+        for (int k = tid; k < P * wpr; k += kGeomThreads) rows[k] = p.bitmask[i * P * wpr + k];
+    __syncthreads();
+
+    if (RASTER) {
+        if (tid == 0) {
+            // utils.rs:56-64 -- sequential f32 fold in stored order, then one division each
+            float ax = 0.f, ay = 0.f;
+            for (int k = 0; k < V; ++k) {
+                ax = __fadd_rn(ax, pts[k].x);
+                ay = __fadd_rn(ay, pts[k].y);
+            }
+            const float cx = __fdiv_rn(ax, (float)V), cy = __fdiv_rn(ay, (float)V);
+            s_c[0] = cx;
+            s_c[1] = cy;
+            p.centroid[i] = make_float2(cx, cy);
+            // utils.rs:159-162 -- `as i64` truncates toward zero and saturates (NaN -> 0)
+            const float half = (float)P / 2.0f;
+            auto cast = [](float v) -> long long { return (v == v) ? __float2ll_rz(v) : 0ll; };
+            const long long top = cast(__fsub_rn(cy, half)), left = cast(__fsub_rn(cx, half));
+            const long long bottom = cast(__fadd_rn(cy, half)), right = cast(__fadd_rn(cx, half));
+            auto clamp32 = [](long long v) -> int {
+                return (int)max(-(1ll << 30), min(1ll << 30, v));
+            };
+            NucInfo inf;
+            inf.left = clamp32(left - p.tile_ox);
+            inf.top = clamp32(top - p.tile_oy);
+            inf.nvc = (int)max(0ll, min((long long)P, right - left));
+            inf.nvr = (int)max(0ll, min((long long)P, bottom - top));
+            p.info[i] = inf;
+        }
+        __syncthreads();
+        const float cx = s_c[0], cy = s_c[1];
+        for (int k = tid; k < V; k += kGeomThreads) {   // utils.rs:65-72
+            float2 v = pts[k];
+            v.x = __fsub_rn(v.x, cx);
+            v.y = __fsub_rn(v.y, cy);
+            pts[k] = v;
+        }
+        __syncthreads();
+
+        // ---- SPEC.md B1: edge-parallel scanline, float64 crossing abscissa ----
+        const double half = 0.5 * (double)P;
+        for (int k = tid; k < V; k += kGeomThreads) {
+            const float2 a = pts[k], b = pts[(k + 1 == V) ? 0 : k + 1];
+            if (a.y == b.y || !(a.y == a.y) || !(b.y == b.y)) continue;
+            const double ylo = fmin((double)a.y, (double)b.y), yhi = fmax((double)a.y, (double)b.y);
+            const int r0 = first_index_geq(ylo, P), r1 = first_index_geq(yhi, P);
+            const double xi = a.x, yi = a.y, dxe = __dsub_rn((double)b.x, xi),
+                         dye = __dsub_rn((double)b.y, yi);
+            for (int r = r0; r < r1; ++r) {
+                const double y = (double)r - half;
+                const double X =
+                    __dadd_rn(xi, __ddiv_rn(__dmul_rn(__dsub_rn(y, yi), dxe), dye));
+                const int nb = first_index_geq(X, P);   // pixels c < nb satisfy (c - P/2) < X
+                for (int w = 0; w < wpr; ++w) {
+                    const uint32_t m = prefix_bits(nb - 32 * w);
+                    if (m) atomicXor(&rows[r * wpr + w], m);
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < P * wpr; k += kGeomThreads) p.bitmask[i * P * wpr + k] = rows[k];
+    }
+
+    if (!SHAPE) return;
+    float* out = p.out + i * (int64_t)p.out_stride + p.col_shape;
+
+    // ---- polygon scalars, SPEC.md B7 (float64 on the centred ring) ----
+    {
+        double v2[2] = {0.0, 0.0};   // shoelace sum, perimeter
+        for (int k = tid; k < V; k += kGeomThreads) {
+            const float2 a = pts[k], b = pts[(k + 1 == V) ? 0 : k + 1];
+            v2[0] += (double)a.x * (double)b.y - (double)b.x * (double)a.y;
+            const double ex = (double)b.x - (double)a.x, ey = (double)b.y - (double)a.y;
+            v2[1] += sqrt(ex * ex + ey * ey);
+        }
+        block_sum<2>(v2, s_red);
+        if (tid == 0) {
+            const double area = 0.5 * fabs(v2[0]), per = v2[1];
+            out[0] = (float)area;
+            out[5] = (float)per;
+            out[6] = (float)(2.0 * sqrt(CUDART_PI * area));
+            out[7] = (float)((4.0 * CUDART_PI * area) / (per * per));
+            s_red[8] = area;
+        }
+    }
+    // ---- convex hull, SPEC.md B8: rank sort + two monotone chains (threads 0 and 32) ----
+    for (int k = tid; k < V; k += kGeomThreads) {
+        const float2 a = pts[k];
+        int rank = 0;
+        for (int m = 0; m < V; ++m) {
+            const float2 b = pts[m];
+            rank += (b.x < a.x) || (b.x == a.x && (b.y < a.y || (b.y == a.y && m < k)));
+        }
+        sorted[rank] = a;
+    }
+    __syncthreads();
+    if (tid == 0 || tid == 32) {
+        int* S = stk + (tid == 0 ? 0 : p.vmax);
+        int sz = 0;
+        for (int t = 0; t < V; ++t) {
+            const int idx = (tid == 0) ? t : V - 1 - t;
+            const float2 q = sorted[idx];
+            while (sz >= 2 && cross3(sorted[S[sz - 2]], sorted[S[sz - 1]], q) <= 0.0) --sz;
+            S[sz++] = idx;
+        }
+        s_hull[tid == 0 ? 0 : 1] = sz;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int nl = max(s_hull[0] - 1, 0), nu = max(s_hull[1] - 1, 0), h = nl + nu;
+        auto hp = [&](int k) -> float2 { return sorted[k < nl ? stk[k] : stk[p.vmax + (k - nl)]]; };
+        double sh = 0.0, per = 0.0;
+        for (int k = 0; k < h; ++k) {
+            const float2 a = hp(k), b = hp(k + 1 == h ? 0 : k + 1);
+            sh += (double)a.x * (double)b.y - (double)b.x * (double)a.y;
+            const double ex = (double)b.x - (double)a.x, ey = (double)b.y - (double)a.y;
+            per += sqrt(ex * ex + ey * ey);
+        }
+        const double harea = (h >= 3) ? 0.5 * fabs(sh) : 0.0;
+        if (h < 2) per = 0.0;
+        out[9] = (float)harea;
+        out[10] = (float)((harea - s_red[8]) / harea);
+        out[11] = (float)per;
+    }
+
+    // ---- mask moments (shape.rs:149-157, 219-226): exact integer sums over set bits ----
+    double mom[6] = {0, 0, 0, 0, 0, 0};   // K, Sr, Sc, Srr, Src, Scc
+    for (int r = tid; r < P; r += kGeomThreads) {
+        unsigned long long n = 0, sc = 0, scc = 0;
+        for (int w = 0; w < wpr; ++w) {
+            uint32_t bits = rows[r * wpr + w];
+            while (bits) {
+                const int c = 32 * w + __ffs(bits) - 1;
+                bits &= bits - 1;
+                ++n;
+                sc += c;
+                scc += (unsigned)(c * c);
+            }
+        }
+        mom[0] += (double)n;
+        mom[1] += (double)(n * r);
+        mom[2] += (double)sc;
+        mom[3] += (double)(n * r * r);
+        mom[4] += (double)(sc * r);
+        mom[5] += (double)scc;
+    }
+    block_sum<6>(mom, s_red);   // sums of integers < 2^53: exact in any order
+
+    // every thread derives the same scalars (cheap) so no extra broadcast is needed
+    const double K = mom[0];
+    const float nanf_ = CUDART_NAN_F;
+    float major = nanf_, minor = nanf_, angle = nanf_;
+    // center_of_mass: f32 sum of exact integers / K in f32 (ATen mean = sum then true division)
+    const float mr = __fdiv_rn((float)mom[1], (float)K), mc = __fdiv_rn((float)mom[2], (float)K);
+    if (K > 0.0) {
+        const double er = mom[1] / K, ec = mom[2] / K;
+        const float a = (float)(mom[3] / K - er * er);      // var rows
+        const float b = (float)(mom[4] / K - er * ec);      // cov
+        const float d = (float)(mom[5] / K - ec * ec);      // var cols
+        // LAPACK sgeev on [[a,b],[b,d]] (slanv2 closed form, oracle eig2x2_lapack)
+        float l0, l1, v00, v01, v10, v11;   // V columns are the eigenvectors
+        if (b == 0.f) {
+            l0 = a; l1 = d; v00 = 1.f; v01 = 0.f; v10 = 0.f; v11 = 1.f;
+        } else {
+            const float pp = 0.5f * (a - d);
+            const float rr = hypotf(pp, b);
+            const float z = pp + copysignf(rr, pp);
+            l0 = d + z;
+            l1 = d - (b / z) * b;
+            const float tau = hypotf(b, z);
+            const float cs = z / tau, sn = b / tau;
+            v00 = cs; v01 = -sn; v10 = sn; v11 = cs;
+        }
+        float m0, m1;   // shape.rs:192-196: ROW 0 of the eigenvector matrix if l0 > l1 else row 1
+        if (l0 > l1) { major = sqrtf(l0); minor = sqrtf(l1); m0 = v00; m1 = v01; }
+        else         { major = sqrtf(l1); minor = sqrtf(l0); m0 = v10; m1 = v11; }
+        angle = atan2f(m0, m1);
+        major *= 2.0f;
+        minor *= 2.0f;
+    }
+    if (tid == 0) {
+        out[1] = major;
+        out[2] = minor;
+        const float M = major * 0.5f, m = minor * 0.5f;                 // shape.rs:205-207
+        out[3] = __fdiv_rn(sqrtf(__fsub_rn(__fmul_rn(M, M), __fmul_rn(m, m))), M);
+        out[4] = angle;
+    }
+
+    // ---- ellipse raster (SPEC.md B2) by exact row intervals + |mask - ellipse| ----
+    const float halfP = (float)P / 2.0f;
+    const double ecx = (double)__fsub_rn(mc, halfP), ecy = (double)__fsub_rn(mr, halfP);   // shape.rs:71-73,84
+    const double ea = (double)major, eb = (double)minor, ang = (double)angle;
+    const bool drawable = (ea > 0.0) && (eb > 0.0) && isfinite(ea) && isfinite(eb) && isfinite(ang) &&
+                          isfinite(ecx) && isfinite(ecy);
+    double cs = 0.0, sn = 0.0;
+    if (drawable) sincos(ang, &sn, &cs);
+    const double half = 0.5 * (double)P;
+    const double ia2 = 1.0 / (ea * ea), ib2 = 1.0 / (eb * eb);
+    const double qa = cs * cs * ia2 + sn * sn * ib2;
+    double diff[1] = {0.0};
+    for (int r = tid; r < P; r += kGeomThreads) {
+        int clo = 1, chi = 0;   // empty
+        if (drawable) {
+            const double y = (double)r - half, dy = y - ecy;
+            const double qb = 2.0 * dy * cs * sn * (ia2 - ib2);
+            const double qc = dy * dy * (sn * sn * ia2 + cs * cs * ib2) - 1.0;
+            const double disc = qb * qb - 4.0 * qa * qc;
+            if (disc >= -1e-6 * (qb * qb + 4.0 * fabs(qa * qc))) {
+                const double sq = sqrt(fmax(disc, 0.0));
+                const double x1 = (-qb - sq) / (2.0 * qa) + ecx, x2 = (-qb + sq) / (2.0 * qa) + ecx;
+                clo = max(0, (int)fmin(fmax(ceil(x1 + half) - 1.0, -1.0), (double)P));
+                chi = min(P - 1, (int)fmax(fmin(floor(x2 + half) + 1.0, (double)P), -1.0));
+                while (clo <= chi && !ellipse_inside((double)clo - half, y, ecx, ecy, cs, sn, ea, eb)) ++clo;
+                while (chi >= clo && !ellipse_inside((double)chi - half, y, ecx, ecy, cs, sn, ea, eb)) --chi;
+                // grow if the estimate was one pixel short (cannot happen for a well-conditioned row)
+                while (clo > 0 && clo <= chi && ellipse_inside((double)(clo - 1) - half, y, ecx, ecy, cs, sn, ea, eb)) --clo;
+                while (chi < P - 1 && clo <= chi && ellipse_inside((double)(chi + 1) - half, y, ecx, ecy, cs, sn, ea, eb)) ++chi;
+            }
+        }
+        for (int w = 0; w < wpr; ++w) {
+            uint32_t e = 0u;
+            if (clo <= chi) {
+                const int lo = max(clo - 32 * w, 0), hi = min(chi - 32 * w, 31);
+                if (lo <= hi) e = prefix_bits(hi + 1) & ~prefix_bits(lo);
+            }
+            diff[0] += (double)__popc(e ^ rows[r * wpr + w]);
+            if (p.ellipse_bits) p.ellipse_bits[i * P * wpr + r * wpr + w] = e;
+        }
+    }
+    block_sum<1>(diff, s_red);
+    if (tid == 0) out[8] = __fdiv_rn((float)diff[0], (float)K);   // shape.rs:209-217 (f32 tensor / scalar)
+}
+
+}  // namespace
+
+cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s) {
+    if (p.n <= 0) return cudaSuccess;
+    const int wpr = mask_wpr(p.P);
+    size_t smem = (size_t)((p.P * wpr + 1) & ~1) * 4 + (size_t)p.vmax * 8;
+    if (shape) smem += (size_t)p.vmax * 8 + (size_t)p.vmax * 2 * 4;
+    auto go = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)p.n, kGeomThreads, smem, s>>>(p);
+        return cudaGetLastError();
+    };
+    if (raster) return shape ? go(k_geom<true, true>) : go(k_geom<true, false>);
+    return shape ? go(k_geom<false, true>) : cudaSuccess;
+}
+
+}  // namespace nfx

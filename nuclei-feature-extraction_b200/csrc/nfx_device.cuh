@@ -1,0 +1,160 @@
+// Device-side helpers shared by every kernel: mbarrier + TMA (cp.async.bulk.tensor) wrappers,
+// warp/block reductions, and the per-nucleus record the kernels exchange through HBM.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nfx {
+
+// One record per nucleus, written by the geometry/raster kernel and read by every consumer.
+// (left, top) = patch origin (utils.rs:159-160, f32 arithmetic, trunc toward zero) minus the tile
+// origin. The reference copies image rows max(top,0)..min(bottom,H) to patch rows starting at
+// -min(top,0) (utils.rs:161-192): patch row pr shows image row top+pr iff that row exists AND
+// pr < bottom-top. TMA's zero fill covers the first condition, (nvc, nvr) the second (bottom-top is
+// P-1 when cy-P/2 < 0 < cy+P/2 has a fractional part, because both casts truncate toward zero).
+struct NucInfo {
+    int32_t left, top;     // window origin in TILE coordinates (may be negative / beyond the tile)
+    int32_t nvc, nvr;      // min(right-left, P), min(bottom-top, P): patch columns/rows >= these are 0
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    // make the init visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- TMA: 2D tiled bulk tensor copy global -> shared, completion on an mbarrier ---------------
+// Coordinates are signed element indices; out-of-bounds elements are filled with zeros, which is
+// exactly the reference's zero padding at image borders (utils.rs:174-192).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int32_t x,
+                                            int32_t y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global 2D store (bulk group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_t x,
+                                             int32_t y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::
+                     "l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(x), "r"(y), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// ---- reductions -------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Reduce NV values per thread over the whole CTA. `scratch` needs NV * (blockDim/32) elements.
+// Result valid in every thread of warp 0 (and broadcast through scratch[0..NV) after the call).
+template <int NV, typename T>
+__device__ __forceinline__ void block_sum(T (&v)[NV], T* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();   // scratch may still be read from a previous call
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) scratch[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            T s = (lane < nw) ? scratch[lane * NV + k] : T(0);
+            s = warp_sum(s);
+            v[k] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) scratch[k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = scratch[k];
+}
+
+// Patch layout in shared memory: column PANELS of 64 pixels (192 bytes, a multiple of both the
+// 16-byte TMA granule and the 12-byte pixel quad), each panel a dense [P rows][192 B] TMA box.
+//   addr(r, c) = (c >> 6) * 192 * P + r * 192 + (c & 63) * 3
+constexpr int kPanelPx = 64;
+constexpr int kPanelBytes = 192;
+__host__ __device__ __forceinline__ int patch_panels(int P) { return (P + kPanelPx - 1) / kPanelPx; }
+__host__ __device__ __forceinline__ int patch_smem_bytes(int P) { return patch_panels(P) * kPanelBytes * P; }
+__device__ __forceinline__ int patch_addr(int P, int r, int c) {
+    return (c >> 6) * (kPanelBytes * P) + r * kPanelBytes + (c & 63) * 3;
+}
+// 32-bit words per bitmask row
+__host__ __device__ __forceinline__ int mask_wpr(int P) { return (P + 31) / 32; }
+
+// Issue the TMA boxes ({192 B, P rows} each) that bring one P x P RGB window into shared memory.
+// Called by ONE thread after mbar_expect_tx(bar, patch_smem_bytes(P)).
+__device__ __forceinline__ void tma_load_patch(uint8_t* smem_patch, const CUtensorMap* map, int left,
+                                               int top, int P, uint64_t* bar) {
+    const int np = patch_panels(P);
+    for (int k = 0; k < np; ++k)
+        tma_load_2d(smem_patch + (size_t)k * kPanelBytes * P, map, (left + k * kPanelPx) * 3, top, bar);
+}
+
+}  // namespace nfx

@@ -1,0 +1,90 @@
+// Host-visible launchers of the sm_100a kernels (one translation unit per kernel family).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nfx_device.cuh"
+
+namespace nfx {
+
+// Column counts per feature set (schema.cpp holds the names).
+constexpr int kShapeCols = 12;
+constexpr int kColorCols = 18;
+constexpr int kGlcmFeat = 14;
+constexpr int kGlcmLevels = 4;
+constexpr int kGlcmOffsets = 4;
+constexpr int kGlcmCols = kGlcmFeat * kGlcmLevels * kGlcmOffsets;   // 224
+constexpr int kGlrlmCols = 68;
+constexpr int kGaborCols = 96;
+
+// ---- geom.cu: centroid + window + polygon raster + shape set --------------------------------
+struct GeomParams {
+    const float2* poly_xy;     // CSR vertices (slide coordinates, or CENTRED when centred_input)
+    const int64_t* poly_off;   // [n+1]
+    int64_t n;
+    int P;
+    int tile_ox, tile_oy;      // slide coordinates of tile pixel (0,0)
+    int vmax;                  // max ring length in this launch (sizes dynamic shared memory)
+    float2* centroid;          // [n] out (RASTER) / unused
+    NucInfo* info;             // [n] out (RASTER) / unused
+    uint32_t* bitmask;         // [n][P][wpr]: out when RASTER, in otherwise
+    float* out;                // [n][out_stride] feature matrix, or nullptr
+    int out_stride;
+    int col_shape;             // first column of the geometry set in `out`, or -1
+    uint32_t* ellipse_bits;    // optional debug tap [n][P][wpr], or nullptr
+};
+// raster=true : polygons are raw rings; computes centroid/info, rasterises, writes bitmask.
+// raster=false: polygons are already centred and bitmask is an input (trait-level path).
+cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s);
+
+// ---- color.cu ---------------------------------------------------------------------------------
+struct ColorParams {
+    int64_t n;
+    int P;
+    int batch_size;
+    const NucInfo* info;
+    const uint32_t* bitmask;
+    float* out;
+    int out_stride;
+    int col_color;             // first column of the colour set
+    float* hue_partial;        // [n][slabs][2] (sum sin, sum cos) scratch
+    int slabs;
+};
+cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStream_t s);
+cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int slab_rows,
+                             cudaStream_t s);
+cudaError_t launch_hue_finalize(const ColorParams& p, cudaStream_t s);
+int color_smem_bytes(int P);
+int hue_slab_rows(int P);
+
+// ---- glcm.cu ----------------------------------------------------------------------------------
+struct GlcmParams {
+    int64_t n;
+    int P;
+    const NucInfo* info;
+    const uint32_t* bitmask;
+    float* out;
+    int out_stride;
+    int col_glcm;
+    // debug taps (nullptr unless requested)
+    uint32_t* dbg_counts;      // [n][L][L] symmetric counts for (dbg_levels, dbg_dy, dbg_dx)
+    int dbg_levels, dbg_dy, dbg_dx;
+    uint8_t* dbg_grey;         // [n][P][P] quantised grey for dbg_levels
+};
+cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s);
+
+// ---- staged.cu: kernels (1) gather and the f32 batch packer -----------------------------------
+// tile window -> u8 patch array [n*P rows][pitch bytes] through TMA load + TMA store.
+cudaError_t launch_gather(int64_t n, int P, const NucInfo* info, const CUtensorMap* map_tile,
+                          const CUtensorMap* map_patches, cudaStream_t s);
+// expand bitmask -> u8 0/1 masks [n][P][P]
+cudaError_t launch_expand_mask(int64_t n, int P, const uint32_t* bitmask, uint8_t* out,
+                               cudaStream_t s);
+// reference Batch layout (patchs [n,3,P,P] f32 k/255, masks [n,1,P,P] f32) -> u8 patch array +
+// bitmask + NucInfo rows pointing into the patch array.
+cudaError_t launch_pack_batch(int64_t n, int P, const float* patchs, const float* masks,
+                              uint8_t* patches_u8, int64_t pitch, uint32_t* bitmask, NucInfo* info,
+                              int* bad_count, cudaStream_t s);
+
+}  // namespace nfx

@@ -1,0 +1,279 @@
+"""nfx -- host-side mirror of the reference's operator interface over the C ABI of libnfx.so.
+
+Mirrors (same names, argument meaning and error behaviour):
+  * `trait FeatureSet { name(); compute_features_batched(centroids, polygons, patchs, masks) }`
+    (src/features/mod.rs:12-28) -> ShapeFeatureSet / ColorFeatureSet / GlcmFeatureSet;
+  * `args::FeatureSet::{from_str, flat, to_fs}` (src/args.rs:7-73) -> parse_feature_sets / to_fs;
+  * the stage triple patch_loader -> move_tensors_to_device -> extract_features
+    (src/main.rs:149-151) -> Extractor.extract.
+All compute goes through libnfx.so (sm_100a CUDA); nothing here computes features on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import (FS_ALL, FS_COLOR, FS_GABOR, FS_GEOMETRY, FS_GLCM, FS_GLRLM, FS_TEXTURE, NFX_OK,
+                   NfxConfig, NfxError, NfxKernelTime, lib)
+
+_FLAT_BITS = (FS_GEOMETRY, FS_COLOR, FS_GLCM, FS_GLRLM, FS_GABOR)
+
+
+def parse_feature_sets(names) -> int:
+    """args::FeatureSet::from_str + flat (src/args.rs:18-49). Duplicates raise like the reference's
+    DataFrame::new does (src/main.rs:89); an empty list raises like `features[0]` (src/main.rs:76)."""
+    if isinstance(names, str):
+        names = [names]
+    if len(names) == 0:
+        raise NfxError(-1, "no feature set given")
+    mask = 0
+    for s in names:
+        bits = C.c_uint32(0)
+        if lib().nfx_parse_feature_set(s.encode(), C.byref(bits)) != NFX_OK:
+            raise NfxError(-1, f"{s} is not a valid feature set")
+        if mask & bits.value:
+            raise NfxError(-1, f"duplicate feature set {s!r}")
+        mask |= bits.value
+    return mask
+
+
+def feature_names(mask: int):
+    n = lib().nfx_feature_count(mask)
+    return [lib().nfx_feature_name(mask, i).decode() for i in range(n)]
+
+
+def centroid_key(x, y) -> str:
+    buf = C.create_string_buffer(128)
+    n = lib().nfx_centroid_key(float(np.float32(x)), float(np.float32(y)), buf, 128)
+    if n < 0:
+        raise NfxError(n, "key buffer too small")
+    return buf.value.decode()
+
+
+def partition(n: int, batch_size: int, parts: int):
+    b = (C.c_int64 * (parts + 1))()
+    rc = lib().nfx_partition(n, batch_size, parts, b)
+    if rc != NFX_OK:
+        raise NfxError(rc, "bad partition arguments")
+    return list(b)
+
+
+def pack_polygons(rings):
+    """list of (V_i,2) arrays -> CSR (poly_xy f32 [sum V,2], poly_off int64 [n+1])."""
+    off = np.zeros(len(rings) + 1, dtype=np.int64)
+    for i, r in enumerate(rings):
+        off[i + 1] = off[i] + len(r)
+    xy = np.zeros((int(off[-1]), 2), dtype=np.float32)
+    for i, r in enumerate(rings):
+        xy[off[i]:off[i + 1]] = np.asarray(r, dtype=np.float32).reshape(-1, 2)
+    return xy, off
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Extractor:
+    """One context per (host thread, GPU) -- the analogue of one rayon worker (src/utils.rs:215-221)."""
+
+    def __init__(self, device: int = 0, patch_size: int = 64, batch_size: int = 100):
+        self._h = C.c_void_p()
+        cfg = NfxConfig(patch_size, batch_size)
+        rc = lib().nfx_create(device, C.byref(cfg), C.byref(self._h))
+        if rc != NFX_OK:
+            raise NfxError(rc, (lib().nfx_last_error(None) or b"").decode())
+        self.patch_size, self.batch_size, self.device = patch_size, batch_size, device
+        self.n = 0
+        self._mask = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().nfx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != NFX_OK:
+            raise NfxError(rc, (lib().nfx_last_error(self._h) or b"").decode())
+
+    # -- inputs --
+    def upload_tile(self, rgb, origin=(0, 0)):
+        """rgb: [H,W,3] u8 (C-contiguous rows). Replaces load_input_image (src/main.rs:20-35)."""
+        rgb = np.asarray(rgb)
+        if rgb.dtype != np.uint8 or rgb.ndim != 3 or rgb.shape[2] != 3 or rgb.strides[2] != 1 \
+                or rgb.strides[1] != 3:
+            raise NfxError(-1, "tile must be [H,W,3] u8 with contiguous rows")
+        self._tile_ref = rgb
+        self._ck(lib().nfx_tile_upload(self._h, _ptr(rgb), rgb.shape[1], rgb.shape[0], rgb.strides[0],
+                                       int(origin[0]), int(origin[1])))
+
+    def upload_polygons(self, poly_xy, poly_off):
+        poly_xy = np.ascontiguousarray(poly_xy, dtype=np.float32)
+        poly_off = np.ascontiguousarray(poly_off, dtype=np.int64)
+        self.n = len(poly_off) - 1
+        self._ck(lib().nfx_polygons_upload(self._h, self.n, _ptr(poly_xy), _ptr(poly_off)))
+
+    # -- hot path --
+    def compute(self, mask: int):
+        self._mask = mask
+        self._ck(lib().nfx_compute(self._h, mask))
+
+    def sync(self):
+        self._ck(lib().nfx_sync(self._h))
+
+    def download(self, centroids=None, features=None):
+        F = lib().nfx_feature_count(self._mask)
+        if centroids is None:
+            centroids = np.empty((self.n, 2), dtype=np.float32)
+        if features is None:
+            features = np.empty((self.n, F), dtype=np.float32)
+        self._ck(lib().nfx_download(self._h, _ptr(centroids), _ptr(features)))
+        return centroids, features
+
+    def extract(self, poly_xy, poly_off, feature_sets):
+        """chunk(s) -> features, rows in input order. Returns (keys, centroids, features, names)."""
+        mask = feature_sets if isinstance(feature_sets, int) else parse_feature_sets(feature_sets)
+        self.upload_polygons(poly_xy, poly_off)
+        self.compute(mask)
+        cents, feats = self.download()
+        keys = [centroid_key(c[0], c[1]) for c in cents]
+        return keys, cents, feats, feature_names(mask)
+
+    # -- staged kernels / parity taps --
+    def rasterize(self):
+        out = np.empty((self.n, self.patch_size, self.patch_size), dtype=np.uint8)
+        self._ck(lib().nfx_rasterize(self._h, _ptr(out)))
+        return out
+
+    def gather_patches(self, want=True):
+        out = np.empty((self.n, self.patch_size, self.patch_size, 3), dtype=np.uint8) if want else None
+        self._ck(lib().nfx_gather_patches(self._h, _ptr(out)))
+        return out
+
+    def debug_ellipses(self):
+        out = np.empty((self.n, self.patch_size, self.patch_size), dtype=np.uint8)
+        self._ck(lib().nfx_debug_ellipses(self._h, _ptr(out)))
+        return out
+
+    def debug_glcm_counts(self, levels, offset):
+        out = np.empty((self.n, levels, levels), dtype=np.uint32)
+        self._ck(lib().nfx_debug_glcm_counts(self._h, levels, offset[0], offset[1], _ptr(out)))
+        return out
+
+    def debug_grey_levels(self, levels):
+        out = np.empty((self.n, self.patch_size, self.patch_size), dtype=np.uint8)
+        self._ck(lib().nfx_debug_grey_levels(self._h, levels, _ptr(out)))
+        return out
+
+    def compute_features_batched(self, bit, centroids, polygons, patchs, masks):
+        n = int(patchs.shape[0])
+        patchs = np.ascontiguousarray(patchs, dtype=np.float32)
+        masks = np.ascontiguousarray(masks, dtype=np.float32)
+        cents = np.ascontiguousarray(centroids, dtype=np.float32)
+        xy, off = pack_polygons(polygons)
+        out = np.empty((n, lib().nfx_feature_count(bit)), dtype=np.float32)
+        self._ck(lib().nfx_compute_features_batched(self._h, bit, n, _ptr(cents), _ptr(xy), _ptr(off),
+                                                    _ptr(patchs), _ptr(masks), _ptr(out)))
+        return out
+
+    # -- measurement --
+    def profile(self, on=True):
+        self._ck(lib().nfx_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(lib().nfx_profile_reset(self._h))
+
+    def profile_get(self):
+        arr = (NfxKernelTime * 32)()
+        n = lib().nfx_profile_get(self._h, arr, 32)
+        if n < 0:
+            self._ck(n)
+        return {arr[i].name.decode(): (arr[i].launches, arr[i].total_ms) for i in range(min(n, 32))}
+
+    def timer_start(self):
+        self._ck(lib().nfx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._ck(lib().nfx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(lib().nfx_launch_count(self._h))
+
+    def flush_l2(self):
+        self._ck(lib().nfx_flush_l2(self._h))
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over cudaHostAlloc memory (for asynchronous H2D / D2H in the e2e path)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    rc = lib().nfx_host_alloc(C.byref(p), nbytes)
+    if rc != NFX_OK:
+        raise NfxError(rc, (lib().nfx_last_error(None) or b"").decode())
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
+
+
+class _FeatureSetBase:
+    """trait FeatureSet (src/features/mod.rs:12-28) over nfx_compute_features_batched."""
+    BIT = 0
+
+    def __init__(self, extractor: Extractor):
+        self._ex = extractor
+
+    def name(self) -> str:
+        return lib().nfx_feature_set_name(self.BIT).decode()
+
+    def columns(self):
+        return feature_names(self.BIT)
+
+    def compute_features_batched(self, centroids, polygons, patchs, masks):
+        """Returns (keys, [N,F] f32): the DataFrame's `centroid` column and feature columns."""
+        # the asserts of src/features/shape.rs:23-47 and color.rs:18-42
+        assert patchs.ndim == 4, "The patchs tensor must be 4 dimensional"
+        assert masks.ndim == 4, "The masks tensor must be 4 dimensional"
+        assert patchs.shape[1] == 3, "The patchs tensor must have 3 channels"
+        assert masks.shape[1] == 1, "The masks tensor must have 1 channel"
+        assert patchs.shape[0] == masks.shape[0], "The number of patchs and masks must be the same"
+        assert patchs.shape[0] == len(centroids), "The number of patchs and centroids must be the same"
+        assert patchs.shape[0] == len(polygons), "The number of patchs and polygons must be the same"
+        out = self._ex.compute_features_batched(self.BIT, centroids, polygons, patchs, masks)
+        keys = [centroid_key(c[0], c[1]) for c in np.asarray(centroids, dtype=np.float32)]
+        return keys, out
+
+
+class ShapeFeatureSet(_FeatureSetBase):      # src/features/shape.rs:13
+    BIT = FS_GEOMETRY
+
+
+class ColorFeatureSet(_FeatureSetBase):      # src/features/color.rs:8
+    BIT = FS_COLOR
+
+
+class GlcmFeatureSet(_FeatureSetBase):       # src/features/texture.rs:22
+    BIT = FS_GLCM
+
+
+def to_fs(names, extractor):
+    """args::FeatureSet::to_fs (src/args.rs:51-73)."""
+    mask = parse_feature_sets(names)
+    table = {FS_GEOMETRY: ShapeFeatureSet, FS_COLOR: ColorFeatureSet, FS_GLCM: GlcmFeatureSet}
+    out = []
+    for b in _FLAT_BITS:
+        if mask & b:
+            if b not in table:
+                raise NfxError(-4, f"feature set {lib().nfx_feature_set_name(b).decode()} not built yet")
+            out.append(table[b](extractor))
+    return out

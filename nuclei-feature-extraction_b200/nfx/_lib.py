@@ -1,0 +1,82 @@
+"""ctypes binding of libnfx.so (include/nfx.h). Fails loudly when the CUDA library is missing:
+there is no CPU fallback in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libnfx.so")
+
+NFX_OK = 0
+FS_GEOMETRY, FS_COLOR, FS_GLCM, FS_GLRLM, FS_GABOR = 0x01, 0x02, 0x04, 0x08, 0x10
+FS_TEXTURE = FS_GLCM | FS_GLRLM | FS_GABOR
+FS_ALL = 0x1F
+
+
+class NfxConfig(C.Structure):
+    _fields_ = [("patch_size", C.c_int32), ("batch_size", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class NfxKernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("total_ms", C.c_double)]
+
+
+# every symbol include/nfx.h declares: (restype, argtypes)
+_vp, _i, _i64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_float
+SYMBOLS = {
+    "nfx_create": (_i, [_i, C.POINTER(NfxConfig), C.POINTER(_vp)]),
+    "nfx_destroy": (_i, [_vp]),
+    "nfx_last_error": (C.c_char_p, [_vp]),
+    "nfx_version": (C.c_char_p, []),
+    "nfx_tile_upload": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64]),
+    "nfx_polygons_upload": (_i, [_vp, _i64, _vp, _vp]),
+    "nfx_compute": (_i, [_vp, _u32]),
+    "nfx_download": (_i, [_vp, _vp, _vp]),
+    "nfx_extract": (_i, [_vp, _i64, _vp, _vp, _u32, _vp, _vp]),
+    "nfx_sync": (_i, [_vp]),
+    "nfx_compute_features_batched": (_i, [_vp, _u32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nfx_gather_patches": (_i, [_vp, _vp]),
+    "nfx_rasterize": (_i, [_vp, _vp]),
+    "nfx_debug_ellipses": (_i, [_vp, _vp]),
+    "nfx_debug_glcm_counts": (_i, [_vp, _i, _i, _i, _vp]),
+    "nfx_debug_grey_levels": (_i, [_vp, _i, _vp]),
+    "nfx_feature_count": (_i, [_u32]),
+    "nfx_feature_name": (C.c_char_p, [_u32, _i]),
+    "nfx_parse_feature_set": (_i, [C.c_char_p, C.POINTER(_u32)]),
+    "nfx_feature_set_name": (C.c_char_p, [_u32]),
+    "nfx_centroid_key": (_i, [_f, _f, C.c_char_p, _i]),
+    "nfx_partition": (_i, [_i64, C.c_int32, C.c_int32, C.POINTER(_i64)]),
+    "nfx_profile_enable": (_i, [_vp, _i]),
+    "nfx_profile_reset": (_i, [_vp]),
+    "nfx_profile_get": (_i, [_vp, C.POINTER(NfxKernelTime), _i]),
+    "nfx_timer_start": (_i, [_vp]),
+    "nfx_timer_stop": (_i, [_vp, C.POINTER(_f)]),
+    "nfx_launch_count": (_i64, [_vp]),
+    "nfx_flush_l2": (_i, [_vp]),
+    "nfx_host_alloc": (_i, [C.POINTER(_vp), _i64]),
+    "nfx_host_free": (_i, [_vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                "(nvcc, sm_100a). nfx has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)          # AttributeError if the .so does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class NfxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"nfx error {code}: {msg}")
+        self.code = code

@@ -1,0 +1,585 @@
+"""CPU oracle for the per-nucleus feature pipeline of oxabz/nuclei-feature-extraction.
+
+TEST INFRASTRUCTURE ONLY -- never imported by the product path (`nfx`, `libnfx.so`).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+
+PARITY UNPINNED for the functions marked [B*]: their arithmetic lives in the un-vendored git
+dependencies tch-utils@d1c10c0 and geometric-features@163ae81 (Cargo.lock:932-935, 2591-2598), the
+reference ships no tests/golden vectors and cannot be built here (no rustc).  They follow the rules
+written in oracle/SPEC.md section B.  Functions marked [A*] restate in-tree reference code
+op-for-op with torch CPU float32 (the same ATen kernels `tch` binds); the cited file:line is
+relative to /root/reference.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+F32 = np.float32
+
+GLCM_LEVELS = (32, 64, 128, 254)                      # src/features/texture.rs:19
+GLCM_OFFSETS = ((0, 1), (1, 1), (1, 0), (1, -1))      # src/features/texture.rs:20  (dy, dx)
+GLRLM_LEVELS = 24                                     # src/features/texture.rs:174
+GLRLM_MAX_LENGTH = 16                                 # src/features/texture.rs:175
+GLRLM_DIRECTIONS = ((1, 0), (1, 1), (0, 1), (-1, 1))  # src/features/texture.rs:176 (dx, dy)
+GABOR_ANGLES = 8                                      # src/features/texture.rs:319
+GABOR_FREQUENCIES = (0.5, 1.0, 2.0, 4.0, 6.0, 8.0)    # src/features/texture.rs:320
+GABOR_KERNEL = 30                                     # src/features/texture.rs:334
+GABOR_SIGMA = 0.45                                    # src/features/texture.rs:334
+
+
+# --------------------------------------------------------------------------------------------
+# Schema (A14)
+# --------------------------------------------------------------------------------------------
+SHAPE_COLUMNS = [  # src/features/shape.rs:114-128
+    "area", "major_axis", "minor_axis", "eccentricity", "orientation", "perimeter",
+    "equivalent_perimeter", "compacity", "eliptic_deviation", "convex_hull_area",
+    "convex_deffect", "convex_perimeter",
+]
+COLOR_COLUMNS = [  # src/features/color.rs:80-100
+    "mean_r", "mean_g", "mean_b", "std_r", "std_g", "std_b", "mean_h", "mean_s", "mean_v",
+    "std_h", "std_s", "std_v", "mean_haematoxylin", "mean_eosin", "mean_dab",
+    "std_haematoxylin", "std_eosin", "std_dab",
+]
+GLCM_FEATURES = [  # src/features/texture.rs:81-157 (push order; note the two IMC column names)
+    "correlation", "contrast", "dissimilarity", "entropy", "angular_second_moment",
+    "sum_average", "sum_variance", "sum_entropy", "sum_of_squares",
+    "inverse_difference_moment", "difference_average", "difference_variance",
+    "information_measure_correlation1", "information_measure_correlation2",
+]
+GLCM_COLUMNS = [f"{f}_{o[0]}_{o[1]}_{L}" for L in GLCM_LEVELS for o in GLCM_OFFSETS
+                for f in GLCM_FEATURES]
+GLRLM_FEATURES = [  # src/features/texture.rs:243-301 (vec! order)
+    "short_run_emphasis", "long_run_emphasis", "gray_level_nonuniformity",
+    "run_length_nonuniformity", "low_gray_level_run_emphasis", "high_gray_level_run_emphasis",
+    "short_run_low_gray_level_emphasis", "short_run_high_gray_level_emphasis",
+    "long_run_low_gray_level_emphasis", "long_run_high_gray_level_emphasis",
+    "short_run_mid_gray_level_emphasis", "long_run_mid_gray_level_emphasis",
+    "short_run_extreme_gray_level_emphasis", "long_run_extreme_gray_level_emphasis",
+    "run_percentage", "run_length_mean", "run_length_variance",
+]
+GLRLM_COLUMNS = [f"{f}_{d[0]}_{d[1]}" for d in GLRLM_DIRECTIONS for f in GLRLM_FEATURES]
+
+
+def rust_f32_display(x) -> str:
+    """Rust `Display` for f32: shortest round-trip decimal, never an exponent (utils.rs:226-228)."""
+    x = np.float32(x)
+    if np.isnan(x):
+        return "NaN"
+    if np.isinf(x):
+        return "inf" if x > 0 else "-inf"
+    return np.format_float_positional(x, unique=True, trim="-")
+
+
+GABOR_COLUMNS = [  # src/features/texture.rs:346-361
+    f"gabor_angle_{rust_f32_display(np.float32(j // len(GABOR_FREQUENCIES)) * np.float32(45.0))}"
+    f"_frequency_{rust_f32_display(np.float32(GABOR_FREQUENCIES[j % len(GABOR_FREQUENCIES)]))}_{s}"
+    for j in range(GABOR_ANGLES * len(GABOR_FREQUENCIES)) for s in ("mean", "variance")
+]
+FLAT_ORDER = ("geometry", "color", "glcm", "glrlm", "gabor")        # src/args.rs:38-44
+SET_COLUMNS = {"geometry": SHAPE_COLUMNS, "color": COLOR_COLUMNS, "glcm": GLCM_COLUMNS,
+               "glrlm": GLRLM_COLUMNS, "gabor": GABOR_COLUMNS}
+
+
+def flat(names):
+    """args::FeatureSet::flat (src/args.rs:35-49), case-insensitive FromStr (src/args.rs:18-32)."""
+    out = []
+    for s in names:
+        s = s.lower()
+        if s == "all":
+            out += list(FLAT_ORDER)
+        elif s == "texture":
+            out += ["glcm", "glrlm", "gabor"]
+        elif s in SET_COLUMNS:
+            out.append(s)
+        else:
+            raise ValueError(f"{s} is not a valid feature set")
+    return out
+
+
+def centroid_key(c) -> str:
+    """centroid_to_key_string (src/utils.rs:226-228)."""
+    return f"{rust_f32_display(c[0])},{rust_f32_display(c[1])}"
+
+
+# --------------------------------------------------------------------------------------------
+# Batch builder (A1, A2, B1)
+# --------------------------------------------------------------------------------------------
+def preprocess_polygon(ring):
+    """[A1] src/utils.rs:54-74. ring: (V,2) f32 as stored in the GeoJSON (closing duplicate kept).
+    Returns (centroid f32[2], centred f32[V,2]); accumulation is sequential f32."""
+    ring = np.asarray(ring, dtype=F32).reshape(-1, 2)
+    acc = np.cumsum(ring, axis=0, dtype=F32)[-1]          # add.accumulate is sequential
+    centroid = (acc / F32(len(ring))).astype(F32)
+    return centroid, (ring - centroid).astype(F32)
+
+
+def polygon_mask(w, h, pts):
+    """[B1] tch_utils::shapes::polygon(w, h, &pts_f64, (Float, Cpu)) -> [h,w] bool. SPEC.md B1."""
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+    X = (np.arange(w, dtype=np.float64) - w / 2.0)[None, :]
+    Y = (np.arange(h, dtype=np.float64) - h / 2.0)[:, None]
+    inside = np.zeros((h, w), dtype=bool)
+    n = len(pts)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(n):
+            xi, yi = pts[i]
+            xj, yj = pts[(i + 1) % n]
+            cross = (yi <= Y) != (yj <= Y)                         # [h,1]
+            xint = xi + (Y - yi) * (xj - xi) / (yj - yi)           # [h,1]
+            inside ^= cross & (X < xint)
+    return inside
+
+
+def ellipse_mask(w, h, center, radii, angle):
+    """[B2] tch_utils::shapes::ellipse(w, h, center, radii, angle, ..) -> [h,w] bool. SPEC.md B2."""
+    cx, cy = np.float64(center[0]), np.float64(center[1])
+    a, b = np.float64(radii[0]), np.float64(radii[1])
+    ang = np.float64(angle)
+    X = (np.arange(w, dtype=np.float64) - w / 2.0)[None, :]
+    Y = (np.arange(h, dtype=np.float64) - h / 2.0)[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cs, sn = np.cos(ang), np.sin(ang)
+        dx, dy = X - cx, Y - cy
+        xr = dx * cs + dy * sn
+        yr = dy * cs - dx * sn
+        u = xr / a
+        v = yr / b
+        val = u * u + v * v
+        return np.broadcast_to(val <= 1.0, (h, w)).copy()
+
+
+def patch_window(centroid, P):
+    """[A2] src/utils.rs:159-162: f32 arithmetic, Rust `as i64` truncates toward zero."""
+    half = F32(P) / F32(2.0)
+    cx, cy = F32(centroid[0]), F32(centroid[1])
+    top, left = int(np.trunc(cy - half)), int(np.trunc(cx - half))
+    bottom, right = int(np.trunc(cy + half)), int(np.trunc(cx + half))
+    return top, left, bottom, right
+
+
+def gather_patch_u8(image_hwc, centroid, P):
+    """[A2] src/utils.rs:159-192 on an interleaved [H,W,3] u8 image; returns [P,P,3] u8 (zero padded).
+    The reference's f32 patch is exactly this / 255 (see `gather_patch`)."""
+    H, W = image_hwc.shape[:2]
+    top, left, bottom, right = patch_window(centroid, P)
+    r0, r1 = max(top, 0), min(bottom, H)
+    c0, c1 = max(left, 0), min(right, W)
+    out = np.zeros((P, P, 3), dtype=np.uint8)
+    if r1 <= r0 or c1 <= c0:
+        return out
+    oy, ox = -min(top, 0), -min(left, 0)
+    nr, nc = min(r1 - r0, P - oy), min(c1 - c0, P - ox)       # clip (reference would panic)
+    if nr > 0 and nc > 0:
+        out[oy:oy + nr, ox:ox + nc] = image_hwc[r0:r0 + nr, c0:c0 + nc]
+    return out
+
+
+def gather_patch(image_hwc, centroid, P):
+    """[A2] [3,P,P] f32 in [0,1] = u8.to_kind(Float)/255.0 (src/utils.rs:172)."""
+    u8 = gather_patch_u8(image_hwc, centroid, P)
+    return (torch.from_numpy(u8).permute(2, 0, 1).to(torch.float32) / 255.0)
+
+
+def load_image_dataset(rings, image_hwc, P):
+    """[A1,A2,B1] src/utils.rs:141-206 -> (centroids [N,2] f32, centred polygons, patches
+    [N,3,P,P] f32, masks [N,1,P,P] f32)."""
+    cents, polys, patches, masks = [], [], [], []
+    for ring in rings:
+        c, cp = preprocess_polygon(ring)
+        m = polygon_mask(P, P, cp.astype(np.float64))
+        cents.append(c)
+        polys.append(cp)
+        masks.append(torch.from_numpy(m.astype(np.float32))[None])
+        patches.append(gather_patch(image_hwc, c, P))
+    return (np.stack(cents).astype(F32), polys, torch.stack(patches, 0), torch.stack(masks, 0))
+
+
+# --------------------------------------------------------------------------------------------
+# Shape set (A3-A8, B2, B7, B8)
+# --------------------------------------------------------------------------------------------
+def center_of_mass(mask):
+    """[A3] src/features/shape.rs:219-226. mask: [1,P,P] tensor."""
+    nz = mask.nonzero()[:, -2:]
+    c = nz.mean(dim=[0], keepdim=False, dtype=torch.float32)
+    return [F32(c[0].item()), F32(c[1].item())]
+
+
+def eig2x2_lapack(a, b, d):
+    """[A5] closed form of LAPACK sgeev on the symmetric 2x2 [[a,b],[b,d]] (slanv2), float32.
+    Returns (l0, l1, V) with V's COLUMNS the eigenvectors, exactly as torch.linalg.eig orders them.
+    Checked against torch.linalg.eig in tests/test_oracle.py."""
+    a, b, d = F32(a), F32(b), F32(d)
+    if b == 0:
+        return a, d, np.array([[1, 0], [0, 1]], dtype=F32)
+    p = F32(0.5) * (a - d)
+    r = F32(np.hypot(p, b))
+    z = p + F32(math.copysign(r, p))
+    l0 = d + z
+    l1 = d - (b / z) * b
+    tau = F32(np.hypot(b, z))
+    cs, sn = z / tau, b / tau
+    return F32(l0), F32(l1), np.array([[cs, -sn], [sn, cs]], dtype=F32)
+
+
+def major_minor_axes_w_angle(mask):
+    """[A4,A5] src/features/shape.rs:141-203. Returns (major, minor, angle) as f32."""
+    nan = F32(np.nan)
+    nz = mask.squeeze().nonzero()
+    centroid = nz.mean(dim=[0], keepdim=False, dtype=torch.float32)
+    if centroid.size(0) == 0:
+        return nan, nan, nan
+    points = nz - centroid
+    cov = points.transpose(0, 1).mm(points) / points.size(0)
+    if bool(cov.isnan().any()):
+        return nan, nan, nan
+    if cov.size(0) != 2 or cov.size(1) != 2:
+        return nan, nan, nan
+    if bool(cov.isinf().any()):
+        return nan, nan, nan
+    eigenvalues, eigenvector = torch.linalg.eig(cov)
+    a = F32(eigenvalues[0].real.item())
+    b = F32(eigenvalues[1].real.item())
+    with np.errstate(invalid="ignore"):
+        if a > b:
+            major, minor, mc = np.sqrt(a), np.sqrt(b), eigenvector[0]
+        else:
+            major, minor, mc = np.sqrt(b), np.sqrt(a), eigenvector[1]
+    x = F32(mc[0].real.item())
+    y = F32(mc[1].real.item())
+    angle = F32(np.arctan2(x, y))
+    return F32(major * F32(2.0)), F32(minor * F32(2.0)), angle
+
+
+def eccentricity(major, minor):
+    """[A6] src/features/shape.rs:205-207 (f32)."""
+    M, m = F32(major) * F32(0.5), F32(minor) * F32(0.5)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return F32(np.sqrt(F32(M * M - m * m)) / M)
+
+
+def eliptic_deviation(mask, ellipse):
+    """[A8] src/features/shape.rs:209-217."""
+    mask = mask.to(torch.float32)
+    ellipse = ellipse.to(torch.float32)
+    mask_area = float(F32(mask.sum(dtype=torch.float32).item()))
+    delta = mask - ellipse
+    return F32((delta.abs().sum(dtype=torch.float32) / mask_area).item())
+
+
+def polygon_area(pts):
+    """[B7] shoelace, float64."""
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+    x, y = pts[:, 0], pts[:, 1]
+    xn, yn = np.roll(x, -1), np.roll(y, -1)
+    return 0.5 * abs(float(np.sum(x * yn - xn * y)))
+
+
+def polygon_perimeter(pts):
+    """[B7] closed polyline length, float64."""
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+    d = np.roll(pts, -1, axis=0) - pts
+    return float(np.sum(np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2)))
+
+
+def convex_hull(pts):
+    """[B8] Andrew's monotone chain (strict turns; collinear points dropped)."""
+    P = sorted(set(map(tuple, np.asarray(pts, dtype=np.float64).reshape(-1, 2).tolist())))
+    if len(P) <= 2:
+        return np.array(P, dtype=np.float64).reshape(-1, 2)
+
+    def cross(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    lo, up = [], []
+    for p in P:
+        while len(lo) >= 2 and cross(lo[-2], lo[-1], p) <= 0:
+            lo.pop()
+        lo.append(p)
+    for p in reversed(P):
+        while len(up) >= 2 and cross(up[-2], up[-1], p) <= 0:
+            up.pop()
+        up.append(p)
+    return np.array(lo[:-1] + up[:-1], dtype=np.float64)
+
+
+def polygon_geometry(pts):
+    """[B7,B8] the 7 polygon scalars of src/features/shape.rs:89-97, float64."""
+    area = polygon_area(pts)
+    per = polygon_perimeter(pts)
+    hull = convex_hull(pts)
+    harea = polygon_area(hull) if len(hull) >= 3 else 0.0
+    hper = polygon_perimeter(hull) if len(hull) >= 2 else 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return dict(
+            area=area, perimeter=per,
+            equivalent_perimeter=2.0 * math.sqrt(math.pi * area),
+            compacity=float(np.float64(4.0 * math.pi * area) / np.float64(per * per)),
+            convex_hull_area=harea, convex_perimeter=hper,
+            convex_deffect=float((np.float64(harea) - np.float64(area)) / np.float64(harea)),
+        )
+
+
+def shape_features(centred_polygons, masks, return_debug=False):
+    """[A3-A8] ShapeFeatureSet::compute_features_batched (src/features/shape.rs:16-130).
+    Returns [N,12] float64 in SHAPE_COLUMNS order (f32-valued where the reference is f32)."""
+    N = masks.shape[0]
+    P = masks.shape[3]
+    out = np.zeros((N, 12), dtype=np.float64)
+    dbg = []
+    for i in range(N):
+        poly = np.asarray(centred_polygons[i], dtype=F32).astype(np.float64)   # utils.rs:24-31
+        mask = masks[i]
+        com = center_of_mass(mask)
+        com = [F32(com[0] - F32(P) / F32(2.0)), F32(com[1] - F32(P) / F32(2.0))]
+        major, minor, angle = major_minor_axes_w_angle(mask)
+        ecc = eccentricity(major, minor)
+        ell = ellipse_mask(P, P, (float(com[1]), float(com[0])), (float(major), float(minor)),
+                           float(angle))
+        ell_t = torch.from_numpy(ell.astype(np.float32))[None]
+        g = polygon_geometry(poly)
+        dev = eliptic_deviation(mask, ell_t)
+        out[i] = [g["area"], major, minor, ecc, angle, g["perimeter"], g["equivalent_perimeter"],
+                  g["compacity"], dev, g["convex_hull_area"], g["convex_deffect"],
+                  g["convex_perimeter"]]
+        if return_debug:
+            dbg.append(dict(com=com, ellipse=ell,
+                            abs_diff=int(np.sum(ell != (mask[0].numpy() != 0))),
+                            area_px=int((mask[0] != 0).sum().item())))
+    return (out, dbg) if return_debug else out
+
+
+# --------------------------------------------------------------------------------------------
+# Colour set (A9-A11, B3, B4)
+# --------------------------------------------------------------------------------------------
+def hsv_from_rgb(rgb):
+    """[B3] tch_utils::color::hsv_from_rgb, [N,3,P,P] f32 in [0,1] -> HSV, H in degrees."""
+    r, g, b = rgb[:, 0], rgb[:, 1], rgb[:, 2]
+    maxc = torch.maximum(torch.maximum(r, g), b)
+    minc = torch.minimum(torch.minimum(r, g), b)
+    delta = maxc - minc
+    zero = torch.zeros_like(maxc)
+    safe = torch.where(delta == 0, torch.ones_like(delta), delta)
+    hr = torch.remainder((g - b) / safe, 6.0)
+    hg = (b - r) / safe + 2.0
+    hb = (r - g) / safe + 4.0
+    h = torch.where(maxc == r, hr, torch.where(maxc == g, hg, hb)) * 60.0
+    h = torch.where(delta == 0, zero, h)
+    s = torch.where(maxc > 0, delta / torch.where(maxc > 0, maxc, torch.ones_like(maxc)), zero)
+    return torch.stack([h, s, maxc], dim=1)
+
+
+_RGB_FROM_HED = np.array([[0.65, 0.70, 0.29], [0.07, 0.99, 0.11], [0.27, 0.57, 0.78]],
+                         dtype=np.float64)
+HED_FROM_RGB = np.linalg.inv(_RGB_FROM_HED).astype(np.float32)      # M[k][c]
+LOG_1E6 = np.float32(math.log(1e-6))
+
+
+def hed_from_rgb(rgb):
+    """[B4] tch_utils::color::hed_from_rgb (scikit-image rgb2hed), [N,3,P,P] f32 -> H,E,D."""
+    od = torch.log(torch.clamp(rgb, min=1e-6)) / float(LOG_1E6)
+    M = HED_FROM_RGB
+    chans = []
+    for c in range(3):
+        v = od[:, 0] * float(M[0, c]) + od[:, 1] * float(M[1, c]) + od[:, 2] * float(M[2, c])
+        chans.append(torch.clamp(v, min=0.0))
+    return torch.stack(chans, dim=1)
+
+
+def mean_std(img, mask):
+    """[A9] src/features/color.rs:117-134."""
+    masked = img * mask
+    mask_area = mask.sum(dim=[-1, -2], keepdim=True, dtype=torch.float32)
+    mean = masked.sum(dim=[-1, -2], keepdim=True, dtype=torch.float32)
+    mean /= mask_area
+    std = img - mean
+    std = std.square() * mask
+    std = std.sum(dim=[-1, -2], keepdim=True, dtype=torch.float32)
+    std /= mask_area
+    std = std.sqrt()
+    std.squeeze_()
+    mean.squeeze_()
+    return mean, std
+
+
+def circular_mean(image, mask):
+    """[A10] src/features/color.rs:144-155 -- called with image [N,P,P], mask [N,1,P,P]: the
+    product broadcasts to [N,N,P,P] (batch-coupled hue mean)."""
+    mask_area = mask.sum(dim=[-1, -2, -3], keepdim=False, dtype=torch.float32)
+    img = image.deg2rad()
+    cos = img.cos() * mask
+    sin = img.sin() * mask
+    cos = cos.sum(dim=[-1, -2, -3], keepdim=False, dtype=torch.float32) / mask_area
+    sin = sin.sum(dim=[-1, -2, -3], keepdim=False, dtype=torch.float32) / mask_area
+    return (sin.atan2(cos).rad2deg_() + 360.0).fmod_(360.0)
+
+
+def circular_mean_vectors(image, mask):
+    """The two resultant components (Σ sin, Σ cos) of A10 before atan2 -- the well-conditioned
+    quantity the parity test falls back to when the resultant is ~0."""
+    img = image.deg2rad()
+    cos = (img.cos() * mask).sum(dim=[-1, -2, -3], dtype=torch.float32)
+    sin = (img.sin() * mask).sum(dim=[-1, -2, -3], dtype=torch.float32)
+    return sin, cos
+
+
+def color_features(patchs, masks):
+    """[A9-A11] ColorFeatureSet::compute_features_batched (src/features/color.rs:10-102) for ONE
+    batch. Returns [N,18] f32 in COLOR_COLUMNS order."""
+    N = patchs.shape[0]
+    hsv = hsv_from_rgb(patchs)
+    hed = hed_from_rgb(patchs)
+    mean_rgb, std_rgb = mean_std(patchs, masks)
+    mean_hed, std_hed = mean_std(hed, masks)
+    h = hsv.select(-3, 0)
+    mean_h = circular_mean(h, masks)
+    h -= mean_h.view(-1, 1, 1)
+    mean_hsv, std_hsv = mean_std(hsv, masks)
+
+    def col(t, c):
+        return t.select(-1, c).reshape(N)
+
+    cols = [col(mean_rgb, 0), col(mean_rgb, 1), col(mean_rgb, 2),
+            col(std_rgb, 0), col(std_rgb, 1), col(std_rgb, 2),
+            mean_h.reshape(N), col(mean_hsv, 1), col(mean_hsv, 2),
+            col(std_hsv, 0), col(std_hsv, 1), col(std_hsv, 2),
+            col(mean_hed, 0), col(mean_hed, 1), col(mean_hed, 2),
+            col(std_hed, 0), col(std_hed, 1), col(std_hed, 2)]
+    return torch.stack(cols, dim=1).numpy().astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
+# GLCM set (A12, A13, B5, B6)
+# --------------------------------------------------------------------------------------------
+def grey_scale(patchs):
+    """[A12] src/features/texture.rs:36."""
+    return patchs.mean(dim=[-3], keepdim=True, dtype=torch.float32)
+
+
+def quantise(grey, levels):
+    """[B5] q = min(floor(grey*L), L-1) with an f32 multiply."""
+    q = torch.floor(grey * float(levels)).to(torch.int64)
+    return torch.clamp(q, max=int(levels) - 1)
+
+
+def glcm_counts(grey, offset, levels, masks):
+    """[B5] symmetric masked co-occurrence COUNTS G = C + C^T, [N,L,L] int64."""
+    N, _, H, W = grey.shape
+    L = int(levels)
+    dy, dx = offset
+    q = quantise(grey, L)[:, 0]
+    m = masks[:, 0] != 0
+    r0, r1 = max(0, -dy), min(H, H - dy)
+    c0, c1 = max(0, -dx), min(W, W - dx)
+    src_q, dst_q = q[:, r0:r1, c0:c1], q[:, r0 + dy:r1 + dy, c0 + dx:c1 + dx]
+    valid = m[:, r0:r1, c0:c1] & m[:, r0 + dy:r1 + dy, c0 + dx:c1 + dx]
+    n_idx = torch.arange(N).view(N, 1, 1).expand_as(src_q)
+    flat_idx = (n_idx * L * L + src_q * L + dst_q)[valid]
+    C = torch.bincount(flat_idx, minlength=N * L * L).view(N, L, L)
+    return C + C.transpose(1, 2)
+
+
+def glcm(grey, offset, levels, masks):
+    """[B5] normalised symmetric masked GLCM, [N,L,L] f32."""
+    G = glcm_counts(grey, offset, levels, masks).to(torch.float32)
+    return G / G.sum(dim=[-1, -2], keepdim=True)
+
+
+def _xlogx(p):
+    return torch.where(p > 0, p * torch.log(torch.where(p > 0, p, torch.ones_like(p))),
+                       torch.zeros_like(p))
+
+
+def glcm_features(p):
+    """[B6] tch_utils::glcm::features::glcm_features; p [N,L,L] f32 -> [N,14] f32 in
+    GLCM_FEATURES order. SPEC.md B6. Evaluated in float64 from the f32 matrix so that the oracle
+    value is the mathematically defined one (the kernel accumulates in f32/f64, tolerance 1e-4)."""
+    N, L, _ = p.shape
+    nanrow = torch.isnan(p).flatten(1).any(dim=1)
+    p = torch.nan_to_num(p, nan=0.0).to(torch.float64)
+    i = torch.arange(L, dtype=torch.float64).view(1, L, 1)
+    j = torch.arange(L, dtype=torch.float64).view(1, 1, L)
+    px = p.sum(dim=2)
+    py = p.sum(dim=1)
+    lv = torch.arange(L, dtype=torch.float64).view(1, L)
+    mux = (lv * px).sum(1)
+    muy = (lv * py).sum(1)
+    varx = (((lv - mux[:, None]) ** 2) * px).sum(1)
+    vary = (((lv - muy[:, None]) ** 2) * py).sum(1)
+    corr = ((i * j * p).sum(dim=[1, 2]) - mux * muy) / torch.sqrt(varx * vary)
+    contrast = (((i - j) ** 2) * p).sum(dim=[1, 2])
+    dissim = ((i - j).abs() * p).sum(dim=[1, 2])
+    entropy = -_xlogx(p).sum(dim=[1, 2])
+    asm = (p * p).sum(dim=[1, 2])
+    # p_{x+y}, p_{x-y}
+    ks = (torch.arange(L).view(L, 1) + torch.arange(L).view(1, L)).flatten()
+    kd = (torch.arange(L).view(L, 1) - torch.arange(L).view(1, L)).abs().flatten()
+    pf = p.flatten(1)
+    psum = torch.zeros(N, 2 * L - 1, dtype=torch.float64).index_add_(1, ks, pf)
+    pdif = torch.zeros(N, L, dtype=torch.float64).index_add_(1, kd, pf)
+    k2 = torch.arange(2 * L - 1, dtype=torch.float64).view(1, -1)
+    k1 = torch.arange(L, dtype=torch.float64).view(1, -1)
+    sum_avg = (k2 * psum).sum(1)
+    sum_var = (((k2 - sum_avg[:, None]) ** 2) * psum).sum(1)
+    sum_ent = -_xlogx(psum).sum(1)
+    sos = (((i - mux.view(N, 1, 1)) ** 2) * p).sum(dim=[1, 2])
+    idm = (p / (1.0 + (i - j) ** 2)).sum(dim=[1, 2])
+    dif_avg = (k1 * pdif).sum(1)
+    dif_var = (((k1 - dif_avg[:, None]) ** 2) * pdif).sum(1)
+    hx = -_xlogx(px).sum(1)
+    hy = -_xlogx(py).sum(1)
+    pxpy = px[:, :, None] * py[:, None, :]
+    logpxpy = torch.log(torch.where(pxpy > 0, pxpy, torch.ones_like(pxpy)))
+    hxy1 = -(p * logpxpy).sum(dim=[1, 2])
+    hxy2 = -(pxpy * logpxpy).sum(dim=[1, 2])
+    imc1 = (entropy - hxy1) / torch.maximum(hx, hy)
+    imc2 = torch.sqrt(torch.clamp(1.0 - torch.exp(-2.0 * (hxy2 - entropy)), min=0.0))
+    out = torch.stack([corr, contrast, dissim, entropy, asm, sum_avg, sum_var, sum_ent, sos, idm,
+                       dif_avg, dif_var, imc1, imc2], dim=1)
+    out[nanrow] = float("nan")
+    return out.to(torch.float32).numpy()
+
+
+def glcm_feature_set(patchs, masks, levels=GLCM_LEVELS, offsets=GLCM_OFFSETS):
+    """[A12,A13] GlcmFeatureSet::compute_features_batched (src/features/texture.rs:24-168):
+    [N, 14*len(levels)*len(offsets)] f32, loop order levels outer, offsets inner."""
+    grey = grey_scale(patchs)
+    cols = []
+    for L in levels:
+        for off in offsets:
+            cols.append(glcm_features(glcm(grey, off, L, masks)))
+    return np.concatenate(cols, axis=1).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
+# Whole pipeline, batch by batch (src/main.rs:146-158, 47-91)
+# --------------------------------------------------------------------------------------------
+def extract(rings, image_hwc, feature_sets, patch_size=64, batch_size=100):
+    """Reference pipeline restated: par_chunks(batch_size) -> load_image_dataset ->
+    compute_features_batched per set -> hstack in flat() order. Rows are returned in INPUT order
+    (the reference's completion order is non-deterministic; join on the key).
+    Returns (keys list[str], centroids [N,2] f32, features [N,F] float64, column names)."""
+    sets = flat(feature_sets)
+    if len(set(sets)) != len(sets):
+        raise ValueError("duplicate feature set (reference: DataFrame::new fails, main.rs:89)")
+    names = [c for s in sets for c in SET_COLUMNS[s]]
+    keys, cents, rows = [], [], []
+    for k in range(0, len(rings), batch_size):
+        chunk = rings[k:k + batch_size]
+        c, polys, patches, masks = load_image_dataset(chunk, image_hwc, patch_size)
+        blocks = []
+        for s in sets:
+            if s == "geometry":
+                blocks.append(shape_features(polys, masks))
+            elif s == "color":
+                blocks.append(color_features(patches, masks).astype(np.float64))
+            elif s == "glcm":
+                blocks.append(glcm_feature_set(patches, masks).astype(np.float64))
+            else:
+                raise NotImplementedError(f"oracle for feature set {s!r} not written yet")
+        rows.append(np.concatenate(blocks, axis=1))
+        cents.append(c)
+        keys += [centroid_key(x) for x in c]
+    return keys, np.concatenate(cents, 0), np.concatenate(rows, 0), names

@@ -1,0 +1,237 @@
+"""GPU parity tests: every kernel through the C ABI (ctypes) against the oracle on the same seeded
+inputs. Integer outputs bit-exact; floats within tolerances.py. Run on a B200 via gpurun."""
+import numpy as np
+import pytest
+import torch
+
+import nfx
+import nfx_oracle as o
+from cases import small_case, stress_case
+from tolerances import mismatches
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def case(libnfx):
+    tile, rings = small_case()
+    xy, off = nfx.pack_polygons(rings)
+    cents, polys, patches, masks = o.load_image_dataset(rings, tile, 64)
+    return dict(tile=tile, rings=rings, xy=xy, off=off, cents=cents, polys=polys, patches=patches, masks=masks)
+
+
+@pytest.fixture(scope="module")
+def ex(case):
+    e = nfx.Extractor(0, 64, 100)
+    e.upload_tile(case["tile"])
+    e.upload_polygons(case["xy"], case["off"])
+    yield e
+    e.close()
+
+
+def _report(bad, limit=12):
+    return "\n".join(f"row {r} {c}: got {g!r} want {w!r}" for r, c, g, w in bad[:limit]) + f"\n({len(bad)} mismatches)"
+
+
+def test_masks_bit_exact(case, ex):
+    got = ex.rasterize()
+    want = (case["masks"][:, 0].numpy() != 0).astype(np.uint8)
+    diff = (got != want).reshape(len(want), -1).sum(1)
+    assert diff.sum() == 0, f"mask mismatch in nuclei {np.where(diff)[0][:10]} ({diff.sum()} px)"
+
+
+def test_centroids_and_keys_exact(case, ex):
+    keys, cents, feats, names = ex.extract(case["xy"], case["off"], ["geometry"])
+    assert np.array_equal(cents.view(np.uint32), case["cents"].view(np.uint32))
+    assert keys == [o.centroid_key(c) for c in case["cents"]]
+
+
+def test_gather_bit_exact(case, ex):
+    ex.upload_polygons(case["xy"], case["off"])
+    got = ex.gather_patches()
+    want = np.stack([o.gather_patch_u8(case["tile"], c, 64) for c in case["cents"]])
+    diff = (got != want).reshape(len(want), -1).sum(1)
+    assert diff.sum() == 0, f"patch mismatch in nuclei {np.where(diff)[0][:10]}"
+
+
+def test_shape_features(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["geometry"])
+    want, dbg = o.shape_features(case["polys"], case["masks"], return_debug=True)
+    assert names == o.SHAPE_COLUMNS
+    # ill-conditioned rows: rank-1 masks (lambda_min ~ 0) -> compare minor axis relative to major
+    got = got.astype(np.float64).copy()
+    w2 = want.copy()
+    j_min, j_maj, j_ecc, j_ori, j_dev = 2, 1, 3, 4, 8
+    with np.errstate(invalid="ignore"):
+        degenerate = ~(w2[:, j_min] > 1e-2 * w2[:, j_maj])
+    for j in (j_min, j_ecc, j_ori, j_dev):
+        got[degenerate, j] = 0
+        w2[degenerate, j] = 0
+    # near-isotropic masks: the eigenvector direction is ill-conditioned in the reference's own f32
+    with np.errstate(invalid="ignore"):
+        iso = (w2[:, j_maj] - w2[:, j_min]) < 1e-3 * w2[:, j_maj]
+    for j in (j_ori, j_dev):
+        got[iso, j] = 0
+        w2[iso, j] = 0
+    # orientation is an angle: compare modulo pi-wrap at +-pi
+    d = np.abs(got[:, j_ori] - w2[:, j_ori])
+    wrap = np.isclose(d, 2 * np.pi, atol=1e-3)
+    got[wrap, j_ori] = w2[wrap, j_ori]
+    bad = mismatches(got, w2, names, "geometry")
+    # the deviation is a ratio of two integer counts: f32 noise upstream of the ellipse parameters may
+    # flip a boundary pixel in the REFERENCE's own arithmetic; allow +-2 px on <1% of the nuclei ...
+    dev_bad = [b for b in bad if b[1] == "eliptic_deviation"]
+    other = [b for b in bad if b[1] != "eliptic_deviation"]
+    assert not other, _report(other)
+    for r, _, g, w in dev_bad:
+        K = dbg[r]["area_px"]
+        assert abs(g * K - w * K) <= 2.5, f"row {r}: deviation count {g*K} vs {w*K}"
+    assert len(dev_bad) <= max(2, len(want) // 100), _report(dev_bad)
+
+
+def test_ellipse_raster_bit_exact_given_kernel_parameters(case, ex):
+    """... and the ellipse rule itself (SPEC.md B2) is bit-exact: feeding the kernel's own f32
+    (centre, axes, angle) to the oracle rasteriser reproduces the kernel's ellipse mask exactly."""
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["geometry"])
+    ell = ex.debug_ellipses()
+    masks = (case["masks"][:, 0].numpy() != 0)
+    P = 64
+    for i in range(len(masks)):
+        K = masks[i].sum()
+        if K == 0:
+            assert ell[i].sum() == 0
+            continue
+        rr, cc = np.nonzero(masks[i])
+        mr = np.float32(np.float32(rr.sum()) / np.float32(K)) - np.float32(P / 2)
+        mc = np.float32(np.float32(cc.sum()) / np.float32(K)) - np.float32(P / 2)
+        want = o.ellipse_mask(P, P, (float(mc), float(mr)), (float(got[i, 1]), float(got[i, 2])), float(got[i, 4]))
+        assert np.array_equal(ell[i] != 0, want), f"ellipse raster differs for nucleus {i}"
+        dev = np.float32(np.float32((want != masks[i]).sum()) / np.float32(K))
+        assert dev == got[i, 8], f"deviation differs for nucleus {i}: {got[i, 8]} vs {dev}"
+
+
+def _color_oracle(case, batch):
+    rows = []
+    n = len(case["rings"])
+    for k in range(0, n, batch):
+        rows.append(o.color_features(case["patches"][k:k + batch].clone(), case["masks"][k:k + batch]))
+    return np.concatenate(rows, 0)
+
+
+def _check_color(got, want, names, case, batch):
+    got = got.astype(np.float64).copy()
+    want = want.astype(np.float64).copy()
+    j = names.index("mean_h")
+    # hue mean: compare as an angle (wrap) and skip rows whose resultant vector is ~0 (atan2 of noise)
+    n = len(want)
+    for k in range(0, n, batch):
+        hsv = o.hsv_from_rgb(case["patches"][k:k + batch])
+        s, c = o.circular_mean_vectors(hsv[:, 0], case["masks"][k:k + batch])
+        area = case["masks"][k:k + batch].sum(dim=[1, 2, 3]) * len(hsv)
+        R = (torch.sqrt(s * s + c * c) / area).numpy()
+        illc = ~(R > 1e-2)
+        got[k:k + batch][illc, j] = 0
+        want[k:k + batch][illc, j] = 0
+    d = np.abs(got[:, j] - want[:, j])
+    wrap = np.abs(d - 360.0) < 0.05
+    got[wrap, j] = want[wrap, j]
+    bad = mismatches(got, want, names, "color")
+    assert not bad, _report(bad)
+
+
+@pytest.mark.parametrize("batch", [100, 37])
+def test_color_features(case, batch):
+    with nfx.Extractor(0, 64, batch) as e:
+        e.upload_tile(case["tile"])
+        keys, cents, got, names = e.extract(case["xy"], case["off"], ["color"])
+    assert names == o.COLOR_COLUMNS
+    _check_color(got, _color_oracle(case, batch), names, case, batch)
+
+
+def test_grey_levels_bit_exact(case, ex):
+    ex.upload_polygons(case["xy"], case["off"])
+    grey = o.grey_scale(case["patches"])
+    for L in o.GLCM_LEVELS:
+        got = ex.debug_grey_levels(L)
+        want = o.quantise(grey, L)[:, 0].numpy().astype(np.uint8)
+        assert np.array_equal(got, want), f"quantised grey differs at L={L}: {(got != want).sum()} px"
+
+
+@pytest.mark.parametrize("L,off", [(32, (0, 1)), (64, (1, 1)), (128, (1, 0)), (254, (1, -1)), (254, (0, 1))])
+def test_glcm_counts_bit_exact(case, ex, L, off):
+    ex.upload_polygons(case["xy"], case["off"])
+    got = ex.debug_glcm_counts(L, off)
+    want = o.glcm_counts(o.grey_scale(case["patches"]), off, L, case["masks"]).numpy().astype(np.uint32)
+    diff = (got != want).reshape(len(want), -1).sum(1)
+    assert diff.sum() == 0, f"GLCM counts differ for nuclei {np.where(diff)[0][:10]}"
+
+
+def test_glcm_features(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["glcm"])
+    want = o.glcm_feature_set(case["patches"], case["masks"])
+    assert names == o.GLCM_COLUMNS
+    got = got.astype(np.float64).copy()
+    want = want.astype(np.float64).copy()
+    # correlation / IMC are 0/0-like when the marginal variance is ~0 (one grey level): mask them
+    for L_i, L in enumerate(o.GLCM_LEVELS):
+        for o_i in range(4):
+            b = (L_i * 4 + o_i) * 14
+            sos = want[:, b + 8]
+            with np.errstate(invalid="ignore"):
+                flat = ~(sos > 1e-6)
+            for f in (0, 12, 13):
+                got[flat, b + f] = 0
+                want[flat, b + f] = 0
+    bad = mismatches(got, want, names, "glcm")
+    assert not bad, _report(bad)
+
+
+def test_all_sets_multi_batch_matches_reference_pipeline(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["geometry", "color", "glcm"])
+    wkeys, wc, want, wnames = o.extract(case["rings"], case["tile"], ["geometry", "color", "glcm"], 64, 100)
+    assert names == wnames and keys == wkeys
+    # the set-specific tests hold the fine print; here: layout/column offsets of the fused run
+    sel = [names.index(c) for c in ("area", "perimeter", "mean_r", "std_b", "mean_v", "contrast_0_1_32",
+                                    "sum_average_1_-1_254", "entropy_1_0_128")]
+    g, w = got[:, sel].astype(np.float64), want[:, sel]
+    ok = np.isclose(g, w, rtol=1e-4, atol=1e-6, equal_nan=True)
+    assert ok.all(), f"{(~ok).sum()} mismatches in fused layout"
+
+
+def test_trait_level_compute_features_batched(case, ex):
+    """FeatureSet::compute_features_batched(centroids, polygons, patchs, masks) on the reference's
+    own Batch layout (src/features/mod.rs:12-28)."""
+    n = 100
+    cents, polys = case["cents"][:n], case["polys"][:n]
+    patches, masks = case["patches"][:n].numpy(), case["masks"][:n].numpy()
+    for fs in nfx.to_fs(["geometry", "color", "glcm"], ex):
+        keys, got = fs.compute_features_batched(cents, polys, patches, masks)
+        assert keys == [o.centroid_key(c) for c in cents]
+        if fs.name() == "geometry":
+            want = o.shape_features(polys, case["masks"][:n])
+            sel = [0, 1, 5, 6, 7, 9, 11]
+            assert np.allclose(got[:, sel], want[:, sel], rtol=1e-4, atol=1e-5, equal_nan=True)
+        elif fs.name() == "color":
+            want = o.color_features(case["patches"][:n].clone(), case["masks"][:n])
+            sel = [i for i, c in enumerate(o.COLOR_COLUMNS) if c != "mean_h"]
+            assert np.allclose(got[:, sel], want[:, sel], rtol=1e-4, atol=2e-6, equal_nan=True)
+        else:
+            assert fs.name() == "GLCM"
+            want = o.glcm_feature_set(case["patches"][:n], case["masks"][:n])
+            sel = [k * 14 + f for k in range(16) for f in (1, 2, 3, 4, 5, 9)]
+            assert np.allclose(got[:, sel], want[:, sel], rtol=1e-4, atol=1e-6, equal_nan=True)
+    ex.upload_tile(case["tile"])
+
+
+def test_errors_do_not_abort(case):
+    with nfx.Extractor(0, 64, 100) as e:
+        with pytest.raises(nfx.NfxError):
+            e.compute(nfx.FS_COLOR)            # nothing staged
+        e.upload_tile(case["tile"])
+        with pytest.raises(nfx.NfxError):
+            e.compute(nfx.FS_COLOR)            # no polygons
+        e.upload_polygons(case["xy"], case["off"])
+        with pytest.raises(nfx.NfxError):
+            e.compute(0)
+    with pytest.raises(nfx.NfxError):
+        nfx.Extractor(99)                      # args.rs:176-180 "GPU {} does not exist"

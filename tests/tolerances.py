@@ -1,0 +1,41 @@
+"""Tolerance of the floating-point parity tests: |a-b| <= RTOL * max(|b|, floor) with NaN == NaN.
+RTOL is the 1e-4 relative tolerance BASELINE.json's north_star states. `floor` keeps columns whose
+value can legitimately be ~0 (std of a flat region, DAB of an H&E pixel, orientation near 0) from
+demanding an absolute accuracy below f32 accumulation noise of the REFERENCE itself."""
+import numpy as np
+
+RTOL = 1e-4
+
+# per-column absolute scale floors (same unit as the column)
+FLOORS = {
+    # shape: radians / pixels / ratios
+    "orientation": 1.0, "eccentricity": 0.1, "eliptic_deviation": 0.05, "convex_deffect": 0.05,
+    "compacity": 0.1,
+    # colour: channels are in [0,1], hue in degrees
+    "mean_h": 360.0, "std_h": 1.0,
+}
+DEFAULT_FLOOR = {"color": 0.02, "glcm": 0.05, "geometry": 1.0}
+
+
+def floor_for(name, set_name):
+    if name in FLOORS:
+        return FLOORS[name]
+    return DEFAULT_FLOOR[set_name]
+
+
+def mismatches(a, b, names, set_name, rtol=RTOL):
+    """Returns list of (row, col_name, got, want) outside tolerance."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    bad = []
+    for j, nm in enumerate(names):
+        fl = floor_for(nm, set_name)
+        x, y = a[:, j], b[:, j]
+        both_nan = np.isnan(x) & np.isnan(y)
+        same_inf = np.isinf(x) & np.isinf(y) & (np.sign(x) == np.sign(y))
+        with np.errstate(invalid="ignore"):
+            ok = np.abs(x - y) <= rtol * np.maximum(np.abs(y), fl)
+        ok = ok | both_nan | same_inf
+        for i in np.where(~ok)[0]:
+            bad.append((int(i), nm, float(x[i]), float(y[i])))
+    return bad
