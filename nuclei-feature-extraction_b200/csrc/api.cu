@@ -268,12 +268,13 @@ int need_inputs(nfx_ctx* ctx, bool tile) {
 
 int make_patch_array(nfx_ctx* ctx, int64_t n) {
     const int P = ctx->P;
-    ctx->ppitch = ((3 * P + 15) / 16) * 16;
+    // rows carry 16 bytes of padding so that the 208-byte TMA box of the last panel stays inside the tensor
+    ctx->ppitch = ((3 * P + 15) / 16) * 16 + 16;
     CK(ctx->patches.ensure((size_t)n * P * ctx->ppitch));
     const int R = hue_slab_rows(P);
     int rc;
-    if ((rc = make_map(ctx, &ctx->map_pat_patch, ctx->patches.p, 3 * P, n * P, ctx->ppitch, P))) return rc;
-    if ((rc = make_map(ctx, &ctx->map_pat_slab, ctx->patches.p, 3 * P, n * P, ctx->ppitch, R))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_pat_patch, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, P))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_pat_slab, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, R))) return rc;
     return NFX_OK;
 }
 
@@ -512,7 +513,7 @@ int nfx_gather_patches(nfx_ctx* ctx, uint8_t* out) {
         if ((rc = run_geom(ctx, false, nullptr, 0, -1, nullptr))) return rc;
     if ((rc = make_patch_array(ctx, ctx->n))) return rc;
     CK(timed(ctx, "k_gather", 1, [&] {
-        return launch_gather(ctx->n, ctx->P, ctx->info.p, &ctx->map_tile_patch, &ctx->map_pat_patch, ctx->stream);
+        return launch_gather(ctx->n, ctx->P, ctx->info.p, &ctx->map_tile_patch, ctx->patches.p, ctx->ppitch, ctx->stream);
     }));
     if (out)
         CK(cudaMemcpy2DAsync(out, (size_t)3 * ctx->P, ctx->patches.p, ctx->ppitch, (size_t)3 * ctx->P,

@@ -103,12 +103,12 @@ __device__ __forceinline__ HsvHed convert(const Px& p, const float* lut) {
 }
 
 // Zero the part of the window the reference never copies (NucInfo comment): rare, warp-uniform.
-__device__ __forceinline__ void zero_uncopied(uint8_t* patch, int P, int nvc, int nvr) {
+__device__ __forceinline__ void zero_uncopied(uint8_t* patch, int P, int o, int nvc, int nvr) {
     if (nvc >= P && nvr >= P) return;
     for (int k = threadIdx.x; k < P * P; k += blockDim.x) {
         const int r = k / P, c = k - r * P;
         if (r >= nvr || c >= nvc) {
-            const int a = patch_addr(P, r, c);
+            const int a = patch_addr(P, o, r, c);
             patch[a] = 0; patch[a + 1] = 0; patch[a + 2] = 0;
         }
     }
@@ -173,13 +173,14 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
     __syncthreads();
     rmin = s_box[0]; rmax = s_box[1]; cmin = s_box[2]; cmax = s_box[3];
 
+    const int o = patch_byte_offset(inf.left);
     mbar_wait(&bar, 0);
-    zero_uncopied(patch, P, inf.nvc, inf.nvr);
+    zero_uncopied(patch, P, o, inf.nvc, inf.nvr);
 
     // pivots (any value of the right magnitude removes the cancellation of the one-pass variance)
     HsvHed pv;
     {
-        const int a = patch_addr(P, P / 2, P / 2);
+        const int a = patch_addr(P, o, P / 2, P / 2);
         Px c = {patch[a], patch[a + 1], patch[a + 2]};
         pv = convert(c, lut);
     }
@@ -192,8 +193,8 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
             const int r = rmin + it / nq, q = q0 + it % nq;
             const uint32_t nib = (rows[r * wpr + (q >> 3)] >> ((q & 7) * 4)) & 0xFu;
             if (!nib) continue;
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(patch + patch_addr(P, r, q * 4));
-            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            uint32_t w0, w1, w2;
+            load_quad(patch, patch_addr(P, o, r, q * 4), w0, w1, w2);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (!((nib >> k) & 1u)) continue;
@@ -249,8 +250,7 @@ __global__ void __launch_bounds__(kHueThreads)
 k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int np = patch_panels(P);
-    const int stage_bytes = np * kPanelBytes * R;
+    const int stage_bytes = patch_panels(P) * kPanelBytes * R;
     const int64_t b0 = (int64_t)blockIdx.x * p.batch_size;
     const int nb = (int)min((int64_t)p.batch_size, p.n - b0);
     const int slab = blockIdx.y, row0 = slab * R;
@@ -270,7 +270,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     const bool owner = (tid < kHueConsumers) && (rr < R) && (row0 + rr < P);
     float C[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
     const int c0 = qc * 4;
-    const int soff = (c0 >> 6) * (kPanelBytes * R) + rr * kPanelBytes + (c0 & 63) * 3;
+    const int soff = (c0 >> 6) * (kPanelBytes * R) + rr * kPanelBytes + (c0 & 63) * 3;   // + o per nucleus
 
     int it = 0;   // global iteration counter over the batch's nuclei (ring position)
     for (int base = 0; base < nb; base += kHueChunk) {
@@ -286,9 +286,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                     if (g >= kHueStages) mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
                     const NucInfo inf = s_info[j];
-                    for (int k = 0; k < np; ++k)
-                        tma_load_2d(ring + (size_t)s * stage_bytes + (size_t)k * kPanelBytes * R, &map,
-                                    (inf.left + k * kPanelPx) * 3, inf.top + row0, &full[s]);
+                    tma_load_window(ring + (size_t)s * stage_bytes, &map, inf.left, inf.top + row0, P, R, &full[s]);
                 }
             }
         } else {
@@ -296,10 +294,8 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                 const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
                 mbar_wait(&full[s], ph);
                 uint32_t w0 = 0, w1 = 0, w2 = 0;
-                if (owner) {
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(ring + (size_t)s * stage_bytes + soff);
-                    w0 = wp[0]; w1 = wp[1]; w2 = wp[2];
-                }
+                if (owner)
+                    load_quad(ring + (size_t)s * stage_bytes, soff + patch_byte_offset(s_info[j].left), w0, w1, w2);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
                 if (owner) {

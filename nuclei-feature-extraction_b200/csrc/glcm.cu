@@ -107,12 +107,13 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     }
     __syncthreads();
     const int rmin = s_box[0], rmax = s_box[1];
+    const int o = patch_byte_offset(inf.left);
     mbar_wait(&bar, 0);
     if (inf.nvc < P || inf.nvr < P) {
         for (int k = tid; k < P * P; k += kGlcmThreads) {
             const int r = k / P, c = k - r * P;
             if (r >= inf.nvr || c >= inf.nvc) {
-                const int a = patch_addr(P, r, c);
+                const int a = patch_addr(P, o, r, c);
                 patch[a] = 0; patch[a + 1] = 0; patch[a + 2] = 0;
             }
         }
@@ -124,7 +125,7 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         const int r0 = dbg_all ? 0 : max(rmin, 0), r1 = dbg_all ? P - 1 : rmax;
         for (int k = r0 * P + tid; k < (r1 + 1) * P; k += kGlcmThreads) {
             const int r = k / P, c = k - r * P;
-            const int a = patch_addr(P, r, c);
+            const int a = patch_addr(P, o, r, c);
             const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[patch[a]], s_lut[patch[a + 1]]), s_lut[patch[a + 2]]), 3.0f);
             q128[k] = (uint8_t)(int)floorf(__fmul_rn(g, 128.0f));
             q254[k] = (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253);

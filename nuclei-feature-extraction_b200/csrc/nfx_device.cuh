@@ -135,26 +135,47 @@ __device__ __forceinline__ void block_sum(T (&v)[NV], T* scratch) {
     for (int k = 0; k < NV; ++k) v[k] = scratch[k];
 }
 
-// Patch layout in shared memory: column PANELS of 64 pixels (192 bytes, a multiple of both the
-// 16-byte TMA granule and the 12-byte pixel quad), each panel a dense [P rows][192 B] TMA box.
-//   addr(r, c) = (c >> 6) * 192 * P + r * 192 + (c & 63) * 3
+// Patch layout in shared memory.
+// MEASURED on B200 (scripts/tma_probe.cu): a tiled u8 TMA load faults ("illegal instruction") unless
+// the innermost box coordinate is a multiple of 16 BYTES (negative / out-of-bounds coordinates are
+// fine and zero-filled). A nucleus window starts at byte 3*left of the tile row, so each box starts
+// at the 16-byte boundary below it and is 16 bytes wider: rows are 208 B (= 13 x 16) for a 64-pixel
+// panel and the pixel data begins `o = (3*left) & 15` bytes into the row.
+//   addr(r, c) = (c >> 6) * 208 * P + r * 208 + o + (c & 63) * 3
 constexpr int kPanelPx = 64;
-constexpr int kPanelBytes = 192;
+constexpr int kPanelData = 192;    // payload bytes of a panel row
+constexpr int kPanelBytes = 208;   // TMA box width (payload + alignment slack)
 __host__ __device__ __forceinline__ int patch_panels(int P) { return (P + kPanelPx - 1) / kPanelPx; }
 __host__ __device__ __forceinline__ int patch_smem_bytes(int P) { return patch_panels(P) * kPanelBytes * P; }
-__device__ __forceinline__ int patch_addr(int P, int r, int c) {
-    return (c >> 6) * (kPanelBytes * P) + r * kPanelBytes + (c & 63) * 3;
+__host__ __device__ __forceinline__ int patch_byte_offset(int left) { return (3 * left) & 15; }
+__device__ __forceinline__ int patch_addr(int P, int o, int r, int c) {
+    return (c >> 6) * (kPanelBytes * P) + r * kPanelBytes + o + (c & 63) * 3;
 }
 // 32-bit words per bitmask row
 __host__ __device__ __forceinline__ int mask_wpr(int P) { return (P + 31) / 32; }
 
-// Issue the TMA boxes ({192 B, P rows} each) that bring one P x P RGB window into shared memory.
-// Called by ONE thread after mbar_expect_tx(bar, patch_smem_bytes(P)).
+// Issue the TMA boxes ({208 B, rows} each) that bring `rows` rows of one nucleus window into shared
+// memory, panel k at smem + k*208*rows. ONE thread, after mbar_expect_tx(bar, panels*208*rows).
+__device__ __forceinline__ void tma_load_window(uint8_t* smem, const CUtensorMap* map, int left, int top,
+                                                int P, int rows, uint64_t* bar) {
+    const int np = patch_panels(P);
+    const int xal = ((3 * left) >> 4) << 4;   // arithmetic shift: floor for negative origins
+    for (int k = 0; k < np; ++k)
+        tma_load_2d(smem + (size_t)k * kPanelBytes * rows, map, xal + k * kPanelData, top, bar);
+}
 __device__ __forceinline__ void tma_load_patch(uint8_t* smem_patch, const CUtensorMap* map, int left,
                                                int top, int P, uint64_t* bar) {
-    const int np = patch_panels(P);
-    for (int k = 0; k < np; ++k)
-        tma_load_2d(smem_patch + (size_t)k * kPanelBytes * P, map, (left + k * kPanelPx) * 3, top, bar);
+    tma_load_window(smem_patch, map, left, top, P, P, bar);
+}
+
+// Four consecutive pixels (12 bytes) starting at byte address `b` of shared memory (any alignment).
+__device__ __forceinline__ void load_quad(const uint8_t* smem, int b, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(smem + (b & ~3));
+    const uint32_t sh = (b & 3) * 8;
+    const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3];
+    w0 = __funnelshift_r(a0, a1, sh);
+    w1 = __funnelshift_r(a1, a2, sh);
+    w2 = __funnelshift_r(a2, a3, sh);
 }
 
 }  // namespace nfx

@@ -77,7 +77,7 @@ cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_
 // ---- staged.cu: kernels (1) gather and the f32 batch packer -----------------------------------
 // tile window -> u8 patch array [n*P rows][pitch bytes] through TMA load + TMA store.
 cudaError_t launch_gather(int64_t n, int P, const NucInfo* info, const CUtensorMap* map_tile,
-                          const CUtensorMap* map_patches, cudaStream_t s);
+                          uint8_t* patches, int64_t pitch, cudaStream_t s);
 // expand bitmask -> u8 0/1 masks [n][P][P]
 cudaError_t launch_expand_mask(int64_t n, int P, const uint32_t* bitmask, uint8_t* out,
                                cudaStream_t s);

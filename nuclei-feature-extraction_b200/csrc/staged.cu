@@ -1,9 +1,9 @@
 // staged.cu -- north-star kernel (1) on its own (batched patch gather, tile -> u8 patch array) and
 // the adapters of the trait-level entry point.
 //
-//   k_gather     src/utils.rs:159-192  one TMA box load (zero fill = the reference's zero padding)
-//                                      + one TMA box store per 64-pixel panel; the only SM work is
-//                                      the rare fix-up of the trunc-toward-zero window quirk.
+//   k_gather     src/utils.rs:159-192  TMA box load (zero fill = the reference's zero padding) of the
+//                                      16-byte aligned superset of the window, re-aligned with
+//                                      funnel shifts and written with coalesced 128-bit stores.
 //   k_expand     bitmask -> u8 0/1 masks (parity tap for src/utils.rs:152-157)
 //   k_pack_batch reference `Batch` layout (patchs [n,3,P,P] f32 = k/255, masks [n,1,P,P] f32;
 //                src/utils.rs:17, 172, 198-199) -> u8 interleaved patch array + bitmask, so that
@@ -14,9 +14,14 @@ namespace nfx {
 
 namespace {
 
-__global__ void __launch_bounds__(32)
+constexpr int kGatherThreads = 128;
+
+// One CTA per nucleus: TMA box load(s) of the 16-byte-aligned superset of the window (zero fill
+// outside the tile), then every thread re-aligns 16 output bytes with funnel shifts and writes them
+// with one 128-bit store (output rows are 16-byte aligned, 3P bytes of payload each).
+__global__ void __launch_bounds__(kGatherThreads)
 k_gather(const int64_t n, const int P, const NucInfo* __restrict__ info,
-         const __grid_constant__ CUtensorMap map_tile, const __grid_constant__ CUtensorMap map_out) {
+         const __grid_constant__ CUtensorMap map_tile, uint8_t* __restrict__ out, const int64_t pitch) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int64_t i = blockIdx.x;
@@ -27,25 +32,39 @@ k_gather(const int64_t n, const int P, const NucInfo* __restrict__ info,
         mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
         tma_load_patch(smem_raw, &map_tile, inf.left, inf.top, P, &bar);
     }
-    __syncwarp();
+    __syncthreads();
     mbar_wait(&bar, 0);
-    if (inf.nvc < P || inf.nvr < P) {
-        for (int k = threadIdx.x; k < P * P; k += 32) {
-            const int r = k / P, c = k - r * P;
-            if (r >= inf.nvr || c >= inf.nvc) {
-                const int a = patch_addr(P, r, c);
-                smem_raw[a] = 0; smem_raw[a + 1] = 0; smem_raw[a + 2] = 0;
+    const int o = patch_byte_offset(inf.left);
+    const int vecs_per_row = (int)(pitch >> 4);   // 16-byte vectors per output row
+    const int row_bytes = 3 * P;
+    for (int k = threadIdx.x; k < P * vecs_per_row; k += kGatherThreads) {
+        const int r = k / vecs_per_row, v = k - r * vecs_per_row;
+        const int ob = v * 16;                                    // first payload byte of this vector
+        // source: panel (ob / 192), byte (ob % 192) + o within the 208-byte panel row
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int b = ob + 4 * q;
+            uint32_t val = 0u;
+            if (b < row_bytes) {
+                const int pn = b / kPanelData, within = b - pn * kPanelData;
+                const int a = pn * (kPanelBytes * P) + r * kPanelBytes + o + within;
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(smem_raw + (a & ~3));
+                val = __funnelshift_r(wp[0], wp[1], (a & 3) * 8);
+                // utils.rs:161-192: columns/rows the reference never copies stay zero
+                const int c0 = b / 3;   // first pixel touched by this word
+                if (r >= inf.nvr) val = 0u;
+                else if (inf.nvc < P) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if ((b + t) / 3 >= inf.nvc) val &= ~(0xffu << (8 * t));
+                }
+                (void)c0;
+                if (b + 4 > row_bytes) val &= (1u << (8 * (row_bytes - b))) - 1u;   // pitch padding
             }
+            w[q] = val;
         }
-        fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
-        __syncwarp();
-    }
-    if (threadIdx.x == 0) {
-        const int np = patch_panels(P);
-        for (int k = 0; k < np; ++k)
-            tma_store_2d(&map_out, smem_raw + (size_t)k * kPanelBytes * P, k * kPanelBytes, (int32_t)(i * P));
-        tma_store_commit();
-        tma_store_wait_all();
+        *reinterpret_cast<uint4*>(out + (i * P + r) * pitch + ob) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -97,14 +116,14 @@ k_pack_batch(const int64_t n, const int P, const float* __restrict__ patchs,
 }  // namespace
 
 cudaError_t launch_gather(int64_t n, int P, const NucInfo* info, const CUtensorMap* map_tile,
-                          const CUtensorMap* map_patches, cudaStream_t s) {
+                          uint8_t* patches, int64_t pitch, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    const int smem = patch_smem_bytes(P);
+    const int smem = patch_smem_bytes(P) + 16;   // the re-alignment reads one word past the payload
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    k_gather<<<(unsigned)n, 32, smem, s>>>(n, P, info, *map_tile, *map_patches);
+    k_gather<<<(unsigned)n, kGatherThreads, smem, s>>>(n, P, info, *map_tile, patches, pitch);
     return cudaGetLastError();
 }
 

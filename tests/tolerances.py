@@ -20,6 +20,10 @@ DEFAULT_FLOOR = {"color": 0.02, "glcm": 0.05, "geometry": 1.0}
 def floor_for(name, set_name):
     if name in FLOORS:
         return FLOORS[name]
+    # normalised GLCM quantities live in [-1,1]: (E[ij]-mu^2)/sigma^2 cancels ~2 digits, and the f32
+    # normalised matrix of the reference carries 6e-8 per entry, so 1e-4 is meaningful on scale 1.
+    if name.startswith(("correlation_", "information_measure_")):
+        return 1.0
     return DEFAULT_FLOOR[set_name]
 
 
