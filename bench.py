@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- nuclei/s of the per-nucleus feature pipeline on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libnfx.so)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic input: config[1] of BASELINE.json
+(colour/intensity feature set, 100k nuclei, 64x64 windows, one B200) unless --workload says
+otherwise. Under torchrun every rank owns one GPU, its own synthetic tile and its own contiguous
+range of nuclei (weak scaling, no data-path collective); torch.distributed is used only for the
+barrier and the max-over-ranks of the device time.
+
+value : nuclei/s with tile and polygons already resident in HBM (CUDA events on the context stream)
+e2e   : nuclei/s through the public host API with HOST buffers: pinned H2D of the tile and the
+        polygons, kernels, D2H of the feature matrix, every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "nuclei-feature-extraction_b200"))
+
+WORKLOADS = {
+    # name: (feature sets, nuclei, tile side, patch, polygon kwargs)
+    "color": (["color"], 100_000, 16384, 64, {}),
+    "shape": (["geometry"], 10_000, 4096, 64, {}),
+    "glcm": (["glcm"], 1_000_000, 49152, 64, {}),
+    "all": (["geometry", "color", "glcm"], 100_000, 16384, 64, {}),
+}
+V_MEAN = 30.0   # mean ring length of the synthetic polygons (12..48 vertices + closing duplicate)
+
+
+def algorithmic_bytes(workload: str, P: int, F: int) -> float:
+    """SURVEY.md 8d, fused per-feature-set pipeline: 3*P^2 (u8 window, read once) + polygon ring
+    + 4*F output bytes per nucleus."""
+    b_px = 3 * P * P
+    b_poly = 8 * (V_MEAN + 1) + 8
+    if workload == "shape":
+        return b_poly + 4 * F
+    return b_px + b_poly + 4 * F
+
+
+def kernel_bytes(name: str, P: int, slabs: int) -> float:
+    """Per-nucleus compulsory traffic of one kernel."""
+    px, bm, info = 3 * P * P, P * P / 8, 16
+    if name == "k_color":
+        return px + bm + info + 4 * 17
+    if name == "k_hue_batch":
+        return px + bm + info + 8 * slabs
+    if name == "k_glcm":
+        return px + bm + info + 4 * 224
+    if name.startswith("k_geom"):
+        return 8 * (V_MEAN + 1) + bm + info + 8 + (4 * 12 if "shape" in name else 0)
+    if name == "k_hue_finalize":
+        return 8 * slabs + 8
+    return 0.0
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(workload, nuclei, side, P, seed, pinned):
+    from nfx import pinned_empty, synth
+    block = min(side, 4096)
+    base = synth.synth_tile(block, block, seed)
+    tile = pinned_empty((side, side, 3), np.uint8) if pinned else np.empty((side, side, 3), np.uint8)
+    for r in range(0, side, block):
+        for c in range(0, side, block):
+            tile[r:r + block, c:c + block] = base[:min(block, side - r), :min(block, side - c)]
+    xy, off = synth.synth_polygons(nuclei, side, side, seed, patch=P)
+    if pinned:
+        pxy = pinned_empty(xy.shape, np.float32)
+        pxy[...] = xy
+        poff = pinned_empty(off.shape, np.int64)
+        poff[...] = off
+        xy, off = pxy, poff
+    return tile, xy, off
+
+
+def cpu_reference_rate(sets, tile, xy, off, P, batch, sample, workers):
+    """The reference's CPU path (oracle = op-for-op torch-CPU restatement): patch_loader +
+    compute_features_batched per chunk, chunks in parallel over `workers` host threads like the
+    reference's rayon par_chunks (src/main.rs:146-158), on the first `sample` nuclei."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from concurrent.futures import ThreadPoolExecutor
+    import torch
+    import nfx_oracle as o
+    from nfx import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores // workers))
+    rings = synth.rings_of(np.asarray(xy), np.asarray(off)[:sample + 1])
+    tile = np.asarray(tile)
+    chunks = [rings[k:k + batch] for k in range(0, len(rings), batch)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(lambda ch: o.extract(ch, tile, sets, P, batch), chunks))
+    dt = time.perf_counter() - t0
+    return sample / dt, dt
+
+
+def cpu_workers():
+    return max(1, min(os.cpu_count() or 1, 16))   # bounded: each colour chunk holds ~1 GB of [N,N,P,P] f32
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nfx", choices=["nfx", "reference"])
+    ap.add_argument("--workload", default="color", choices=sorted(WORKLOADS))
+    ap.add_argument("--nuclei", type=int, default=0)
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--batch-size", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="nuclei of the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sets, nuclei, side, P, _ = WORKLOADS[args.workload]
+    nuclei = args.nuclei or nuclei
+    side = args.tile or side
+    W = max(args.warmup, 3) if args.impl == "nfx" else args.warmup
+    K = max(args.steps, 1)
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        workers = cpu_workers()
+        sample = args.cpu_sample or workers * args.batch_size * {"color": 2, "shape": 4, "glcm": 1, "all": 1}[args.workload]
+        tile, xy, off = make_inputs(args.workload, max(sample, 1000), min(side, 4096), P, 2, pinned=False)
+        rates = []
+        for it in range(args.warmup + K):
+            r, dt = cpu_reference_rate(sets, tile, xy, off, P, args.batch_size, sample, workers)
+            if it >= args.warmup:
+                rates.append((r, dt))
+        total_t = sum(d for _, d in rates)
+        value = sample * len(rates) / total_t
+        line = {
+            "impl": "reference", "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(rates), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {'+'.join(sets)} feature set(s), P={P}, batch_size={args.batch_size}",
+                       "sample": f"{sample} nuclei per step on a {min(side, 4096)}^2 tile"},
+            "cpu_baseline": {"value": value, "unit": "nuclei/s", "cores": workers, "kind": "port",
+                             "sample": f"{sample} nuclei/step x {K} steps, oracle (torch-CPU restatement of the tch path), "
+                                       f"{workers} chunk-parallel host threads of {cores} cores"},
+            "e2e": {"value": value, "unit": "nuclei/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ this repo's CUDA path
+    import nfx
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    mask = nfx.parse_feature_sets(sets)
+    F = len(nfx.feature_names(mask))
+    tile, xy, off = make_inputs(args.workload, nuclei, side, P, 2 + rank, pinned=True)
+    ex = nfx.Extractor(local_rank, P, args.batch_size)
+    ex.upload_tile(tile)
+    ex.upload_polygons(xy, off)
+    cents = nfx.pinned_empty((nuclei, 2), np.float32)
+    feats = nfx.pinned_empty((nuclei, F), np.float32)
+
+    # ---- device-resident throughput ----
+    for _ in range(W):
+        ex.compute(mask)
+    ex.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ex.profile(True)
+    ex.profile_reset()
+    l0 = ex.launch_count()
+    ex.sync()
+    barrier()
+    ex.timer_start()
+    for _ in range(K):
+        ex.compute(mask)
+    ms = ex.timer_stop()
+    barrier()
+    launches = ex.launch_count() - l0
+    prof = ex.profile_get()
+    ex.profile(False)
+    clocks = sampler.stop()
+    ex.download(cents, feats)
+    checksum = float(np.nansum(feats[:: max(1, nuclei // 997)]))
+
+    # ---- end to end through the host API with host buffers ----
+    e2e_ms = None
+    h2d = tile.nbytes + xy.nbytes + off.nbytes
+    d2h = cents.nbytes + feats.nbytes
+    if not args.no_e2e:
+        def e2e_step():
+            ex.upload_tile(tile)
+            ex.upload_polygons(xy, off)
+            ex.compute(mask)
+            ex.download(cents, feats)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(K, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
+
+    # ---- max over ranks ----
+    step_ms = ms / K
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_ms, e2e_ms or 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_max = float(t[0]), float(t[1])
+        e2e_ms = e2e_max if e2e_ms is not None else None
+    total = nuclei * world
+    value = total / (step_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        R = max(1, min(P, 1024 // P))
+        slabs = (P + R - 1) // R
+        kern = {k: {"launches": v[0], "avg_ms": v[1] / max(v[0], 1)} for k, v in prof.items()}
+        tot = sum(v["avg_ms"] for v in kern.values()) or 1.0
+        for k, v in kern.items():
+            v["share"] = v["avg_ms"] / tot
+            v["gbs"] = kernel_bytes(k, P, slabs) * nuclei / (v["avg_ms"] * 1e-3) / 1e9 if v["avg_ms"] > 0 else 0.0
+        dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
+        roof = None
+        if dom:
+            roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kern[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                    "bytes_per_nucleus": kernel_bytes(dom, P, slabs), "avg_launch_ms": kern[dom]["avg_ms"],
+                    "pipeline_bytes_per_nucleus": algorithmic_bytes(args.workload, P, F),
+                    "pipeline_frac": value / world * algorithmic_bytes(args.workload, P, F) / 1e9 / hbm_peak}
+        cpu = None
+        if not args.no_cpu_baseline:
+            workers = cpu_workers()
+            sample = args.cpu_sample or workers * args.batch_size * {"color": 3, "shape": 6, "glcm": 1, "all": 1}[args.workload]
+            sample = min(sample, nuclei)
+            rate, dt = cpu_reference_rate(sets, tile, xy, off, P, args.batch_size, sample, workers)
+            cpu = {"value": rate, "unit": "nuclei/s", "cores": workers, "kind": "port",
+                   "sample": f"first {sample} nuclei of the same workload ({dt:.1f} s), oracle = torch-CPU restatement of the "
+                             f"tch path, {workers} chunk-parallel host threads of {cores} cores"}
+        line = {
+            "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {'+'.join(sets)} feature set(s), {nuclei} nuclei per GPU, "
+                                   f"{P}x{P} windows, tile {side}x{side} u8 RGB per GPU, batch_size={args.batch_size}",
+                       "l2": f"inputs > L2: tile {tile.nbytes / 1e6:.0f} MB per GPU (L2 126 MB)",
+                       "partition": "contiguous index ranges per GPU, no collective"},
+            "e2e": None if e2e_ms is None else {"value": total / (e2e_ms * 1e-3), "unit": "nuclei/s",
+                                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                                 "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": kern,
+            "cpu_baseline": cpu,
+            "checksum": checksum,
+        }
+        print(json.dumps(line))
+    ex.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

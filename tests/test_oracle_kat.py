@@ -1,0 +1,238 @@
+"""Known-answer tests the oracle itself must satisfy. The reference has no tests or
+golden vectors, so the oracle is pinned on analytic cases, on independent implementations
+(cv2, colorsys) and on torch.linalg.eig for the LAPACK convention."""
+import colorsys
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import nfx_oracle as o
+
+
+def test_centroid_is_sequential_f32_mean_including_closing_duplicate():
+    ring = np.array([[0.1, 0.2], [1e7, 3.3], [0.7, -2.5], [0.1, 0.2]], np.float32)
+    c, cp = o.preprocess_polygon(ring)
+    ax = np.float32(0)
+    ay = np.float32(0)
+    for p in ring:
+        ax = np.float32(ax + p[0])
+        ay = np.float32(ay + p[1])
+    assert c[0] == np.float32(ax / np.float32(4)) and c[1] == np.float32(ay / np.float32(4))
+    assert np.array_equal(cp, (ring - c).astype(np.float32))
+
+
+def test_rectangle_mask_half_open_rule():
+    # centred rectangle [-8,12) x [-6,4): sample points are integers -> half-open on both axes
+    pts = np.array([[-8, -6], [12, -6], [12, 4], [-8, 4], [-8, -6]], np.float64)
+    m = o.polygon_mask(64, 64, pts)
+    rr, cc = np.nonzero(m)
+    assert rr.min() == 26 and rr.max() == 35 and cc.min() == 24 and cc.max() == 43
+    assert m.sum() == 200
+
+
+def test_mask_matches_winding_number_on_simple_polygons():
+    """Independent algorithm: for a simple (non self-intersecting) polygon the even-odd rule equals
+    winding number != 0, computed here by summing signed angles."""
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        V = rng.integers(5, 30)
+        th = np.sort(rng.uniform(0, 2 * np.pi, V))
+        r = rng.uniform(8, 28, V)
+        pts = np.stack([r * np.cos(th), r * np.sin(th)], 1) + rng.uniform(-3, 3, 2)
+        m = o.polygon_mask(64, 64, pts)
+        X, Y = np.meshgrid(np.arange(64) - 32.0, np.arange(64) - 32.0)
+        a = pts[None, None] - np.stack([X, Y], -1)[:, :, None, :]          # [64,64,V,2]
+        b = np.roll(a, -1, axis=2)
+        ang = np.arctan2(a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0], (a * b).sum(-1))
+        wn = np.rint(ang.sum(-1) / (2 * np.pi)).astype(int)
+        # ignore sample points within 1e-6 of an edge (boundary convention differs by design)
+        d = np.abs(a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]) / np.maximum(np.linalg.norm(b - a, axis=-1), 1e-30)
+        safe = d.min(-1) > 1e-6
+        assert np.array_equal(m[safe], (wn != 0)[safe])
+
+
+def test_even_odd_rule_on_bow_tie_and_unclosed_ring():
+    bow = np.array([[-15, -15], [15, 15], [15, -15], [-15, 15]], np.float64)      # unclosed, self-intersecting
+    m = o.polygon_mask(64, 64, bow)
+    assert m[32 - 10, 32 + 12] and m[32 + 10, 32 + 12]          # right lobe: 0 < x < 15, |y| < x
+    assert m[32, 32 - 10]                                        # left lobe (closing edge x = -15)
+    assert not m[32 - 12, 32 + 2] and not m[32 + 12, 32 - 2]    # above / below the crossing point
+    closed = np.vstack([bow, bow[:1]])
+    assert np.array_equal(m, o.polygon_mask(64, 64, closed))    # closing duplicate adds a null edge
+
+
+def test_patch_window_truncates_toward_zero_and_pads():
+    img = np.arange(40 * 50 * 3, dtype=np.uint32).reshape(40, 50, 3).astype(np.uint8)
+    # cy - 8 = -2.5 -> top = -2 (not -3), bottom = trunc(13.5) = 13 -> 13 rows pasted at offset 2, row 15 zero
+    p = o.gather_patch_u8(img, (25.0, 5.5), 16)
+    assert o.patch_window((25.0, 5.5), 16) == (-2, 17, 13, 33)
+    assert (p[:2] == 0).all() and (p[15] == 0).all()
+    assert np.array_equal(p[2:15], img[0:13, 17:33])
+    # fully interior
+    q = o.gather_patch_u8(img, (20.2, 20.9), 16)
+    assert np.array_equal(q, img[12:28, 12:28])
+    # f32 patch is exactly u8/255
+    t = o.gather_patch(img, (20.2, 20.9), 16)
+    assert torch.equal(t, torch.from_numpy(q).permute(2, 0, 1).float() / 255.0)
+
+
+def test_eig_closed_form_matches_lapack_convention():
+    rng = np.random.default_rng(1)
+    for t in range(3000):
+        pts = rng.integers(0, 64, size=(rng.integers(2, 300), 2)).astype(np.float32)
+        if t % 5 == 0:
+            pts[:, 1] = pts[0, 1]
+        c = pts - pts.mean(0)
+        cov = torch.from_numpy((c.T @ c / len(c)).astype(np.float32))
+        w, v = torch.linalg.eig(cov)
+        l0, l1, V = o.eig2x2_lapack(cov[0, 0].item(), cov[0, 1].item(), cov[1, 1].item())
+        scale = max(abs(w.real).max().item(), 1e-30)
+        assert abs(w[0].real.item() - l0) <= 2e-6 * scale and abs(w[1].real.item() - l1) <= 2e-6 * scale
+        assert np.allclose(v.real.numpy(), V, atol=2e-6)
+
+
+def test_shape_features_of_axis_aligned_rectangle():
+    pts = np.array([[-10, -5], [10, -5], [10, 5], [-10, 5], [-10, -5]], np.float32)
+    m = torch.from_numpy(o.polygon_mask(64, 64, pts.astype(np.float64)).astype(np.float32))[None, None]
+    f = o.shape_features([pts], m)[0]
+    d = dict(zip(o.SHAPE_COLUMNS, f))
+    assert d["area"] == 200 and d["perimeter"] == 60 and d["convex_hull_area"] == 200
+    assert d["convex_perimeter"] == 60 and d["convex_deffect"] == 0
+    assert math.isclose(d["equivalent_perimeter"], 2 * math.sqrt(math.pi * 200), rel_tol=1e-12)
+    assert math.isclose(d["compacity"], 4 * math.pi * 200 / 3600, rel_tol=1e-12)
+    # mask = 20 cols x 10 rows: var_c = (20^2-1)/12, var_r = (10^2-1)/12; axes = 2*2*sqrt(var)... = 2 sqrt(l)*2/2
+    assert math.isclose(d["major_axis"], 2 * math.sqrt((400 - 1) / 12), rel_tol=1e-5)
+    assert math.isclose(d["minor_axis"], 2 * math.sqrt((100 - 1) / 12), rel_tol=1e-5)
+    # cov = [[var_r, 0],[0, var_c]], b == 0 -> V = I, l0 = var_r < l1 -> row 1 = (0,1) -> atan2(0,1) = 0
+    assert d["orientation"] == 0.0
+    assert math.isclose(d["eccentricity"], math.sqrt(1 - 99 / 399), rel_tol=1e-5)
+
+
+def test_polygon_geometry_against_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2)
+    for _ in range(30):
+        V = rng.integers(6, 40)
+        th = np.sort(rng.uniform(0, 2 * np.pi, V))
+        r = rng.uniform(5, 30, V)
+        pts = np.stack([r * np.cos(th), r * np.sin(th)], 1).astype(np.float32)
+        g = o.polygon_geometry(pts.astype(np.float64))
+        assert math.isclose(g["area"], cv2.contourArea(pts), rel_tol=1e-4)
+        assert math.isclose(g["perimeter"], cv2.arcLength(pts, True), rel_tol=1e-4)
+        hull = cv2.convexHull(pts)
+        assert math.isclose(g["convex_hull_area"], cv2.contourArea(hull), rel_tol=1e-4)
+        assert math.isclose(g["convex_perimeter"], cv2.arcLength(hull, True), rel_tol=1e-4)
+
+
+def test_regular_ngon_closed_forms():
+    n, R = 12, 20.0
+    th = 2 * np.pi * np.arange(n) / n
+    pts = np.stack([R * np.cos(th), R * np.sin(th)], 1)
+    g = o.polygon_geometry(pts)
+    assert math.isclose(g["area"], 0.5 * n * R * R * math.sin(2 * math.pi / n), rel_tol=1e-12)
+    assert math.isclose(g["perimeter"], 2 * n * R * math.sin(math.pi / n), rel_tol=1e-12)
+    assert abs(g["convex_deffect"]) < 1e-12
+
+
+def test_hsv_matches_colorsys():
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 256, size=(200, 3)).astype(np.uint8)
+    u8[:5] = [[0, 0, 0], [255, 255, 255], [255, 0, 0], [10, 10, 200], [7, 200, 200]]
+    rgb = torch.from_numpy(u8.astype(np.float32) / np.float32(255)).T.reshape(1, 3, 1, 200)
+    hsv = o.hsv_from_rgb(rgb)[0, :, 0].T.numpy()
+    for k in range(200):
+        h, s, v = colorsys.rgb_to_hsv(*(u8[k] / 255.0))
+        assert abs(hsv[k, 0] - 360 * h) < 2e-3 or abs(abs(hsv[k, 0] - 360 * h) - 360) < 2e-3
+        assert abs(hsv[k, 1] - s) < 1e-6 and abs(hsv[k, 2] - v) < 1e-6
+
+
+def test_hed_is_the_ruifrok_deconvolution():
+    rgb_from_hed = np.array([[0.65, 0.70, 0.29], [0.07, 0.99, 0.11], [0.27, 0.57, 0.78]])
+    conc = np.array([0.4, 0.2, 0.05])                    # stain concentrations
+    od = conc @ rgb_from_hed                             # optical density per RGB channel (log_1e-6 units)
+    rgb = np.exp(od * math.log(1e-6))
+    t = torch.tensor(rgb, dtype=torch.float32).reshape(1, 3, 1, 1)
+    hed = o.hed_from_rgb(t).reshape(3).numpy()
+    assert np.allclose(hed, conc, atol=2e-6)
+    white = o.hed_from_rgb(torch.ones(1, 3, 1, 1)).reshape(3).numpy()
+    assert np.allclose(white, 0)
+
+
+def test_constant_colour_patch_statistics_and_batch_coupled_hue():
+    P, N = 16, 3
+    cols = np.array([[200, 40, 40], [40, 200, 40], [40, 40, 200]], np.float32) / np.float32(255)
+    patches = torch.from_numpy(cols).reshape(N, 3, 1, 1).expand(N, 3, P, P).contiguous()
+    masks = torch.zeros(N, 1, P, P)
+    masks[:, :, 4:12, 4:12] = 1
+    f = o.color_features(patches.clone(), masks)
+    d = {c: f[:, j] for j, c in enumerate(o.COLOR_COLUMNS)}
+    assert np.allclose(d["std_r"], 0, atol=1e-7) and np.allclose(d["std_s"], 0, atol=1e-7)
+    assert np.allclose(d["mean_r"], cols[:, 0], atol=1e-7)
+    # hues are 0, 120, 240 degrees: every nucleus sees the SUM over the batch (color.rs:50-51 broadcast)
+    # -> resultant ~ 0 for all three, so mean_h is the same (ill-conditioned) value for every row
+    assert np.allclose(d["mean_h"], d["mean_h"][0], atol=1e-3)
+    # with a single-patch batch the hue mean is that patch's own hue
+    f1 = o.color_features(patches[1:2].clone(), masks[1:2])
+    assert abs(f1[0, o.COLOR_COLUMNS.index("mean_h")] - 120.0) < 1e-3
+
+
+def test_glcm_counts_of_a_two_level_checkerboard():
+    P = 8
+    g = (np.indices((P, P)).sum(0) % 2).astype(np.float32) * np.float32(0.9)          # levels 0 and floor(.9*L)
+    grey = torch.from_numpy(g)[None, None]
+    masks = torch.ones(1, 1, P, P)
+    L = 32
+    hi = int(math.floor(np.float32(0.9) * L))
+    G = o.glcm_counts(grey, (0, 1), L, masks)[0].numpy()
+    assert G[0, hi] == G[hi, 0] == P * (P - 1) and G.sum() == 2 * P * (P - 1)
+    G = o.glcm_counts(grey, (1, 1), L, masks)[0].numpy()
+    assert G[0, 0] + G[hi, hi] == 2 * (P - 1) ** 2 and G[0, hi] == 0
+    # masked: only pairs with both pixels inside the mask count
+    masks[:, :, :, 4:] = 0
+    G = o.glcm_counts(grey, (0, 1), L, masks)[0].numpy()
+    assert G.sum() == 2 * P * 3
+
+
+def test_glcm_features_known_values():
+    # p = [[.5, 0],[0, .5]] (perfectly correlated two-level texture)
+    p = torch.tensor([[[0.5, 0.0], [0.0, 0.5]]])
+    f = dict(zip(o.GLCM_FEATURES, o.glcm_features(p)[0]))
+    assert math.isclose(f["correlation"], 1.0, rel_tol=1e-6) and f["contrast"] == 0 and f["dissimilarity"] == 0
+    assert math.isclose(f["entropy"], math.log(2), rel_tol=1e-6)
+    assert math.isclose(f["angular_second_moment"], 0.5, rel_tol=1e-6)
+    assert math.isclose(f["sum_average"], 1.0, rel_tol=1e-6) and math.isclose(f["sum_variance"], 1.0, rel_tol=1e-6)
+    assert math.isclose(f["sum_of_squares"], 0.25, rel_tol=1e-6)
+    assert math.isclose(f["inverse_difference_moment"], 1.0, rel_tol=1e-6)
+    assert math.isclose(f["information_measure_correlation1"], -1.0, rel_tol=1e-6)
+    assert math.isclose(f["information_measure_correlation2"], math.sqrt(1 - math.exp(-2 * math.log(2))), rel_tol=1e-6)
+    # HXY1 == HXY2 == HX + HY for any symmetric p (used by the kernel's factorisation)
+    rng = np.random.default_rng(4)
+    a = rng.random((1, 6, 6))
+    a = a + a.transpose(0, 2, 1)
+    a[0, 2] = 0
+    a[0, :, 2] = 0
+    a /= a.sum()
+    f = dict(zip(o.GLCM_FEATURES, o.glcm_features(torch.tensor(a, dtype=torch.float32))[0]))
+    px = a[0].sum(1)
+    hx = -(px[px > 0] * np.log(px[px > 0])).sum()
+    hxy = -(a[a > 0] * np.log(a[a > 0])).sum()
+    assert math.isclose(f["information_measure_correlation1"], (hxy - 2 * hx) / hx, rel_tol=1e-4)
+    # empty mask -> 0/0 -> NaN everywhere
+    assert np.isnan(o.glcm_features(torch.full((1, 4, 4), float("nan")))).all()
+
+
+def test_empty_mask_gives_nan_like_the_reference():
+    m = torch.zeros(1, 1, 64, 64)
+    pts = np.array([[0.2, 0.2], [0.6, 0.2], [0.6, 0.6], [0.2, 0.2]], np.float32)
+    f = dict(zip(o.SHAPE_COLUMNS, o.shape_features([pts], m)[0]))
+    assert np.isnan(f["major_axis"]) and np.isnan(f["minor_axis"]) and np.isnan(f["orientation"])
+    assert np.isnan(f["eliptic_deviation"]) and f["area"] > 0
+
+
+def test_key_string_is_rust_display():
+    assert o.centroid_key(np.array([1024.0, 33.5], np.float32)) == "1024,33.5"
+    assert o.centroid_key(np.array([0.1, 1e-7], np.float32)) == "0.1,0.0000001"
+    assert o.centroid_key(np.array([16777216.0, -0.0], np.float32)) == "16777216,-0"
+    assert o.centroid_key(np.array([np.nan, np.inf], np.float32)) == "NaN,inf"
