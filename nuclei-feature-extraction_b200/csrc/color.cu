@@ -69,18 +69,22 @@ __device__ __forceinline__ Px quad_px(uint32_t w0, uint32_t w1, uint32_t w2, int
     return p;
 }
 
-// hexcone hue in sextants t in [0,6] (SPEC.md B3): H = 60 t. d = max - min > 0 required.
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, ~1 ulp
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// hexcone hue in sextants (SPEC.md B3): H = 60 t. Branch-free; d = max - min may be 0 (then t = 0).
+// WRAP=true folds t into [0,6] like the reference's `mod 6`; the trigonometric consumers skip it.
+template <bool WRAP>
 __device__ __forceinline__ float hue_sextant(const Px& p, uint32_t mx, uint32_t d) {
-    const float rd = __frcp_rn(u8f(d));
-    float t;
-    if (mx == p.r) {
-        t = ((float)((int)p.g - (int)p.b)) * rd;
-        if (t < 0.f) t += 6.0f;
-    } else if (mx == p.g) {
-        t = ((float)((int)p.b - (int)p.r)) * rd + 2.0f;
-    } else {
-        t = ((float)((int)p.r - (int)p.g)) * rd + 4.0f;
-    }
+    const bool isr = (mx == p.r), isg = (mx == p.g);
+    const int gb = (int)p.g - (int)p.b, br = (int)p.b - (int)p.r, rg = (int)p.r - (int)p.g;
+    const int num = isr ? gb : (isg ? br : rg);
+    const float offs = isr ? 0.0f : (isg ? 2.0f : 4.0f);
+    float t = fmaf((float)num, rcp_approx(u8f(max(d, 1u))), offs);
+    if (WRAP) t += (t < 0.f) ? 6.0f : 0.0f;
     return t;
 }
 
@@ -93,8 +97,8 @@ __device__ __forceinline__ HsvHed convert(const Px& p, const float* lut) {
     HsvHed o;
     const uint32_t mx = max(p.r, max(p.g, p.b)), mn = min(p.r, min(p.g, p.b)), d = mx - mn;
     o.mx = mx;
-    o.s = mx ? __fdividef(u8f(d), u8f(mx)) : 0.f;
-    o.h = d ? 60.0f * hue_sextant(p, mx, d) : 0.f;
+    o.s = u8f(d) * rcp_approx(u8f(max(mx, 1u)));
+    o.h = 60.0f * hue_sextant<true>(p, mx, d);
     const float a = lut[p.r], b = lut[p.g], c = lut[p.b];
     o.hed[0] = fmaxf(0.f, a * HED_M00 + b * HED_M10 + c * HED_M20);
     o.hed[1] = fmaxf(0.f, a * HED_M01 + b * HED_M11 + c * HED_M21);
@@ -116,64 +120,64 @@ __device__ __forceinline__ void zero_uncopied(uint8_t* patch, int P, int o, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kColorThreads)
+// Dynamic smem: patch | rows[P*wpr] u32 | lut[256] f32 | list[P*P] u16 ((row << 8) | col).
+__global__ void __launch_bounds__(kColorThreads, 8)
 k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x;
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kColorThreads / 32;
     const int64_t i = blockIdx.x;
     uint8_t* patch = smem_raw;
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + patch_smem_bytes(P));
     float* lut = reinterpret_cast<float*>(rows + P * wpr);
+    uint16_t* list = reinterpret_cast<uint16_t*>(lut + 256);
     __shared__ __align__(8) uint64_t bar;
-    __shared__ double s_red[19 * (kColorThreads / 32)];
-    __shared__ int s_box[4];
+    __shared__ int s_scan[NW + 1];
+    __shared__ uint32_t s_ri[NW][9];
+    __shared__ float s_rf[NW][10];
 
     const NucInfo inf = p.info[i];
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        s_box[0] = P; s_box[1] = -1; s_box[2] = P; s_box[3] = -1;
-    }
-    __syncthreads();
-    if (tid == 0) {
         mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
         tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
     }
-    // while the window is in flight: mask rows, OD table, bounding box of the mask
-    int rmin = P, rmax = -1;
-    uint32_t colbits[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wpr <= 8 (P <= 256)
-    const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
-    for (int r = tid; r < P; r += kColorThreads) {
-        uint32_t any = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            if (w < wpr) {
-                const uint32_t b = gm[r * wpr + w];
-                rows[r * wpr + w] = b;
-                colbits[w] |= b;
-                any |= b;
-            }
-        }
-        if (any) { rmin = min(rmin, r); rmax = max(rmax, r); }
-    }
+    // ---- while the window is in flight: compact the mask into a list of pixel coordinates ----
     for (int k = tid; k < 256; k += kColorThreads) lut[k] = g_od_lut[k];
-    int cmin = P, cmax = -1;
+    const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
+    int K = 0;
+    for (int base = 0; base < P * wpr; base += kColorThreads) {
+        const int k = base + tid;
+        uint32_t bits = (k < P * wpr) ? gm[k] : 0u;
+        const int cnt = __popc(bits);
+        int incl = cnt;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        if (w < wpr) {
-            const uint32_t b = __reduce_or_sync(0xffffffffu, colbits[w]);
-            if (b) { cmin = min(cmin, 32 * w + __ffs(b) - 1); cmax = max(cmax, 32 * w + 31 - __clz(b)); }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        __syncthreads();   // s_scan reuse
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int t = 0; t < NW; ++t) {
+            const int v = s_scan[t];
+            wbase += (t < warp) ? v : 0;
+            total += v;
+        }
+        int pos = K + wbase + incl - cnt;
+        const int r = k / wpr, cb = (k - r * wpr) * 32;
+        while (bits) {
+            const int c = cb + __ffs(bits) - 1;
+            bits &= bits - 1;
+            list[pos++] = (uint16_t)((r << 8) | c);
+        }
+        K += total;
     }
-    rmin = warp_min(rmin); rmax = warp_max(rmax);
-    if ((tid & 31) == 0) {
-        atomicMin(&s_box[0], rmin); atomicMax(&s_box[1], rmax);
-        atomicMin(&s_box[2], cmin); atomicMax(&s_box[3], cmax);
-    }
-    __syncthreads();
-    rmin = s_box[0]; rmax = s_box[1]; cmin = s_box[2]; cmax = s_box[3];
-
     const int o = patch_byte_offset(inf.left);
+    __syncthreads();   // list + lut visible
     mbar_wait(&bar, 0);
     zero_uncopied(patch, P, o, inf.nvc, inf.nvr);
 
@@ -185,51 +189,63 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
         pv = convert(c, lut);
     }
 
-    uint32_t n = 0, sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
+    uint32_t sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
     float s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};   // hed0, hed1, hed2, s, h (pivoted)
-    if (rmax >= rmin) {
-        const int q0 = cmin >> 2, nq = (cmax >> 2) - q0 + 1, items = (rmax - rmin + 1) * nq;
-        for (int it = tid; it < items; it += kColorThreads) {
-            const int r = rmin + it / nq, q = q0 + it % nq;
-            const uint32_t nib = (rows[r * wpr + (q >> 3)] >> ((q & 7) * 4)) & 0xFu;
-            if (!nib) continue;
-            uint32_t w0, w1, w2;
-            load_quad(patch, patch_addr(P, o, r, q * 4), w0, w1, w2);
+    for (int j = tid; j < K; j += kColorThreads) {
+        const uint32_t rc = list[j];
+        const int a = patch_addr(P, o, rc >> 8, rc & 255);
+        const Px px = {patch[a], patch[a + 1], patch[a + 2]};
+        const HsvHed c = convert(px, lut);
+        sr += px.r; sg += px.g; sb += px.b;
+        srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
+        sv += c.mx; svv += c.mx * c.mx;
+        float d;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!((nib >> k) & 1u)) continue;
-                const Px px = quad_px(w0, w1, w2, k);
-                const HsvHed c = convert(px, lut);
-                ++n;
-                sr += px.r; sg += px.g; sb += px.b;
-                srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
-                sv += c.mx; svv += c.mx * c.mx;
-                float d;
+        for (int q = 0; q < 3; ++q) { d = c.hed[q] - pv.hed[q]; s1[q] += d; s2[q] = fmaf(d, d, s2[q]); }
+        d = c.s - pv.s; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
+        d = c.h - pv.h; s1[4] += d; s2[4] = fmaf(d, d, s2[4]);
+    }
+    // ---- warp level: REDUX for the exact integer sums, shuffles for the floats ----
+    {
+        const uint32_t vi[8] = {sr, sg, sb, srr, sgg, sbb, sv, svv};
 #pragma unroll
-                for (int j = 0; j < 3; ++j) { d = c.hed[j] - pv.hed[j]; s1[j] += d; s2[j] = fmaf(d, d, s2[j]); }
-                d = c.s - pv.s; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
-                d = c.h - pv.h; s1[4] += d; s2[4] = fmaf(d, d, s2[4]);
-            }
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t t = __reduce_add_sync(0xffffffffu, vi[q]);
+            if (lane == 0) s_ri[warp][q] = t;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float a1 = warp_sum(s1[q]), a2 = warp_sum(s2[q]);
+            if (lane == 0) { s_rf[warp][q] = a1; s_rf[warp][5 + q] = a2; }
         }
     }
-    double v[19];
-    v[0] = n; v[1] = sr; v[2] = sg; v[3] = sb; v[4] = srr; v[5] = sgg; v[6] = sbb; v[7] = sv; v[8] = svv;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) { v[9 + j] = s1[j]; v[14 + j] = s2[j]; }
-    block_sum<19>(v, s_red);
-
+    __syncthreads();
     if (tid == 0) {
+        double v[19];
+        v[0] = (double)K;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            unsigned long long t = 0;
+            for (int w = 0; w < NW; ++w) t += s_ri[w][q];
+            v[1 + q] = (double)t;
+        }
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+            double t = 0.0;
+            for (int w = 0; w < NW; ++w) t += (double)s_rf[w][q];
+            v[9 + q] = t;
+        }
         float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
-        const double K = v[0];
-        auto mean8 = [&](double s) { return (float)(s / K / 255.0); };
+        const double Kd = v[0];
+        auto mean8 = [&](double s) { return (float)(s / Kd / 255.0); };
         auto std8 = [&](double s, double ss) {
-            const double m = s / K;
-            return (float)(sqrt(fmax(ss / K - m * m, 0.0)) / 255.0);
+            const double m = s / Kd;
+            return (float)(sqrt(fmax(ss / Kd - m * m, 0.0)) / 255.0);
         };
-        auto meanp = [&](int j, float pivot) { return (float)((double)pivot + v[9 + j] / K); };
-        auto stdp = [&](int j) {
-            const double m = v[9 + j] / K;
-            return (float)sqrt(fmax(v[14 + j] / K - m * m, 0.0));
+        auto meanp = [&](int q, float pivot) { return (float)((double)pivot + v[9 + q] / Kd); };
+        auto stdp = [&](int q) {
+            const double m = v[9 + q] / Kd;
+            return (float)sqrt(fmax(v[14 + q] / Kd - m * m, 0.0));
         };
         out[0] = mean8(v[1]); out[1] = mean8(v[2]); out[2] = mean8(v[3]);
         out[3] = std8(v[1], v[4]); out[4] = std8(v[2], v[5]); out[5] = std8(v[3], v[6]);
@@ -300,21 +316,23 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                 if (lane == 0) mbar_arrive(&empty[s]);
                 if (owner) {
                     const NucInfo inf = s_info[j];
-                    const bool rowdead = (row0 + rr) >= inf.nvr;
+                    if (inf.nvc < P || inf.nvr < P) {   // rare: window partly never copied (NucInfo)
+                        const bool rowdead = (row0 + rr) >= inf.nvr;
+                        const int nlive = rowdead ? 0 : min(max(inf.nvc - c0, 0), 4);   // live pixels of the quad
+                        // zero the dead bytes: pixel k occupies bytes 3k..3k+2 of the 12-byte quad
+                        const int nb = 3 * nlive;
+                        w0 = nb >= 4 ? w0 : (nb > 0 ? (w0 & ((1u << (8 * nb)) - 1u)) : 0u);
+                        w1 = nb >= 8 ? w1 : (nb > 4 ? (w1 & ((1u << (8 * (nb - 4))) - 1u)) : 0u);
+                        w2 = nb >= 12 ? w2 : (nb > 8 ? (w2 & ((1u << (8 * (nb - 8))) - 1u)) : 0u);
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        Px px = quad_px(w0, w1, w2, k);
-                        if (rowdead || (c0 + k) >= inf.nvc) { px.r = 0; px.g = 0; px.b = 0; }
-                        const uint32_t mx = max(px.r, max(px.g, px.b)), mn = min(px.r, min(px.g, px.b)), d = mx - mn;
-                        float cs = 1.0f, sn = 0.0f;
-                        if (d) {
-                            // h = 60 t degrees = t/6 turns; sin/cos.approx take radians
-                            const float ang = hue_sextant(px, mx, d) * 1.0471975511965976f;
-                            cs = __cosf(ang);
-                            sn = __sinf(ang);
-                        }
-                        C[k] += cs;
-                        S[k] += sn;
+                        const Px px = quad_px(w0, w1, w2, k);
+                        const uint32_t mx = max(px.r, max(px.g, px.b)), mn = min(px.r, min(px.g, px.b));
+                        // h = 60 t degrees = t * pi/3 radians (no wrap needed under sin/cos); d = 0 -> t = 0
+                        const float ang = hue_sextant<false>(px, mx, mx - mn) * 1.0471975511965976f;
+                        C[k] += __cosf(ang);
+                        S[k] += __sinf(ang);
                     }
                 }
             }
@@ -374,7 +392,7 @@ __global__ void k_hue_finalize(const ColorParams p) {
 }  // namespace
 
 int hue_slab_rows(int P) { return max(1, min(P, 1024 / P)); }
-int color_smem_bytes(int P) { return patch_smem_bytes(P) + P * mask_wpr(P) * 4 + 256 * 4; }
+int color_smem_bytes(int P) { return patch_smem_bytes(P) + P * mask_wpr(P) * 4 + 256 * 4 + P * P * 2; }
 
 static bool g_lut_ready[64] = {};
 static cudaError_t ensure_lut(cudaStream_t s) {
