@@ -8,13 +8,15 @@
 // for levels {32,64,128,254} x offsets {(0,1),(1,1),(1,0),(1,-1)} (texture.rs:19-20).
 //
 // The L x L matrix is never scanned: a nucleus has only ~K co-occurring pixel pairs per offset
-// (K = mask area), so everything is driven by the compacted pair list.
+// (K = mask area), so everything is driven by the compacted pair list (one packed u32 per pair).
 //   * G = C + C^T is kept as a TRIANGULAR u16 histogram (cell (min,max)), L(L+1)/2 entries, and is
 //     only needed for the two features that are non-linear in p_ij (entropy, angular second moment):
 //     sum_cells f(G) = sum_pairs 2 f(G_pair)/G_pair.
 //   * every other feature is a moment of the three marginal histograms p_x, p_{x+y}, p_{x-y}
-//     (HXY1 = HXY2 = 2 HX identically).
+//     (HXY1 = HXY2 = 2 HX identically); the moments are exact integer sums (REDUX).
 //   * after each (offset, level) the triangular histogram is cleared by replaying the pair list.
+//   * per-warp partial sums of all 16 combinations are parked in shared memory; the 14 features of
+//     each combination are computed once at the end by one thread per combination.
 #include <math_constants.h>
 
 #include "nfx_kernels.h"
@@ -31,9 +33,13 @@ constexpr int kTriBytes = ((kTriEntries * 2 + 15) / 16) * 16;
 __device__ __constant__ int c_levels[4] = {32, 64, 128, 254};
 __device__ __constant__ int c_off[4][2] = {{0, 1}, {1, 1}, {1, 0}, {1, -1}};   // (dy, dx)
 
+constexpr int kCombos = kGlcmLevels * kGlcmOffsets;   // 16
+constexpr int kNI = 7, kNF = 4;                        // integer / float partial sums per combination
+constexpr int kNW = kGlcmThreads / 32;
+
 struct GlcmSmem {
     int region_a;   // patch (until quantised) aliased with the triangular histogram
-    int rows, q128, q254, pairs, hist, total;
+    int rows, q128, q254, pairs, hist, part_i, part_f, total;
 };
 __host__ __device__ inline GlcmSmem glcm_layout(int P) {
     GlcmSmem L;
@@ -43,23 +49,30 @@ __host__ __device__ inline GlcmSmem glcm_layout(int P) {
     L.rows = a;
     L.q128 = L.rows + ((P * mask_wpr(P) * 4 + 15) & ~15);
     L.q254 = L.q128 + P * P;
-    L.pairs = L.q254 + P * P;
-    L.hist = L.pairs + P * P * 2;
-    L.total = L.hist + (256 + 512 + 256) * 4;
+    L.pairs = L.q254 + P * P;                       // u32 per pair: a254 | b254<<8 | a128<<16 | b128<<24
+    L.hist = L.pairs + P * P * 4;
+    L.part_i = L.hist + (256 + 512 + 256) * 4;
+    L.part_f = L.part_i + kCombos * kNW * kNI * 8;  // u64
+    L.total = L.part_f + kCombos * kNW * kNF * 4;
     return L;
 }
 
-__device__ __forceinline__ int quant_level(const uint8_t* q128, const uint8_t* q254, int pos, int lv) {
-    // SPEC.md B5: q = min(floor(grey * L), L-1). x32/x64/x128 are exact scalings of the same f32 grey,
-    // so floor(grey*64) == floor(grey*128) >> 1 (and >> 2 for 32); only 254 needs its own plane.
-    switch (lv) {
-        case 0: return min((int)q128[pos] >> 2, 31);
-        case 1: return min((int)q128[pos] >> 1, 63);
-        case 2: return min((int)q128[pos], 127);
-        default: return (int)q254[pos];
+// Levels of one pair for level index lv from its packed record (SPEC.md B5: q = min(floor(g*L), L-1)).
+// x32/x64/x128 are exact scalings of the same f32 grey, so floor(g*64) = floor(g*128) >> 1 and
+// floor(g*32) = floor(g*128) >> 2; the q128 plane is stored pre-clamped to 127, which commutes with
+// the shifts (128 only occurs for g == 1). Only 254 needs its own plane.
+__device__ __forceinline__ void pair_levels(uint32_t rec, int lv, int& a, int& b) {
+    if (lv == 3) {
+        a = rec & 0xff;
+        b = (rec >> 8) & 0xff;
+    } else {
+        const int sh = 2 - lv;
+        a = ((rec >> 16) & 0xff) >> sh;
+        b = (rec >> 24) >> sh;
     }
 }
 
+template <bool SMALL>   // SMALL: P <= 64, every integer moment fits u32 (REDUX path)
 __global__ void __launch_bounds__(kGlcmThreads)
 k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -72,21 +85,24 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + L.rows);
     uint8_t* q128 = smem_raw + L.q128;
     uint8_t* q254 = smem_raw + L.q254;
-    uint16_t* pairs = reinterpret_cast<uint16_t*>(smem_raw + L.pairs);
+    uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);
     uint32_t* hx = reinterpret_cast<uint32_t*>(smem_raw + L.hist);   // [256]
     uint32_t* hs = hx + 256;                                           // [512]
     uint32_t* hd = hs + 512;                                           // [256]
+    unsigned long long* part_i = reinterpret_cast<unsigned long long*>(smem_raw + L.part_i);   // [combo][warp][kNI]
+    float* part_f = reinterpret_cast<float*>(smem_raw + L.part_f);                               // [combo][warp][kNF]
     __shared__ __align__(8) uint64_t bar;
-    __shared__ double s_red[12 * (kGlcmThreads / 32)];
     __shared__ float s_lut[256];
-    __shared__ int s_scan[kGlcmThreads / 32 + 1];
+    __shared__ int s_scan[kNW + 1];
     __shared__ int s_box[2];
+    __shared__ int s_npairs[kGlcmOffsets];
 
     const NucInfo inf = p.info[i];
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        s_box[0] = P; s_box[1] = -1;
+        s_box[0] = P;
+        s_box[1] = -1;
     }
     __syncthreads();
     if (tid == 0) {
@@ -99,11 +115,19 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         for (int k = tid; k < P * wpr; k += kGlcmThreads) {
             const uint32_t b = gm[k];
             rows[k] = b;
-            if (b) { const int r = k / wpr; rmin = min(rmin, r); rmax = max(rmax, r); }
+            if (b) {
+                const int r = k / wpr;
+                rmin = min(rmin, r);
+                rmax = max(rmax, r);
+            }
         }
         s_lut[tid] = __fdiv_rn((float)tid, 255.0f);   // utils.rs:172  u8 -> f32 / 255.0
-        rmin = warp_min(rmin); rmax = warp_max(rmax);
-        if (lane == 0) { atomicMin(&s_box[0], rmin); atomicMax(&s_box[1], rmax); }
+        rmin = warp_min(rmin);
+        rmax = warp_max(rmax);
+        if (lane == 0) {
+            atomicMin(&s_box[0], rmin);
+            atomicMax(&s_box[1], rmax);
+        }
     }
     __syncthreads();
     const int rmin = s_box[0], rmax = s_box[1];
@@ -114,7 +138,9 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
             const int r = k / P, c = k - r * P;
             if (r >= inf.nvr || c >= inf.nvc) {
                 const int a = patch_addr(P, o, r, c);
-                patch[a] = 0; patch[a + 1] = 0; patch[a + 2] = 0;
+                patch[a] = 0;
+                patch[a + 1] = 0;
+                patch[a + 2] = 0;
             }
         }
         __syncthreads();
@@ -126,22 +152,25 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         for (int k = r0 * P + tid; k < (r1 + 1) * P; k += kGlcmThreads) {
             const int r = k / P, c = k - r * P;
             const int a = patch_addr(P, o, r, c);
-            const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[patch[a]], s_lut[patch[a + 1]]), s_lut[patch[a + 2]]), 3.0f);
-            q128[k] = (uint8_t)(int)floorf(__fmul_rn(g, 128.0f));
+            const float g = __fdiv_rn(
+                __fadd_rn(__fadd_rn(s_lut[patch[a]], s_lut[patch[a + 1]]), s_lut[patch[a + 2]]), 3.0f);
+            q128[k] = (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
             q254[k] = (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253);
         }
     }
     __syncthreads();   // patch is dead from here on: region A becomes the triangular histogram
     for (int k = tid; k < kTriBytes / 16; k += kGlcmThreads)
         reinterpret_cast<uint4*>(smem_raw + L.region_a)[k] = make_uint4(0, 0, 0, 0);
+    for (int k = tid; k < 1024; k += kGlcmThreads) hx[k] = 0u;   // hx, hs, hd are contiguous
     if (dbg_all) {
         int lv = 3;
-        for (int t = 0; t < 4; ++t) if (c_levels[t] == p.dbg_levels) lv = t;
-        for (int k = tid; k < P * P; k += kGlcmThreads)
-            p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)quant_level(q128, q254, k, lv);
+        for (int t = 0; t < 4; ++t)
+            if (c_levels[t] == p.dbg_levels) lv = t;
+        for (int k = tid; k < P * P; k += kGlcmThreads) {
+            const int v = (lv == 3) ? q254[k] : (q128[k] >> (2 - lv));
+            p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)v;
+        }
     }
-
-    float* out = p.out ? p.out + i * (int64_t)p.out_stride + p.col_glcm : nullptr;
 
     for (int oi = 0; oi < kGlcmOffsets; ++oi) {
         const int dy = c_off[oi][0], dx = c_off[oi][1];
@@ -157,55 +186,55 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
                 uint32_t pb = 0;
                 int r = 0, w = 0;
                 if (k < items) {
-                    r = k / wpr; w = k - r * wpr;
+                    r = k / wpr;
+                    w = k - r * wpr;
                     const int r2 = r + dy;
                     if (r >= rmin && r <= rmax && r2 < P) {
                         const uint32_t* nr = rows + r2 * wpr;
                         uint32_t nb = nr[w];
                         if (dx == 1) nb = (nb >> 1) | ((w + 1 < wpr) ? (nr[w + 1] << 31) : 0u);
                         else if (dx == -1) nb = (nb << 1) | ((w > 0) ? (nr[w - 1] >> 31) : 0u);
-                        pb = rows[k] & nb;
-                        // neighbour column must exist inside the patch when P is not a multiple of 32
-                        if (dx == 1 && w == wpr - 1 && (P & 31)) pb &= (1u << ((P & 31) - 1)) - 1u;
+                        pb = rows[k] & nb;   // bits >= P are never set, so column P-1 has no right neighbour
                     }
                 }
                 const int cnt = __popc(pb);
-                // block exclusive scan of cnt
                 int incl = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+                    if (lane >= o2) incl += t;
                 }
                 if (lane == 31) s_scan[warp] = incl;
                 __syncthreads();
-                if (tid == 0) {
-                    int acc = 0;
-                    for (int t = 0; t < kGlcmThreads / 32; ++t) { const int v = s_scan[t]; s_scan[t] = acc; acc += v; }
-                    s_scan[kGlcmThreads / 32] = acc;
+                int wbase = 0, total = 0;
+#pragma unroll
+                for (int t = 0; t < kNW; ++t) {
+                    const int v = s_scan[t];
+                    wbase += (t < warp) ? v : 0;
+                    total += v;
                 }
-                __syncthreads();
-                int pos = running + s_scan[warp] + incl - cnt;
+                int pos = running + wbase + incl - cnt;
                 while (pb) {
                     const int c = 32 * w + __ffs(pb) - 1;
                     pb &= pb - 1;
-                    pairs[pos++] = (uint16_t)(r * P + c);
+                    const int src = r * P + c, dst = src + dpos;
+                    pairs[pos++] = (uint32_t)q254[src] | ((uint32_t)q254[dst] << 8) |
+                                   ((uint32_t)q128[src] << 16) | ((uint32_t)q128[dst] << 24);
                 }
-                running += s_scan[kGlcmThreads / 32];
+                running += total;
                 __syncthreads();
             }
             npairs = running;
         }
-        const double T = 2.0 * (double)npairs;
+        if (tid == 0) s_npairs[oi] = npairs;
 
         for (int lv = 0; lv < kGlcmLevels; ++lv) {
             const int NL = c_levels[lv];
-            for (int k = tid; k < 1024; k += kGlcmThreads) hx[k] = 0u;   // hx, hs, hd are contiguous
-            __syncthreads();
-            // ---- pass 1: shared-memory atomics ----
+            const int combo = lv * kGlcmOffsets + oi;
+            // ---- pass 1: shared-memory atomics (tri + marginal histograms are all-zero here) ----
             for (int k = tid; k < npairs; k += kGlcmThreads) {
-                const int pos = pairs[k];
-                const int a = quant_level(q128, q254, pos, lv), b = quant_level(q128, q254, pos + dpos, lv);
+                int a, b;
+                pair_levels(pairs[k], lv, a, b);
                 const int lo = min(a, b), hi = max(a, b);
                 const int cell = ((hi * (hi + 1)) >> 1) + lo;
                 atomicAdd(&tri32[cell >> 1], 1u << ((cell & 1) * 16));
@@ -215,86 +244,119 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
                 atomicAdd(&hd[hi - lo], 2u);
             }
             __syncthreads();
-            // ---- pass 2: entropy and ASM from the cell counts ----
-            double acc[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) acc[k] = 0.0;
-            {
-                float sum_g = 0.f, sum_lng = 0.f;
-                for (int k = tid; k < npairs; k += kGlcmThreads) {
-                    const int pos = pairs[k];
-                    const int a = quant_level(q128, q254, pos, lv), b = quant_level(q128, q254, pos + dpos, lv);
-                    const int lo = min(a, b), hi = max(a, b);
-                    const int cell = ((hi * (hi + 1)) >> 1) + lo;
-                    const uint32_t g = (uint32_t)tri16[cell] << (a == b ? 1 : 0);   // G_ab
-                    sum_g += (float)g;
-                    sum_lng += logf((float)g);
-                    if (p.dbg_counts && p.dbg_levels == NL && p.dbg_dy == dy && p.dbg_dx == dx) {
-                        uint32_t* dc = p.dbg_counts + i * (int64_t)NL * NL;
-                        dc[a * NL + b] = g;
-                        dc[b * NL + a] = g;
-                    }
+            // ---- pass 2: entropy / ASM from the cell counts; moments of the marginals ----
+            uint32_t vi[kNI] = {0, 0, 0, 0, 0, 0, 0};
+            unsigned long long vl[kNI] = {0, 0, 0, 0, 0, 0, 0};
+            float vf[kNF] = {0.f, 0.f, 0.f, 0.f};
+            const bool dbg = p.dbg_counts && p.dbg_levels == NL && p.dbg_dy == dy && p.dbg_dx == dx;
+            for (int k = tid; k < npairs; k += kGlcmThreads) {
+                int a, b;
+                pair_levels(pairs[k], lv, a, b);
+                const int lo = min(a, b), hi = max(a, b);
+                const uint32_t g = (uint32_t)tri16[((hi * (hi + 1)) >> 1) + lo] << (a == b ? 1 : 0);   // G_ab
+                if (SMALL) vi[0] += g;
+                else vl[0] += g;
+                vf[0] += __logf((float)g);
+                if (dbg) {
+                    uint32_t* dc = p.dbg_counts + i * (int64_t)NL * NL;
+                    dc[a * NL + b] = g;
+                    dc[b * NL + a] = g;
                 }
-                acc[0] = sum_g;
-                acc[1] = sum_lng;
-            }
-            // ---- marginal moments ----
-            for (int k = tid; k < NL; k += kGlcmThreads) {
-                const double c = (double)hx[k], kk = (double)k;
-                acc[2] += kk * c;
-                acc[3] += kk * kk * c;
-                if (c > 0.0) acc[4] += c * log(c);
-                const double d = (double)hd[k];
-                acc[5] += kk * d;
-                acc[6] += kk * kk * d;
-                acc[7] += d / (1.0 + kk * kk);
             }
             for (int k = tid; k < 2 * NL - 1; k += kGlcmThreads) {
-                const double c = (double)hs[k], kk = (double)k;
-                acc[8] += kk * c;
-                acc[9] += kk * kk * c;
-                if (c > 0.0) acc[10] += c * log(c);
+                const uint32_t c = hs[k], kk = (uint32_t)k;
+                if (SMALL) {
+                    vi[5] += kk * c;
+                    vi[6] += kk * kk * c;
+                } else {
+                    vl[5] += (unsigned long long)kk * c;
+                    vl[6] += (unsigned long long)kk * kk * c;
+                }
+                if (c) vf[2] += (float)c * __logf((float)c);
+                if (k < NL) {
+                    const uint32_t cx = hx[k], cd = hd[k];
+                    if (SMALL) {
+                        vi[1] += kk * cx;
+                        vi[2] += kk * kk * cx;
+                        vi[3] += kk * cd;
+                        vi[4] += kk * kk * cd;
+                    } else {
+                        vl[1] += (unsigned long long)kk * cx;
+                        vl[2] += (unsigned long long)kk * kk * cx;
+                        vl[3] += (unsigned long long)kk * cd;
+                        vl[4] += (unsigned long long)kk * kk * cd;
+                    }
+                    if (cx) vf[1] += (float)cx * __logf((float)cx);
+                    vf[3] += __fdividef((float)cd, 1.0f + (float)(kk * kk));
+                }
             }
-            block_sum<12>(acc, s_red);
-            // ---- clear the triangular histogram by replaying the pairs ----
+#pragma unroll
+            for (int q = 0; q < kNI; ++q) {
+                unsigned long long t;
+                if (SMALL) t = __reduce_add_sync(0xffffffffu, vi[q]);
+                else t = warp_sum(vl[q]);
+                if (lane == 0) part_i[(combo * kNW + warp) * kNI + q] = t;
+            }
+#pragma unroll
+            for (int q = 0; q < kNF; ++q) {
+                const float t = warp_sum(vf[q]);
+                if (lane == 0) part_f[(combo * kNW + warp) * kNF + q] = t;
+            }
+            __syncthreads();
+            // ---- clear: triangular histogram by replaying the pairs, marginals densely ----
             for (int k = tid; k < npairs; k += kGlcmThreads) {
-                const int pos = pairs[k];
-                const int a = quant_level(q128, q254, pos, lv), b = quant_level(q128, q254, pos + dpos, lv);
+                int a, b;
+                pair_levels(pairs[k], lv, a, b);
                 const int lo = min(a, b), hi = max(a, b);
                 tri16[((hi * (hi + 1)) >> 1) + lo] = 0;
             }
-            if (tid == 0 && out) {
-                float* o = out + (lv * kGlcmOffsets + oi) * kGlcmFeat;
-                if (npairs == 0) {
-                    for (int f = 0; f < kGlcmFeat; ++f) o[f] = CUDART_NAN_F;   // 0/0 (SPEC.md B5)
-                } else {
-                    const double lnT = log(T);
-                    const double asm_ = 2.0 * acc[0] / (T * T);
-                    const double hxy = lnT - 2.0 * acc[1] / T;
-                    const double mu = acc[2] / T, ei2 = acc[3] / T;
-                    const double var = ei2 - mu * mu;
-                    const double hxm = lnT - acc[4] / T;
-                    const double dav = acc[5] / T, contrast = acc[6] / T, idm = acc[7] / T;
-                    const double sav = acc[8] / T, es2 = acc[9] / T;
-                    const double sent = lnT - acc[10] / T;
-                    const double eij = 0.5 * (es2 - 2.0 * ei2);
-                    o[0] = (float)((eij - mu * mu) / var);            // correlation
-                    o[1] = (float)contrast;
-                    o[2] = (float)dav;                                // dissimilarity
-                    o[3] = (float)hxy;                                // entropy
-                    o[4] = (float)asm_;
-                    o[5] = (float)sav;
-                    o[6] = (float)(es2 - sav * sav);                  // sum variance
-                    o[7] = (float)sent;
-                    o[8] = (float)var;                                // sum of squares
-                    o[9] = (float)idm;
-                    o[10] = (float)dav;                               // difference average
-                    o[11] = (float)(contrast - dav * dav);            // difference variance
-                    o[12] = (float)((hxy - 2.0 * hxm) / hxm);         // IMC1 (HXY1 = 2 HX)
-                    o[13] = (float)sqrt(fmax(1.0 - exp(-2.0 * (2.0 * hxm - hxy)), 0.0));   // IMC2
-                }
-            }
+            for (int k = tid; k < 1024; k += kGlcmThreads) hx[k] = 0u;
             __syncthreads();
+        }
+    }
+    // ---- 14 Haralick features per (level, offset): one thread per combination ----
+    if (tid < kCombos && p.out) {
+        const int combo = tid, oi = combo % kGlcmOffsets;
+        float* o_ = p.out + i * (int64_t)p.out_stride + p.col_glcm + combo * kGlcmFeat;
+        const int npairs = s_npairs[oi];
+        if (npairs == 0) {
+            for (int f = 0; f < kGlcmFeat; ++f) o_[f] = CUDART_NAN_F;   // 0/0 (SPEC.md B5)
+        } else {
+            double acc[kNI + kNF];
+            for (int q = 0; q < kNI; ++q) {
+                unsigned long long t = 0;
+                for (int w = 0; w < kNW; ++w) t += part_i[(combo * kNW + w) * kNI + q];
+                acc[q] = (double)t;
+            }
+            for (int q = 0; q < kNF; ++q) {
+                double t = 0.0;
+                for (int w = 0; w < kNW; ++w) t += (double)part_f[(combo * kNW + w) * kNF + q];
+                acc[kNI + q] = t;
+            }
+            const double T = 2.0 * (double)npairs, lnT = log(T);
+            const double asm_ = 2.0 * acc[0] / (T * T);
+            const double hxy = lnT - 2.0 * acc[kNI + 0] / T;
+            const double mu = acc[1] / T, ei2 = acc[2] / T;
+            const double var = ei2 - mu * mu;
+            const double hxm = lnT - acc[kNI + 1] / T;
+            const double dav = acc[3] / T, contrast = acc[4] / T, idm = acc[kNI + 3] / T;
+            const double sav = acc[5] / T, es2 = acc[6] / T;
+            const double sent = lnT - acc[kNI + 2] / T;
+            const double eij = 0.5 * (es2 - 2.0 * ei2);
+            o_[0] = (float)((eij - mu * mu) / var);            // correlation
+            o_[1] = (float)contrast;
+            o_[2] = (float)dav;                                // dissimilarity
+            o_[3] = (float)hxy;                                // entropy
+            o_[4] = (float)asm_;
+            o_[5] = (float)sav;
+            o_[6] = (float)(es2 - sav * sav);                  // sum variance
+            o_[7] = (float)sent;
+            o_[8] = (float)var;                                // sum of squares
+            o_[9] = (float)idm;
+            o_[10] = (float)dav;                               // difference average
+            o_[11] = (float)(contrast - dav * dav);            // difference variance
+            o_[12] = (float)((hxy - 2.0 * hxm) / hxm);         // IMC1 (HXY1 = 2 HX)
+            o_[13] = (float)sqrt(fmax(1.0 - exp(-2.0 * (2.0 * hxm - hxy)), 0.0));   // IMC2
         }
     }
 }
@@ -304,10 +366,13 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
 cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     const GlcmSmem L = glcm_layout(p.P);
-    cudaError_t e = cudaFuncSetAttribute(k_glcm, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
-    if (e != cudaSuccess) return e;
-    k_glcm<<<(unsigned)p.n, kGlcmThreads, L.total, s>>>(p, *map);
-    return cudaGetLastError();
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)p.n, kGlcmThreads, L.total, s>>>(p, *map);
+        return cudaGetLastError();
+    };
+    return p.P <= 64 ? go(k_glcm<true>) : go(k_glcm<false>);
 }
 
 }  // namespace nfx
