@@ -72,9 +72,9 @@ __device__ __forceinline__ void pair_levels(uint32_t rec, int lv, int& a, int& b
     }
 }
 
-template <bool SMALL>   // SMALL: P <= 64, every integer moment fits u32 (REDUX path)
+template <bool SMALL>   // generic path (64 < P <= 128 in practice): one (offset, level) at a time
 __global__ void __launch_bounds__(kGlcmThreads)
-k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
+k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t i = blockIdx.x;
@@ -361,18 +361,363 @@ k_glcm(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     }
 }
 
+
+// =================================================================================================
+// k_glcm64: P <= 64. All four levels of one offset are processed in ONE sweep over the pairs:
+//   * the masked pixels are compacted once into a coordinate list (shared by the 4 offsets);
+//   * pass 1 walks that list, tests the neighbour bit, emits the packed pair record by ballot
+//     compaction and issues the shared-memory atomics of all 4 levels (17 per pair);
+//   * G for 32/64/128 levels lives in dense triangular u16 histograms (22 KB together); G for 254
+//     levels (32 385 cells, <= K occupied) lives in an open-addressing hash table sized 2K..8192;
+//   * p_x of 32 and 64 levels is the 128-level histogram folded by 4 / 2 (exact: q32 = q128 >> 2);
+//   * every partial sum is an integer (moments exactly, logarithmic terms in fixed point with a
+//     2^-16 quantum, far below the 1e-4 tolerance) so that warp reduction is one REDUX each;
+//   * tables are cleared densely with 128-bit stores. 3 block barriers per offset.
+// =================================================================================================
+constexpr int kTri32 = 32 * 33 / 2, kTri64 = 64 * 65 / 2, kTri128 = 128 * 129 / 2;
+constexpr int kOffTri128 = 0;                                  // bytes inside region A
+constexpr int kOffTri64 = kOffTri128 + kTri128 * 2;            // 16512
+constexpr int kOffTri32 = kOffTri64 + kTri64 * 2;              // 20672
+constexpr int kOffHash = ((kOffTri32 + kTri32 * 2 + 127) / 128) * 128;   // 21760
+constexpr int kHashMax = 8192;
+constexpr int kRegionA64 = kOffHash + kHashMax * 4;            // 54528
+constexpr int kMargWords = 2048;                               // m32 @0, m64 @128, m128 @384, m254 @896
+constexpr int kNP = 11;                                        // partial sums per (level, offset)
+constexpr float kLnFix = 0.6931471805599453f * 65536.0f;      // log2 -> ln, 16 fractional bits
+constexpr float kIdmFix = 262144.0f;                           // 18 fractional bits
+
+struct Glcm64Smem {
+    int rows, q128, q254, list, pairs, marg, parts, total;
+};
+__host__ __device__ inline Glcm64Smem glcm64_layout(int P) {
+    Glcm64Smem L;
+    L.marg = kRegionA64;
+    L.rows = L.marg + kMargWords * 4;
+    L.q128 = L.rows + ((P * mask_wpr(P) * 4 + 15) & ~15);
+    L.q254 = L.q128 + P * P;
+    L.list = L.q254 + P * P;
+    L.pairs = L.list + P * P * 2;
+    L.parts = L.pairs + P * P * 4;
+    L.total = L.parts + kCombos * kNW * kNP * 4;
+    return L;
+}
+
+__device__ __forceinline__ int tri_cell(int a, int b) {
+    const int lo = min(a, b), hi = max(a, b);
+    return ((hi * (hi + 1)) >> 1) + lo;
+}
+__device__ __forceinline__ void tri_add(uint32_t* tri32w, int cell) {
+    atomicAdd(&tri32w[cell >> 1], 1u << ((cell & 1) * 16));
+}
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int lg) { return (key * 0x9E3779B1u) >> (32 - lg); }
+// slot = (key+1) << 16 | count
+__device__ __forceinline__ void hash_add(uint32_t* tab, int lg, uint32_t key) {
+    const uint32_t mask = (1u << lg) - 1u, tag = (key + 1u) << 16;
+    uint32_t h = hash_slot(key, lg);
+    while (true) {
+        uint32_t cur = tab[h];
+        if (cur == 0u) cur = atomicCAS(&tab[h], 0u, tag | 1u);
+        else if ((cur & 0xffff0000u) == tag) { atomicAdd(&tab[h], 1u); return; }
+        else { h = (h + 1u) & mask; continue; }
+        if (cur == 0u) return;                                            // we inserted it
+        if ((cur & 0xffff0000u) == tag) { atomicAdd(&tab[h], 1u); return; }   // somebody else did
+        h = (h + 1u) & mask;
+    }
+}
+__device__ __forceinline__ uint32_t hash_get(const uint32_t* tab, int lg, uint32_t key) {
+    const uint32_t mask = (1u << lg) - 1u, tag = (key + 1u) << 16;
+    uint32_t h = hash_slot(key, lg);
+    while (true) {
+        const uint32_t cur = tab[h];
+        if ((cur & 0xffff0000u) == tag) return cur & 0xffffu;
+        if (cur == 0u) return 0u;
+        h = (h + 1u) & mask;
+    }
+}
+__device__ __forceinline__ uint32_t fix_ln(uint32_t g) {   // ln(g) in 16.16 fixed point, g >= 1
+    return __float2uint_rn(__log2f((float)g) * kLnFix);
+}
+__device__ __forceinline__ uint32_t fix_clnc(uint32_t c) {   // c ln c, 15 fractional bits: sum <= T ln T * 2^15 < 2^32 for T <= 8192
+    return c ? __float2uint_rn((float)c * __log2f((float)c) * (0.5f * kLnFix)) : 0u;
+}
+
+__global__ void __launch_bounds__(kGlcmThreads, 2)
+k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = blockIdx.x;
+    const Glcm64Smem L = glcm64_layout(P);
+    uint8_t* patch = smem_raw;
+    uint32_t* tri128 = reinterpret_cast<uint32_t*>(smem_raw + kOffTri128);
+    uint32_t* tri64 = reinterpret_cast<uint32_t*>(smem_raw + kOffTri64);
+    uint32_t* tri32 = reinterpret_cast<uint32_t*>(smem_raw + kOffTri32);
+    uint32_t* hash = reinterpret_cast<uint32_t*>(smem_raw + kOffHash);
+    uint32_t* marg = reinterpret_cast<uint32_t*>(smem_raw + L.marg);
+    uint32_t* m32 = marg, *m64 = marg + 128, *m128 = marg + 384, *m254 = marg + 896;   // each: hx[L] hs[2L] hd[L]
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + L.rows);
+    uint8_t* q128 = smem_raw + L.q128;
+    uint8_t* q254 = smem_raw + L.q254;
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + L.list);
+    uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);
+    uint32_t* parts = reinterpret_cast<uint32_t*>(smem_raw + L.parts);   // [combo][warp][kNP]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float s_lut[256];
+    __shared__ int s_scan[kNW + 1];
+    __shared__ int s_np[kGlcmOffsets];
+
+    const NucInfo inf = p.info[i];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
+        tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
+    }
+    if (tid < kGlcmOffsets) s_np[tid] = 0;
+    s_lut[tid] = __fdiv_rn((float)tid, 255.0f);   // utils.rs:172  u8 -> f32 / 255.0
+    // ---- mask rows -> shared memory + compacted pixel list ((row << 8) | col) ----
+    const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
+    int K = 0;
+    for (int base = 0; base < P * wpr; base += kGlcmThreads) {
+        const int k = base + tid;
+        uint32_t bits = (k < P * wpr) ? gm[k] : 0u;
+        if (k < P * wpr) rows[k] = bits;
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+            if (lane >= o2) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int t = 0; t < kNW; ++t) {
+            const int v = s_scan[t];
+            wbase += (t < warp) ? v : 0;
+            total += v;
+        }
+        int pos = K + wbase + incl - cnt;
+        const int r = k / wpr, cb = (k - r * wpr) * 32;
+        while (bits) {
+            const int c = cb + __ffs(bits) - 1;
+            bits &= bits - 1;
+            list[pos++] = (uint16_t)((r << 8) | c);
+        }
+        K += total;
+    }
+    int lg = 10;
+    while ((1 << lg) < 2 * K && lg < 13) ++lg;   // hash slots = 2^lg >= 2K (distinct cells <= pairs <= K)
+    const int o = patch_byte_offset(inf.left);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    // ---- grey quantisation (texture.rs:36 + SPEC.md B5), bit-exact, masked pixels only ----
+    const bool dbg_all = (p.dbg_grey != nullptr);
+    auto quantise = [&](int r, int c) {
+        uint32_t pr = 0, pg = 0, pb = 0;
+        if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
+            const int a = patch_addr(P, o, r, c);
+            pr = patch[a]; pg = patch[a + 1]; pb = patch[a + 2];
+        }
+        const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
+        q128[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
+        q254[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253);
+    };
+    if (dbg_all) {
+        for (int k = tid; k < P * P; k += kGlcmThreads) quantise(k / P, k % P);
+    } else {
+        for (int j = tid; j < K; j += kGlcmThreads) { const uint32_t rc = list[j]; quantise(rc >> 8, rc & 255); }
+    }
+    __syncthreads();   // the window is dead from here on: region A becomes the histograms
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem_raw);
+        for (int k = tid; k < (kOffHash + (4 << lg)) / 16; k += kGlcmThreads) z[k] = make_uint4(0, 0, 0, 0);
+        uint4* zm = reinterpret_cast<uint4*>(marg);
+        for (int k = tid; k < kMargWords / 4; k += kGlcmThreads) zm[k] = make_uint4(0, 0, 0, 0);
+    }
+    if (dbg_all) {
+        int lv = 3;
+        for (int t = 0; t < 4; ++t)
+            if (c_levels[t] == p.dbg_levels) lv = t;
+        for (int k = tid; k < P * P; k += kGlcmThreads)
+            p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)((lv == 3) ? q254[k] : (q128[k] >> (2 - lv)));
+    }
+    __syncthreads();
+
+    for (int oi = 0; oi < kGlcmOffsets; ++oi) {
+        const int dy = c_off[oi][0], dx = c_off[oi][1];
+        const int dpos = dy * P + dx;
+        // ---- pass 1: neighbour test, pair record, atomics of all four levels ----
+        for (int jb = 0; jb < K; jb += kGlcmThreads) {
+            const int j = jb + tid;
+            bool has = false;
+            int src = 0;
+            if (j < K) {
+                const uint32_t rc = list[j];
+                const int r = rc >> 8, c = rc & 255, r2 = r + dy, c2 = c + dx;
+                src = r * P + c;
+                has = (r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u);
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, has);
+            int wb = 0;
+            if (lane == 0 && bal) wb = atomicAdd(&s_np[oi], __popc(bal));
+            wb = __shfl_sync(0xffffffffu, wb, 0);
+            if (has) {
+                const int a3 = q254[src], b3 = q254[src + dpos], a2 = q128[src], b2 = q128[src + dpos];
+                pairs[wb + __popc(bal & ((1u << lane) - 1u))] =
+                    (uint32_t)a3 | ((uint32_t)b3 << 8) | ((uint32_t)a2 << 16) | ((uint32_t)b2 << 24);
+                // 254 levels
+                hash_add(hash, lg, (uint32_t)(min(a3, b3) * 256 + max(a3, b3)));
+                atomicAdd(&m254[a3], 1u);
+                atomicAdd(&m254[b3], 1u);
+                atomicAdd(&m254[256 + a3 + b3], 2u);
+                atomicAdd(&m254[768 + abs(a3 - b3)], 2u);
+                // 128 levels
+                tri_add(tri128, tri_cell(a2, b2));
+                atomicAdd(&m128[a2], 1u);
+                atomicAdd(&m128[b2], 1u);
+                atomicAdd(&m128[128 + a2 + b2], 2u);
+                atomicAdd(&m128[384 + abs(a2 - b2)], 2u);
+                // 64 levels (p_x is folded from the 128-level histogram later)
+                const int a1 = a2 >> 1, b1 = b2 >> 1;
+                tri_add(tri64, tri_cell(a1, b1));
+                atomicAdd(&m64[64 + a1 + b1], 2u);
+                atomicAdd(&m64[192 + abs(a1 - b1)], 2u);
+                // 32 levels
+                const int a0 = a2 >> 2, b0 = b2 >> 2;
+                tri_add(tri32, tri_cell(a0, b0));
+                atomicAdd(&m32[32 + a0 + b0], 2u);
+                atomicAdd(&m32[96 + abs(a0 - b0)], 2u);
+            }
+        }
+        __syncthreads();
+        const int npairs = s_np[oi];
+        // ---- pass 2: per-pair cell counts (entropy, ASM) for the four levels ----
+        uint32_t sg[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0};
+        for (int k = tid; k < npairs; k += kGlcmThreads) {
+            const uint32_t rec = pairs[k];
+            const int a3 = rec & 0xff, b3 = (rec >> 8) & 0xff, a2 = (rec >> 16) & 0xff, b2 = rec >> 24;
+            const int a1 = a2 >> 1, b1 = b2 >> 1, a0 = a2 >> 2, b0 = b2 >> 2;
+            uint32_t g[4];
+            g[3] = hash_get(hash, lg, (uint32_t)(min(a3, b3) * 256 + max(a3, b3))) << (a3 == b3 ? 1 : 0);
+            g[2] = (uint32_t)reinterpret_cast<const uint16_t*>(tri128)[tri_cell(a2, b2)] << (a2 == b2 ? 1 : 0);
+            g[1] = (uint32_t)reinterpret_cast<const uint16_t*>(tri64)[tri_cell(a1, b1)] << (a1 == b1 ? 1 : 0);
+            g[0] = (uint32_t)reinterpret_cast<const uint16_t*>(tri32)[tri_cell(a0, b0)] << (a0 == b0 ? 1 : 0);
+#pragma unroll
+            for (int lv = 0; lv < 4; ++lv) {
+                sg[lv] += g[lv];
+                sl[lv] += fix_ln(g[lv]);
+            }
+            if (p.dbg_counts && p.dbg_dy == dy && p.dbg_dx == dx) {
+                const int NL = p.dbg_levels;
+                const int lv = NL == 32 ? 0 : (NL == 64 ? 1 : (NL == 128 ? 2 : 3));
+                const int a = lv == 3 ? a3 : (a2 >> (2 - lv)), b = lv == 3 ? b3 : (b2 >> (2 - lv));
+                uint32_t* dc = p.dbg_counts + i * (int64_t)NL * NL;
+                dc[a * NL + b] = g[lv];
+                dc[b * NL + a] = g[lv];
+            }
+        }
+        // ---- marginal moments, one level at a time; warp REDUX, per-warp partials to shared memory ----
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {
+            const int NL = 32 << lv;   // table geometry (254 levels use the 256-wide layout)
+            const uint32_t* m = lv == 0 ? m32 : (lv == 1 ? m64 : (lv == 2 ? m128 : m254));
+            uint32_t v[kNP];
+#pragma unroll
+            for (int q = 0; q < kNP; ++q) v[q] = 0u;
+            v[0] = sg[lv];
+            v[7] = sl[lv];
+            for (int k = tid; k < 2 * NL; k += kGlcmThreads) {
+                const uint32_t kk = (uint32_t)k, c = m[NL + k];           // p_{x+y}
+                v[5] += kk * c;
+                v[6] += kk * kk * c;
+                v[9] += fix_clnc(c);
+                if (k < NL) {
+                    uint32_t cx;                                            // p_x
+                    if (lv >= 2) cx = m[k];
+                    else if (lv == 1) cx = m128[2 * k] + m128[2 * k + 1];
+                    else cx = m128[4 * k] + m128[4 * k + 1] + m128[4 * k + 2] + m128[4 * k + 3];
+                    const uint32_t cd = m[3 * NL + k];                      // p_{x-y}
+                    v[1] += kk * cx;
+                    v[2] += kk * kk * cx;
+                    v[3] += kk * cd;
+                    v[4] += kk * kk * cd;
+                    v[8] += fix_clnc(cx);
+                    v[10] += __float2uint_rn(__fdividef((float)cd, 1.0f + (float)(kk * kk)) * kIdmFix);
+                }
+            }
+            const int combo = lv * kGlcmOffsets + oi;
+#pragma unroll
+            for (int q = 0; q < kNP; ++q) {
+                const uint32_t t = __reduce_add_sync(0xffffffffu, v[q]);
+                if (lane == 0) parts[(combo * kNW + warp) * kNP + q] = t;
+            }
+        }
+        __syncthreads();
+        // ---- dense clear of every table ----
+        if (oi + 1 < kGlcmOffsets) {
+            uint4* z = reinterpret_cast<uint4*>(smem_raw);
+            for (int k = tid; k < (kOffHash + (4 << lg)) / 16; k += kGlcmThreads) z[k] = make_uint4(0, 0, 0, 0);
+            uint4* zm = reinterpret_cast<uint4*>(marg);
+            for (int k = tid; k < kMargWords / 4; k += kGlcmThreads) zm[k] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+        }
+    }
+    // ---- 14 Haralick features per (level, offset): one thread per combination ----
+    if (tid < kCombos && p.out) {
+        const int combo = tid, oi = combo % kGlcmOffsets;
+        float* o_ = p.out + i * (int64_t)p.out_stride + p.col_glcm + combo * kGlcmFeat;
+        const int npairs = s_np[oi];
+        if (npairs == 0) {
+            for (int f = 0; f < kGlcmFeat; ++f) o_[f] = CUDART_NAN_F;   // 0/0 (SPEC.md B5)
+        } else {
+            double acc[kNP];
+            for (int q = 0; q < kNP; ++q) {
+                unsigned long long t = 0;
+                for (int w = 0; w < kNW; ++w) t += parts[(combo * kNW + w) * kNP + q];
+                acc[q] = (double)t;
+            }
+            const double T = 2.0 * (double)npairs, lnT = log(T);
+            const double asm_ = 2.0 * acc[0] / (T * T);
+            const double hxy = lnT - 2.0 * (acc[7] / 65536.0) / T;
+            const double mu = acc[1] / T, ei2 = acc[2] / T;
+            const double var = ei2 - mu * mu;
+            const double hxm = lnT - (acc[8] / 32768.0) / T;
+            const double dav = acc[3] / T, contrast = acc[4] / T, idm = (acc[10] / 262144.0) / T;
+            const double sav = acc[5] / T, es2 = acc[6] / T;
+            const double sent = lnT - (acc[9] / 32768.0) / T;
+            const double eij = 0.5 * (es2 - 2.0 * ei2);
+            o_[0] = (float)((eij - mu * mu) / var);            // correlation
+            o_[1] = (float)contrast;
+            o_[2] = (float)dav;                                // dissimilarity
+            o_[3] = (float)hxy;                                // entropy
+            o_[4] = (float)asm_;
+            o_[5] = (float)sav;
+            o_[6] = (float)(es2 - sav * sav);                  // sum variance
+            o_[7] = (float)sent;
+            o_[8] = (float)var;                                // sum of squares
+            o_[9] = (float)idm;
+            o_[10] = (float)dav;                               // difference average
+            o_[11] = (float)(contrast - dav * dav);            // difference variance
+            o_[12] = (float)((hxy - 2.0 * hxm) / hxm);         // IMC1 (HXY1 = 2 HX)
+            o_[13] = (float)sqrt(fmax(1.0 - exp(-2.0 * (2.0 * hxm - hxy)), 0.0));   // IMC2
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
-    const GlcmSmem L = glcm_layout(p.P);
-    auto go = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    auto go = [&](auto kern, int smem) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)p.n, kGlcmThreads, L.total, s>>>(p, *map);
+        kern<<<(unsigned)p.n, kGlcmThreads, smem, s>>>(p, *map);
         return cudaGetLastError();
     };
-    return p.P <= 64 ? go(k_glcm<true>) : go(k_glcm<false>);
+    if (p.P <= 64) return go(k_glcm64, glcm64_layout(p.P).total);
+    return go(k_glcm_generic<false>, glcm_layout(p.P).total);
 }
 
 }  // namespace nfx
