@@ -62,7 +62,7 @@ struct nfx_ctx {
     DevBuf<uint8_t> tile;
     int64_t tw = 0, th = 0, tpitch = 0, tox = 0, toy = 0;
     bool have_tile = false;
-    CUtensorMap map_tile_patch, map_tile_slab;
+    CUtensorMap map_tile_patch, map_tile_slab, map_tile_cslab;
 
     // polygons
     DevBuf<float2> xy;
@@ -85,7 +85,7 @@ struct nfx_ctx {
     // staged patch array (kernel (1) output / trait-level input)
     DevBuf<uint8_t> patches;
     int64_t ppitch = 0;
-    CUtensorMap map_pat_patch, map_pat_slab, map_pat_store;
+    CUtensorMap map_pat_patch, map_pat_slab, map_pat_cslab;
 
     // scratch
     DevBuf<uint8_t> scratch8;
@@ -234,6 +234,7 @@ int run_color(nfx_ctx* ctx, int64_t n, int batch, const CUtensorMap* mp, const C
     c.col_color = col;
     c.hue_partial = ctx->hue.p;
     c.slabs = slabs;
+    c.slab_rows = color_slab_rows(ctx->P);
     CK(timed(ctx, "k_color", 1, [&] { return launch_color(c, mp, ctx->stream); }));
     CK(timed(ctx, "k_hue_batch", 1, [&] { return launch_hue_batch(c, ms, R, ctx->stream); }));
     CK(timed(ctx, "k_hue_finalize", 1, [&] { return launch_hue_finalize(c, ctx->stream); }));
@@ -275,6 +276,7 @@ int make_patch_array(nfx_ctx* ctx, int64_t n) {
     int rc;
     if ((rc = make_map(ctx, &ctx->map_pat_patch, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, P))) return rc;
     if ((rc = make_map(ctx, &ctx->map_pat_slab, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, R))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_pat_cslab, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, color_slab_rows(P)))) return rc;
     return NFX_OK;
 }
 
@@ -349,6 +351,7 @@ int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h, int6
     ctx->tw = w; ctx->th = h; ctx->tpitch = pitch; ctx->tox = origin_x; ctx->toy = origin_y;
     if ((rc = make_map(ctx, &ctx->map_tile_patch, ctx->tile.p, 3 * w, h, pitch, ctx->P))) return rc;
     if ((rc = make_map(ctx, &ctx->map_tile_slab, ctx->tile.p, 3 * w, h, pitch, hue_slab_rows(ctx->P)))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_tile_cslab, ctx->tile.p, 3 * w, h, pitch, color_slab_rows(ctx->P)))) return rc;
     ctx->have_tile = true;
     ctx->have_geom = false;   // window origins depend on the tile origin
     return NFX_OK;
@@ -397,7 +400,7 @@ int nfx_compute(nfx_ctx* ctx, uint32_t mask) {
     if (n == 0) { ctx->computed_mask = mask; return NFX_OK; }
     if ((rc = run_geom(ctx, (mask & NFX_FS_GEOMETRY) != 0, ctx->out.p, c.total, c.shape, nullptr))) return rc;
     if (mask & NFX_FS_COLOR)
-        if ((rc = run_color(ctx, n, ctx->B, &ctx->map_tile_patch, &ctx->map_tile_slab, ctx->out.p, c.total, c.color))) return rc;
+        if ((rc = run_color(ctx, n, ctx->B, &ctx->map_tile_cslab, &ctx->map_tile_slab, ctx->out.p, c.total, c.color))) return rc;
     if (mask & NFX_FS_GLCM)
         if ((rc = run_glcm(ctx, n, &ctx->map_tile_patch, ctx->out.p, c.total, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
     ctx->computed_mask = mask;
@@ -473,7 +476,7 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
         g.bitmask = ctx->bitmask.p; g.out = ctx->out.p; g.out_stride = cols; g.col_shape = 0; g.ellipse_bits = nullptr;
         CK(timed(ctx, "k_geom<shape>", 1, [&] { return launch_geom(g, false, true, ctx->stream); }));
     } else if (fs == NFX_FS_COLOR) {
-        if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_patch, &ctx->map_pat_slab, ctx->out.p, cols, 0))) return rc;
+        if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_cslab, &ctx->map_pat_slab, ctx->out.p, cols, 0))) return rc;
     } else if (fs == NFX_FS_GLCM) {
         if ((rc = run_glcm(ctx, n, &ctx->map_pat_patch, ctx->out.p, cols, 0, nullptr, 0, 0, 0, nullptr))) return rc;
     }

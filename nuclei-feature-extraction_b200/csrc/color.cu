@@ -120,15 +120,20 @@ __device__ __forceinline__ void zero_uncopied(uint8_t* patch, int P, int o, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dynamic smem: patch | rows[P*wpr] u32 | lut[256] f32 | list[P*P] u16 ((row << 8) | col).
+// The window is processed in row slabs of CS = min(P, 64) rows (one slab for the default P = 64):
+// dynamic smem = slab[panels*208*CS] | rows[P*wpr] u32 | lut[256] f32 | list[CS*P] u16 ((row << 8) | col).
+// The slab holding the patch centre goes first because its centre pixel provides the pivots.
 __global__ void __launch_bounds__(kColorThreads, 8)
 k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CS = p.slab_rows, nslab = (P + CS - 1) / CS;
+    const int slab_bytes = window_smem_bytes(P, CS);
+    const uint32_t slab_tx = (uint32_t)(patch_panels(P) * kPanelBytes * CS);
     constexpr int NW = kColorThreads / 32;
     const int64_t i = blockIdx.x;
     uint8_t* patch = smem_raw;
-    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + patch_smem_bytes(P));
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + slab_bytes);
     float* lut = reinterpret_cast<float*>(rows + P * wpr);
     uint16_t* list = reinterpret_cast<uint16_t*>(lut + 256);
     __shared__ __align__(8) uint64_t bar;
@@ -137,74 +142,96 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
     __shared__ float s_rf[NW][10];
 
     const NucInfo inf = p.info[i];
+    const int o = patch_byte_offset(inf.left);
+    const int centre_slab = (P / 2) / CS;
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
-        tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
+        mbar_expect_tx(&bar, slab_tx);   // first slab: in flight while the mask is fetched
+        tma_load_window(patch, &map, inf.left, inf.top + centre_slab * CS, P, CS, &bar);
     }
-    // ---- while the window is in flight: compact the mask into a list of pixel coordinates ----
     for (int k = tid; k < 256; k += kColorThreads) lut[k] = g_od_lut[k];
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
-    int K = 0;
-    for (int base = 0; base < P * wpr; base += kColorThreads) {
-        const int k = base + tid;
-        uint32_t bits = (k < P * wpr) ? gm[k] : 0u;
-        const int cnt = __popc(bits);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        __syncthreads();   // s_scan reuse
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        int wbase = 0, total = 0;
-#pragma unroll
-        for (int t = 0; t < NW; ++t) {
-            const int v = s_scan[t];
-            wbase += (t < warp) ? v : 0;
-            total += v;
-        }
-        int pos = K + wbase + incl - cnt;
-        const int r = k / wpr, cb = (k - r * wpr) * 32;
-        while (bits) {
-            const int c = cb + __ffs(bits) - 1;
-            bits &= bits - 1;
-            list[pos++] = (uint16_t)((r << 8) | c);
-        }
-        K += total;
-    }
-    const int o = patch_byte_offset(inf.left);
-    __syncthreads();   // list + lut visible
-    mbar_wait(&bar, 0);
-    zero_uncopied(patch, P, o, inf.nvc, inf.nvr);
+    for (int k = tid; k < P * wpr; k += kColorThreads) rows[k] = gm[k];
+    __syncthreads();
 
-    // pivots (any value of the right magnitude removes the cancellation of the one-pass variance)
     HsvHed pv;
-    {
-        const int a = patch_addr(P, o, P / 2, P / 2);
-        Px c = {patch[a], patch[a + 1], patch[a + 2]};
-        pv = convert(c, lut);
-    }
-
+    int Ktot = 0;
     uint32_t sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
     float s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};   // hed0, hed1, hed2, s, h (pivoted)
-    for (int j = tid; j < K; j += kColorThreads) {
-        const uint32_t rc = list[j];
-        const int a = patch_addr(P, o, rc >> 8, rc & 255);
-        const Px px = {patch[a], patch[a + 1], patch[a + 2]};
-        const HsvHed c = convert(px, lut);
-        sr += px.r; sg += px.g; sb += px.b;
-        srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
-        sv += c.mx; svv += c.mx * c.mx;
-        float d;
+    for (int it = 0; it < nslab; ++it) {
+        const int sidx = (it == 0) ? centre_slab : (it <= centre_slab ? it - 1 : it);
+        const int row0 = sidx * CS, nrows = min(CS, P - row0);
+        if (tid == 0 && it > 0) {
+            mbar_expect_tx(&bar, slab_tx);
+            tma_load_window(patch, &map, inf.left, inf.top + row0, P, CS, &bar);
+        }
+        // ---- while the slab is in flight: compact its mask rows into a list of pixel coordinates ----
+        int K = 0;
+        for (int base = 0; base < nrows * wpr; base += kColorThreads) {
+            const int k = base + tid;
+            uint32_t bits = (k < nrows * wpr) ? rows[row0 * wpr + k] : 0u;
+            const int cnt = __popc(bits);
+            int incl = cnt;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { d = c.hed[q] - pv.hed[q]; s1[q] += d; s2[q] = fmaf(d, d, s2[q]); }
-        d = c.s - pv.s; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
-        d = c.h - pv.h; s1[4] += d; s2[4] = fmaf(d, d, s2[4]);
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+                if (lane >= o2) incl += t;
+            }
+            __syncthreads();   // s_scan reuse
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            int wbase = 0, total = 0;
+#pragma unroll
+            for (int t = 0; t < NW; ++t) {
+                const int v = s_scan[t];
+                wbase += (t < warp) ? v : 0;
+                total += v;
+            }
+            int pos = K + wbase + incl - cnt;
+            const int r = k / wpr, cb = (k - r * wpr) * 32;
+            while (bits) {
+                const int c = cb + __ffs(bits) - 1;
+                bits &= bits - 1;
+                list[pos++] = (uint16_t)((r << 8) | c);
+            }
+            K += total;
+        }
+        Ktot += K;
+        __syncthreads();   // list visible
+        mbar_wait(&bar, it & 1);
+        if (inf.nvc < P || inf.nvr < row0 + nrows) {   // rare: part of the window is never copied (NucInfo)
+            for (int k = tid; k < nrows * P; k += kColorThreads) {
+                const int r = k / P, c = k - r * P;
+                if (row0 + r >= inf.nvr || c >= inf.nvc) {
+                    const int a = patch_addr(CS, o, r, c);
+                    patch[a] = 0; patch[a + 1] = 0; patch[a + 2] = 0;
+                }
+            }
+            __syncthreads();
+        }
+        if (it == 0) {   // pivots (any value of the right magnitude removes the one-pass cancellation)
+            const int a = patch_addr(CS, o, P / 2 - row0, P / 2);
+            Px c = {patch[a], patch[a + 1], patch[a + 2]};
+            pv = convert(c, lut);
+        }
+        for (int j = tid; j < K; j += kColorThreads) {
+            const uint32_t rc = list[j];
+            const int a = patch_addr(CS, o, rc >> 8, rc & 255);
+            const Px px = {patch[a], patch[a + 1], patch[a + 2]};
+            const HsvHed c = convert(px, lut);
+            sr += px.r; sg += px.g; sb += px.b;
+            srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
+            sv += c.mx; svv += c.mx * c.mx;
+            float d;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { d = c.hed[q] - pv.hed[q]; s1[q] += d; s2[q] = fmaf(d, d, s2[q]); }
+            d = c.s - pv.s; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
+            d = c.h - pv.h; s1[4] += d; s2[4] = fmaf(d, d, s2[4]);
+        }
+        if (it + 1 < nslab) __syncthreads();   // slab buffer and list are reused
     }
+    const int K = Ktot;
     // ---- warp level: REDUX for the exact integer sums, shuffles for the floats ----
     {
         const uint32_t vi[8] = {sr, sg, sb, srr, sgg, sbb, sv, svv};
@@ -266,7 +293,8 @@ __global__ void __launch_bounds__(kHueThreads)
 k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int stage_bytes = patch_panels(P) * kPanelBytes * R;
+    const int stage_bytes = window_smem_bytes(P, R);
+    const uint32_t stage_tx = (uint32_t)(patch_panels(P) * kPanelBytes * R);
     const int64_t b0 = (int64_t)blockIdx.x * p.batch_size;
     const int nb = (int)min((int64_t)p.batch_size, p.n - b0);
     const int slab = blockIdx.y, row0 = slab * R;
@@ -286,7 +314,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     const bool owner = (tid < kHueConsumers) && (rr < R) && (row0 + rr < P);
     float C[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
     const int c0 = qc * 4;
-    const int soff = (c0 >> 6) * (kPanelBytes * R) + rr * kPanelBytes + (c0 & 63) * 3;   // + o per nucleus
+    const int soff = (c0 >> 6) * panel_stride(R) + rr * kPanelBytes + (c0 & 63) * 3;   // + o per nucleus
 
     int it = 0;   // global iteration counter over the batch's nuclei (ring position)
     for (int base = 0; base < nb; base += kHueChunk) {
@@ -300,7 +328,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                 for (int j = 0; j < cnt; ++j) {
                     const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
                     if (g >= kHueStages) mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                    mbar_expect_tx(&full[s], stage_tx);
                     const NucInfo inf = s_info[j];
                     tma_load_window(ring + (size_t)s * stage_bytes, &map, inf.left, inf.top + row0, P, R, &full[s]);
                 }
@@ -392,7 +420,11 @@ __global__ void k_hue_finalize(const ColorParams p) {
 }  // namespace
 
 int hue_slab_rows(int P) { return max(1, min(P, 1024 / P)); }
-int color_smem_bytes(int P) { return patch_smem_bytes(P) + P * mask_wpr(P) * 4 + 256 * 4 + P * P * 2; }
+int color_slab_rows(int P) { return P < 64 ? P : 64; }
+int color_smem_bytes(int P) {
+    const int cs = color_slab_rows(P);
+    return window_smem_bytes(P, cs) + P * mask_wpr(P) * 4 + 256 * 4 + cs * P * 2;
+}
 
 static bool g_lut_ready[64] = {};
 static cudaError_t ensure_lut(cudaStream_t s) {
@@ -422,7 +454,7 @@ cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStrea
 cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int R, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
-    const int smem = kHueStages * patch_panels(p.P) * kPanelBytes * R + 2 * R * p.P * 4;
+    const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * p.P * 4;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_hue_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

@@ -106,7 +106,7 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
+        mbar_expect_tx(&bar, (uint32_t)(patch_panels(P) * kPanelBytes * P));
         tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
     }
     {
@@ -469,7 +469,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
+        mbar_expect_tx(&bar, (uint32_t)(patch_panels(P) * kPanelBytes * P));
         tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
     }
     if (tid < kGlcmOffsets) s_np[tid] = 0;

@@ -146,22 +146,27 @@ constexpr int kPanelPx = 64;
 constexpr int kPanelData = 192;    // payload bytes of a panel row
 constexpr int kPanelBytes = 208;   // TMA box width (payload + alignment slack)
 __host__ __device__ __forceinline__ int patch_panels(int P) { return (P + kPanelPx - 1) / kPanelPx; }
-__host__ __device__ __forceinline__ int patch_smem_bytes(int P) { return patch_panels(P) * kPanelBytes * P; }
+// bytes between consecutive panels of a `rows`-row window (TMA destinations must stay 128-byte aligned)
+__host__ __device__ __forceinline__ int panel_stride(int rows) { return (kPanelBytes * rows + 127) & ~127; }
+__host__ __device__ __forceinline__ int window_smem_bytes(int P, int rows) { return patch_panels(P) * panel_stride(rows); }
+__host__ __device__ __forceinline__ int patch_smem_bytes(int P) { return window_smem_bytes(P, P); }
 __host__ __device__ __forceinline__ int patch_byte_offset(int left) { return (3 * left) & 15; }
-__device__ __forceinline__ int patch_addr(int P, int o, int r, int c) {
-    return (c >> 6) * (kPanelBytes * P) + r * kPanelBytes + o + (c & 63) * 3;
+// `rows` = rows per panel of the window in shared memory (P for a whole patch, the slab height otherwise)
+__device__ __forceinline__ int patch_addr(int rows, int o, int r, int c) {
+    return (c >> 6) * panel_stride(rows) + r * kPanelBytes + o + (c & 63) * 3;
 }
 // 32-bit words per bitmask row
 __host__ __device__ __forceinline__ int mask_wpr(int P) { return (P + 31) / 32; }
 
 // Issue the TMA boxes ({208 B, rows} each) that bring `rows` rows of one nucleus window into shared
-// memory, panel k at smem + k*208*rows. ONE thread, after mbar_expect_tx(bar, panels*208*rows).
+// memory, panel k at smem + k*208*rows. ONE thread, after mbar_expect_tx(bar, panels*208*rows) -- the
+// transaction count is the box payload, not the padded stride.
 __device__ __forceinline__ void tma_load_window(uint8_t* smem, const CUtensorMap* map, int left, int top,
                                                 int P, int rows, uint64_t* bar) {
     const int np = patch_panels(P);
     const int xal = ((3 * left) >> 4) << 4;   // arithmetic shift: floor for negative origins
     for (int k = 0; k < np; ++k)
-        tma_load_2d(smem + (size_t)k * kPanelBytes * rows, map, xal + k * kPanelData, top, bar);
+        tma_load_2d(smem + (size_t)k * panel_stride(rows), map, xal + k * kPanelData, top, bar);
 }
 __device__ __forceinline__ void tma_load_patch(uint8_t* smem_patch, const CUtensorMap* map, int left,
                                                int top, int P, uint64_t* bar) {

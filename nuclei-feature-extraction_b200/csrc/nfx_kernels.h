@@ -50,12 +50,14 @@ struct ColorParams {
     int col_color;             // first column of the colour set
     float* hue_partial;        // [n][slabs][2] (sum sin, sum cos) scratch
     int slabs;
+    int slab_rows;             // k_color row-slab height = color_slab_rows(P)
 };
 cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStream_t s);
 cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int slab_rows,
                              cudaStream_t s);
 cudaError_t launch_hue_finalize(const ColorParams& p, cudaStream_t s);
 int color_smem_bytes(int P);
+int color_slab_rows(int P);
 int hue_slab_rows(int P);
 
 // ---- glcm.cu ----------------------------------------------------------------------------------

@@ -29,7 +29,7 @@ k_gather(const int64_t n, const int P, const NucInfo* __restrict__ info,
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        mbar_expect_tx(&bar, (uint32_t)patch_smem_bytes(P));
+        mbar_expect_tx(&bar, (uint32_t)(patch_panels(P) * kPanelBytes * P));
         tma_load_patch(smem_raw, &map_tile, inf.left, inf.top, P, &bar);
     }
     __syncthreads();
@@ -48,7 +48,7 @@ k_gather(const int64_t n, const int P, const NucInfo* __restrict__ info,
             uint32_t val = 0u;
             if (b < row_bytes) {
                 const int pn = b / kPanelData, within = b - pn * kPanelData;
-                const int a = pn * (kPanelBytes * P) + r * kPanelBytes + o + within;
+                const int a = pn * panel_stride(P) + r * kPanelBytes + o + within;
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(smem_raw + (a & ~3));
                 val = __funnelshift_r(wp[0], wp[1], (a & 3) * 8);
                 // utils.rs:161-192: columns/rows the reference never copies stay zero

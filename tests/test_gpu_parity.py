@@ -235,3 +235,33 @@ def test_errors_do_not_abort(case):
             e.compute(0)
     with pytest.raises(nfx.NfxError):
         nfx.Extractor(99)                      # args.rs:176-180 "GPU {} does not exist"
+
+
+# ---- config-5-like stress shapes: 256x256 windows, 500-vertex polygons -------------------------------
+@pytest.fixture(scope="module")
+def stress(libnfx):
+    tile, rings = stress_case()
+    xy, off = nfx.pack_polygons(rings)
+    cents, polys, patches, masks = o.load_image_dataset(rings, tile, 256)
+    return dict(tile=tile, rings=rings, xy=xy, off=off, cents=cents, polys=polys, patches=patches, masks=masks)
+
+
+def test_stress_p256_masks_gather_shape_color(stress):
+    with nfx.Extractor(0, 256, 8) as e:
+        e.upload_tile(stress["tile"])
+        e.upload_polygons(stress["xy"], stress["off"])
+        masks = e.rasterize()
+        want = (stress["masks"][:, 0].numpy() != 0).astype(np.uint8)
+        assert np.array_equal(masks, want), "P=256 masks differ"
+        got = e.gather_patches()
+        wantp = np.stack([o.gather_patch_u8(stress["tile"], c, 256) for c in stress["cents"]])
+        assert np.array_equal(got, wantp), "P=256 patches differ"
+        keys, cents, feats, names = e.extract(stress["xy"], stress["off"], ["geometry", "color"])
+    assert np.array_equal(cents.view(np.uint32), stress["cents"].view(np.uint32))
+    wshape = o.shape_features(stress["polys"], stress["masks"])
+    sel = [0, 1, 2, 3, 5, 6, 7, 9, 10, 11]
+    bad = mismatches(feats[:, :12][:, sel], wshape[:, sel], [o.SHAPE_COLUMNS[j] for j in sel], "geometry")
+    assert not bad, _report(bad)
+    n = len(stress["rings"])
+    rows = [o.color_features(stress["patches"][k:k + 8].clone(), stress["masks"][k:k + 8]) for k in range(0, n, 8)]
+    _check_color(feats[:, 12:], np.concatenate(rows, 0), o.COLOR_COLUMNS, stress, 8)

@@ -9,11 +9,16 @@ RTOL = 1e-4
 # per-column absolute scale floors (same unit as the column)
 FLOORS = {
     # shape: radians / pixels / ratios
-    "orientation": 1.0, "eccentricity": 0.1, "eliptic_deviation": 0.05, "convex_deffect": 0.05,
+    "orientation": 1.0, "eccentricity": 1.0, "eliptic_deviation": 0.05, "convex_deffect": 0.05,
     "compacity": 0.1,
     # colour: channels are in [0,1], hue in degrees
     "mean_h": 360.0, "std_h": 1.0,
 }
+# eccentricity = sqrt(1 - (m/M)^2) has an unbounded condition number as m -> M (near-isotropic masks:
+# a 1e-6 relative f32 error of the reference's own covariance moves it by 1e-6/ecc^2); the
+# well-conditioned quantity is its square, compared on scale 1.
+TRANSFORMS = {"eccentricity": lambda v: v * v}
+
 DEFAULT_FLOOR = {"color": 0.02, "glcm": 0.05, "geometry": 1.0}
 
 
@@ -35,6 +40,8 @@ def mismatches(a, b, names, set_name, rtol=RTOL):
     for j, nm in enumerate(names):
         fl = floor_for(nm, set_name)
         x, y = a[:, j], b[:, j]
+        if nm in TRANSFORMS:
+            x, y = TRANSFORMS[nm](x), TRANSFORMS[nm](y)
         both_nan = np.isnan(x) & np.isnan(y)
         same_inf = np.isinf(x) & np.isinf(y) & (np.sign(x) == np.sign(y))
         with np.errstate(invalid="ignore"):
