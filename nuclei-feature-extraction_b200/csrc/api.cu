@@ -183,8 +183,6 @@ Cols columns(uint32_t mask) {
 }
 
 int check_patch_size(nfx_ctx* ctx, uint32_t mask) {
-    if ((mask & NFX_FS_GLCM) && ctx->P > 128)
-        return fail(ctx, NFX_ERR_UNSUPPORTED, "GLCM kernel handles patch_size <= 128 in this build");
     if (mask & (NFX_FS_GLRLM | NFX_FS_GABOR))
         return fail(ctx, NFX_ERR_UNSUPPORTED, "GLRLM / Gabor feature sets are not built yet (SURVEY.md 8f-1)");
     if (mask == 0 || (mask & ~NFX_FS_ALL)) return fail(ctx, NFX_ERR_INVALID, "empty or unknown feature mask");
@@ -402,7 +400,7 @@ int nfx_compute(nfx_ctx* ctx, uint32_t mask) {
     if (mask & NFX_FS_COLOR)
         if ((rc = run_color(ctx, n, ctx->B, &ctx->map_tile_cslab, &ctx->map_tile_slab, ctx->out.p, c.total, c.color))) return rc;
     if (mask & NFX_FS_GLCM)
-        if ((rc = run_glcm(ctx, n, &ctx->map_tile_patch, ctx->out.p, c.total, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
+        if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_tile_cslab : &ctx->map_tile_patch, ctx->out.p, c.total, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
     ctx->computed_mask = mask;
     return NFX_OK;
 }
@@ -478,7 +476,7 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
     } else if (fs == NFX_FS_COLOR) {
         if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_cslab, &ctx->map_pat_slab, ctx->out.p, cols, 0))) return rc;
     } else if (fs == NFX_FS_GLCM) {
-        if ((rc = run_glcm(ctx, n, &ctx->map_pat_patch, ctx->out.p, cols, 0, nullptr, 0, 0, 0, nullptr))) return rc;
+        if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_pat_cslab : &ctx->map_pat_patch, ctx->out.p, cols, 0, nullptr, 0, 0, 0, nullptr))) return rc;
     }
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -564,7 +562,7 @@ static int glcm_debug(nfx_ctx* ctx, int levels, int dy, int dx, uint32_t* counts
         CK(ctx->scratch8.ensure((size_t)ctx->n * ctx->P * ctx->P));
         d_grey = ctx->scratch8.p;
     }
-    if ((rc = run_glcm(ctx, ctx->n, &ctx->map_tile_patch, nullptr, 0, 0, d_counts, levels, dy, dx, d_grey))) return rc;
+    if ((rc = run_glcm(ctx, ctx->n, glcm_uses_slab_map(ctx->P) ? &ctx->map_tile_cslab : &ctx->map_tile_patch, nullptr, 0, 0, d_counts, levels, dy, dx, d_grey))) return rc;
     if (counts) CK(cudaMemcpyAsync(counts, d_counts, (size_t)ctx->n * levels * levels * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (grey) CK(cudaMemcpyAsync(grey, d_grey, (size_t)ctx->n * ctx->P * ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

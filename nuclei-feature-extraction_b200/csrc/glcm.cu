@@ -72,6 +72,39 @@ __device__ __forceinline__ void pair_levels(uint32_t rec, int lv, int& a, int& b
     }
 }
 
+// The 14 Haralick features (SPEC.md B6) from the sufficient statistics of one symmetric GLCM.
+//   T = sum G = 2*pairs, sg = sum_pairs G_pair, slg = sum_pairs ln G_pair,
+//   x1,x2 = sum k hx, sum k^2 hx ; d1,d2 = same for the difference histogram ; s1,s2 = sum histogram,
+//   cx, cs = sum c ln c over hx / hs ; idm_sum = sum hd[k] / (1 + k^2).
+__device__ __forceinline__ void haralick_write(float* o_, double T, double sg, double slg, double x1, double x2,
+                                               double d1, double d2, double s1, double s2, double cx, double cs,
+                                               double idm_sum) {
+    const double lnT = log(T);
+    const double asm_ = 2.0 * sg / (T * T);
+    const double hxy = lnT - 2.0 * slg / T;
+    const double mu = x1 / T, ei2 = x2 / T;
+    const double var = ei2 - mu * mu;
+    const double hxm = lnT - cx / T;
+    const double dav = d1 / T, contrast = d2 / T, idm = idm_sum / T;
+    const double sav = s1 / T, es2 = s2 / T;
+    const double sent = lnT - cs / T;
+    const double eij = 0.5 * (es2 - 2.0 * ei2);
+    o_[0] = (float)((eij - mu * mu) / var);            // correlation
+    o_[1] = (float)contrast;
+    o_[2] = (float)dav;                                // dissimilarity
+    o_[3] = (float)hxy;                                // entropy
+    o_[4] = (float)asm_;
+    o_[5] = (float)sav;
+    o_[6] = (float)(es2 - sav * sav);                  // sum variance
+    o_[7] = (float)sent;
+    o_[8] = (float)var;                                // sum of squares
+    o_[9] = (float)idm;
+    o_[10] = (float)dav;                               // difference average
+    o_[11] = (float)(contrast - dav * dav);            // difference variance
+    o_[12] = (float)((hxy - 2.0 * hxm) / hxm);         // IMC1 (HXY1 = 2 HX)
+    o_[13] = (float)sqrt(fmax(1.0 - exp(-2.0 * (2.0 * hxm - hxy)), 0.0));   // IMC2
+}
+
 template <bool SMALL>   // generic path (64 < P <= 128 in practice): one (offset, level) at a time
 __global__ void __launch_bounds__(kGlcmThreads)
 k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
@@ -333,30 +366,8 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
                 for (int w = 0; w < kNW; ++w) t += (double)part_f[(combo * kNW + w) * kNF + q];
                 acc[kNI + q] = t;
             }
-            const double T = 2.0 * (double)npairs, lnT = log(T);
-            const double asm_ = 2.0 * acc[0] / (T * T);
-            const double hxy = lnT - 2.0 * acc[kNI + 0] / T;
-            const double mu = acc[1] / T, ei2 = acc[2] / T;
-            const double var = ei2 - mu * mu;
-            const double hxm = lnT - acc[kNI + 1] / T;
-            const double dav = acc[3] / T, contrast = acc[4] / T, idm = acc[kNI + 3] / T;
-            const double sav = acc[5] / T, es2 = acc[6] / T;
-            const double sent = lnT - acc[kNI + 2] / T;
-            const double eij = 0.5 * (es2 - 2.0 * ei2);
-            o_[0] = (float)((eij - mu * mu) / var);            // correlation
-            o_[1] = (float)contrast;
-            o_[2] = (float)dav;                                // dissimilarity
-            o_[3] = (float)hxy;                                // entropy
-            o_[4] = (float)asm_;
-            o_[5] = (float)sav;
-            o_[6] = (float)(es2 - sav * sav);                  // sum variance
-            o_[7] = (float)sent;
-            o_[8] = (float)var;                                // sum of squares
-            o_[9] = (float)idm;
-            o_[10] = (float)dav;                               // difference average
-            o_[11] = (float)(contrast - dav * dav);            // difference variance
-            o_[12] = (float)((hxy - 2.0 * hxm) / hxm);         // IMC1 (HXY1 = 2 HX)
-            o_[13] = (float)sqrt(fmax(1.0 - exp(-2.0 * (2.0 * hxm - hxy)), 0.0));   // IMC2
+            haralick_write(o_, 2.0 * (double)npairs, acc[0], acc[kNI + 0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6],
+                           acc[kNI + 1], acc[kNI + 2], acc[kNI + 3]);
         }
     }
 }
@@ -678,38 +689,231 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
                 for (int w = 0; w < kNW; ++w) t += parts[(combo * kNW + w) * kNP + q];
                 acc[q] = (double)t;
             }
-            const double T = 2.0 * (double)npairs, lnT = log(T);
-            const double asm_ = 2.0 * acc[0] / (T * T);
-            const double hxy = lnT - 2.0 * (acc[7] / 65536.0) / T;
-            const double mu = acc[1] / T, ei2 = acc[2] / T;
-            const double var = ei2 - mu * mu;
-            const double hxm = lnT - (acc[8] / 32768.0) / T;
-            const double dav = acc[3] / T, contrast = acc[4] / T, idm = (acc[10] / 262144.0) / T;
-            const double sav = acc[5] / T, es2 = acc[6] / T;
-            const double sent = lnT - (acc[9] / 32768.0) / T;
-            const double eij = 0.5 * (es2 - 2.0 * ei2);
-            o_[0] = (float)((eij - mu * mu) / var);            // correlation
-            o_[1] = (float)contrast;
-            o_[2] = (float)dav;                                // dissimilarity
-            o_[3] = (float)hxy;                                // entropy
-            o_[4] = (float)asm_;
-            o_[5] = (float)sav;
-            o_[6] = (float)(es2 - sav * sav);                  // sum variance
-            o_[7] = (float)sent;
-            o_[8] = (float)var;                                // sum of squares
-            o_[9] = (float)idm;
-            o_[10] = (float)dav;                               // difference average
-            o_[11] = (float)(contrast - dav * dav);            // difference variance
-            o_[12] = (float)((hxy - 2.0 * hxm) / hxm);         // IMC1 (HXY1 = 2 HX)
-            o_[13] = (float)sqrt(fmax(1.0 - exp(-2.0 * (2.0 * hxm - hxy)), 0.0));   // IMC2
+            haralick_write(o_, 2.0 * (double)npairs, acc[0], acc[7] / 65536.0, acc[1], acc[2], acc[3], acc[4], acc[5], acc[6],
+                           acc[8] / 32768.0, acc[9] / 32768.0, acc[10] / 262144.0);
         }
+    }
+}
+
+
+// =================================================================================================
+// k_glcm_large: 128 < P <= 256 (BASELINE config 5, 256x256 windows). The quantised plane of ONE level
+// family lives in shared memory at a time (q254, then q128: 64 KB), the window is streamed through
+// 64-row slabs (aliased with the histogram region), co-occurring pairs are enumerated straight from
+// the mask words, G is a dense triangular u16 histogram (counts <= 65 280 fit), moments are u64.
+// =================================================================================================
+constexpr int kLargeThreads = 512;
+constexpr int kLNW = kLargeThreads / 32;
+struct GlcmLargeSmem {
+    int plane, region_t, rows, hist, part_i, part_f, total;
+};
+__host__ __device__ inline GlcmLargeSmem glcm_large_layout(int P) {
+    GlcmLargeSmem L;
+    L.plane = 0;
+    L.region_t = (P * P + 127) & ~127;
+    int t = window_smem_bytes(P, 64) > kTriBytes ? window_smem_bytes(P, 64) : kTriBytes;
+    L.rows = L.region_t + ((t + 127) & ~127);
+    L.hist = L.rows + P * mask_wpr(P) * 4;
+    L.part_i = L.hist + 1024 * 4;
+    L.part_f = L.part_i + kCombos * kLNW * kNI * 8;
+    L.total = L.part_f + kCombos * kLNW * kNF * 4;
+    return L;
+}
+
+__global__ void __launch_bounds__(kLargeThreads, 1)
+k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box {208, 64 rows} */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = blockIdx.x;
+    const GlcmLargeSmem L = glcm_large_layout(P);
+    uint8_t* plane = smem_raw + L.plane;
+    uint8_t* slab = smem_raw + L.region_t;
+    uint32_t* tri32 = reinterpret_cast<uint32_t*>(smem_raw + L.region_t);
+    uint16_t* tri16 = reinterpret_cast<uint16_t*>(smem_raw + L.region_t);
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + L.rows);
+    uint32_t* hx = reinterpret_cast<uint32_t*>(smem_raw + L.hist);
+    uint32_t* hs = hx + 256;
+    uint32_t* hd = hs + 512;
+    unsigned long long* part_i = reinterpret_cast<unsigned long long*>(smem_raw + L.part_i);
+    float* part_f = reinterpret_cast<float*>(smem_raw + L.part_f);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float s_lut[256];
+    __shared__ unsigned long long s_npairs[kGlcmOffsets];
+
+    const NucInfo inf = p.info[i];
+    const int o = patch_byte_offset(inf.left);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (tid < 256) s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
+    for (int k = tid; k < P * wpr; k += kLargeThreads) rows[k] = gm[k];
+    __syncthreads();
+    const int nslab = (P + 63) / 64;
+    const uint32_t slab_tx = (uint32_t)(patch_panels(P) * kPanelBytes * 64);
+    uint32_t phase = 0;
+
+    for (int round = 0; round < 2; ++round) {   // round 0: 254 levels (q254 plane); round 1: 128/64/32 (q128 plane)
+        // ---- stream the window and quantise it (texture.rs:36 + SPEC.md B5, bit-exact) ----
+        for (int sidx = 0; sidx < nslab; ++sidx) {
+            const int row0 = sidx * 64, nrows = min(64, P - row0);
+            __syncthreads();   // slab buffer (aliased with the histograms) is free
+            if (tid == 0) {
+                mbar_expect_tx(&bar, slab_tx);
+                tma_load_window(slab, &map, inf.left, inf.top + row0, P, 64, &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            for (int k = tid; k < nrows * P; k += kLargeThreads) {
+                const int lr = k / P, c = k - lr * P, r = row0 + lr;
+                uint32_t pr = 0, pg = 0, pb = 0;
+                if (r < inf.nvr && c < inf.nvc) {
+                    const int a = patch_addr(64, o, lr, c);
+                    pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
+                }
+                const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
+                plane[r * P + c] = round == 0 ? (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253)
+                                              : (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
+            }
+        }
+        __syncthreads();
+        if (p.dbg_grey) {
+            const int lvd = p.dbg_levels == 32 ? 0 : (p.dbg_levels == 64 ? 1 : (p.dbg_levels == 128 ? 2 : 3));
+            if ((round == 0) == (lvd == 3))
+                for (int k = tid; k < P * P; k += kLargeThreads)
+                    p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)(lvd == 3 ? plane[k] : (plane[k] >> (2 - lvd)));
+        }
+        for (int k = tid; k < kTriBytes / 16; k += kLargeThreads)
+            reinterpret_cast<uint4*>(smem_raw + L.region_t)[k] = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < 1024; k += kLargeThreads) hx[k] = 0u;
+        __syncthreads();
+
+        const int lv_hi = round == 0 ? 3 : 2, lv_lo = round == 0 ? 3 : 0;
+        for (int oi = 0; oi < kGlcmOffsets; ++oi) {
+            const int dy = c_off[oi][0], dx = c_off[oi][1], dpos = dy * P + dx;
+            for (int lv = lv_hi; lv >= lv_lo; --lv) {
+                const int NL = c_levels[lv], sh = lv == 3 ? 0 : 2 - lv, combo = lv * kGlcmOffsets + oi;
+                const int tri_words = ((NL * (NL + 1) / 2) + 1) / 2;
+                unsigned long long vl[kNI] = {0, 0, 0, 0, 0, 0, 0}, np_local = 0;
+                float vf[kNF] = {0.f, 0.f, 0.f, 0.f};
+                const bool dbg = p.dbg_counts && p.dbg_levels == NL && p.dbg_dy == dy && p.dbg_dx == dx;
+                for (int pass = 0; pass < 2; ++pass) {
+                    for (int k = tid; k < P * wpr; k += kLargeThreads) {
+                        const int r = k / wpr, w = k - r * wpr, r2 = r + dy;
+                        if (r2 >= P) continue;
+                        const uint32_t* nr = rows + r2 * wpr;
+                        uint32_t nb = nr[w];
+                        if (dx == 1) nb = (nb >> 1) | ((w + 1 < wpr) ? (nr[w + 1] << 31) : 0u);
+                        else if (dx == -1) nb = (nb << 1) | ((w > 0) ? (nr[w - 1] >> 31) : 0u);
+                        uint32_t pb = rows[k] & nb;
+                        while (pb) {
+                            const int c = 32 * w + __ffs(pb) - 1;
+                            pb &= pb - 1;
+                            const int src = r * P + c;
+                            const int a = plane[src] >> sh, b = plane[src + dpos] >> sh;
+                            const int lo = min(a, b), hi = max(a, b);
+                            const int cell = ((hi * (hi + 1)) >> 1) + lo;
+                            if (pass == 0) {
+                                atomicAdd(&tri32[cell >> 1], 1u << ((cell & 1) * 16));
+                                atomicAdd(&hx[a], 1u);
+                                atomicAdd(&hx[b], 1u);
+                                atomicAdd(&hs[a + b], 2u);
+                                atomicAdd(&hd[hi - lo], 2u);
+                                ++np_local;
+                            } else {
+                                const uint32_t g = (uint32_t)tri16[cell] << (a == b ? 1 : 0);
+                                vl[0] += g;
+                                vf[0] += __logf((float)g);
+                                if (dbg) {
+                                    uint32_t* dc = p.dbg_counts + i * (int64_t)NL * NL;
+                                    dc[a * NL + b] = g;
+                                    dc[b * NL + a] = g;
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                for (int k = tid; k < 2 * NL - 1; k += kLargeThreads) {
+                    const unsigned long long c = hs[k], kk = (unsigned long long)k;
+                    vl[5] += kk * c;
+                    vl[6] += kk * kk * c;
+                    if (c) vf[2] += (float)c * __logf((float)c);
+                    if (k < NL) {
+                        const unsigned long long cx = hx[k], cd = hd[k];
+                        vl[1] += kk * cx;
+                        vl[2] += kk * kk * cx;
+                        vl[3] += kk * cd;
+                        vl[4] += kk * kk * cd;
+                        if (cx) vf[1] += (float)cx * __logf((float)cx);
+                        vf[3] += __fdividef((float)cd, 1.0f + (float)(kk * kk));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kNI; ++q) {
+                    const unsigned long long t = warp_sum(vl[q]);
+                    if (lane == 0) part_i[(combo * kLNW + warp) * kNI + q] = t;
+                }
+#pragma unroll
+                for (int q = 0; q < kNF; ++q) {
+                    const float t = warp_sum(vf[q]);
+                    if (lane == 0) part_f[(combo * kLNW + warp) * kNF + q] = t;
+                }
+                np_local = warp_sum(np_local);
+                if (lv == lv_hi) {
+                    if (tid == 0) s_npairs[oi] = 0ull;
+                    __syncthreads();
+                    if (lane == 0 && np_local) atomicAdd(&s_npairs[oi], np_local);
+                }
+                __syncthreads();
+                for (int k = tid; k < tri_words; k += kLargeThreads) tri32[k] = 0u;
+                for (int k = tid; k < 1024; k += kLargeThreads) hx[k] = 0u;
+                __syncthreads();
+            }
+        }
+        // ---- features of this round's levels ----
+        if (tid < kCombos && p.out) {
+            const int combo = tid, lv = combo / kGlcmOffsets, oi = combo - lv * kGlcmOffsets;
+            if (lv >= lv_lo && lv <= lv_hi) {
+                float* o_ = p.out + i * (int64_t)p.out_stride + p.col_glcm + combo * kGlcmFeat;
+                const unsigned long long npairs = s_npairs[oi];
+                if (npairs == 0) {
+                    for (int f = 0; f < kGlcmFeat; ++f) o_[f] = CUDART_NAN_F;
+                } else {
+                    double acc[kNI + kNF];
+                    for (int q = 0; q < kNI; ++q) {
+                        unsigned long long t = 0;
+                        for (int w = 0; w < kLNW; ++w) t += part_i[(combo * kLNW + w) * kNI + q];
+                        acc[q] = (double)t;
+                    }
+                    for (int q = 0; q < kNF; ++q) {
+                        double t = 0.0;
+                        for (int w = 0; w < kLNW; ++w) t += (double)part_f[(combo * kLNW + w) * kNF + q];
+                        acc[kNI + q] = t;
+                    }
+                    haralick_write(o_, 2.0 * (double)npairs, acc[0], acc[kNI + 0], acc[1], acc[2], acc[3], acc[4], acc[5],
+                                   acc[6], acc[kNI + 1], acc[kNI + 2], acc[kNI + 3]);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
 }  // namespace
 
+int glcm_uses_slab_map(int P) { return P > 128; }
+
 cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
+    if (p.P > 128) {   // `map` must be the 64-row slab map
+        const int smem = glcm_large_layout(p.P).total;
+        cudaError_t e = cudaFuncSetAttribute(k_glcm_large, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        k_glcm_large<<<(unsigned)p.n, kLargeThreads, smem, s>>>(p, *map);
+        return cudaGetLastError();
+    }
     auto go = [&](auto kern, int smem) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

@@ -74,7 +74,9 @@ struct GlcmParams {
     int dbg_levels, dbg_dy, dbg_dx;
     uint8_t* dbg_grey;         // [n][P][P] quantised grey for dbg_levels
 };
+// map = whole-window map for P <= 128, the 64-row slab map (color_slab_rows) when glcm_uses_slab_map(P)
 cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s);
+int glcm_uses_slab_map(int P);
 
 // ---- staged.cu: kernels (1) gather and the f32 batch packer -----------------------------------
 // tile window -> u8 patch array [n*P rows][pitch bytes] through TMA load + TMA store.

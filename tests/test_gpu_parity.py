@@ -265,3 +265,37 @@ def test_stress_p256_masks_gather_shape_color(stress):
     n = len(stress["rings"])
     rows = [o.color_features(stress["patches"][k:k + 8].clone(), stress["masks"][k:k + 8]) for k in range(0, n, 8)]
     _check_color(feats[:, 12:], np.concatenate(rows, 0), o.COLOR_COLUMNS, stress, 8)
+
+
+def test_stress_p256_glcm(stress):
+    grey = o.grey_scale(stress["patches"])
+    with nfx.Extractor(0, 256, 8) as e:
+        e.upload_tile(stress["tile"])
+        e.upload_polygons(stress["xy"], stress["off"])
+        for L, off in [(254, (0, 1)), (128, (1, -1)), (32, (1, 1))]:
+            got = e.debug_glcm_counts(L, off)
+            want = o.glcm_counts(grey, off, L, stress["masks"]).numpy().astype(np.uint32)
+            assert np.array_equal(got, want), f"P=256 GLCM counts differ at L={L} off={off}"
+        for L in (254, 64):
+            assert np.array_equal(e.debug_grey_levels(L), o.quantise(grey, L)[:, 0].numpy().astype(np.uint8))
+        keys, cents, got, names = e.extract(stress["xy"], stress["off"], ["glcm"])
+    want = o.glcm_feature_set(stress["patches"], stress["masks"])
+    bad = mismatches(got, want, names, "glcm")
+    assert not bad, _report(bad)
+
+
+def test_mid_p128_all_sets(libnfx):
+    """P = 128 exercises the two-panel window, the two-slab colour path and the generic GLCM kernel."""
+    tile, rings = stress_case(n=12, size=512, seed=8, patch=128)
+    rings = [((r - r.mean(0)) * 0.45 + r.mean(0)).astype(np.float32) for r in rings]
+    xy, off = nfx.pack_polygons(rings)
+    with nfx.Extractor(0, 128, 5) as e:
+        e.upload_tile(tile)
+        keys, cents, got, names = e.extract(xy, off, ["geometry", "color", "glcm"])
+    wkeys, wc, want, wnames = o.extract(rings, tile, ["geometry", "color", "glcm"], 128, 5)
+    assert names == wnames and keys == wkeys
+    sel = [names.index(c) for c in ("area", "major_axis", "perimeter", "convex_hull_area", "mean_r", "std_g", "mean_s",
+                                    "std_v", "mean_eosin", "std_dab", "contrast_0_1_32", "entropy_1_1_64",
+                                    "angular_second_moment_1_0_128", "sum_entropy_1_-1_254", "sum_variance_0_1_254")]
+    ok = np.isclose(got[:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-6, equal_nan=True)
+    assert ok.all(), f"{(~ok).sum()} mismatches at P=128: {np.argwhere(~ok)[:5]}"
