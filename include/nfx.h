@@ -69,6 +69,16 @@ const char* nfx_version(void);
 int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h,
                     int64_t row_stride_bytes, int64_t origin_x, int64_t origin_y);
 
+/* Slides larger than one upload: reserve a W x H u8 RGB slide in HBM (a 100k x 100k slide is 30 GB of
+ * the 180 GB) and stream tiles/bands into it with any number of nfx_slide_write_tile calls, from
+ * pinned buffers the caller may reuse after nfx_sync. nfx_tile_upload(rgb,w,h,..) is exactly
+ * nfx_slide_alloc(w,h,..) + one nfx_slide_write_tile of the whole image. Regions never written
+ * read as undefined data; pixels outside the slide read as 0. */
+int nfx_slide_alloc(nfx_ctx* ctx, int64_t w, int64_t h, int64_t origin_x, int64_t origin_y);
+/* (x0, y0) = position of the tile's pixel (0,0) inside the slide allocated above. */
+int nfx_slide_write_tile(nfx_ctx* ctx, const uint8_t* rgb, int64_t x0, int64_t y0, int64_t w, int64_t h,
+                         int64_t row_stride_bytes);
+
 /* Stage n polygons (GeoJSON ring 0 of each feature, closing duplicate included, exactly as
  * `geometry.coordinates[0]` parses to f32: src/geojson.rs:8-24) in CSR form:
  * poly_xy = [poly_off[n]][2] f32 (x,y) slide coordinates, poly_off = [n+1] vertex offsets.

@@ -336,23 +336,44 @@ int nfx_destroy(nfx_ctx* ctx) {
     return NFX_OK;
 }
 
-int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h, int64_t row_stride_bytes,
-                    int64_t origin_x, int64_t origin_y) {
+int nfx_slide_alloc(nfx_ctx* ctx, int64_t w, int64_t h, int64_t origin_x, int64_t origin_y) {
     if (!ctx) return NFX_ERR_INVALID;
-    if (!rgb || w <= 0 || h <= 0 || row_stride_bytes < 3 * w) return fail(ctx, NFX_ERR_INVALID, "nfx_tile_upload: bad arguments");
-    if (3 * w >= (1ll << 31) || h >= (1ll << 31)) return fail(ctx, NFX_ERR_UNSUPPORTED, "tile too large for 32-bit TMA coordinates");
+    if (w <= 0 || h <= 0) return fail(ctx, NFX_ERR_INVALID, "nfx_slide_alloc: bad size");
+    if (3 * w >= (1ll << 31) || h >= (1ll << 31)) return fail(ctx, NFX_ERR_UNSUPPORTED, "slide too large for 32-bit TMA coordinates");
     int rc = set_device(ctx);
     if (rc) return rc;
     const int64_t pitch = ((3 * w + 15) / 16) * 16;
+    ctx->have_tile = false;
     CK(ctx->tile.ensure((size_t)pitch * h + 256));
-    CK(cudaMemcpy2DAsync(ctx->tile.p, pitch, rgb, row_stride_bytes, 3 * w, h, cudaMemcpyHostToDevice, ctx->stream));
     ctx->tw = w; ctx->th = h; ctx->tpitch = pitch; ctx->tox = origin_x; ctx->toy = origin_y;
     if ((rc = make_map(ctx, &ctx->map_tile_patch, ctx->tile.p, 3 * w, h, pitch, ctx->P))) return rc;
     if ((rc = make_map(ctx, &ctx->map_tile_slab, ctx->tile.p, 3 * w, h, pitch, hue_slab_rows(ctx->P)))) return rc;
     if ((rc = make_map(ctx, &ctx->map_tile_cslab, ctx->tile.p, 3 * w, h, pitch, color_slab_rows(ctx->P)))) return rc;
     ctx->have_tile = true;
-    ctx->have_geom = false;   // window origins depend on the tile origin
+    ctx->have_geom = false;   // window origins depend on the slide origin
     return NFX_OK;
+}
+
+int nfx_slide_write_tile(nfx_ctx* ctx, const uint8_t* rgb, int64_t x0, int64_t y0, int64_t w, int64_t h,
+                         int64_t row_stride_bytes) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (!ctx->have_tile) return fail(ctx, NFX_ERR_STATE, "no slide allocated: call nfx_slide_alloc first");
+    if (!rgb || w <= 0 || h <= 0 || row_stride_bytes < 3 * w || x0 < 0 || y0 < 0 || x0 + w > ctx->tw || y0 + h > ctx->th)
+        return fail(ctx, NFX_ERR_INVALID, "nfx_slide_write_tile: tile does not fit the slide");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(ctx->tile.p + (size_t)y0 * ctx->tpitch + 3 * x0, ctx->tpitch, rgb, row_stride_bytes, 3 * w, h,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h, int64_t row_stride_bytes,
+                    int64_t origin_x, int64_t origin_y) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (!rgb || w <= 0 || h <= 0 || row_stride_bytes < 3 * w) return fail(ctx, NFX_ERR_INVALID, "nfx_tile_upload: bad arguments");
+    int rc = nfx_slide_alloc(ctx, w, h, origin_x, origin_y);
+    if (rc) return rc;
+    return nfx_slide_write_tile(ctx, rgb, 0, 0, w, h, row_stride_bytes);
 }
 
 int nfx_polygons_upload(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* poly_off) {

@@ -115,6 +115,17 @@ class Extractor:
         self._ck(lib().nfx_tile_upload(self._h, _ptr(rgb), rgb.shape[1], rgb.shape[0], rgb.strides[0],
                                        int(origin[0]), int(origin[1])))
 
+    def slide_alloc(self, w, h, origin=(0, 0)):
+        """Reserve a W x H slide in HBM; fill it with write_tile (tiles / row bands, any order)."""
+        self._ck(lib().nfx_slide_alloc(self._h, int(w), int(h), int(origin[0]), int(origin[1])))
+
+    def write_tile(self, rgb, x0, y0):
+        rgb = np.asarray(rgb)
+        if rgb.dtype != np.uint8 or rgb.ndim != 3 or rgb.shape[2] != 3 or rgb.strides[2] != 1 or rgb.strides[1] != 3:
+            raise NfxError(-1, "tile must be [h,w,3] u8 with contiguous rows")
+        self._ck(lib().nfx_slide_write_tile(self._h, _ptr(rgb), int(x0), int(y0), rgb.shape[1], rgb.shape[0],
+                                            rgb.strides[0]))
+
     def upload_polygons(self, poly_xy, poly_off):
         poly_xy = np.ascontiguousarray(poly_xy, dtype=np.float32)
         poly_off = np.ascontiguousarray(poly_off, dtype=np.int64)

@@ -30,6 +30,8 @@ SYMBOLS = {
     "nfx_last_error": (C.c_char_p, [_vp]),
     "nfx_version": (C.c_char_p, []),
     "nfx_tile_upload": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64]),
+    "nfx_slide_alloc": (_i, [_vp, _i64, _i64, _i64, _i64]),
+    "nfx_slide_write_tile": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64]),
     "nfx_polygons_upload": (_i, [_vp, _i64, _vp, _vp]),
     "nfx_compute": (_i, [_vp, _u32]),
     "nfx_download": (_i, [_vp, _vp, _vp]),

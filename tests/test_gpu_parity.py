@@ -299,3 +299,47 @@ def test_mid_p128_all_sets(libnfx):
                                     "angular_second_moment_1_0_128", "sum_entropy_1_-1_254", "sum_variance_0_1_254")]
     ok = np.isclose(got[:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-6, equal_nan=True)
     assert ok.all(), f"{(~ok).sum()} mismatches at P=128: {np.argwhere(~ok)[:5]}"
+
+
+def test_slide_streamed_as_tiles_equals_single_upload(case):
+    """BASELINE config 4 mechanics: the slide is written tile by tile (and band by band) into HBM."""
+    tile = case["tile"]
+    H, W = tile.shape[:2]
+    with nfx.Extractor(0, 64, 100) as e:
+        e.upload_tile(tile)
+        k0, c0, f0, _ = e.extract(case["xy"], case["off"], ["color", "glcm"])
+    with nfx.Extractor(0, 64, 100) as e:
+        e.slide_alloc(W, H)
+        ts = 256
+        for y in range(0, H, ts):
+            for x in range(0, W, ts):
+                e.write_tile(np.ascontiguousarray(tile[y:y + ts, x:x + ts]), x, y)
+        k1, c1, f1, _ = e.extract(case["xy"], case["off"], ["color", "glcm"])
+        with pytest.raises(nfx.NfxError):
+            e.write_tile(np.ascontiguousarray(tile[:64, :64]), W - 10, 0)
+    assert k0 == k1 and np.array_equal(f0, f1, equal_nan=True)
+
+
+def test_tile_origin_offsets_slide_coordinates(case):
+    """A tile with origin (ox, oy) serves polygons given in slide coordinates: same result as the
+    reference pipeline run on the whole slide with the tile embedded at (ox, oy)."""
+    tile = case["tile"]
+    H, W = tile.shape[:2]
+    ox, oy = 1000, 700
+    slide = np.zeros((oy + H + 64, ox + W + 64, 3), np.uint8)
+    slide[oy:oy + H, ox:ox + W] = tile
+    n = 120
+    rings = [(r + np.array([ox, oy], np.float32)).astype(np.float32) for r in case["rings"][:n]]
+    xy, off = nfx.pack_polygons(rings)
+    with nfx.Extractor(0, 64, 100) as e:
+        e.upload_tile(tile, origin=(ox, oy))
+        keys, cents, got, names = e.extract(xy, off, ["color"])
+        masks = e.rasterize()
+        patches = e.gather_patches()
+    wc, wpolys, wpatches, wmasks = o.load_image_dataset(rings, slide, 64)
+    assert keys == [o.centroid_key(c) for c in wc]
+    assert np.array_equal(masks != 0, wmasks[:, 0].numpy() != 0)
+    assert np.array_equal(patches, np.stack([o.gather_patch_u8(slide, c, 64) for c in wc]))
+    sub = dict(patches=wpatches, masks=wmasks, rings=rings)
+    rows = [o.color_features(wpatches[k:k + 100].clone(), wmasks[k:k + 100]) for k in range(0, n, 100)]
+    _check_color(got, np.concatenate(rows, 0), names, sub, 100)
