@@ -35,6 +35,11 @@ WORKLOADS = {
     "shape": (["geometry"], 10_000, 4096, 64, {}),
     "glcm": (["glcm"], 1_000_000, 49152, 64, {}),
     "all": (["geometry", "color", "glcm"], 100_000, 16384, 64, {}),
+    # BASELINE config 5: large irregular nuclei, 256x256 windows, 500-vertex polygons
+    "stress": (["geometry", "color", "glcm"], 20_000, 16384, 256,
+               dict(r0_range=(40.0, 110.0), v_range=(500, 500), harmonics=(3, 7, 19))),
+    # BASELINE config 4: one slide resident in HBM, written tile by tile; nuclei split over the ranks (strong scaling)
+    "slide": (["geometry", "color", "glcm"], 5_000_000, 100_000, 64, {}),
 }
 V_MEAN = 30.0   # mean ring length of the synthetic polygons (12..48 vertices + closing duplicate)
 
@@ -65,47 +70,54 @@ def kernel_bytes(name: str, P: int, slabs: int) -> float:
     return 0.0
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+class ClockSampler:
+    """`nvidia-smi -lms 20` running from the first warm-up step to the end of the timed region (the
+    warm-up is the same kernel sequence, so every sample is taken under the measured load)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[x.strip() for x in ln.split(",")] for ln in out.strip().splitlines()]
+            except Exception:
+                pass
+        rows = [r for r in rows if len(r) >= 6]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 6:
-                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+        for r in rows:
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def make_inputs(workload, nuclei, side, P, seed, pinned):
     from nfx import pinned_empty, synth
+    kw = WORKLOADS[workload][4]
     block = min(side, 4096)
     base = synth.synth_tile(block, block, seed)
     tile = pinned_empty((side, side, 3), np.uint8) if pinned else np.empty((side, side, 3), np.uint8)
     for r in range(0, side, block):
         for c in range(0, side, block):
             tile[r:r + block, c:c + block] = base[:min(block, side - r), :min(block, side - c)]
-    xy, off = synth.synth_polygons(nuclei, side, side, seed, patch=P)
+    xy, off = synth.synth_polygons(nuclei, side, side, seed, patch=P, **kw)
     if pinned:
         pxy = pinned_empty(xy.shape, np.float32)
         pxy[...] = xy
@@ -113,6 +125,108 @@ def make_inputs(workload, nuclei, side, P, seed, pinned):
         poff[...] = off
         xy, off = pxy, poff
     return tile, xy, off
+
+
+def synth_polygons_chunked(nuclei, side, P, seed, kw, chunk=500_000):
+    from nfx import synth
+    xs, offs, base = [], [np.zeros(1, np.int64)], 0
+    for k in range(0, nuclei, chunk):
+        xy, off = synth.synth_polygons(min(chunk, nuclei - k), side, side, seed + 7919 * (k // chunk), patch=P, **kw)
+        xs.append(xy)
+        offs.append(off[1:] + base)
+        base += int(off[-1])
+    return np.concatenate(xs), np.concatenate(offs)
+
+
+def run_slide(args, rank, local_rank, world, dist):
+    """BASELINE config 4: a side x side slide lives in HBM (30 GB at 100k x 100k), streamed from the host
+    as 8192^2 tiles through two pinned staging buffers; the nuclei are split over the ranks in
+    contiguous index ranges aligned to batch_size (every rank keeps the whole slide: index order is
+    not spatial order). A step = stream the tiles + upload the range's polygons + all kernels + D2H."""
+    import nfx
+    from nfx import synth
+    sets, nuclei, side, P, kw = WORKLOADS["slide"]
+    nuclei = args.nuclei or nuclei
+    side = args.tile or side
+    mask = nfx.parse_feature_sets(sets)
+    F = len(nfx.feature_names(mask))
+    T = 8192
+    block = synth.synth_tile(4096, 4096, 4)
+    stage = [nfx.pinned_empty((T, T, 3), np.uint8) for _ in range(2)]
+    for b in stage:
+        for r in range(0, T, 4096):
+            for c in range(0, T, 4096):
+                b[r:r + 4096, c:c + 4096] = block
+    xy, off = synth_polygons_chunked(nuclei, side, P, 4, kw)
+    bounds = nfx.partition(nuclei, args.batch_size, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n = hi - lo
+    pxy = nfx.pinned_empty((int(off[hi] - off[lo]), 2), np.float32)
+    pxy[...] = xy[off[lo]:off[hi]]
+    poff = nfx.pinned_empty((n + 1,), np.int64)
+    poff[...] = off[lo:hi + 1] - off[lo]
+    cents = nfx.pinned_empty((n, 2), np.float32)
+    feats = nfx.pinned_empty((n, F), np.float32)
+    ex = nfx.Extractor(local_rank, P, args.batch_size)
+    ex.slide_alloc(side, side)
+
+    def stream_tiles():
+        k = 0
+        for y in range(0, side, T):
+            for x in range(0, side, T):
+                h, w = min(T, side - y), min(T, side - x)
+                ex.write_tile(stage[k & 1][:h, :w], x, y)
+                k += 1
+        return k
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    ntiles = stream_tiles()
+    ex.upload_polygons(pxy, poff)
+    for _ in range(max(args.warmup, 3) if n < 500_000 else 1):
+        ex.compute(mask)
+    ex.sync()
+    barrier()
+    K = max(1, min(args.steps, 3))
+    ex.profile(True)
+    ex.profile_reset()
+    l0 = ex.launch_count()
+    ex.timer_start()
+    for _ in range(K):
+        ex.compute(mask)
+    ms = ex.timer_stop() / K
+    launches = ex.launch_count() - l0
+    prof = ex.profile_get()
+    ex.profile(False)
+    barrier()
+    t0 = time.perf_counter()
+    stream_tiles()
+    ex.upload_polygons(pxy, poff)
+    ex.compute(mask)
+    ex.download(cents, feats)
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        kern = {k: {"launches": v[0], "avg_ms": v[1] / max(v[0], 1)} for k, v in prof.items()}
+        print(json.dumps({
+            "metric": "nuclei/sec", "value": nuclei / (ms * 1e-3), "unit": "nuclei/s", "n_gpus": world, "steps": K,
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8/f32", "data": "synthetic",
+            "config": {"workload": f"slide: {'+'.join(sets)}, {nuclei} nuclei over a {side}x{side} u8 RGB slide resident in HBM "
+                                   f"({3 * side * side / 1e9:.1f} GB per GPU), streamed as {ntiles} tiles of {T}^2, P={P}, "
+                                   f"batch_size={args.batch_size}",
+                       "partition": f"contiguous index ranges aligned to batch_size, {n} nuclei on rank 0"},
+            "e2e": {"value": nuclei / (e2e_ms * 1e-3), "unit": "nuclei/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 3 * side * side + pxy.nbytes + poff.nbytes, "d2h_bytes_per_step": cents.nbytes + feats.nbytes},
+            "gpu_launches": launches, "kernels": kern, "checksum": float(np.nansum(feats[:: max(1, n // 997)])),
+        }))
+    ex.close()
 
 
 def cpu_reference_rate(sets, tile, xy, off, P, batch, sample, workers):
@@ -143,7 +257,7 @@ def cpu_workers():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nfx", choices=["nfx", "reference"])
     ap.add_argument("--workload", default="color", choices=sorted(WORKLOADS))
@@ -170,7 +284,7 @@ def main():
         if rank != 0:
             return
         workers = cpu_workers()
-        sample = args.cpu_sample or workers * args.batch_size * {"color": 2, "shape": 4, "glcm": 1, "all": 1}[args.workload]
+        sample = args.cpu_sample or workers * args.batch_size * {"color": 2, "shape": 4}.get(args.workload, 1)
         tile, xy, off = make_inputs(args.workload, max(sample, 1000), min(side, 4096), P, 2, pinned=False)
         rates = []
         for it in range(args.warmup + K):
@@ -207,6 +321,12 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    if args.workload == "slide":
+        run_slide(args, rank, local_rank, world, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     mask = nfx.parse_feature_sets(sets)
     F = len(nfx.feature_names(mask))
     tile, xy, off = make_inputs(args.workload, nuclei, side, P, 2 + rank, pinned=True)
@@ -217,12 +337,17 @@ def main():
     feats = nfx.pinned_empty((nuclei, F), np.float32)
 
     # ---- device-resident throughput ----
-    for _ in range(W):
-        ex.compute(mask)
-    ex.sync()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_w = time.perf_counter()
+    nw = 0
+    while nw < W or (time.perf_counter() - t_w < 0.25 and nw < 2000):   # >= W warm-up steps, >= 0.25 s under load
+        ex.compute(mask)
+        nw += 1
+        if nw % 8 == 0:
+            ex.sync()
+    ex.sync()
+    barrier()
     ex.profile(True)
     ex.profile_reset()
     l0 = ex.launch_count()
@@ -295,14 +420,14 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             workers = cpu_workers()
-            sample = args.cpu_sample or workers * args.batch_size * {"color": 3, "shape": 6, "glcm": 1, "all": 1}[args.workload]
+            sample = args.cpu_sample or workers * args.batch_size * {"color": 3, "shape": 6}.get(args.workload, 1)
             sample = min(sample, nuclei)
             rate, dt = cpu_reference_rate(sets, tile, xy, off, P, args.batch_size, sample, workers)
             cpu = {"value": rate, "unit": "nuclei/s", "cores": workers, "kind": "port",
                    "sample": f"first {sample} nuclei of the same workload ({dt:.1f} s), oracle = torch-CPU restatement of the "
                              f"tch path, {workers} chunk-parallel host threads of {cores} cores"}
         line = {
-            "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_steps_run": nw,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {'+'.join(sets)} feature set(s), {nuclei} nuclei per GPU, "
