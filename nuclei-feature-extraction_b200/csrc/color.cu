@@ -26,9 +26,10 @@ namespace nfx {
 namespace {
 
 constexpr int kColorThreads = 128;
-constexpr int kHueConsumers = 256;               // 8 consumer warps
+constexpr int kHueConsumers = 128;               // 4 consumer warps, 2 pixel quads (8 px) per thread
 constexpr int kHueThreads = kHueConsumers + 32;  // + 1 TMA producer warp
-constexpr int kHueStages = 4;
+constexpr int kHueQpt = 2;                       // quads per consumer thread: slab holds <= 256 quads
+constexpr int kHueStages = 8;
 constexpr int kHueChunk = 128;                   // nuclei whose NucInfo is staged in smem at a time
 
 // OD(v) = ln(max(v/255, 1e-6)) / ln(1e-6), f32 (SPEC.md B4); filled once per process.
@@ -232,7 +233,8 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
         if (it + 1 < nslab) __syncthreads();   // slab buffer and list are reused
     }
     const int K = Ktot;
-    // ---- warp level: REDUX for the exact integer sums, shuffles for the floats ----
+    // ---- exact integer sums: one REDUX per warp; float sums: folded across the warps through shared
+    //      memory first, then ONE warp runs the shuffle tree (4x fewer shuffles than a tree per warp) ----
     {
         const uint32_t vi[8] = {sr, sg, sb, srr, sgg, sbb, sv, svv};
 #pragma unroll
@@ -240,10 +242,23 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
             const uint32_t t = __reduce_add_sync(0xffffffffu, vi[q]);
             if (lane == 0) s_ri[warp][q] = t;
         }
+        __syncthreads();   // the pixel list is dead: reuse it as float scratch [10][kColorThreads]
+        float* fs = reinterpret_cast<float*>(list);
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            const float a1 = warp_sum(s1[q]), a2 = warp_sum(s2[q]);
-            if (lane == 0) { s_rf[warp][q] = a1; s_rf[warp][5 + q] = a2; }
+            fs[q * kColorThreads + tid] = s1[q];
+            fs[(5 + q) * kColorThreads + tid] = s2[q];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < 10; ++q) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) a += fs[q * kColorThreads + w * 32 + lane];
+                a = warp_sum(a);
+                if (lane == 0) s_rf[0][q] = a;
+            }
         }
     }
     __syncthreads();
@@ -257,11 +272,7 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
             v[1 + q] = (double)t;
         }
 #pragma unroll
-        for (int q = 0; q < 10; ++q) {
-            double t = 0.0;
-            for (int w = 0; w < NW; ++w) t += (double)s_rf[w][q];
-            v[9 + q] = t;
-        }
+        for (int q = 0; q < 10; ++q) v[9 + q] = (double)s_rf[0][q];
         float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
         const double Kd = v[0];
         auto mean8 = [&](double s) { return (float)(s / Kd / 255.0); };
@@ -308,13 +319,23 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
         for (int s = 0; s < kHueStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kHueConsumers / 32); }
         mbar_fence_init();
     }
-    // consumer pixel ownership: one quad (4 px) per consumer thread
-    const int qpr = P >> 2;
-    const int rr = tid / qpr, qc = tid - rr * qpr;
-    const bool owner = (tid < kHueConsumers) && (rr < R) && (row0 + rr < P);
-    float C[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
-    const int c0 = qc * 4;
-    const int soff = (c0 >> 6) * panel_stride(R) + rr * kPanelBytes + (c0 & 63) * 3;   // + o per nucleus
+    // consumer pixel ownership: quads tid and tid + 128 of the slab (4 px each)
+    const int qpr = P >> 2, nquads = R * qpr;
+    bool owner[kHueQpt];
+    int rr[kHueQpt], c0[kHueQpt], soff[kHueQpt];
+#pragma unroll
+    for (int u = 0; u < kHueQpt; ++u) {
+        const int q = tid + u * kHueConsumers;
+        rr[u] = q / qpr;
+        c0[u] = (q - rr[u] * qpr) * 4;
+        owner[u] = (tid < kHueConsumers) && (q < nquads) && (row0 + rr[u] < P);
+        soff[u] = (c0[u] >> 6) * panel_stride(R) + rr[u] * kPanelBytes + (c0[u] & 63) * 3;   // + o per nucleus
+    }
+    float C[kHueQpt][4], S[kHueQpt][4];
+#pragma unroll
+    for (int u = 0; u < kHueQpt; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { C[u][k] = 0.f; S[u][k] = 0.f; }
 
     int it = 0;   // global iteration counter over the batch's nuclei (ring position)
     for (int base = 0; base < nb; base += kHueChunk) {
@@ -337,30 +358,37 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
             for (int j = 0; j < cnt; ++j) {
                 const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
                 mbar_wait(&full[s], ph);
-                uint32_t w0 = 0, w1 = 0, w2 = 0;
-                if (owner)
-                    load_quad(ring + (size_t)s * stage_bytes, soff + patch_byte_offset(s_info[j].left), w0, w1, w2);
+                const NucInfo inf = s_info[j];
+                const int ob = patch_byte_offset(inf.left);
+                uint32_t w[kHueQpt][3];
+#pragma unroll
+                for (int u = 0; u < kHueQpt; ++u) {
+                    w[u][0] = w[u][1] = w[u][2] = 0u;
+                    if (owner[u]) load_quad(ring + (size_t)s * stage_bytes, soff[u] + ob, w[u][0], w[u][1], w[u][2]);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
-                if (owner) {
-                    const NucInfo inf = s_info[j];
-                    if (inf.nvc < P || inf.nvr < P) {   // rare: window partly never copied (NucInfo)
-                        const bool rowdead = (row0 + rr) >= inf.nvr;
-                        const int nlive = rowdead ? 0 : min(max(inf.nvc - c0, 0), 4);   // live pixels of the quad
-                        // zero the dead bytes: pixel k occupies bytes 3k..3k+2 of the 12-byte quad
-                        const int nb = 3 * nlive;
-                        w0 = nb >= 4 ? w0 : (nb > 0 ? (w0 & ((1u << (8 * nb)) - 1u)) : 0u);
-                        w1 = nb >= 8 ? w1 : (nb > 4 ? (w1 & ((1u << (8 * (nb - 4))) - 1u)) : 0u);
-                        w2 = nb >= 12 ? w2 : (nb > 8 ? (w2 & ((1u << (8 * (nb - 8))) - 1u)) : 0u);
+                if (inf.nvc < P || inf.nvr < P) {   // rare: window partly never copied (NucInfo)
+#pragma unroll
+                    for (int u = 0; u < kHueQpt; ++u) {
+                        const bool rowdead = (row0 + rr[u]) >= inf.nvr;
+                        const int nlive = rowdead ? 0 : min(max(inf.nvc - c0[u], 0), 4);   // live pixels of the quad
+                        const int nbytes = 3 * nlive;   // pixel k occupies bytes 3k..3k+2 of the 12-byte quad
+                        w[u][0] = nbytes >= 4 ? w[u][0] : (nbytes > 0 ? (w[u][0] & ((1u << (8 * nbytes)) - 1u)) : 0u);
+                        w[u][1] = nbytes >= 8 ? w[u][1] : (nbytes > 4 ? (w[u][1] & ((1u << (8 * (nbytes - 4))) - 1u)) : 0u);
+                        w[u][2] = nbytes >= 12 ? w[u][2] : (nbytes > 8 ? (w[u][2] & ((1u << (8 * (nbytes - 8))) - 1u)) : 0u);
                     }
+                }
+#pragma unroll
+                for (int u = 0; u < kHueQpt; ++u) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const Px px = quad_px(w0, w1, w2, k);
+                        const Px px = quad_px(w[u][0], w[u][1], w[u][2], k);
                         const uint32_t mx = max(px.r, max(px.g, px.b)), mn = min(px.r, min(px.g, px.b));
                         // h = 60 t degrees = t * pi/3 radians (no wrap needed under sin/cos); d = 0 -> t = 0
                         const float ang = hue_sextant<false>(px, mx, mx - mn) * 1.0471975511965976f;
-                        C[k] += __cosf(ang);
-                        S[k] += __sinf(ang);
+                        C[u][k] += __cosf(ang);
+                        S[u][k] += __sinf(ang);
                     }
                 }
             }
@@ -368,12 +396,14 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
         it += cnt;
     }
     __syncthreads();
-    if (owner) {
+#pragma unroll
+    for (int u = 0; u < kHueQpt; ++u) {
+        if (!owner[u]) continue;   // non-owners accumulated cos(0) = 1 of zero words: never stored
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (c0 + k < P) {
-                Cs[rr * P + c0 + k] = C[k];
-                Ss[rr * P + c0 + k] = S[k];
+            if (c0[u] + k < P) {
+                Cs[rr[u] * P + c0[u] + k] = C[u][k];
+                Ss[rr[u] * P + c0[u] + k] = S[u][k];
             }
         }
     }
@@ -423,7 +453,8 @@ int hue_slab_rows(int P) { return max(1, min(P, 1024 / P)); }
 int color_slab_rows(int P) { return P < 64 ? P : 64; }
 int color_smem_bytes(int P) {
     const int cs = color_slab_rows(P);
-    return window_smem_bytes(P, cs) + P * mask_wpr(P) * 4 + 256 * 4 + cs * P * 2;
+    const int list_bytes = cs * P * 2 > 10 * kColorThreads * 4 ? cs * P * 2 : 10 * kColorThreads * 4;   // list / float scratch
+    return window_smem_bytes(P, cs) + P * mask_wpr(P) * 4 + 256 * 4 + list_bytes;
 }
 
 static bool g_lut_ready[64] = {};
