@@ -171,20 +171,22 @@ int set_device(nfx_ctx* ctx) {
 }
 
 struct Cols {
-    int shape, color, glcm, total;
+    int shape, color, glcm, glrlm, gabor, total;
 };
 Cols columns(uint32_t mask) {
     Cols c;
     c.shape = column_offset(mask, NFX_FS_GEOMETRY);
     c.color = column_offset(mask, NFX_FS_COLOR);
     c.glcm = column_offset(mask, NFX_FS_GLCM);
+    c.glrlm = column_offset(mask, NFX_FS_GLRLM);
+    c.gabor = column_offset(mask, NFX_FS_GABOR);
     c.total = nfx_feature_count(mask);
     return c;
 }
 
 int check_patch_size(nfx_ctx* ctx, uint32_t mask) {
-    if (mask & (NFX_FS_GLRLM | NFX_FS_GABOR))
-        return fail(ctx, NFX_ERR_UNSUPPORTED, "GLRLM / Gabor feature sets are not built yet (SURVEY.md 8f-1)");
+    if ((mask & NFX_FS_GABOR) && ctx->P > gabor_max_patch())
+        return fail(ctx, NFX_ERR_UNSUPPORTED, "Gabor kernel handles patch_size <= 64 in this build");
     if (mask == 0 || (mask & ~NFX_FS_ALL)) return fail(ctx, NFX_ERR_INVALID, "empty or unknown feature mask");
     return NFX_OK;
 }
@@ -255,6 +257,23 @@ int run_glcm(nfx_ctx* ctx, int64_t n, const CUtensorMap* mp, float* out, int str
     g.dbg_dx = ddx;
     g.dbg_grey = dbg_grey;
     CK(timed(ctx, "k_glcm", 1, [&] { return launch_glcm(g, mp, ctx->stream); }));
+    return NFX_OK;
+}
+
+int run_tex2(nfx_ctx* ctx, int64_t n, uint32_t mask, const CUtensorMap* map_cslab, const CUtensorMap* map_patch, float* out,
+             int stride, int col_glrlm, int col_gabor) {
+    TexParams t;
+    t.n = n;
+    t.P = ctx->P;
+    t.slab_rows = color_slab_rows(ctx->P);
+    t.info = ctx->info.p;
+    t.bitmask = ctx->bitmask.p;
+    t.out = out;
+    t.out_stride = stride;
+    t.col_glrlm = col_glrlm;
+    t.col_gabor = col_gabor;
+    if (mask & NFX_FS_GLRLM) CK(timed(ctx, "k_glrlm", 1, [&] { return launch_glrlm(t, map_cslab, ctx->stream); }));
+    if (mask & NFX_FS_GABOR) CK(timed(ctx, "k_gabor", 1, [&] { return launch_gabor(t, map_patch, ctx->stream); }));
     return NFX_OK;
 }
 
@@ -422,6 +441,8 @@ int nfx_compute(nfx_ctx* ctx, uint32_t mask) {
         if ((rc = run_color(ctx, n, ctx->B, &ctx->map_tile_cslab, &ctx->map_tile_slab, ctx->out.p, c.total, c.color))) return rc;
     if (mask & NFX_FS_GLCM)
         if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_tile_cslab : &ctx->map_tile_patch, ctx->out.p, c.total, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
+    if (mask & (NFX_FS_GLRLM | NFX_FS_GABOR))
+        if ((rc = run_tex2(ctx, n, mask, &ctx->map_tile_cslab, &ctx->map_tile_patch, ctx->out.p, c.total, c.glrlm, c.gabor))) return rc;
     ctx->computed_mask = mask;
     return NFX_OK;
 }
@@ -498,6 +519,8 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
         if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_cslab, &ctx->map_pat_slab, ctx->out.p, cols, 0))) return rc;
     } else if (fs == NFX_FS_GLCM) {
         if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_pat_cslab : &ctx->map_pat_patch, ctx->out.p, cols, 0, nullptr, 0, 0, 0, nullptr))) return rc;
+    } else {
+        if ((rc = run_tex2(ctx, n, fs, &ctx->map_pat_cslab, &ctx->map_pat_patch, ctx->out.p, cols, 0, 0))) return rc;
     }
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

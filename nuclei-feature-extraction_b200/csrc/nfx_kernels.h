@@ -78,6 +78,21 @@ struct GlcmParams {
 cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s);
 int glcm_uses_slab_map(int P);
 
+// ---- texture2.cu: GLRLM and Gabor sets -------------------------------------------------------------
+struct TexParams {
+    int64_t n;
+    int P;
+    int slab_rows;             // color_slab_rows(P): TMA box height of the slab map
+    const NucInfo* info;
+    const uint32_t* bitmask;
+    float* out;
+    int out_stride;
+    int col_glrlm, col_gabor;  // first column of each set (or -1)
+};
+cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaStream_t s);
+cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map_patch, cudaStream_t s);   // P <= gabor_max_patch()
+int gabor_max_patch();
+
 // ---- staged.cu: kernels (1) gather and the f32 batch packer -----------------------------------
 // tile window -> u8 patch array [n*P rows][pitch bytes] through TMA load + TMA store.
 cudaError_t launch_gather(int64_t n, int P, const NucInfo* info, const CUtensorMap* map_tile,

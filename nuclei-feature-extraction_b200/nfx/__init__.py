@@ -277,10 +277,19 @@ class GlcmFeatureSet(_FeatureSetBase):       # src/features/texture.rs:22
     BIT = FS_GLCM
 
 
+class GLRLMFeatureSet(_FeatureSetBase):      # src/features/texture.rs:178
+    BIT = FS_GLRLM
+
+
+class GaborFilterFeatureSet(_FeatureSetBase):  # src/features/texture.rs:317
+    BIT = FS_GABOR
+
+
 def to_fs(names, extractor):
     """args::FeatureSet::to_fs (src/args.rs:51-73)."""
     mask = parse_feature_sets(names)
-    table = {FS_GEOMETRY: ShapeFeatureSet, FS_COLOR: ColorFeatureSet, FS_GLCM: GlcmFeatureSet}
+    table = {FS_GEOMETRY: ShapeFeatureSet, FS_COLOR: ColorFeatureSet, FS_GLCM: GlcmFeatureSet,
+             FS_GLRLM: GLRLMFeatureSet, FS_GABOR: GaborFilterFeatureSet}
     out = []
     for b in _FLAT_BITS:
         if mask & b:

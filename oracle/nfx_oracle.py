@@ -554,6 +554,117 @@ def glcm_feature_set(patchs, masks, levels=GLCM_LEVELS, offsets=GLCM_OFFSETS):
 
 
 # --------------------------------------------------------------------------------------------
+# GLRLM set (SPEC.md B9) -- "next" row of SURVEY.md 8f; every definition below is UNPINNED
+# --------------------------------------------------------------------------------------------
+def glrlm_counts(grey, levels, max_length, direction, masks):
+    """[B9] tch_utils::glrlm::glrlm(&gs, levels, max_length, direction, Some(masks)) -> [N,levels,max_length]
+    int64. q = min(floor(grey*levels), levels-1); direction = (dx, dy) (texture.rs:243 names them so);
+    a run is a maximal sequence p, p+d, p+2d, ... of masked-in pixels with equal level (masked-out
+    pixels and the patch border break runs); runs longer than max_length fall in the last bin."""
+    N, _, H, W = grey.shape
+    q = quantise(grey, levels)[:, 0].numpy()
+    m = (masks[:, 0] != 0).numpy()
+    dx, dy = direction
+    R = np.zeros((N, levels, max_length), dtype=np.int64)
+    for n in range(N):
+        rr, cc = np.nonzero(m[n])
+        for r, c in zip(rr.tolist(), cc.tolist()):
+            pr, pc = r - dy, c - dx
+            if 0 <= pr < H and 0 <= pc < W and m[n, pr, pc] and q[n, pr, pc] == q[n, r, c]:
+                continue                                   # not the start of a run
+            lv, l, r2, c2 = q[n, r, c], 1, r + dy, c + dx
+            while 0 <= r2 < H and 0 <= c2 < W and m[n, r2, c2] and q[n, r2, c2] == lv:
+                l, r2, c2 = l + 1, r2 + dy, c2 + dx
+            R[n, lv, min(l, max_length) - 1] += 1
+    return torch.from_numpy(R)
+
+
+def glrlm_features(R, pixel_count):
+    """[B9] tch_utils::glrlm::features::glrlm_features(&glrlm, Some(&pixel_count)) -> [N,17] f32 in
+    GLRLM_FEATURES order. i = 1-based grey level, j = 1-based run length, Nr = sum R:
+    Galloway / Chu / Dasarathy emphases; the reference's non-standard "mid"/"extreme" grey-level
+    emphases use m(i) = 1 - u^2 and e(i) = u^2 with u = (i - c)/(c - 1), c = (L+1)/2."""
+    R = R.to(torch.float64)
+    N, L, M = R.shape
+    i = torch.arange(1, L + 1, dtype=torch.float64).view(1, L, 1)
+    j = torch.arange(1, M + 1, dtype=torch.float64).view(1, 1, M)
+    nr = R.sum(dim=[1, 2])
+    c = (L + 1) / 2.0
+    u2 = ((i - c) / (c - 1.0)) ** 2
+
+    def S(w):
+        return (R * w).sum(dim=[1, 2]) / nr
+
+    sre, lre = S(1 / j ** 2), S(j ** 2)
+    gln = (R.sum(dim=2) ** 2).sum(dim=1) / nr
+    rln = (R.sum(dim=1) ** 2).sum(dim=1) / nr
+    lgre, hgre = S(1 / i ** 2), S(i ** 2)
+    srlge, srhge = S(1 / (i ** 2 * j ** 2)), S(i ** 2 / j ** 2)
+    lrlge, lrhge = S(j ** 2 / i ** 2), S(i ** 2 * j ** 2)
+    srmge, lrmge = S((1 - u2) / j ** 2), S((1 - u2) * j ** 2)
+    srege, lrege = S(u2 / j ** 2), S(u2 * j ** 2)
+    rp = nr / pixel_count.to(torch.float64)
+    rlm = S(j + 0 * i)
+    rlv = (R * (j - rlm.view(N, 1, 1)) ** 2).sum(dim=[1, 2]) / nr
+    out = torch.stack([sre, lre, gln, rln, lgre, hgre, srlge, srhge, lrlge, lrhge, srmge, lrmge, srege, lrege,
+                       rp, rlm, rlv], dim=1)
+    return out.to(torch.float32).numpy()
+
+
+def glrlm_feature_set(patchs, masks):
+    """GLRLMFeatureSet::compute_features_batched (src/features/texture.rs:178-310): [N,68] f32."""
+    gs = grey_scale(patchs)
+    pixel_count = masks.sum(dim=[-3, -2, -1])
+    cols = []
+    for d in GLRLM_DIRECTIONS:
+        R = glrlm_counts(gs, GLRLM_LEVELS, GLRLM_MAX_LENGTH, d, masks)
+        cols.append(glrlm_features(R, pixel_count))
+    return np.concatenate(cols, axis=1).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
+# Gabor set (SPEC.md B9) -- "next" row; UNPINNED
+# --------------------------------------------------------------------------------------------
+def gabor_bank(angles=GABOR_ANGLES, ksize=GABOR_KERNEL, freqs=GABOR_FREQUENCIES, sigma=GABOR_SIGMA):
+    """[B9] the 48 kernels of tch_utils::gabor::apply_gabor_filter, filter j = angle_idx*len(freqs)+freq_idx
+    (texture.rs:349-350), float32 [48, ksize, ksize]. Taps on the normalised grid u,v in
+    linspace(-1,1,ksize) (sigma and frequency are in those units), theta = angle_idx * 2*pi/angles:
+        x' = u cos(theta) + v sin(theta) ;  g = exp(-(u^2+v^2)/(2 sigma^2)) * cos(2 pi f x')
+    (isotropic envelope, real part, no normalisation). v = row axis, u = column axis."""
+    t = np.linspace(-1.0, 1.0, ksize)
+    U, V = np.meshgrid(t, t)          # U varies along columns, V along rows
+    bank = []
+    for a in range(angles):
+        th = a * 2.0 * np.pi / angles
+        xr = U * np.cos(th) + V * np.sin(th)
+        for f in freqs:
+            bank.append(np.exp(-(U * U + V * V) / (2.0 * sigma * sigma)) * np.cos(2.0 * np.pi * f * xr))
+    return np.stack(bank).astype(np.float32)
+
+
+def apply_gabor_filter(gs):
+    """[B9] -> [N,48,P,P]: cross-correlation (torch conv2d) with zero padding 'same'; for the even
+    30-tap kernel that is 14 taps before and 15 after the output pixel."""
+    k = torch.from_numpy(gabor_bank())[:, None]                       # [48,1,30,30]
+    pad_lo = (GABOR_KERNEL - 1) // 2
+    pad_hi = GABOR_KERNEL - 1 - pad_lo
+    x = torch.nn.functional.pad(gs, (pad_lo, pad_hi, pad_lo, pad_hi))
+    return torch.nn.functional.conv2d(x, k)
+
+
+def gabor_feature_set(patchs, masks):
+    """GaborFilterFeatureSet::compute_features_batched (src/features/texture.rs:322-369): [N,96] f32,
+    (mean, variance) interleaved per filter."""
+    gs = grey_scale(patchs)
+    filtered = apply_gabor_filter(gs)
+    N, Fc = patchs.shape[0], filtered.shape[1]
+    areas = masks.sum(dim=[-3, -2, -1])
+    mean = (filtered * masks).sum(dim=[-2, -1]) / areas.unsqueeze(-1)
+    var = ((filtered - mean.view(N, Fc, 1, 1)).square() * masks).sum(dim=[-2, -1]) / areas.unsqueeze(-1)
+    return torch.stack([mean, var], dim=2).reshape(N, 2 * Fc).numpy().astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
 # Whole pipeline, batch by batch (src/main.rs:146-158, 47-91)
 # --------------------------------------------------------------------------------------------
 def extract(rings, image_hwc, feature_sets, patch_size=64, batch_size=100):
@@ -577,6 +688,10 @@ def extract(rings, image_hwc, feature_sets, patch_size=64, batch_size=100):
                 blocks.append(color_features(patches, masks).astype(np.float64))
             elif s == "glcm":
                 blocks.append(glcm_feature_set(patches, masks).astype(np.float64))
+            elif s == "glrlm":
+                blocks.append(glrlm_feature_set(patches, masks).astype(np.float64))
+            elif s == "gabor":
+                blocks.append(gabor_feature_set(patches, masks).astype(np.float64))
             else:
                 raise NotImplementedError(f"oracle for feature set {s!r} not written yet")
         rows.append(np.concatenate(blocks, axis=1))

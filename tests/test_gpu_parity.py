@@ -343,3 +343,42 @@ def test_tile_origin_offsets_slide_coordinates(case):
     sub = dict(patches=wpatches, masks=wmasks, rings=rings)
     rows = [o.color_features(wpatches[k:k + 100].clone(), wmasks[k:k + 100]) for k in range(0, n, 100)]
     _check_color(got, np.concatenate(rows, 0), names, sub, 100)
+
+
+def test_glrlm_features(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["glrlm"])
+    want = o.glrlm_feature_set(case["patches"], case["masks"])
+    assert names == o.GLRLM_COLUMNS
+    bad = mismatches(got, want, names, "glrlm")
+    assert not bad, _report(bad)
+
+
+def test_gabor_features(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["gabor"])
+    want = o.gabor_feature_set(case["patches"], case["masks"])
+    assert names == o.GABOR_COLUMNS
+    bad = mismatches(got, want, names, "gabor")
+    assert not bad, _report(bad)
+
+
+def test_all_418_columns_in_flat_order(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["all"])
+    assert len(names) == 418 and names == [c for s_ in o.FLAT_ORDER for c in o.SET_COLUMNS[s_]]
+    n = 60
+    wkeys, wc, want, wnames = o.extract(case["rings"][:n], case["tile"], ["all"], 64, 100)
+    assert wnames == names and keys[:n] == wkeys
+    # chunk 0 is rows 0..99 in both runs only when n covers it: compare the batch-independent columns
+    sel = [names.index(c) for c in ("area", "mean_g", "std_eosin", "contrast_1_1_64", "short_run_emphasis_1_0",
+                                    "run_percentage_-1_1", "gabor_angle_0_frequency_0.5_mean",
+                                    "gabor_angle_90_frequency_2_variance", "gabor_angle_315_frequency_8_mean")]
+    ok = np.isclose(got[:n][:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-4, equal_nan=True)
+    assert ok.all(), f"{(~ok).sum()} mismatches: {np.argwhere(~ok)[:6]}"
+
+
+def test_glrlm_p256(stress):
+    with nfx.Extractor(0, 256, 8) as e:
+        e.upload_tile(stress["tile"])
+        keys, cents, got, names = e.extract(stress["xy"][:stress["off"][6]], stress["off"][:7], ["glrlm"])
+    want = o.glrlm_feature_set(stress["patches"][:6], stress["masks"][:6])
+    bad = mismatches(got, want, names, "glrlm")
+    assert not bad, _report(bad)

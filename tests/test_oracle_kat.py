@@ -236,3 +236,51 @@ def test_key_string_is_rust_display():
     assert o.centroid_key(np.array([0.1, 1e-7], np.float32)) == "0.1,0.0000001"
     assert o.centroid_key(np.array([16777216.0, -0.0], np.float32)) == "16777216,-0"
     assert o.centroid_key(np.array([np.nan, np.inf], np.float32)) == "NaN,inf"
+
+
+def test_glrlm_counts_known_answer():
+    # 4x6 patch, two grey levels in horizontal stripes of known run lengths, full mask
+    g = np.zeros((4, 6), np.float32)
+    g[0] = [0, 0, 0, .9, .9, 0]          # runs: 3x lvl0, 2x lvlH, 1x lvl0
+    g[1] = .9                            # one run of 6
+    g[2] = [0, .9, 0, .9, 0, .9]         # six runs of 1
+    g[3] = 0                             # one run of 6
+    grey = torch.from_numpy(g)[None, None]
+    masks = torch.ones(1, 1, 4, 6)
+    hi = int(np.floor(np.float32(.9) * 24))
+    R = o.glrlm_counts(grey, 24, 16, (1, 0), masks)[0].numpy()
+    assert R[0, 2] == 1 and R[hi, 1] == 1 and R[0, 0] == 1 + 3 and R[hi, 0] == 3 and R[hi, 5] == 1 and R[0, 5] == 1
+    assert R.sum() == 3 + 1 + 6 + 1
+    # vertical direction (dx,dy) = (0,1): column 0 has levels 0,H,0,0 -> runs 1,1,2
+    Rv = o.glrlm_counts(grey, 24, 16, (0, 1), masks)[0].numpy()
+    assert (Rv * np.arange(1, 17)[None]).sum() == 24          # every pixel belongs to exactly one run
+    # a masked-out pixel breaks a run
+    masks[0, 0, 1, 2] = 0
+    Rm = o.glrlm_counts(grey, 24, 16, (1, 0), masks)[0].numpy()
+    assert Rm[hi, 5] == 0 and Rm[hi, 1] == 2 and Rm[hi, 2] == 1
+    f = o.glrlm_features(torch.from_numpy(R)[None], torch.tensor([24.0]))[0]
+    d = dict(zip(o.GLRLM_FEATURES, f))
+    assert math.isclose(d["run_percentage"], 11 / 24, rel_tol=1e-6)
+    assert math.isclose(d["run_length_mean"], 24 / 11, rel_tol=1e-6)
+
+
+def test_gabor_bank_and_same_padding():
+    bank = o.gabor_bank()
+    assert bank.shape == (48, 30, 30)
+    # theta = 0, f = 0.5: g(u,v) = exp(-(u^2+v^2)/(2 0.45^2)) cos(pi u): symmetric in v, even in u
+    assert np.allclose(bank[0], bank[0][::-1], atol=1e-7) and np.allclose(bank[0], bank[0][:, ::-1], atol=1e-7)
+    # angle index 2 = 90 degrees: the carrier runs along v (rows)
+    assert np.allclose(bank[2 * 6 + 3], bank[0 * 6 + 3].T, atol=1e-6)
+    # separable factorisation used by the kernel
+    t = np.linspace(-1, 1, 30)
+    G = np.exp(-t * t / (2 * 0.45 ** 2))
+    th, f = 3 * 2 * np.pi / 8, 4.0
+    a, b = 2 * np.pi * f * np.cos(th), 2 * np.pi * f * np.sin(th)
+    sep = np.outer(G * np.cos(b * t), G * np.cos(a * t)) - np.outer(G * np.sin(b * t), G * np.sin(a * t))
+    assert np.allclose(bank[3 * 6 + 3], sep, atol=1e-6)
+    # impulse response: 'same' padding puts tap (14,14) on the output pixel
+    x = torch.zeros(1, 1, 64, 64)
+    x[0, 0, 20, 30] = 1.0
+    y = o.apply_gabor_filter(x)
+    assert y.shape == (1, 48, 64, 64)
+    assert np.allclose(y[0, 5, 20 - 3, 30 + 2].item(), bank[5, 14 + 3, 14 - 2], atol=1e-7)

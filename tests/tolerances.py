@@ -19,7 +19,9 @@ FLOORS = {
 # well-conditioned quantity is its square, compared on scale 1.
 TRANSFORMS = {"eccentricity": lambda v: v * v}
 
-DEFAULT_FLOOR = {"color": 0.02, "glcm": 0.05, "geometry": 1.0}
+# gabor: a 900-tap f32 convolution of values ~0.5 with taps of alternating sign carries ~1e-5 absolute
+# noise in the reference's own conv2d; outputs range from 0.04 to 70, so scale 1 is the floor.
+DEFAULT_FLOOR = {"color": 0.02, "glcm": 0.05, "geometry": 1.0, "glrlm": 0.01, "gabor": 1.0}
 
 
 def floor_for(name, set_name):
