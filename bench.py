@@ -34,7 +34,7 @@ WORKLOADS = {
     "color": (["color"], 100_000, 16384, 64, {}),
     "shape": (["geometry"], 10_000, 4096, 64, {}),
     "glcm": (["glcm"], 1_000_000, 49152, 64, {}),
-    "all": (["geometry", "color", "glcm"], 100_000, 16384, 64, {}),
+    "all": (["all"], 100_000, 16384, 64, {}),
     # BASELINE config 5: large irregular nuclei, 256x256 windows, 500-vertex polygons
     "stress": (["geometry", "color", "glcm"], 20_000, 16384, 256,
                dict(r0_range=(40.0, 110.0), v_range=(500, 500), harmonics=(3, 7, 19))),
@@ -67,6 +67,10 @@ def kernel_bytes(name: str, P: int, slabs: int) -> float:
         return 8 * (V_MEAN + 1) + bm + info + 8 + (4 * 12 if "shape" in name else 0)
     if name == "k_hue_finalize":
         return 8 * slabs + 8
+    if name == "k_glrlm":
+        return px + bm + info + 4 * 68
+    if name == "k_gabor":
+        return px + bm + info + 4 * 96
     return 0.0
 
 

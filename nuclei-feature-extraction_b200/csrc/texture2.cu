@@ -28,7 +28,12 @@ __device__ __constant__ int c_dirs[4][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}};   
 
 constexpr int kTexThreads = 256;
 constexpr int kGaborFilters = 48, kGaborK = 30, kGaborLo = 14;   // 'same' padding: 14 before, 15 after
-__device__ __constant__ float c_gabor[kGaborFilters][4][kGaborK];   // [filter][cu, su, cv, sv][tap]
+// Separable factors of the bank (oracle gabor_bank): per frequency q the 1-D profiles
+//   [0] G(t)cos(w t)  [1] G(t)sin(w t)  with w = 2 pi f           (theta = 0 / 90 degrees)
+//   [2] G(t)cos(w't)  [3] G(t)sin(w't)  with w' = 2 pi f cos(pi/4) (theta = 45 / 135 degrees)
+// and the bare Gaussian envelope G(t). Rows and columns share them (the tap grid is symmetric).
+__device__ __constant__ float c_gtap[6][4][kGaborK];
+__device__ __constant__ float c_genv[kGaborK];
 
 __device__ __forceinline__ float grey_of(const float* lut, uint32_t r, uint32_t g, uint32_t b) {
     // texture.rs:189/332: mean_dim(-3) of u8/255 values = ((r+g)+b)/3 with IEEE f32 operations
@@ -36,19 +41,28 @@ __device__ __forceinline__ float grey_of(const float* lut, uint32_t r, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int kRlCells = kRlLevels * kRlMax;
+static_assert(kRlLevels == 24, "u = (i - 12.5)/11.5 below assumes 24 levels");
+
+// Dynamic smem: region X (slab, later the pixel list u16 (row << 8) | col) | plane[P*P] u8 | rows[P*wpr] u32
 __global__ void __launch_bounds__(kTexThreads)
 k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, CS rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x;
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kTexThreads / 32;
     const int CS = p.slab_rows, nslab = (P + CS - 1) / CS;
     const int64_t i = blockIdx.x;
+    // region X = slab buffer while the window streams in, pixel list afterwards
+    const int region_x = max(window_smem_bytes(P, CS), (P * P * 2 + 127) & ~127);
     uint8_t* slab = smem_raw;
-    uint8_t* plane = smem_raw + window_smem_bytes(P, CS);
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw);
+    uint8_t* plane = smem_raw + region_x;
     uint32_t* rows = reinterpret_cast<uint32_t*>(plane + ((P * P + 15) & ~15));
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
-    __shared__ uint32_t s_R[kRlLevels * kRlMax];
-    __shared__ double s_red[16 * (kTexThreads / 32)];
+    __shared__ uint32_t s_R[kRlCells];
+    __shared__ float s_red[16 * NW];
+    __shared__ int s_scan[NW + 1];
 
     const NucInfo inf = p.info[i];
     const int o = patch_byte_offset(inf.left);
@@ -61,18 +75,17 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     }
     s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
-    double K = 0.0;
-    for (int k = tid; k < P * wpr; k += kTexThreads) {
-        const uint32_t b = gm[k];
-        rows[k] = b;
-        K += (double)__popc(b);
-    }
+    for (int k = tid; k < P * wpr; k += kTexThreads) rows[k] = gm[k];
     __syncthreads();
+    // ---- 24-level plane (texture.rs:189 + SPEC.md B9), rows that hold mask bits only ----
     for (int sidx = 0; sidx < nslab; ++sidx) {
         const int row0 = sidx * CS, nrows = min(CS, P - row0);
         mbar_wait(&bar, sidx & 1);
         for (int k = tid; k < nrows * P; k += kTexThreads) {
             const int lr = k / P, c = k - lr * P, r = row0 + lr;
+            uint32_t any = 0;
+            for (int w = 0; w < wpr; ++w) any |= rows[r * wpr + w];
+            if (!any) continue;
             uint32_t pr = 0, pg = 0, pb = 0;
             if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
                 const int a = patch_addr(CS, o, lr, c);
@@ -86,71 +99,96 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             tma_load_window(slab, &map, inf.left, inf.top + row0 + CS, P, CS, &bar);
         }
     }
-    {
-        double v[1] = {K};
-        block_sum<1>(v, s_red);
-        K = v[0];
+    // ---- compacted list of the masked pixels (overwrites the slab buffer) ----
+    int K = 0;
+    for (int base = 0; base < P * wpr; base += kTexThreads) {
+        const int k = base + tid;
+        uint32_t bits = (k < P * wpr) ? rows[k] : 0u;
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+            if (lane >= o2) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int t = 0; t < NW; ++t) {
+            const int v = s_scan[t];
+            wbase += (t < warp) ? v : 0;
+            total += v;
+        }
+        int pos = K + wbase + incl - cnt;
+        const int r = k / wpr, cb = (k - r * wpr) * 32;
+        while (bits) {
+            const int c = cb + __ffs(bits) - 1;
+            bits &= bits - 1;
+            list[pos++] = (uint16_t)((r << 8) | c);
+        }
+        K += total;
     }
+    __syncthreads();
     float* out = p.out + i * (int64_t)p.out_stride + p.col_glrlm;
-    const double cmid = (kRlLevels + 1) * 0.5;
+    auto masked = [&](int r, int c) -> bool {
+        return (unsigned)r < (unsigned)P && (unsigned)c < (unsigned)P && ((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u);
+    };
     for (int d = 0; d < 4; ++d) {
         const int dx = c_dirs[d][0], dy = c_dirs[d][1];
-        for (int k = tid; k < kRlLevels * kRlMax; k += kTexThreads) s_R[k] = 0u;
+        for (int k = tid; k < kRlCells; k += kTexThreads) s_R[k] = 0u;
         __syncthreads();
-        auto masked = [&](int r, int c) -> bool {
-            return (unsigned)r < (unsigned)P && (unsigned)c < (unsigned)P && ((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u);
-        };
-        for (int k = tid; k < P * wpr; k += kTexThreads) {
-            uint32_t bits = rows[k];
-            const int r = k / wpr, cb = (k - r * wpr) * 32;
-            while (bits) {
-                const int c = cb + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int lv = plane[r * P + c];
-                if (masked(r - dy, c - dx) && plane[(r - dy) * P + (c - dx)] == lv) continue;   // not a run start
-                int len = 1, r2 = r + dy, c2 = c + dx;
-                while (masked(r2, c2) && plane[r2 * P + c2] == lv) { ++len; r2 += dy; c2 += dx; }
-                atomicAdd(&s_R[lv * kRlMax + min(len, kRlMax) - 1], 1u);
-            }
+        for (int j = tid; j < K; j += kTexThreads) {
+            const uint32_t rc = list[j];
+            const int r = rc >> 8, c = rc & 255;
+            const int lv = plane[r * P + c];
+            if (masked(r - dy, c - dx) && plane[(r - dy) * P + (c - dx)] == lv) continue;   // not a run start
+            int len = 1, r2 = r + dy, c2 = c + dx;
+            while (masked(r2, c2) && plane[r2 * P + c2] == lv) { ++len; r2 += dy; c2 += dx; }
+            atomicAdd(&s_R[lv * kRlMax + min(len, kRlMax) - 1], 1u);
         }
         __syncthreads();
-        // ---- 17 features (oracle glrlm_features), float64 sums of exact counts ----
-        double v[16];
+        // ---- 17 features: 14 weighted sums of the counts + squared row/column sums ----
+        float v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = 0.0;
-        for (int k = tid; k < kRlLevels * kRlMax; k += kTexThreads) {
-            const double R = (double)s_R[k];
-            const double ii = (double)(k / kRlMax + 1), jj = (double)(k % kRlMax + 1);
-            const double u = (ii - cmid) / (cmid - 1.0), u2 = u * u;
-            v[0] += R;                       // Nr
-            v[1] += R / (jj * jj);           // SRE
-            v[2] += R * jj * jj;             // LRE
-            v[3] += R / (ii * ii);           // LGRE
-            v[4] += R * ii * ii;             // HGRE
-            v[5] += R / (ii * ii * jj * jj); // SRLGE
-            v[6] += R * ii * ii / (jj * jj); // SRHGE
-            v[7] += R * jj * jj / (ii * ii); // LRLGE
-            v[8] += R * ii * ii * jj * jj;   // LRHGE
-            v[9] += R * (1.0 - u2) / (jj * jj);    // short run, mid grey
-            v[10] += R * (1.0 - u2) * jj * jj;     // long run, mid grey
-            v[11] += R * u2 / (jj * jj);           // short run, extreme grey
-            v[12] += R * u2 * jj * jj;             // long run, extreme grey
-            v[13] += R * jj;                       // sum of run lengths
+        for (int q = 0; q < 16; ++q) v[q] = 0.f;
+        for (int k = tid; k < kRlCells; k += kTexThreads) {
+            const float R = (float)s_R[k];
+            if (R == 0.f) continue;
+            // weights computed in registers: a per-thread index into __constant__ memory would serialise
+            const float fi = (float)(k / kRlMax + 1), fj = (float)(k % kRlMax + 1);
+            const float ii = fi * fi, jj = fj * fj, ri = __fdiv_rn(1.0f, ii), rj = __fdiv_rn(1.0f, jj);
+            const float u = (fi - 12.5f) * (1.0f / 11.5f), u2 = u * u, m2 = 1.0f - u2;
+            v[0] += R;
+            v[1] = fmaf(R, rj, v[1]);
+            v[2] = fmaf(R, jj, v[2]);
+            v[3] = fmaf(R, ri, v[3]);
+            v[4] = fmaf(R, ii, v[4]);
+            v[5] = fmaf(R, ri * rj, v[5]);
+            v[6] = fmaf(R, ii * rj, v[6]);
+            v[7] = fmaf(R, jj * ri, v[7]);
+            v[8] = fmaf(R, ii * jj, v[8]);
+            v[9] = fmaf(R, m2 * rj, v[9]);
+            v[10] = fmaf(R, m2 * jj, v[10]);
+            v[11] = fmaf(R, u2 * rj, v[11]);
+            v[12] = fmaf(R, u2 * jj, v[12]);
+            v[13] = fmaf(R, fj, v[13]);
         }
-        if (tid < kRlLevels) {   // grey-level non-uniformity: squared row sums
-            double rs = 0.0;
-            for (int j = 0; j < kRlMax; ++j) rs += (double)s_R[tid * kRlMax + j];
-            v[14] = rs * rs;
+        if (tid < kRlLevels) {   // grey-level non-uniformity: squared row sums (exact integers)
+            uint32_t rs = 0;
+            for (int j = 0; j < kRlMax; ++j) rs += s_R[tid * kRlMax + j];
+            v[14] = (float)rs * (float)rs;
         }
         if (tid < kRlMax) {      // run-length non-uniformity: squared column sums
-            double cs = 0.0;
-            for (int l = 0; l < kRlLevels; ++l) cs += (double)s_R[l * kRlMax + tid];
-            v[15] = cs * cs;
+            uint32_t cs = 0;
+            for (int l = 0; l < kRlLevels; ++l) cs += s_R[l * kRlMax + tid];
+            v[15] = (float)cs * (float)cs;
         }
         block_sum<16>(v, s_red);
         if (tid == 0) {
             float* o_ = out + d * 17;
-            const double nr = v[0], mean = v[13] / nr;
+            const double nr = v[0], mean = (double)v[13] / nr;
             o_[0] = (float)(v[1] / nr);  o_[1] = (float)(v[2] / nr);
             o_[2] = (float)(v[14] / nr); o_[3] = (float)(v[15] / nr);
             o_[4] = (float)(v[3] / nr);  o_[5] = (float)(v[4] / nr);
@@ -158,34 +196,43 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             o_[8] = (float)(v[7] / nr);  o_[9] = (float)(v[8] / nr);
             o_[10] = (float)(v[9] / nr); o_[11] = (float)(v[10] / nr);
             o_[12] = (float)(v[11] / nr); o_[13] = (float)(v[12] / nr);
-            o_[14] = (float)(nr / K);                        // run percentage
+            o_[14] = (float)(nr / (double)K);                // run percentage
             o_[15] = (float)mean;                            // run length mean
-            o_[16] = (float)(v[2] / nr - mean * mean);       // run length variance
+            o_[16] = (float)((double)v[2] / nr - mean * mean);   // run length variance
         }
         __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dynamic smem: slab(window) | G[(P+29)][GS] f32 | A[(P+29)][P] f32 | B[(P+29)][P] f32 | rows | list u16
+// k_gabor. cos is even, so the kernels of theta and theta + 180 degrees are identical: 24 distinct
+// filters. Per frequency f (w = 2 pi f, w' = w cos 45):
+//   theta =   0: cos(w u)          -> rows with G cos(w u),  columns with G          (1 plane)
+//   theta =  90: cos(w v)          -> rows with G,           columns with G cos(w v) (plane A0, shared by all f)
+//   theta =  45: cos(w'u + w'v)    -> p - q   where p = (G cos w'u rows)(G cos w'v cols),
+//   theta = 135: cos(-w'u + w'v)   -> p + q         q = (G sin w'u rows)(G sin w'v cols)
+// Row passes are register tiled (4 outputs per thread from 9 float4 loads); column passes run at the
+// masked pixels only. Dynamic smem: G[(P+29)][GS] | A0 | A | B ([(P+29)][P] each; the TMA window
+// lands in A) | rows | list.
 __global__ void __launch_bounds__(kTexThreads)
 k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, P rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kTexThreads / 32;
-    const int PH = P + kGaborK - 1, GS = P + kGaborK;   // padded height / row stride of G
+    const int PH = P + kGaborK - 1, GS = (P + kGaborK + 5) & ~3;   // padded height / row stride (multiple of 4 floats, +4 slack)
     const int64_t i = blockIdx.x;
-    uint8_t* patch = smem_raw;
-    float* G = reinterpret_cast<float*>(smem_raw + patch_smem_bytes(P));
-    float* A = G + PH * GS;
+    float* G = reinterpret_cast<float*>(smem_raw);
+    float* A0 = G + PH * GS;
+    float* A = A0 + PH * P;
     float* B = A + PH * P;
+    uint8_t* patch = reinterpret_cast<uint8_t*>(A);   // the window is consumed before A is written
     uint32_t* rows = reinterpret_cast<uint32_t*>(B + PH * P);
     uint16_t* list = reinterpret_cast<uint16_t*>(rows + P * wpr);
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
     __shared__ int s_scan[NW + 1];
     __shared__ int s_box[4];
-    __shared__ double s_red[2 * NW];
+    __shared__ double s_red[8 * NW];
 
     const NucInfo inf = p.info[i];
     const int o = patch_byte_offset(inf.left);
@@ -265,44 +312,102 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         }
         G[(r + kGaborLo) * GS + c + kGaborLo] = g;
     }
-    __syncthreads();
-    const int bw = cmax - cmin + 1, nrow = rmax - rmin + kGaborK;   // row pass: padded rows rmin .. rmax+29
-    for (int f = 0; f < kGaborFilters; ++f) {
-        // ---- row pass: A = G (*) cu, B = G (*) su over the bounding box columns ----
-        for (int k = tid; k < nrow * bw; k += kTexThreads) {
-            const int pr = rmin + k / bw, c = cmin + k % bw;   // padded row, patch column
-            const float* g = G + pr * GS + c;                  // taps cover padded columns c .. c+29
-            float a = 0.f, b = 0.f;
+    __syncthreads();   // the window (aliased with A) is dead from here on
+
+    const int cq0 = cmin & ~3, nquad = ((cmax - cq0) >> 2) + 1;   // column quads of the bounding box
+    const int nrow = rmax - rmin + kGaborK;                       // padded rows rmin .. rmax+29
+    // Row pass, 4 outputs per thread: out[c0+m] = sum_t G[pr][c0+m+t] * tap[t], m = 0..3.
+    // MODE 0: A0 <- envelope; MODE 1: A <- profile 0 (cos w); MODE 2: A,B <- profiles 2,3 (cos/sin w').
+    auto row_pass = [&](int mode, int q) {
+        for (int k = tid; k < nrow * nquad; k += kTexThreads) {
+            const int pr = rmin + k / nquad, c0 = cq0 + 4 * (k % nquad);
+            const float4* g4 = reinterpret_cast<const float4*>(G + pr * GS + c0);
+            float x[36];
+#pragma unroll
+            for (int m = 0; m < 9; ++m) {
+                const float4 v = g4[m];
+                x[4 * m] = v.x; x[4 * m + 1] = v.y; x[4 * m + 2] = v.z; x[4 * m + 3] = v.w;
+            }
+            float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int t = 0; t < kGaborK; ++t) {
-                const float x = g[t];
-                a = fmaf(x, c_gabor[f][0][t], a);
-                b = fmaf(x, c_gabor[f][1][t], b);
-            }
-            A[pr * P + c] = a;
-            B[pr * P + c] = b;
-        }
-        __syncthreads();
-        // ---- column pass at the masked pixels: out = A (*) cv - B (*) sv ; masked mean / variance ----
-        double s[2] = {0.0, 0.0};
-        for (int j = tid; j < K; j += kTexThreads) {
-            const uint32_t rc = list[j];
-            const float* a = A + (rc >> 8) * P + (rc & 255);   // padded rows r .. r+29
-            const float* b = B + (rc >> 8) * P + (rc & 255);
-            float v = 0.f;
+                const float ta = mode == 0 ? c_genv[t] : (mode == 1 ? c_gtap[q][0][t] : c_gtap[q][2][t]);
+                const float tb = c_gtap[q][3][t];
 #pragma unroll
-            for (int t = 0; t < kGaborK; ++t) {
-                v = fmaf(a[t * P], c_gabor[f][2][t], v);
-                v = fmaf(-b[t * P], c_gabor[f][3][t], v);
+                for (int m = 0; m < 4; ++m) {
+                    a[m] = fmaf(x[m + t], ta, a[m]);
+                    if (mode == 2) b[m] = fmaf(x[m + t], tb, b[m]);
+                }
             }
-            s[0] += (double)v;
-            s[1] += (double)v * (double)v;
+            float* dst = (mode == 0 ? A0 : A) + pr * P + c0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (c0 + m < P) {
+                    dst[m] = a[m];
+                    if (mode == 2) B[pr * P + c0 + m] = b[m];
+                }
+            }
         }
-        block_sum<2>(s, s_red);   // also separates this filter's planes from the next row pass
+    };
+    // masked sums of up to 2 filter outputs -> (mean, variance) columns of the given filter indices
+    auto finish = [&](double (&s)[4], int f_a, int f_b) {
+        block_sum<4>(s, s_red);   // also orders this pass before the planes are overwritten
         if (tid == 0) {
-            const double mean = s[0] / (double)K;
-            out[2 * f] = (float)mean;
-            out[2 * f + 1] = (float)fmax(s[1] / (double)K - mean * mean, 0.0);
+            const double Kd = (double)K;
+            const int fs[2] = {f_a, f_b};
+            for (int h = 0; h < 2; ++h) {
+                if (fs[h] < 0) continue;
+                const double mean = s[2 * h] / Kd;
+                const float mf = (float)mean, vf = (float)fmax(s[2 * h + 1] / Kd - mean * mean, 0.0);
+                out[2 * fs[h]] = mf; out[2 * fs[h] + 1] = vf;
+                out[2 * (fs[h] + 24)] = mf; out[2 * (fs[h] + 24) + 1] = vf;   // theta + 180 degrees: same kernel
+            }
+        }
+    };
+
+    row_pass(0, 0);
+    __syncthreads();
+    for (int q = 0; q < 6; ++q) {
+        // theta = 0 (filter q): rows cos(w u) -> A, columns envelope ; theta = 90 (filter 12+q): A0, columns cos(w v)
+        row_pass(1, q);
+        __syncthreads();
+        {
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int j = tid; j < K; j += kTexThreads) {
+                const uint32_t rc = list[j];
+                const float* a = A + (rc >> 8) * P + (rc & 255);    // padded rows r .. r+29
+                const float* a0 = A0 + (rc >> 8) * P + (rc & 255);
+                float v0 = 0.f, v90 = 0.f;
+#pragma unroll
+                for (int t = 0; t < kGaborK; ++t) {
+                    v0 = fmaf(a[t * P], c_genv[t], v0);
+                    v90 = fmaf(a0[t * P], c_gtap[q][0][t], v90);
+                }
+                s[0] += (double)v0;  s[1] += (double)v0 * (double)v0;
+                s[2] += (double)v90; s[3] += (double)v90 * (double)v90;
+            }
+            finish(s, q, 12 + q);
+        }
+        // theta = 45 (filter 6+q) and 135 (filter 18+q): p -/+ q
+        row_pass(2, q);
+        __syncthreads();
+        {
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int j = tid; j < K; j += kTexThreads) {
+                const uint32_t rc = list[j];
+                const float* a = A + (rc >> 8) * P + (rc & 255);
+                const float* b = B + (rc >> 8) * P + (rc & 255);
+                float pp = 0.f, qq = 0.f;
+#pragma unroll
+                for (int t = 0; t < kGaborK; ++t) {
+                    pp = fmaf(a[t * P], c_gtap[q][2][t], pp);
+                    qq = fmaf(b[t * P], c_gtap[q][3][t], qq);
+                }
+                const float v45 = pp - qq, v135 = pp + qq;
+                s[0] += (double)v45;  s[1] += (double)v45 * (double)v45;
+                s[2] += (double)v135; s[3] += (double)v135 * (double)v135;
+            }
+            finish(s, 6 + q, 18 + q);
         }
     }
 }
@@ -318,28 +423,31 @@ static cudaError_t ensure_gabor_taps() {
     if (e != cudaSuccess) return e;
     if (dev < 64 && g_taps_ready[dev]) return cudaSuccess;
     // oracle gabor_bank: taps on linspace(-1,1,30), theta = angle_idx*2*pi/8, sigma = 0.45 (texture.rs:319-334)
-    static float h[kGaborFilters][4][kGaborK];
+    static float h[6][4][kGaborK], env[kGaborK];
     const double freqs[6] = {0.5, 1.0, 2.0, 4.0, 6.0, 8.0}, sigma = 0.45, pi = 3.14159265358979323846;
-    for (int a = 0; a < 8; ++a)
+    for (int t = 0; t < kGaborK; ++t) {
+        const double u = -1.0 + 2.0 * t / (kGaborK - 1), ge = exp(-u * u / (2.0 * sigma * sigma));
+        env[t] = (float)ge;
         for (int q = 0; q < 6; ++q) {
-            const double th = a * 2.0 * pi / 8.0, wa = 2.0 * pi * freqs[q] * cos(th), wb = 2.0 * pi * freqs[q] * sin(th);
-            for (int t = 0; t < kGaborK; ++t) {
-                const double u = -1.0 + 2.0 * t / (kGaborK - 1), ge = exp(-u * u / (2.0 * sigma * sigma));
-                h[a * 6 + q][0][t] = (float)(ge * cos(wa * u));
-                h[a * 6 + q][1][t] = (float)(ge * sin(wa * u));
-                h[a * 6 + q][2][t] = (float)(ge * cos(wb * u));
-                h[a * 6 + q][3][t] = (float)(ge * sin(wb * u));
-            }
+            const double w = 2.0 * pi * freqs[q], w2 = w * cos(pi / 4.0);
+            h[q][0][t] = (float)(ge * cos(w * u));
+            h[q][1][t] = (float)(ge * sin(w * u));
+            h[q][2][t] = (float)(ge * cos(w2 * u));
+            h[q][3][t] = (float)(ge * sin(w2 * u));
         }
-    e = cudaMemcpyToSymbol(c_gabor, h, sizeof(h));
+    }
+    e = cudaMemcpyToSymbol(c_gtap, h, sizeof(h));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_genv, env, sizeof(env));
     if (e == cudaSuccess && dev < 64) g_taps_ready[dev] = true;
     return e;
 }
 
 cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
-    const int smem = window_smem_bytes(p.P, p.slab_rows) + ((p.P * p.P + 15) & ~15) + p.P * mask_wpr(p.P) * 4;
-    cudaError_t e = cudaFuncSetAttribute(k_glrlm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e;
+    const int rx = window_smem_bytes(p.P, p.slab_rows) > ((p.P * p.P * 2 + 127) & ~127) ? window_smem_bytes(p.P, p.slab_rows) : ((p.P * p.P * 2 + 127) & ~127);
+    const int smem = rx + ((p.P * p.P + 15) & ~15) + p.P * mask_wpr(p.P) * 4;
+    e = cudaFuncSetAttribute(k_glrlm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k_glrlm<<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_cslab);
     return cudaGetLastError();
@@ -349,8 +457,8 @@ cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map_patch, cudaS
     if (p.n <= 0) return cudaSuccess;
     cudaError_t e = ensure_gabor_taps();
     if (e != cudaSuccess) return e;
-    const int P = p.P, PH = P + kGaborK - 1;
-    const int smem = patch_smem_bytes(P) + PH * (P + kGaborK) * 4 + 2 * PH * P * 4 + P * mask_wpr(P) * 4 + P * P * 2;
+    const int P = p.P, PH = P + kGaborK - 1, GS = (P + kGaborK + 5) & ~3;
+    const int smem = PH * GS * 4 + 3 * PH * P * 4 + P * mask_wpr(P) * 4 + P * P * 2;
     e = cudaFuncSetAttribute(k_gabor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k_gabor<<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_patch);

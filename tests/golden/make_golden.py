@@ -28,7 +28,7 @@ def golden_case():
 if __name__ == "__main__":
     tile, xy, off = golden_case()
     rings = synth.rings_of(xy, off)
-    keys, cents, feats, names = o.extract(rings, tile, ["all"][:0] + ["geometry", "color", "glcm"], 64, 20)
+    keys, cents, feats, names = o.extract(rings, tile, ["all"], 64, 20)
     masks = np.stack([o.polygon_mask(64, 64, o.preprocess_polygon(r)[1].astype(np.float64)) for r in rings])
     patches = np.stack([o.gather_patch_u8(tile, c, 64) for c in cents])
     np.savez_compressed(os.path.join(HERE, "oracle_small.npz"),

@@ -18,7 +18,7 @@ def test_oracle_reproduces_golden_vectors():
     assert int(tile.astype(np.uint64).sum()) == int(g["tile_crc"][0])
     assert np.array_equal(xy, g["xy"]) and np.array_equal(off, g["off"])
     rings = synth.rings_of(xy, off)
-    keys, cents, feats, names = o.extract(rings, tile, ["geometry", "color", "glcm"], 64, 20)
+    keys, cents, feats, names = o.extract(rings, tile, ["all"], 64, 20)
     assert list(g["names"]) == names and list(g["keys"]) == keys
     assert np.array_equal(cents, g["centroids"])
     assert np.allclose(feats, g["features"], rtol=1e-5, atol=1e-7, equal_nan=True)
