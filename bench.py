@@ -345,7 +345,8 @@ def main():
     sampler.start()
     t_w = time.perf_counter()
     nw = 0
-    while nw < W or (time.perf_counter() - t_w < 0.25 and nw < 2000):   # >= W warm-up steps, >= 0.25 s under load
+    exact = bool(os.environ.get("NFX_BENCH_EXACT_WARMUP"))   # profiling runs: exactly W warm-up steps
+    while nw < W or (not exact and time.perf_counter() - t_w < 0.25 and nw < 2000):   # >= W steps, >= 0.25 s under load
         ex.compute(mask)
         nw += 1
         if nw % 8 == 0:
@@ -414,10 +415,18 @@ def main():
             v["share"] = v["avg_ms"] / tot
             v["gbs"] = kernel_bytes(k, P, slabs) * nuclei / (v["avg_ms"] * 1e-3) / 1e9 if v["avg_ms"] > 0 else 0.0
         dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            ent = tj.get(args.workload, {}).get(dom)
+            if ent and ent["nuclei"] == nuclei and ent["patch"] == P:
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = None
         if dom:
             roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                    "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
                     "bytes_per_nucleus": kernel_bytes(dom, P, slabs), "avg_launch_ms": kern[dom]["avg_ms"],
                     "pipeline_bytes_per_nucleus": algorithmic_bytes(args.workload, P, F),
                     "pipeline_frac": value / world * algorithmic_bytes(args.workload, P, F) / 1e9 / hbm_peak}

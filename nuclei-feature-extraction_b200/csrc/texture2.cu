@@ -208,31 +208,34 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 // k_gabor. cos is even, so the kernels of theta and theta + 180 degrees are identical: 24 distinct
 // filters. Per frequency f (w = 2 pi f, w' = w cos 45):
 //   theta =   0: cos(w u)          -> rows with G cos(w u),  columns with G          (1 plane)
-//   theta =  90: cos(w v)          -> rows with G,           columns with G cos(w v) (plane A0, shared by all f)
+//   theta =  90: cos(w v)          -> rows with G (ONE plane for all six f), columns with G cos(w v)
 //   theta =  45: cos(w'u + w'v)    -> p - q   where p = (G cos w'u rows)(G cos w'v cols),
 //   theta = 135: cos(-w'u + w'v)   -> p + q         q = (G sin w'u rows)(G sin w'v cols)
-// Row passes are register tiled (4 outputs per thread from 9 float4 loads); column passes run at the
-// masked pixels only. Dynamic smem: G[(P+29)][GS] | A0 | A | B ([(P+29)][P] each; the TMA window
-// lands in A) | rows | list.
-__global__ void __launch_bounds__(kTexThreads)
+// Row passes are register tiled (4 outputs per thread from 9 float4 loads, row index fastest across
+// the lanes; the plane strides are 4 (mod 32) floats so that float4 loads and stores are bank-conflict
+// free); column passes run at the masked pixels only.
+// Dynamic smem: G[(P+29)][GS] | A[(P+29)][PS] (the TMA window lands here first) | B[(P+29)][PS] | rows | list.
+__host__ __device__ __forceinline__ int gabor_gs(int P) { return ((P + kGaborK + 31) & ~31) + 4; }   // >= P+34, = 4 mod 32
+__host__ __device__ __forceinline__ int gabor_ps(int P) { return ((P + 27) & ~31) + 4; }             // >= P,    = 4 mod 32
+
+__global__ void __launch_bounds__(kTexThreads, 2)
 k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, P rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kTexThreads / 32;
-    const int PH = P + kGaborK - 1, GS = (P + kGaborK + 5) & ~3;   // padded height / row stride (multiple of 4 floats, +4 slack)
+    const int PH = P + kGaborK - 1, GS = gabor_gs(P), PS = gabor_ps(P);
     const int64_t i = blockIdx.x;
     float* G = reinterpret_cast<float*>(smem_raw);
-    float* A0 = G + PH * GS;
-    float* A = A0 + PH * P;
-    float* B = A + PH * P;
+    float* A = G + ((PH * GS + 31) & ~31);
+    float* B = A + ((PH * PS + 31) & ~31);
     uint8_t* patch = reinterpret_cast<uint8_t*>(A);   // the window is consumed before A is written
-    uint32_t* rows = reinterpret_cast<uint32_t*>(B + PH * P);
+    uint32_t* rows = reinterpret_cast<uint32_t*>(B + ((PH * PS + 31) & ~31));
     uint16_t* list = reinterpret_cast<uint16_t*>(rows + P * wpr);
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
     __shared__ int s_scan[NW + 1];
     __shared__ int s_box[4];
-    __shared__ double s_red[8 * NW];
+    __shared__ double s_red[12 * NW];
 
     const NucInfo inf = p.info[i];
     const int o = patch_byte_offset(inf.left);
@@ -317,10 +320,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const int cq0 = cmin & ~3, nquad = ((cmax - cq0) >> 2) + 1;   // column quads of the bounding box
     const int nrow = rmax - rmin + kGaborK;                       // padded rows rmin .. rmax+29
     // Row pass, 4 outputs per thread: out[c0+m] = sum_t G[pr][c0+m+t] * tap[t], m = 0..3.
-    // MODE 0: A0 <- envelope; MODE 1: A <- profile 0 (cos w); MODE 2: A,B <- profiles 2,3 (cos/sin w').
+    // MODE 0: B <- envelope (the theta = 90 plane); MODE 1: A <- profile 0 (cos w); MODE 2: A,B <- profiles 2,3.
     auto row_pass = [&](int mode, int q) {
         for (int k = tid; k < nrow * nquad; k += kTexThreads) {
-            const int pr = rmin + k / nquad, c0 = cq0 + 4 * (k % nquad);
+            const int pr = rmin + k % nrow, c0 = cq0 + 4 * (k / nrow);   // row index fastest across the lanes
             const float4* g4 = reinterpret_cast<const float4*>(G + pr * GS + c0);
             float x[36];
 #pragma unroll
@@ -339,75 +342,87 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                     if (mode == 2) b[m] = fmaf(x[m + t], tb, b[m]);
                 }
             }
-            float* dst = (mode == 0 ? A0 : A) + pr * P + c0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                if (c0 + m < P) {
-                    dst[m] = a[m];
-                    if (mode == 2) B[pr * P + c0 + m] = b[m];
-                }
-            }
+            float4* da = reinterpret_cast<float4*>((mode == 0 ? B : A) + pr * PS + c0);
+            *da = make_float4(a[0], a[1], a[2], a[3]);
+            if (mode == 2) *reinterpret_cast<float4*>(B + pr * PS + c0) = make_float4(b[0], b[1], b[2], b[3]);
         }
     };
-    // masked sums of up to 2 filter outputs -> (mean, variance) columns of the given filter indices
-    auto finish = [&](double (&s)[4], int f_a, int f_b) {
-        block_sum<4>(s, s_red);   // also orders this pass before the planes are overwritten
+    // masked sums of NF filter outputs -> (mean, variance) columns of filters f0 + h*fstep (and + 24)
+    auto finish = [&](double* s, int nf, int f0, int fstep) {
+        double v[12];
+#pragma unroll
+        for (int h = 0; h < 12; ++h) v[h] = h < 2 * nf ? s[h] : 0.0;
+        block_sum<12>(v, s_red);   // also orders this pass before the planes are overwritten
         if (tid == 0) {
             const double Kd = (double)K;
-            const int fs[2] = {f_a, f_b};
-            for (int h = 0; h < 2; ++h) {
-                if (fs[h] < 0) continue;
-                const double mean = s[2 * h] / Kd;
-                const float mf = (float)mean, vf = (float)fmax(s[2 * h + 1] / Kd - mean * mean, 0.0);
-                out[2 * fs[h]] = mf; out[2 * fs[h] + 1] = vf;
-                out[2 * (fs[h] + 24)] = mf; out[2 * (fs[h] + 24) + 1] = vf;   // theta + 180 degrees: same kernel
+            for (int h = 0; h < nf; ++h) {
+                const int f = f0 + h * fstep;
+                const double mean = v[2 * h] / Kd;
+                const float mf = (float)mean, vf = (float)fmax(v[2 * h + 1] / Kd - mean * mean, 0.0);
+                out[2 * f] = mf; out[2 * f + 1] = vf;
+                out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf;   // theta + 180 degrees: same kernel
             }
         }
     };
 
+    // ---- theta = 90 (filters 12..17): one envelope-filtered plane, six column profiles ----
     row_pass(0, 0);
     __syncthreads();
+    {
+        double s[12];
+#pragma unroll
+        for (int h = 0; h < 12; ++h) s[h] = 0.0;
+        for (int j = tid; j < K; j += kTexThreads) {
+            const uint32_t rc = list[j];
+            const float* a0 = B + (rc >> 8) * PS + (rc & 255);   // padded rows r .. r+29
+            float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < kGaborK; ++t) {
+                const float x = a0[t * PS];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) v[q] = fmaf(x, c_gtap[q][0][t], v[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { s[2 * q] += (double)v[q]; s[2 * q + 1] += (double)v[q] * (double)v[q]; }
+        }
+        finish(s, 6, 12, 1);
+    }
     for (int q = 0; q < 6; ++q) {
-        // theta = 0 (filter q): rows cos(w u) -> A, columns envelope ; theta = 90 (filter 12+q): A0, columns cos(w v)
+        // ---- theta = 0 (filter q): rows cos(w u) -> A, columns envelope ----
         row_pass(1, q);
         __syncthreads();
         {
-            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            double s[2] = {0.0, 0.0};
             for (int j = tid; j < K; j += kTexThreads) {
                 const uint32_t rc = list[j];
-                const float* a = A + (rc >> 8) * P + (rc & 255);    // padded rows r .. r+29
-                const float* a0 = A0 + (rc >> 8) * P + (rc & 255);
-                float v0 = 0.f, v90 = 0.f;
+                const float* a = A + (rc >> 8) * PS + (rc & 255);
+                float v0 = 0.f;
 #pragma unroll
-                for (int t = 0; t < kGaborK; ++t) {
-                    v0 = fmaf(a[t * P], c_genv[t], v0);
-                    v90 = fmaf(a0[t * P], c_gtap[q][0][t], v90);
-                }
-                s[0] += (double)v0;  s[1] += (double)v0 * (double)v0;
-                s[2] += (double)v90; s[3] += (double)v90 * (double)v90;
+                for (int t = 0; t < kGaborK; ++t) v0 = fmaf(a[t * PS], c_genv[t], v0);
+                s[0] += (double)v0; s[1] += (double)v0 * (double)v0;
             }
-            finish(s, q, 12 + q);
+            finish(s, 1, q, 1);
         }
-        // theta = 45 (filter 6+q) and 135 (filter 18+q): p -/+ q
+        // ---- theta = 45 (filter 6+q) and 135 (filter 18+q): p -/+ q ----
         row_pass(2, q);
         __syncthreads();
         {
             double s[4] = {0.0, 0.0, 0.0, 0.0};
             for (int j = tid; j < K; j += kTexThreads) {
                 const uint32_t rc = list[j];
-                const float* a = A + (rc >> 8) * P + (rc & 255);
-                const float* b = B + (rc >> 8) * P + (rc & 255);
+                const float* a = A + (rc >> 8) * PS + (rc & 255);
+                const float* b = B + (rc >> 8) * PS + (rc & 255);
                 float pp = 0.f, qq = 0.f;
 #pragma unroll
                 for (int t = 0; t < kGaborK; ++t) {
-                    pp = fmaf(a[t * P], c_gtap[q][2][t], pp);
-                    qq = fmaf(b[t * P], c_gtap[q][3][t], qq);
+                    pp = fmaf(a[t * PS], c_gtap[q][2][t], pp);
+                    qq = fmaf(b[t * PS], c_gtap[q][3][t], qq);
                 }
                 const float v45 = pp - qq, v135 = pp + qq;
                 s[0] += (double)v45;  s[1] += (double)v45 * (double)v45;
                 s[2] += (double)v135; s[3] += (double)v135 * (double)v135;
             }
-            finish(s, 6 + q, 18 + q);
+            finish(s, 2, 6 + q, 12);
         }
     }
 }
@@ -457,8 +472,8 @@ cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map_patch, cudaS
     if (p.n <= 0) return cudaSuccess;
     cudaError_t e = ensure_gabor_taps();
     if (e != cudaSuccess) return e;
-    const int P = p.P, PH = P + kGaborK - 1, GS = (P + kGaborK + 5) & ~3;
-    const int smem = PH * GS * 4 + 3 * PH * P * 4 + P * mask_wpr(P) * 4 + P * P * 2;
+    const int P = p.P, PH = P + kGaborK - 1, GS = gabor_gs(P), PS = gabor_ps(P);
+    const int smem = (((PH * GS + 31) & ~31) + 2 * ((PH * PS + 31) & ~31)) * 4 + P * mask_wpr(P) * 4 + P * P * 2;
     e = cudaFuncSetAttribute(k_gabor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k_gabor<<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_patch);
