@@ -48,9 +48,8 @@ __device__ __forceinline__ bool ellipse_inside(double x, double y, double cx, do
     return val <= 1.0;
 }
 
-__device__ __forceinline__ double cross3(float2 o, float2 a, float2 b) {
-    return ((double)a.x - (double)o.x) * ((double)b.y - (double)o.y) -
-           ((double)a.y - (double)o.y) * ((double)b.x - (double)o.x);
+__device__ __forceinline__ double cross3(double2 o, double2 a, double2 b) {
+    return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x);
 }
 
 template <bool RASTER, bool SHAPE>
@@ -61,10 +60,10 @@ __global__ void __launch_bounds__(kGeomThreads) k_geom(const GeomParams p) {
     const int64_t o0 = p.poly_off[i];
     const int V = (int)(p.poly_off[i + 1] - o0);
 
-    // shared layout: rows[P*wpr] u32 | pts[vmax] float2 | sorted[vmax] float2 | stk[2*vmax] int
+    // shared layout: rows[P*wpr] u32 | pts[vmax] float2 | sorted[vmax] double2 | stk[2*vmax] int
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw);
-    float2* pts = reinterpret_cast<float2*>(rows + ((P * wpr + 1) & ~1));
-    float2* sorted = pts + p.vmax;
+    float2* pts = reinterpret_cast<float2*>(rows + ((P * wpr + 3) & ~3));
+    double2* sorted = reinterpret_cast<double2*>(pts + ((p.vmax + 1) & ~1));   // 16-byte aligned
     int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? p.vmax : 0));
     __shared__ double s_red[16];
     __shared__ float s_c[2];
@@ -168,7 +167,7 @@ __global__ void __launch_bounds__(kGeomThreads) k_geom(const GeomParams p) {
             const float2 b = pts[m];
             rank += (b.x < a.x) || (b.x == a.x && (b.y < a.y || (b.y == a.y && m < k)));
         }
-        sorted[rank] = a;
+        sorted[rank] = make_double2((double)a.x, (double)a.y);   // converted once: the chain is latency bound
     }
     __syncthreads();
     if (tid == 0 || tid == 32) {
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(kGeomThreads) k_geom(const GeomParams p) {
         int sz = 0;
         for (int t = 0; t < V; ++t) {
             const int idx = (tid == 0) ? t : V - 1 - t;
-            const float2 q = sorted[idx];
+            const double2 q = sorted[idx];
             while (sz >= 2 && cross3(sorted[S[sz - 2]], sorted[S[sz - 1]], q) <= 0.0) --sz;
             S[sz++] = idx;
         }
@@ -185,12 +184,12 @@ __global__ void __launch_bounds__(kGeomThreads) k_geom(const GeomParams p) {
     __syncthreads();
     if (tid == 0) {
         const int nl = max(s_hull[0] - 1, 0), nu = max(s_hull[1] - 1, 0), h = nl + nu;
-        auto hp = [&](int k) -> float2 { return sorted[k < nl ? stk[k] : stk[p.vmax + (k - nl)]]; };
+        auto hp = [&](int k) -> double2 { return sorted[k < nl ? stk[k] : stk[p.vmax + (k - nl)]]; };
         double sh = 0.0, per = 0.0;
         for (int k = 0; k < h; ++k) {
-            const float2 a = hp(k), b = hp(k + 1 == h ? 0 : k + 1);
-            sh += (double)a.x * (double)b.y - (double)b.x * (double)a.y;
-            const double ex = (double)b.x - (double)a.x, ey = (double)b.y - (double)a.y;
+            const double2 a = hp(k), b = hp(k + 1 == h ? 0 : k + 1);
+            sh += a.x * b.y - b.x * a.y;
+            const double ex = b.x - a.x, ey = b.y - a.y;
             per += sqrt(ex * ex + ey * ey);
         }
         const double harea = (h >= 3) ? 0.5 * fabs(sh) : 0.0;
@@ -313,8 +312,8 @@ __global__ void __launch_bounds__(kGeomThreads) k_geom(const GeomParams p) {
 cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     const int wpr = mask_wpr(p.P);
-    size_t smem = (size_t)((p.P * wpr + 1) & ~1) * 4 + (size_t)p.vmax * 8;
-    if (shape) smem += (size_t)p.vmax * 8 + (size_t)p.vmax * 2 * 4;
+    size_t smem = (size_t)((p.P * wpr + 3) & ~3) * 4 + (size_t)((p.vmax + 1) & ~1) * 8;
+    if (shape) smem += (size_t)p.vmax * 16 + (size_t)p.vmax * 2 * 4;
     auto go = [&](auto kern) -> cudaError_t {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
