@@ -20,7 +20,9 @@ namespace nfx {
 
 namespace {
 
-constexpr int kGeomThreads = 64;
+// The raster-only variant runs one warp per nucleus (a ring has ~30 edges: a second warp only doubles the
+// issue slots of the serial parts); the shape variant keeps two warps for its two hull chains.
+template <bool SHAPE> struct GeomCfg { static constexpr int kThreads = SHAPE ? 64 : 32; };
 
 // first index k in [0,P] such that (k - P/2) >= v   (exact; v may be any double)
 __device__ __forceinline__ int first_index_geq(double v, int P) {
@@ -53,7 +55,8 @@ __device__ __forceinline__ double cross3(double2 o, double2 a, double2 b) {
 }
 
 template <bool RASTER, bool SHAPE>
-__global__ void __launch_bounds__(kGeomThreads) k_geom(const GeomParams p) {
+__global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads) k_geom(const GeomParams p) {
+    constexpr int kGeomThreads = GeomCfg<SHAPE>::kThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x;
     const int64_t i = blockIdx.x;
@@ -314,16 +317,16 @@ cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream
     const int wpr = mask_wpr(p.P);
     size_t smem = (size_t)((p.P * wpr + 3) & ~3) * 4 + (size_t)((p.vmax + 1) & ~1) * 8;
     if (shape) smem += (size_t)p.vmax * 16 + (size_t)p.vmax * 2 * 4;
-    auto go = [&](auto kern) -> cudaError_t {
+    auto go = [&](auto kern, int threads) -> cudaError_t {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<(unsigned)p.n, kGeomThreads, smem, s>>>(p);
+        kern<<<(unsigned)p.n, threads, smem, s>>>(p);
         return cudaGetLastError();
     };
-    if (raster) return shape ? go(k_geom<true, true>) : go(k_geom<true, false>);
-    return shape ? go(k_geom<false, true>) : cudaSuccess;
+    if (raster) return shape ? go(k_geom<true, true>, GeomCfg<true>::kThreads) : go(k_geom<true, false>, GeomCfg<false>::kThreads);
+    return shape ? go(k_geom<false, true>, GeomCfg<true>::kThreads) : cudaSuccess;
 }
 
 }  // namespace nfx
