@@ -254,6 +254,14 @@ def cpu_reference_rate(sets, tile, xy, off, P, batch, sample, workers):
     return sample / dt, dt
 
 
+def workload_config(args, sets, nuclei, side, P):
+    """The `config` object: identical for this repo's arm and for the reference arm."""
+    return {"workload": f"{args.workload}: {'+'.join(sets)} feature set(s), {nuclei} nuclei per GPU, "
+                        f"{P}x{P} windows, tile {side}x{side} u8 RGB per GPU, batch_size={args.batch_size}",
+            "l2": f"inputs > L2: tile {3 * side * side / 1e6:.0f} MB per GPU (L2 126 MB)",
+            "partition": "contiguous index ranges per GPU, no collective"}
+
+
 def cpu_workers():
     return max(1, min(os.cpu_count() or 1, 16))   # bounded: each colour chunk holds ~1 GB of [N,N,P,P] f32
 
@@ -301,11 +309,10 @@ def main():
             "impl": "reference", "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": args.gpus,
             "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(rates), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {'+'.join(sets)} feature set(s), P={P}, batch_size={args.batch_size}",
-                       "sample": f"{sample} nuclei per step on a {min(side, 4096)}^2 tile"},
+            "config": workload_config(args, sets, nuclei, side, P),
             "cpu_baseline": {"value": value, "unit": "nuclei/s", "cores": workers, "kind": "port",
-                             "sample": f"{sample} nuclei/step x {K} steps, oracle (torch-CPU restatement of the tch path), "
-                                       f"{workers} chunk-parallel host threads of {cores} cores"},
+                             "sample": f"{sample} nuclei of the workload per step on a {min(side, 4096)}^2 tile x {K} steps, oracle "
+                                       f"(torch-CPU restatement of the tch path), {workers} chunk-parallel host threads of {cores} cores"},
             "e2e": {"value": value, "unit": "nuclei/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -443,10 +450,7 @@ def main():
             "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_steps_run": nw,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {'+'.join(sets)} feature set(s), {nuclei} nuclei per GPU, "
-                                   f"{P}x{P} windows, tile {side}x{side} u8 RGB per GPU, batch_size={args.batch_size}",
-                       "l2": f"inputs > L2: tile {tile.nbytes / 1e6:.0f} MB per GPU (L2 126 MB)",
-                       "partition": "contiguous index ranges per GPU, no collective"},
+            "config": workload_config(args, sets, nuclei, side, P),
             "e2e": None if e2e_ms is None else {"value": total / (e2e_ms * 1e-3), "unit": "nuclei/s",
                                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                                  "ms_per_step": e2e_ms},

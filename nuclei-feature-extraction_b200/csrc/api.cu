@@ -407,7 +407,7 @@ int nfx_polygons_upload(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int
         for (int64_t i = 0; i < n; ++i) {
             const int64_t v = poly_off[i + 1] - poly_off[i];
             if (v < 0) return fail(ctx, NFX_ERR_INVALID, "poly_off must be non-decreasing");
-            if (v > 8000) return fail(ctx, NFX_ERR_UNSUPPORTED, "ring longer than 8000 vertices");
+            if (v > 4000) return fail(ctx, NFX_ERR_UNSUPPORTED, "ring longer than 4000 vertices (k_geom keeps the ring in shared memory)");
             vmax = std::max<int64_t>(vmax, v);
         }
         total = poly_off[n];
