@@ -385,6 +385,7 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
 //     2^-16 quantum, far below the 1e-4 tolerance) so that warp reduction is one REDUX each;
 //   * tables are cleared densely with 128-bit stores. 3 block barriers per offset.
 // =================================================================================================
+constexpr int kG64Threads = 256, kG64NW = kG64Threads / 32;   // 512 threads measured slower (22.6 vs 20.2 ms / 200k)
 constexpr int kTri32 = 32 * 33 / 2, kTri64 = 64 * 65 / 2, kTri128 = 128 * 129 / 2;
 constexpr int kOffTri128 = 0;                                  // bytes inside region A
 constexpr int kOffTri64 = kOffTri128 + kTri128 * 2;            // 16512
@@ -409,7 +410,7 @@ __host__ __device__ inline Glcm64Smem glcm64_layout(int P) {
     L.list = L.q254 + P * P;
     L.pairs = L.list + P * P * 2;
     L.parts = L.pairs + P * P * 4;
-    L.total = L.parts + kCombos * kNW * kNP * 4;
+    L.total = L.parts + kCombos * kG64NW * kNP * 4;
     return L;
 }
 
@@ -452,7 +453,7 @@ __device__ __forceinline__ uint32_t fix_clnc(uint32_t c) {   // c ln c, 15 fract
     return c ? __float2uint_rn((float)c * __log2f((float)c) * (0.5f * kLnFix)) : 0u;
 }
 
-__global__ void __launch_bounds__(kGlcmThreads, 2)
+__global__ void __launch_bounds__(kG64Threads, 2)
 k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -473,7 +474,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     uint32_t* parts = reinterpret_cast<uint32_t*>(smem_raw + L.parts);   // [combo][warp][kNP]
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
-    __shared__ int s_scan[kNW + 1];
+    __shared__ int s_scan[kG64NW + 1];
     __shared__ int s_np[kGlcmOffsets];
 
     const NucInfo inf = p.info[i];
@@ -484,11 +485,11 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
     }
     if (tid < kGlcmOffsets) s_np[tid] = 0;
-    s_lut[tid] = __fdiv_rn((float)tid, 255.0f);   // utils.rs:172  u8 -> f32 / 255.0
+    if (tid < 256) s_lut[tid] = __fdiv_rn((float)tid, 255.0f);   // utils.rs:172  u8 -> f32 / 255.0
     // ---- mask rows -> shared memory + compacted pixel list ((row << 8) | col) ----
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
     int K = 0;
-    for (int base = 0; base < P * wpr; base += kGlcmThreads) {
+    for (int base = 0; base < P * wpr; base += kG64Threads) {
         const int k = base + tid;
         uint32_t bits = (k < P * wpr) ? gm[k] : 0u;
         if (k < P * wpr) rows[k] = bits;
@@ -504,7 +505,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         __syncthreads();
         int wbase = 0, total = 0;
 #pragma unroll
-        for (int t = 0; t < kNW; ++t) {
+        for (int t = 0; t < kG64NW; ++t) {
             const int v = s_scan[t];
             wbase += (t < warp) ? v : 0;
             total += v;
@@ -536,22 +537,22 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         q254[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253);
     };
     if (dbg_all) {
-        for (int k = tid; k < P * P; k += kGlcmThreads) quantise(k / P, k % P);
+        for (int k = tid; k < P * P; k += kG64Threads) quantise(k / P, k % P);
     } else {
-        for (int j = tid; j < K; j += kGlcmThreads) { const uint32_t rc = list[j]; quantise(rc >> 8, rc & 255); }
+        for (int j = tid; j < K; j += kG64Threads) { const uint32_t rc = list[j]; quantise(rc >> 8, rc & 255); }
     }
     __syncthreads();   // the window is dead from here on: region A becomes the histograms
     {
         uint4* z = reinterpret_cast<uint4*>(smem_raw);
-        for (int k = tid; k < (kOffHash + (4 << lg)) / 16; k += kGlcmThreads) z[k] = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < (kOffHash + (4 << lg)) / 16; k += kG64Threads) z[k] = make_uint4(0, 0, 0, 0);
         uint4* zm = reinterpret_cast<uint4*>(marg);
-        for (int k = tid; k < kMargWords / 4; k += kGlcmThreads) zm[k] = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < kMargWords / 4; k += kG64Threads) zm[k] = make_uint4(0, 0, 0, 0);
     }
     if (dbg_all) {
         int lv = 3;
         for (int t = 0; t < 4; ++t)
             if (c_levels[t] == p.dbg_levels) lv = t;
-        for (int k = tid; k < P * P; k += kGlcmThreads)
+        for (int k = tid; k < P * P; k += kG64Threads)
             p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)((lv == 3) ? q254[k] : (q128[k] >> (2 - lv)));
     }
     __syncthreads();
@@ -560,7 +561,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         const int dy = c_off[oi][0], dx = c_off[oi][1];
         const int dpos = dy * P + dx;
         // ---- pass 1: neighbour test, pair record, atomics of all four levels ----
-        for (int jb = 0; jb < K; jb += kGlcmThreads) {
+        for (int jb = 0; jb < K; jb += kG64Threads) {
             const int j = jb + tid;
             bool has = false;
             int src = 0;
@@ -606,7 +607,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         const int npairs = s_np[oi];
         // ---- pass 2: per-pair cell counts (entropy, ASM) for the four levels ----
         uint32_t sg[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0};
-        for (int k = tid; k < npairs; k += kGlcmThreads) {
+        for (int k = tid; k < npairs; k += kG64Threads) {
             const uint32_t rec = pairs[k];
             const int a3 = rec & 0xff, b3 = (rec >> 8) & 0xff, a2 = (rec >> 16) & 0xff, b2 = rec >> 24;
             const int a1 = a2 >> 1, b1 = b2 >> 1, a0 = a2 >> 2, b0 = b2 >> 2;
@@ -639,7 +640,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
             for (int q = 0; q < kNP; ++q) v[q] = 0u;
             v[0] = sg[lv];
             v[7] = sl[lv];
-            for (int k = tid; k < 2 * NL; k += kGlcmThreads) {
+            for (int k = tid; k < 2 * NL; k += kG64Threads) {
                 const uint32_t kk = (uint32_t)k, c = m[NL + k];           // p_{x+y}
                 v[5] += kk * c;
                 v[6] += kk * kk * c;
@@ -662,16 +663,16 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
 #pragma unroll
             for (int q = 0; q < kNP; ++q) {
                 const uint32_t t = __reduce_add_sync(0xffffffffu, v[q]);
-                if (lane == 0) parts[(combo * kNW + warp) * kNP + q] = t;
+                if (lane == 0) parts[(combo * kG64NW + warp) * kNP + q] = t;
             }
         }
         __syncthreads();
         // ---- dense clear of every table ----
         if (oi + 1 < kGlcmOffsets) {
             uint4* z = reinterpret_cast<uint4*>(smem_raw);
-            for (int k = tid; k < (kOffHash + (4 << lg)) / 16; k += kGlcmThreads) z[k] = make_uint4(0, 0, 0, 0);
+            for (int k = tid; k < (kOffHash + (4 << lg)) / 16; k += kG64Threads) z[k] = make_uint4(0, 0, 0, 0);
             uint4* zm = reinterpret_cast<uint4*>(marg);
-            for (int k = tid; k < kMargWords / 4; k += kGlcmThreads) zm[k] = make_uint4(0, 0, 0, 0);
+            for (int k = tid; k < kMargWords / 4; k += kG64Threads) zm[k] = make_uint4(0, 0, 0, 0);
             __syncthreads();
         }
     }
@@ -686,7 +687,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
             double acc[kNP];
             for (int q = 0; q < kNP; ++q) {
                 unsigned long long t = 0;
-                for (int w = 0; w < kNW; ++w) t += parts[(combo * kNW + w) * kNP + q];
+                for (int w = 0; w < kG64NW; ++w) t += parts[(combo * kG64NW + w) * kNP + q];
                 acc[q] = (double)t;
             }
             haralick_write(o_, 2.0 * (double)npairs, acc[0], acc[7] / 65536.0, acc[1], acc[2], acc[3], acc[4], acc[5], acc[6],
@@ -914,14 +915,14 @@ cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_
         k_glcm_large<<<(unsigned)p.n, kLargeThreads, smem, s>>>(p, *map);
         return cudaGetLastError();
     }
-    auto go = [&](auto kern, int smem) -> cudaError_t {
+    auto go = [&](auto kern, int threads, int smem) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)p.n, kGlcmThreads, smem, s>>>(p, *map);
+        kern<<<(unsigned)p.n, threads, smem, s>>>(p, *map);
         return cudaGetLastError();
     };
-    if (p.P <= 64) return go(k_glcm64, glcm64_layout(p.P).total);
-    return go(k_glcm_generic<false>, glcm_layout(p.P).total);
+    if (p.P <= 64) return go(k_glcm64, kG64Threads, glcm64_layout(p.P).total);
+    return go(k_glcm_generic<false>, kGlcmThreads, glcm_layout(p.P).total);
 }
 
 }  // namespace nfx
