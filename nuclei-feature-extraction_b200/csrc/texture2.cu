@@ -215,15 +215,17 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 // the lanes; the plane strides are 4 (mod 32) floats so that float4 loads and stores are bank-conflict
 // free); column passes run at the masked pixels only.
 // Dynamic smem: G[(P+29)][GS] | A[(P+29)][PS] (the TMA window lands here first) | B[(P+29)][PS] | rows | list.
-__host__ __device__ __forceinline__ int gabor_gs(int P) { return ((P + kGaborK + 31) & ~31) + 4; }   // >= P+34, = 4 mod 32
-__host__ __device__ __forceinline__ int gabor_ps(int P) { return ((P + 27) & ~31) + 4; }             // >= P,    = 4 mod 32
+__host__ __device__ constexpr int gabor_gs(int P) { return ((P + kGaborK + 31) & ~31) + 4; }   // >= P+34, = 4 mod 32
+__host__ __device__ constexpr int gabor_ps(int P) { return ((P + 27) & ~31) + 4; }             // >= P,    = 4 mod 32
 
+template <int kP>   // kP = 64: compile-time plane strides (immediate LDS offsets in the 30-tap loops); 0: runtime P
 __global__ void __launch_bounds__(kTexThreads, 2)
 k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, P rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = kP ? kP : p.P;
+    const int wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kTexThreads / 32;
-    const int PH = P + kGaborK - 1, GS = gabor_gs(P), PS = gabor_ps(P);
+    const int PH = P + kGaborK - 1, GS = kP ? gabor_gs(kP) : gabor_gs(P), PS = kP ? gabor_ps(kP) : gabor_ps(P);
     const int64_t i = blockIdx.x;
     float* G = reinterpret_cast<float*>(smem_raw);
     float* A = G + ((PH * GS + 31) & ~31);
@@ -396,9 +398,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             for (int j = tid; j < K; j += kTexThreads) {
                 const uint32_t rc = list[j];
                 const float* a = A + (rc >> 8) * PS + (rc & 255);
-                float v0 = 0.f;
+                float w0[3] = {0.f, 0.f, 0.f};   // three partial sums: break the 30-deep FMA dependency chain
 #pragma unroll
-                for (int t = 0; t < kGaborK; ++t) v0 = fmaf(a[t * PS], c_genv[t], v0);
+                for (int t = 0; t < kGaborK; ++t) w0[t % 3] = fmaf(a[t * PS], c_genv[t], w0[t % 3]);
+                const float v0 = (w0[0] + w0[1]) + w0[2];
                 s[0] += (double)v0; s[1] += (double)v0 * (double)v0;
             }
             finish(s, 1, q, 1);
@@ -412,12 +415,13 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                 const uint32_t rc = list[j];
                 const float* a = A + (rc >> 8) * PS + (rc & 255);
                 const float* b = B + (rc >> 8) * PS + (rc & 255);
-                float pp = 0.f, qq = 0.f;
+                float pw[2] = {0.f, 0.f}, qw[2] = {0.f, 0.f};   // two partial sums each: four independent chains
 #pragma unroll
                 for (int t = 0; t < kGaborK; ++t) {
-                    pp = fmaf(a[t * PS], c_gtap[q][2][t], pp);
-                    qq = fmaf(b[t * PS], c_gtap[q][3][t], qq);
+                    pw[t & 1] = fmaf(a[t * PS], c_gtap[q][2][t], pw[t & 1]);
+                    qw[t & 1] = fmaf(b[t * PS], c_gtap[q][3][t], qw[t & 1]);
                 }
+                const float pp = pw[0] + pw[1], qq = qw[0] + qw[1];
                 const float v45 = pp - qq, v135 = pp + qq;
                 s[0] += (double)v45;  s[1] += (double)v45 * (double)v45;
                 s[2] += (double)v135; s[3] += (double)v135 * (double)v135;
@@ -474,10 +478,13 @@ cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map_patch, cudaS
     if (e != cudaSuccess) return e;
     const int P = p.P, PH = P + kGaborK - 1, GS = gabor_gs(P), PS = gabor_ps(P);
     const int smem = (((PH * GS + 31) & ~31) + 2 * ((PH * PS + 31) & ~31)) * 4 + P * mask_wpr(P) * 4 + P * P * 2;
-    e = cudaFuncSetAttribute(k_gabor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    k_gabor<<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_patch);
-    return cudaGetLastError();
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e2 != cudaSuccess) return e2;
+        kern<<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_patch);
+        return cudaGetLastError();
+    };
+    return P == 64 ? go(k_gabor<64>) : go(k_gabor<0>);
 }
 
 }  // namespace nfx

@@ -7,6 +7,7 @@ import torch
 import nfx
 import nfx_oracle as o
 from cases import small_case, stress_case
+from nfx import synth
 from tolerances import mismatches
 
 pytestmark = pytest.mark.gpu
@@ -382,3 +383,23 @@ def test_glrlm_p256(stress):
     want = o.glrlm_feature_set(stress["patches"][:6], stress["masks"][:6])
     bad = mismatches(got, want, names, "glrlm")
     assert not bad, _report(bad)
+
+
+def test_small_patch_p32_all_sets(libnfx):
+    """P = 32: single-word mask rows, the runtime-stride Gabor variant, small windows at tile borders."""
+    tile = synth.synth_tile(200, 200, 13)
+    xy, off = synth.synth_polygons(70, 200, 200, 13, patch=32, r0_range=(3.0, 13.0), v_range=(6, 20), border_frac=0.1)
+    rings = synth.rings_of(xy, off)
+    with nfx.Extractor(0, 32, 25) as e:
+        e.upload_tile(tile)
+        keys, cents, got, names = e.extract(xy, off, ["all"])
+        masks = e.rasterize()
+    wkeys, wc, want, wnames = o.extract(rings, tile, ["all"], 32, 25)
+    assert names == wnames and keys == wkeys
+    wm = np.stack([o.polygon_mask(32, 32, o.preprocess_polygon(r)[1].astype(np.float64)) for r in rings])
+    assert np.array_equal(masks != 0, wm)
+    sel = [names.index(c) for c in ("area", "perimeter", "mean_b", "std_r", "mean_v", "mean_haematoxylin", "contrast_0_1_32",
+                                    "entropy_1_-1_254", "long_run_emphasis_0_1", "run_percentage_1_1",
+                                    "gabor_angle_45_frequency_1_mean", "gabor_angle_270_frequency_6_variance")]
+    ok = np.isclose(got[:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-4, equal_nan=True)
+    assert ok.all(), f"{(~ok).sum()} mismatches at P=32: {np.argwhere(~ok)[:6]}"
