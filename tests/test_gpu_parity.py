@@ -403,3 +403,60 @@ def test_small_patch_p32_all_sets(libnfx):
                                     "gabor_angle_45_frequency_1_mean", "gabor_angle_270_frequency_6_variance")]
     ok = np.isclose(got[:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-4, equal_nan=True)
     assert ok.all(), f"{(~ok).sum()} mismatches at P=32: {np.argwhere(~ok)[:6]}"
+
+
+# ---- size-independent properties ------------------------------------------------
+def test_batch_size_changes_only_mean_h(case):
+    """Every column is per-nucleus except mean_h, which the reference couples to its chunk (color.rs:50-51)."""
+    outs = {}
+    for B in (100, 37, 1):
+        with nfx.Extractor(0, 64, B) as e:
+            e.upload_tile(case["tile"])
+            outs[B] = e.extract(case["xy"], case["off"], ["geometry", "color", "glcm"])[2]
+    j = 12 + o.COLOR_COLUMNS.index("mean_h")
+    keep = [c for c in range(outs[100].shape[1]) if c != j]
+    assert np.array_equal(outs[100][:, keep], outs[37][:, keep], equal_nan=True)
+    assert np.array_equal(outs[100][:, keep], outs[1][:, keep], equal_nan=True)
+    assert not np.array_equal(outs[100][:, j], outs[37][:, j], equal_nan=True)
+    # batch_size = 1: the circular mean of a nucleus' own hue
+    hsv = o.hsv_from_rgb(case["patches"])
+    own = np.array([o.circular_mean(hsv[i:i + 1, 0], case["masks"][i:i + 1]).item() for i in range(40)])
+    d = np.abs(outs[1][:40, j] - own)
+    d = np.minimum(d, 360 - d)
+    assert np.nanmax(d) < 0.05
+
+
+def test_partitioned_run_is_byte_identical(case):
+    """Multi-GPU path on one device: contiguous ranges aligned to batch_size, one context each, merged at
+    the range offsets -> the same bytes as the single-context run (including mean_h)."""
+    B = 50
+    with nfx.Extractor(0, 64, B) as e:
+        e.upload_tile(case["tile"])
+        keys, cents, full, names = e.extract(case["xy"], case["off"], ["geometry", "color", "glcm", "glrlm"])
+    n = len(case["off"]) - 1
+    bounds = nfx.partition(n, B, 3)
+    merged = np.zeros_like(full)
+    mkeys = [None] * n
+    exs = [nfx.Extractor(0, 64, B) for _ in range(3)]
+    try:
+        for k, e in enumerate(exs):
+            lo, hi = bounds[k], bounds[k + 1]
+            e.upload_tile(case["tile"])
+            e.upload_polygons(case["xy"][case["off"][lo]:case["off"][hi]], case["off"][lo:hi + 1] - case["off"][lo])
+            e.compute(nfx.parse_feature_sets(["geometry", "color", "glcm", "glrlm"]))
+        for k, e in enumerate(exs):                       # all three contexts were in flight together
+            lo, hi = bounds[k], bounds[k + 1]
+            c, f = e.download()
+            merged[lo:hi] = f
+            mkeys[lo:hi] = [nfx.centroid_key(a, b) for a, b in c]
+    finally:
+        for e in exs:
+            e.close()
+    assert mkeys == keys
+    assert merged.tobytes() == full.tobytes()
+
+
+def test_recompute_is_deterministic(case, ex):
+    a = ex.extract(case["xy"], case["off"], ["all"])[2]
+    b = ex.extract(case["xy"], case["off"], ["all"])[2]
+    assert a.tobytes() == b.tobytes()
