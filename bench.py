@@ -39,7 +39,7 @@ WORKLOADS = {
     "stress": (["geometry", "color", "glcm"], 20_000, 16384, 256,
                dict(r0_range=(40.0, 110.0), v_range=(500, 500), harmonics=(3, 7, 19))),
     # BASELINE config 4: one slide resident in HBM, written tile by tile; nuclei split over the ranks (strong scaling)
-    "slide": (["geometry", "color", "glcm"], 5_000_000, 100_000, 64, {}),
+    "slide": (["all"], 5_000_000, 100_000, 64, {}),
 }
 V_MEAN = 30.0   # mean ring length of the synthetic polygons (12..48 vertices + closing duplicate)
 
