@@ -36,7 +36,7 @@ WORKLOADS = {
     "glcm": (["glcm"], 1_000_000, 49152, 64, {}),
     "all": (["all"], 100_000, 16384, 64, {}),
     # BASELINE config 5: large irregular nuclei, 256x256 windows, 500-vertex polygons
-    "stress": (["geometry", "color", "glcm"], 20_000, 16384, 256,
+    "stress": (["all"], 20_000, 16384, 256,
                dict(r0_range=(40.0, 110.0), v_range=(500, 500), harmonics=(3, 7, 19))),
     # BASELINE config 4: one slide resident in HBM, written tile by tile; nuclei split over the ranks (strong scaling)
     "slide": (["all"], 5_000_000, 100_000, 64, {}),

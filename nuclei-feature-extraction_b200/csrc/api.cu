@@ -62,7 +62,7 @@ struct nfx_ctx {
     DevBuf<uint8_t> tile;
     int64_t tw = 0, th = 0, tpitch = 0, tox = 0, toy = 0;
     bool have_tile = false;
-    CUtensorMap map_tile_patch, map_tile_slab, map_tile_cslab;
+    CUtensorMap map_tile_patch, map_tile_slab, map_tile_cslab, map_tile_gabor;
 
     // polygons
     DevBuf<float2> xy;
@@ -78,6 +78,7 @@ struct nfx_ctx {
     DevBuf<float> out;
     DevBuf<float> hue;
     DevBuf<uint32_t> ellipse;
+    DevBuf<double> gabor_part;
     uint32_t computed_mask = 0;
     int out_cols = 0;
     bool have_geom = false;   // centroid/info/bitmask valid for the staged polygons
@@ -85,7 +86,7 @@ struct nfx_ctx {
     // staged patch array (kernel (1) output / trait-level input)
     DevBuf<uint8_t> patches;
     int64_t ppitch = 0;
-    CUtensorMap map_pat_patch, map_pat_slab, map_pat_cslab;
+    CUtensorMap map_pat_patch, map_pat_slab, map_pat_cslab, map_pat_gabor;
 
     // scratch
     DevBuf<uint8_t> scratch8;
@@ -185,8 +186,6 @@ Cols columns(uint32_t mask) {
 }
 
 int check_patch_size(nfx_ctx* ctx, uint32_t mask) {
-    if ((mask & NFX_FS_GABOR) && ctx->P > gabor_max_patch())
-        return fail(ctx, NFX_ERR_UNSUPPORTED, "Gabor kernel handles patch_size <= 64 in this build");
     if (mask == 0 || (mask & ~NFX_FS_ALL)) return fail(ctx, NFX_ERR_INVALID, "empty or unknown feature mask");
     return NFX_OK;
 }
@@ -260,8 +259,8 @@ int run_glcm(nfx_ctx* ctx, int64_t n, const CUtensorMap* mp, float* out, int str
     return NFX_OK;
 }
 
-int run_tex2(nfx_ctx* ctx, int64_t n, uint32_t mask, const CUtensorMap* map_cslab, const CUtensorMap* map_patch, float* out,
-             int stride, int col_glrlm, int col_gabor) {
+int run_tex2(nfx_ctx* ctx, int64_t n, uint32_t mask, const CUtensorMap* map_cslab, const CUtensorMap* map_patch,
+             const CUtensorMap* map_gabor, float* out, int stride, int col_glrlm, int col_gabor) {
     TexParams t;
     t.n = n;
     t.P = ctx->P;
@@ -272,8 +271,15 @@ int run_tex2(nfx_ctx* ctx, int64_t n, uint32_t mask, const CUtensorMap* map_csla
     t.out_stride = stride;
     t.col_glrlm = col_glrlm;
     t.col_gabor = col_gabor;
+    t.gabor_partial = nullptr;
+    const bool gabor_tiled = gabor_tiles(ctx->P) > 1;
+    if ((mask & NFX_FS_GABOR) && gabor_tiled) {
+        CK(ctx->gabor_part.ensure((size_t)n * gabor_tiles(ctx->P) * 49));
+        t.gabor_partial = ctx->gabor_part.p;
+    }
     if (mask & NFX_FS_GLRLM) CK(timed(ctx, "k_glrlm", 1, [&] { return launch_glrlm(t, map_cslab, ctx->stream); }));
-    if (mask & NFX_FS_GABOR) CK(timed(ctx, "k_gabor", 1, [&] { return launch_gabor(t, map_patch, ctx->stream); }));
+    if (mask & NFX_FS_GABOR)
+        CK(timed(ctx, "k_gabor", gabor_tiled ? 2 : 1, [&] { return launch_gabor(t, gabor_tiled ? map_gabor : map_patch, ctx->stream); }));
     return NFX_OK;
 }
 
@@ -294,6 +300,7 @@ int make_patch_array(nfx_ctx* ctx, int64_t n) {
     if ((rc = make_map(ctx, &ctx->map_pat_patch, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, P))) return rc;
     if ((rc = make_map(ctx, &ctx->map_pat_slab, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, R))) return rc;
     if ((rc = make_map(ctx, &ctx->map_pat_cslab, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, color_slab_rows(P)))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_pat_gabor, ctx->patches.p, ctx->ppitch, n * P, ctx->ppitch, gabor_fetch_rows()))) return rc;
     return NFX_OK;
 }
 
@@ -345,7 +352,7 @@ int nfx_destroy(nfx_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     ctx->tile.release(); ctx->xy.release(); ctx->off.release(); ctx->centroid.release(); ctx->info.release();
-    ctx->bitmask.release(); ctx->out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->patches.release();
+    ctx->bitmask.release(); ctx->out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->gabor_part.release(); ctx->patches.release();
     ctx->scratch8.release(); ctx->scratchf.release(); ctx->scratch32.release(); ctx->flush.release();
     if (ctx->d_bad) cudaFree(ctx->d_bad);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -368,6 +375,7 @@ int nfx_slide_alloc(nfx_ctx* ctx, int64_t w, int64_t h, int64_t origin_x, int64_
     if ((rc = make_map(ctx, &ctx->map_tile_patch, ctx->tile.p, 3 * w, h, pitch, ctx->P))) return rc;
     if ((rc = make_map(ctx, &ctx->map_tile_slab, ctx->tile.p, 3 * w, h, pitch, hue_slab_rows(ctx->P)))) return rc;
     if ((rc = make_map(ctx, &ctx->map_tile_cslab, ctx->tile.p, 3 * w, h, pitch, color_slab_rows(ctx->P)))) return rc;
+    if ((rc = make_map(ctx, &ctx->map_tile_gabor, ctx->tile.p, 3 * w, h, pitch, gabor_fetch_rows()))) return rc;
     ctx->have_tile = true;
     ctx->have_geom = false;   // window origins depend on the slide origin
     return NFX_OK;
@@ -442,7 +450,7 @@ int nfx_compute(nfx_ctx* ctx, uint32_t mask) {
     if (mask & NFX_FS_GLCM)
         if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_tile_cslab : &ctx->map_tile_patch, ctx->out.p, c.total, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
     if (mask & (NFX_FS_GLRLM | NFX_FS_GABOR))
-        if ((rc = run_tex2(ctx, n, mask, &ctx->map_tile_cslab, &ctx->map_tile_patch, ctx->out.p, c.total, c.glrlm, c.gabor))) return rc;
+        if ((rc = run_tex2(ctx, n, mask, &ctx->map_tile_cslab, &ctx->map_tile_patch, &ctx->map_tile_gabor, ctx->out.p, c.total, c.glrlm, c.gabor))) return rc;
     ctx->computed_mask = mask;
     return NFX_OK;
 }
@@ -520,7 +528,7 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
     } else if (fs == NFX_FS_GLCM) {
         if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_pat_cslab : &ctx->map_pat_patch, ctx->out.p, cols, 0, nullptr, 0, 0, 0, nullptr))) return rc;
     } else {
-        if ((rc = run_tex2(ctx, n, fs, &ctx->map_pat_cslab, &ctx->map_pat_patch, ctx->out.p, cols, 0, 0))) return rc;
+        if ((rc = run_tex2(ctx, n, fs, &ctx->map_pat_cslab, &ctx->map_pat_patch, &ctx->map_pat_gabor, ctx->out.p, cols, 0, 0))) return rc;
     }
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

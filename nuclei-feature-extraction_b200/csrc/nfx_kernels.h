@@ -88,10 +88,13 @@ struct TexParams {
     float* out;
     int out_stride;
     int col_glrlm, col_gabor;  // first column of each set (or -1)
+    double* gabor_partial;     // [n][gabor_tiles(P)][49] scratch when P > 64, else nullptr
 };
 cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaStream_t s);
-cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map_patch, cudaStream_t s);   // P <= gabor_max_patch()
+cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map, cudaStream_t s);   // map: see texture2.cu
 int gabor_max_patch();
+int gabor_tiles(int P);
+int gabor_fetch_rows();
 
 // ---- staged.cu: kernels (1) gather and the f32 batch packer -----------------------------------
 // tile window -> u8 patch array [n*P rows][pitch bytes] through TMA load + TMA store.

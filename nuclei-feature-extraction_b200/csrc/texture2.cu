@@ -218,19 +218,31 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 __host__ __device__ constexpr int gabor_gs(int P) { return ((P + kGaborK + 31) & ~31) + 4; }   // >= P+34, = 4 mod 32
 __host__ __device__ constexpr int gabor_ps(int P) { return ((P + 27) & ~31) + 4; }             // >= P,    = 4 mod 32
 
-template <int kP>   // kP = 64: compile-time plane strides (immediate LDS offsets in the 30-tap loops); 0: runtime P
+// TILED = false: the whole P x P window (P <= 64) is one tile and everything outside it is the zero
+// padding of the reference's 'same' convolution. TILED = true (P > 64): grid.y enumerates 64 x 64 output
+// tiles of the window; each CTA fetches its tile plus the 14/15-pixel halo (real pixels inside the
+// window, zeros outside), runs the same passes with the planes sized for a 64-pixel tile, and writes
+// per-tile partial sums (sum v, sum v^2 per distinct filter, tile pixel count) that k_gabor_finalize folds.
+constexpr int kGaborTile = 64, kGaborFetch = kGaborTile + kGaborK - 1;   // 93 rows/cols fetched per tile
+constexpr int kGaborPartial = 49;                                        // 24 filters x (sum, sum^2) + pixel count
+
+template <int kP, bool TILED>   // kP = 64: compile-time plane strides (immediate LDS offsets); 0: runtime
 __global__ void __launch_bounds__(kTexThreads, 2)
-k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, P rows} */) {
+k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, P rows} or {208, 93 rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int P = kP ? kP : p.P;
+    const int WP = p.P;                                   // the nucleus window
+    const int P = TILED ? kGaborTile : (kP ? kP : p.P);   // the tile this CTA filters (local coordinates)
     const int wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kTexThreads / 32;
-    const int PH = P + kGaborK - 1, GS = kP ? gabor_gs(kP) : gabor_gs(P), PS = kP ? gabor_ps(kP) : gabor_ps(P);
+    const int PH = P + kGaborK - 1, GS = (kP || TILED) ? gabor_gs(kGaborTile) : gabor_gs(P),
+              PS = (kP || TILED) ? gabor_ps(kGaborTile) : gabor_ps(P);
     const int64_t i = blockIdx.x;
+    const int tiles_x = (WP + kGaborTile - 1) / kGaborTile;
+    const int oy = TILED ? (int)(blockIdx.y / tiles_x) * kGaborTile : 0, ox = TILED ? (int)(blockIdx.y % tiles_x) * kGaborTile : 0;
     float* G = reinterpret_cast<float*>(smem_raw);
     float* A = G + ((PH * GS + 31) & ~31);
     float* B = A + ((PH * PS + 31) & ~31);
-    uint8_t* patch = reinterpret_cast<uint8_t*>(A);   // the window is consumed before A is written
+    uint8_t* patch = reinterpret_cast<uint8_t*>(A);   // the fetched pixels are consumed before A is written
     uint32_t* rows = reinterpret_cast<uint32_t*>(B + ((PH * PS + 31) & ~31));
     uint16_t* list = reinterpret_cast<uint16_t*>(rows + P * wpr);
     __shared__ __align__(8) uint64_t bar;
@@ -240,27 +252,33 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     __shared__ double s_red[12 * NW];
 
     const NucInfo inf = p.info[i];
-    const int o = patch_byte_offset(inf.left);
+    // fetched region: rows/cols [f0, f0 + fetch) of the window, f0 = -14 relative to the tile when TILED
+    const int fy = TILED ? oy - kGaborLo : 0, fx = TILED ? ox - kGaborLo : 0;
+    const int frows = TILED ? kGaborFetch : P;            // rows per panel of the fetched region
+    const int o = patch_byte_offset(inf.left + fx);
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        mbar_expect_tx(&bar, (uint32_t)(patch_panels(P) * kPanelBytes * P));
-        tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
+        const int fw = TILED ? kGaborFetch : P;
+        mbar_expect_tx(&bar, (uint32_t)(patch_panels(fw) * kPanelBytes * frows));
+        tma_load_window(patch, &map, inf.left + fx, inf.top + fy, fw, frows, &bar);
         s_box[0] = P; s_box[1] = -1; s_box[2] = P; s_box[3] = -1;
     }
     s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
     for (int k = tid; k < PH * GS; k += kTexThreads) G[k] = 0.f;
     __syncthreads();
-    // ---- mask rows, bounding box, pixel list ----
-    const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
+    // ---- mask rows of the tile, bounding box, pixel list (tile-local coordinates) ----
+    const int gwpr = mask_wpr(WP);
+    const uint32_t* gm = p.bitmask + i * (int64_t)WP * gwpr;
     int K = 0;
     {
         int rmin = P, rmax = -1, cmin = P, cmax = -1;
         for (int base = 0; base < P * wpr; base += kTexThreads) {
             const int k = base + tid;
-            uint32_t bits = (k < P * wpr) ? gm[k] : 0u;
+            const int r = k / wpr, w = k - r * wpr, cb = w * 32;
+            uint32_t bits = 0u;
+            if (k < P * wpr && oy + r < WP && (ox >> 5) + w < gwpr) bits = gm[(oy + r) * gwpr + (ox >> 5) + w];
             if (k < P * wpr) rows[k] = bits;
-            const int r = k / wpr, cb = (k - r * wpr) * 32;
             if (bits) {
                 rmin = min(rmin, r); rmax = max(rmax, r);
                 cmin = min(cmin, cb + __ffs(bits) - 1); cmax = max(cmax, cb + 31 - __clz(bits));
@@ -299,25 +317,32 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     __syncthreads();
     const int rmin = s_box[0], rmax = s_box[1], cmin = s_box[2], cmax = s_box[3];
     float* out = p.out + i * (int64_t)p.out_stride + p.col_gabor;
+    double* part = TILED ? p.gabor_partial + (i * (int64_t)gridDim.y + blockIdx.y) * kGaborPartial : nullptr;
     mbar_wait(&bar, 0);   // never leave the CTA with a TMA still writing its shared memory
-    if (K == 0) {   // empty mask: 0/0 = NaN (texture.rs:340-344)
-        for (int k = tid; k < 2 * kGaborFilters; k += kTexThreads) out[k] = CUDART_NAN_F;
+    if (K == 0) {
+        if (TILED) {        // empty tile: contributes nothing
+            for (int k = tid; k < kGaborPartial; k += kTexThreads) part[k] = 0.0;
+        } else {            // empty mask: 0/0 = NaN (texture.rs:340-344)
+            for (int k = tid; k < 2 * kGaborFilters; k += kTexThreads) out[k] = CUDART_NAN_F;
+        }
         return;
     }
-    // ---- grey plane with the 'same' zero halo: only the part the bounding box can reach ----
-    const int gr0 = max(rmin - kGaborLo, 0), gr1 = min(rmax + (kGaborK - 1 - kGaborLo), P - 1);
-    const int gc0 = max(cmin - kGaborLo, 0), gc1 = min(cmax + (kGaborK - 1 - kGaborLo), P - 1);
+    if (TILED && tid == 0) part[kGaborPartial - 1] = (double)K;
+    // ---- grey plane with its halo: only the part the bounding box can reach. Outside the nucleus
+    //      window (and beyond what the reference copied, NucInfo) it is the zero padding of 'same' ----
+    const int gr0 = rmin - kGaborLo, gr1 = rmax + (kGaborK - 1 - kGaborLo);   // tile-local rows, may leave [0,P)
+    const int gc0 = cmin - kGaborLo, gc1 = cmax + (kGaborK - 1 - kGaborLo);
     const int gw = gc1 - gc0 + 1;
+    const int wr_lim = min(WP, inf.nvr), wc_lim = min(WP, inf.nvc);
     for (int k = tid; k < (gr1 - gr0 + 1) * gw; k += kTexThreads) {
-        const int r = gr0 + k / gw, c = gc0 + k % gw;
-        float g = 0.f;
-        if (r < inf.nvr && c < inf.nvc) {
-            const int a = patch_addr(P, o, r, c);
-            g = grey_of(s_lut, patch[a], patch[a + 1], patch[a + 2]);
+        const int r = gr0 + k / gw, c = gc0 + k % gw;          // tile-local
+        const int wr = oy + r, wc = ox + c;                    // window coordinates
+        if (wr >= 0 && wr < wr_lim && wc >= 0 && wc < wc_lim) {
+            const int a = patch_addr(frows, o, wr - fy, wc - fx);
+            G[(r + kGaborLo) * GS + c + kGaborLo] = grey_of(s_lut, patch[a], patch[a + 1], patch[a + 2]);
         }
-        G[(r + kGaborLo) * GS + c + kGaborLo] = g;
     }
-    __syncthreads();   // the window (aliased with A) is dead from here on
+    __syncthreads();   // the fetched pixels (aliased with A) are dead from here on
 
     const int cq0 = cmin & ~3, nquad = ((cmax - cq0) >> 2) + 1;   // column quads of the bounding box
     const int nrow = rmax - rmin + kGaborK;                       // padded rows rmin .. rmax+29
@@ -355,7 +380,13 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 #pragma unroll
         for (int h = 0; h < 12; ++h) v[h] = h < 2 * nf ? s[h] : 0.0;
         block_sum<12>(v, s_red);   // also orders this pass before the planes are overwritten
-        if (tid == 0) {
+        if (tid == 0 && TILED) {
+            for (int h = 0; h < nf; ++h) {
+                const int f = f0 + h * fstep;
+                part[2 * f] = v[2 * h];
+                part[2 * f + 1] = v[2 * h + 1];
+            }
+        } else if (tid == 0) {
             const double Kd = (double)K;
             for (int h = 0; h < nf; ++h) {
                 const int f = f0 + h * fstep;
@@ -431,9 +462,35 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     }
 }
 
+// one thread per (nucleus, distinct filter): fold the tiles, write theta and theta + 180 degrees
+__global__ void k_gabor_finalize(const TexParams p, const int ntiles) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n * 24) return;
+    const int64_t i = g / 24;
+    const int f = (int)(g - i * 24);
+    const double* part = p.gabor_partial + i * (int64_t)ntiles * kGaborPartial;
+    double s0 = 0.0, s1 = 0.0, K = 0.0;
+    for (int t = 0; t < ntiles; ++t) {
+        s0 += part[t * kGaborPartial + 2 * f];
+        s1 += part[t * kGaborPartial + 2 * f + 1];
+        K += part[t * kGaborPartial + kGaborPartial - 1];
+    }
+    float* out = p.out + i * (int64_t)p.out_stride + p.col_gabor;
+    float mf = CUDART_NAN_F, vf = CUDART_NAN_F;   // empty mask: 0/0 (texture.rs:340-344)
+    if (K > 0.0) {
+        const double mean = s0 / K;
+        mf = (float)mean;
+        vf = (float)fmax(s1 / K - mean * mean, 0.0);
+    }
+    out[2 * f] = mf; out[2 * f + 1] = vf;
+    out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf;
+}
+
 }  // namespace
 
-int gabor_max_patch() { return 64; }
+int gabor_max_patch() { return 256; }
+int gabor_tiles(int P) { return P <= kGaborTile ? 1 : ((P + kGaborTile - 1) / kGaborTile) * ((P + kGaborTile - 1) / kGaborTile); }
+int gabor_fetch_rows() { return kGaborFetch; }
 
 static bool g_taps_ready[64] = {};
 static cudaError_t ensure_gabor_taps() {
@@ -472,19 +529,28 @@ cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaS
     return cudaGetLastError();
 }
 
-cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map_patch, cudaStream_t s) {
+// P <= 64: `map` is the whole-window map (box height P). P > 64: `map` is the 93-row halo map and
+// p.gabor_partial holds n * gabor_tiles(P) * 49 doubles.
+cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     cudaError_t e = ensure_gabor_taps();
     if (e != cudaSuccess) return e;
-    const int P = p.P, PH = P + kGaborK - 1, GS = gabor_gs(P), PS = gabor_ps(P);
+    const bool tiled = p.P > kGaborTile;
+    const int P = tiled ? kGaborTile : p.P, PH = P + kGaborK - 1;
+    const int GS = (tiled || P == 64) ? gabor_gs(kGaborTile) : gabor_gs(P), PS = (tiled || P == 64) ? gabor_ps(kGaborTile) : gabor_ps(P);
     const int smem = (((PH * GS + 31) & ~31) + 2 * ((PH * PS + 31) & ~31)) * 4 + P * mask_wpr(P) * 4 + P * P * 2;
+    const int ntiles = gabor_tiles(p.P);
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e2 != cudaSuccess) return e2;
-        kern<<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_patch);
+        kern<<<dim3((unsigned)p.n, (unsigned)ntiles), kTexThreads, smem, s>>>(p, *map);
         return cudaGetLastError();
     };
-    return P == 64 ? go(k_gabor<64>) : go(k_gabor<0>);
+    if (!tiled) return p.P == 64 ? go(k_gabor<64, false>) : go(k_gabor<0, false>);
+    e = go(k_gabor<64, true>);
+    if (e != cudaSuccess) return e;
+    k_gabor_finalize<<<(unsigned)((p.n * 24 + 255) / 256), 256, 0, s>>>(p, ntiles);
+    return cudaGetLastError();
 }
 
 }  // namespace nfx

@@ -460,3 +460,24 @@ def test_recompute_is_deterministic(case, ex):
     a = ex.extract(case["xy"], case["off"], ["all"])[2]
     b = ex.extract(case["xy"], case["off"], ["all"])[2]
     assert a.tobytes() == b.tobytes()
+
+
+def test_gabor_tiled_p256_and_p128(stress):
+    """P > 64: 64x64 output tiles with a real-pixel halo inside the window and zero padding outside."""
+    n = 10
+    xy, off = stress["xy"][:stress["off"][n]], stress["off"][:n + 1]
+    with nfx.Extractor(0, 256, 8) as e:
+        e.upload_tile(stress["tile"])
+        keys, cents, got, names = e.extract(xy, off, ["gabor"])
+    want = o.gabor_feature_set(stress["patches"][:n], stress["masks"][:n])
+    bad = mismatches(got, want, names, "gabor")
+    assert not bad, _report(bad)
+    tile, rings = stress_case(n=10, size=512, seed=8, patch=128)
+    rings = [((r - r.mean(0)) * 0.45 + r.mean(0)).astype(np.float32) for r in rings]
+    xy, off = nfx.pack_polygons(rings)
+    with nfx.Extractor(0, 128, 5) as e:
+        e.upload_tile(tile)
+        keys, cents, got, names = e.extract(xy, off, ["gabor"])
+    c, polys, patches, masks = o.load_image_dataset(rings, tile, 128)
+    bad = mismatches(got, o.gabor_feature_set(patches, masks), names, "gabor")
+    assert not bad, _report(bad)
