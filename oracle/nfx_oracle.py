@@ -565,6 +565,38 @@ def glrlm_counts(grey, levels, max_length, direction, masks):
     q = quantise(grey, levels)[:, 0].numpy()
     m = (masks[:, 0] != 0).numpy()
     dx, dy = direction
+
+    def shifted(a, k):
+        """out[n, r, c] = a[n, r + k*dy, c + k*dx] (zero outside the patch)."""
+        out = np.zeros_like(a)
+        r0, r1 = max(0, -k * dy), min(H, H - k * dy)
+        c0, c1 = max(0, -k * dx), min(W, W - k * dx)
+        if r1 > r0 and c1 > c0:
+            out[:, r0:r1, c0:c1] = a[:, r0 + k * dy:r1 + k * dy, c0 + k * dx:c1 + k * dx]
+        return out
+
+    # a pixel CONTINUES a run when its predecessor along the direction is masked-in with the same level
+    cont = m & shifted(m, -1) & (q == shifted(q + 1, -1) - 1)
+    start = m & ~cont
+    length = start.astype(np.int64)
+    alive = start.copy()
+    k = 1
+    while alive.any():
+        alive &= shifted(cont, k)
+        length += alive
+        k += 1
+    R = np.zeros((N, levels, max_length), dtype=np.int64)
+    n_idx, rr, cc = np.nonzero(start)
+    np.add.at(R, (n_idx, q[n_idx, rr, cc], np.minimum(length[n_idx, rr, cc], max_length) - 1), 1)
+    return torch.from_numpy(R)
+
+
+def glrlm_counts_loop(grey, levels, max_length, direction, masks):
+    """Literal per-pixel restatement of glrlm_counts (kept as the cross-check of the vectorised form)."""
+    N, _, H, W = grey.shape
+    q = quantise(grey, levels)[:, 0].numpy()
+    m = (masks[:, 0] != 0).numpy()
+    dx, dy = direction
     R = np.zeros((N, levels, max_length), dtype=np.int64)
     for n in range(N):
         rr, cc = np.nonzero(m[n])

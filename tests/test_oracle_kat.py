@@ -284,3 +284,12 @@ def test_gabor_bank_and_same_padding():
     y = o.apply_gabor_filter(x)
     assert y.shape == (1, 48, 64, 64)
     assert np.allclose(y[0, 5, 20 - 3, 30 + 2].item(), bank[5, 14 + 3, 14 - 2], atol=1e-7)
+
+
+def test_glrlm_vectorised_equals_literal_loop():
+    from cases import small_case
+    tile, rings = small_case(n=12)
+    c, polys, patches, masks = o.load_image_dataset(rings, tile, 64)
+    gs = o.grey_scale(patches)
+    for d in o.GLRLM_DIRECTIONS:
+        assert torch.equal(o.glrlm_counts(gs, 24, 16, d, masks), o.glrlm_counts_loop(gs, 24, 16, d, masks))
