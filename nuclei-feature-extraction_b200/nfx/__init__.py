@@ -164,6 +164,10 @@ class Extractor:
         self._ck(lib().nfx_rasterize(self._h, _ptr(out)))
         return out
 
+    def rasterize_device(self):
+        """Kernel (2) only: masks stay in HBM as bitmasks (no host copy)."""
+        self._ck(lib().nfx_rasterize(self._h, None))
+
     def gather_patches(self, want=True):
         out = np.empty((self.n, self.patch_size, self.patch_size, 3), dtype=np.uint8) if want else None
         self._ck(lib().nfx_gather_patches(self._h, _ptr(out)))
