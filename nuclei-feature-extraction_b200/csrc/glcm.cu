@@ -376,10 +376,13 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
 // =================================================================================================
 // k_glcm64: P <= 64. All four levels of one offset are processed in ONE sweep over the pairs:
 //   * the masked pixels are compacted once into a coordinate list (shared by the 4 offsets);
-//   * pass 1 walks that list, tests the neighbour bit, emits the packed pair record by ballot
-//     compaction and issues the shared-memory atomics of all 4 levels (17 per pair);
+//   * pass 1 walks that list, tests the neighbour bit and issues the shared-memory atomics of all 4
+//     levels (17 per pair); pass 2 walks it again for the cell counts. No pair list is kept: with a
+//     4096-slot hash that brings the CTA to 69 KB of shared memory = 3 CTAs per SM (the kernel is
+//     bound by shared-memory latency, so residency matters more than the re-derived pair);
 //   * G for 32/64/128 levels lives in dense triangular u16 histograms (22 KB together); G for 254
-//     levels (32 385 cells, <= K occupied) lives in an open-addressing hash table sized 2K..8192;
+//     levels (32 385 cells, <= K occupied) lives in an open-addressing hash table of 4096 slots
+//     (linear probing; a 64 x 64 mask has at most 4032 pairs, so it can never fill up);
 //   * p_x of 32 and 64 levels is the 128-level histogram folded by 4 / 2 (exact: q32 = q128 >> 2);
 //   * every partial sum is an integer (moments exactly, logarithmic terms in fixed point with a
 //     2^-16 quantum, far below the 1e-4 tolerance) so that warp reduction is one REDUX each;
@@ -391,7 +394,7 @@ constexpr int kOffTri128 = 0;                                  // bytes inside r
 constexpr int kOffTri64 = kOffTri128 + kTri128 * 2;            // 16512
 constexpr int kOffTri32 = kOffTri64 + kTri64 * 2;              // 20672
 constexpr int kOffHash = ((kOffTri32 + kTri32 * 2 + 127) / 128) * 128;   // 21760
-constexpr int kHashMax = 8192;
+constexpr int kHashMax = 4096, kHashLg = 12;
 constexpr int kRegionA64 = kOffHash + kHashMax * 4;            // 54528
 constexpr int kMargWords = 2048;                               // m32 @0, m64 @128, m128 @384, m254 @896
 constexpr int kNP = 11;                                        // partial sums per (level, offset)
@@ -399,7 +402,7 @@ constexpr float kLnFix = 0.6931471805599453f * 65536.0f;      // log2 -> ln, 16 
 constexpr float kIdmFix = 262144.0f;                           // 18 fractional bits
 
 struct Glcm64Smem {
-    int rows, q128, q254, list, pairs, marg, parts, total;
+    int rows, q128, q254, list, marg, parts, total;
 };
 __host__ __device__ inline Glcm64Smem glcm64_layout(int P) {
     Glcm64Smem L;
@@ -408,8 +411,7 @@ __host__ __device__ inline Glcm64Smem glcm64_layout(int P) {
     L.q128 = L.rows + ((P * mask_wpr(P) * 4 + 15) & ~15);
     L.q254 = L.q128 + P * P;
     L.list = L.q254 + P * P;
-    L.pairs = L.list + P * P * 2;
-    L.parts = L.pairs + P * P * 4;
+    L.parts = L.list + P * P * 2;
     L.total = L.parts + kCombos * kG64NW * kNP * 4;
     return L;
 }
@@ -453,7 +455,7 @@ __device__ __forceinline__ uint32_t fix_clnc(uint32_t c) {   // c ln c, 15 fract
     return c ? __float2uint_rn((float)c * __log2f((float)c) * (0.5f * kLnFix)) : 0u;
 }
 
-__global__ void __launch_bounds__(kG64Threads, 2)
+__global__ void __launch_bounds__(kG64Threads, 3)
 k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,7 +472,6 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     uint8_t* q128 = smem_raw + L.q128;
     uint8_t* q254 = smem_raw + L.q254;
     uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + L.list);
-    uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.pairs);
     uint32_t* parts = reinterpret_cast<uint32_t*>(smem_raw + L.parts);   // [combo][warp][kNP]
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
@@ -519,8 +520,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         }
         K += total;
     }
-    int lg = 10;
-    while ((1 << lg) < 2 * K && lg < 13) ++lg;   // hash slots = 2^lg >= 2K (distinct cells <= pairs <= K)
+    constexpr int lg = kHashLg;
     const int o = patch_byte_offset(inf.left);
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -560,56 +560,49 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     for (int oi = 0; oi < kGlcmOffsets; ++oi) {
         const int dy = c_off[oi][0], dx = c_off[oi][1];
         const int dpos = dy * P + dx;
-        // ---- pass 1: neighbour test, pair record, atomics of all four levels ----
-        for (int jb = 0; jb < K; jb += kG64Threads) {
-            const int j = jb + tid;
-            bool has = false;
-            int src = 0;
-            if (j < K) {
-                const uint32_t rc = list[j];
-                const int r = rc >> 8, c = rc & 255, r2 = r + dy, c2 = c + dx;
-                src = r * P + c;
-                has = (r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u);
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, has);
-            int wb = 0;
-            if (lane == 0 && bal) wb = atomicAdd(&s_np[oi], __popc(bal));
-            wb = __shfl_sync(0xffffffffu, wb, 0);
-            if (has) {
-                const int a3 = q254[src], b3 = q254[src + dpos], a2 = q128[src], b2 = q128[src + dpos];
-                pairs[wb + __popc(bal & ((1u << lane) - 1u))] =
-                    (uint32_t)a3 | ((uint32_t)b3 << 8) | ((uint32_t)a2 << 16) | ((uint32_t)b2 << 24);
-                // 254 levels
-                hash_add(hash, lg, (uint32_t)(min(a3, b3) * 256 + max(a3, b3)));
-                atomicAdd(&m254[a3], 1u);
-                atomicAdd(&m254[b3], 1u);
-                atomicAdd(&m254[256 + a3 + b3], 2u);
-                atomicAdd(&m254[768 + abs(a3 - b3)], 2u);
-                // 128 levels
-                tri_add(tri128, tri_cell(a2, b2));
-                atomicAdd(&m128[a2], 1u);
-                atomicAdd(&m128[b2], 1u);
-                atomicAdd(&m128[128 + a2 + b2], 2u);
-                atomicAdd(&m128[384 + abs(a2 - b2)], 2u);
-                // 64 levels (p_x is folded from the 128-level histogram later)
-                const int a1 = a2 >> 1, b1 = b2 >> 1;
-                tri_add(tri64, tri_cell(a1, b1));
-                atomicAdd(&m64[64 + a1 + b1], 2u);
-                atomicAdd(&m64[192 + abs(a1 - b1)], 2u);
-                // 32 levels
-                const int a0 = a2 >> 2, b0 = b2 >> 2;
-                tri_add(tri32, tri_cell(a0, b0));
-                atomicAdd(&m32[32 + a0 + b0], 2u);
-                atomicAdd(&m32[96 + abs(a0 - b0)], 2u);
-            }
+        // ---- pass 1: neighbour test, atomics of all four levels ----
+        int np_local = 0;
+        for (int j = tid; j < K; j += kG64Threads) {
+            const uint32_t rc = list[j];
+            const int r = rc >> 8, c = rc & 255, r2 = r + dy, c2 = c + dx;
+            if (!((r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u))) continue;
+            ++np_local;
+            const int src = r * P + c;
+            const int a3 = q254[src], b3 = q254[src + dpos], a2 = q128[src], b2 = q128[src + dpos];
+            // 254 levels
+            hash_add(hash, lg, (uint32_t)(min(a3, b3) * 256 + max(a3, b3)));
+            atomicAdd(&m254[a3], 1u);
+            atomicAdd(&m254[b3], 1u);
+            atomicAdd(&m254[256 + a3 + b3], 2u);
+            atomicAdd(&m254[768 + abs(a3 - b3)], 2u);
+            // 128 levels
+            tri_add(tri128, tri_cell(a2, b2));
+            atomicAdd(&m128[a2], 1u);
+            atomicAdd(&m128[b2], 1u);
+            atomicAdd(&m128[128 + a2 + b2], 2u);
+            atomicAdd(&m128[384 + abs(a2 - b2)], 2u);
+            // 64 levels (p_x is folded from the 128-level histogram later)
+            const int a1 = a2 >> 1, b1 = b2 >> 1;
+            tri_add(tri64, tri_cell(a1, b1));
+            atomicAdd(&m64[64 + a1 + b1], 2u);
+            atomicAdd(&m64[192 + abs(a1 - b1)], 2u);
+            // 32 levels
+            const int a0 = a2 >> 2, b0 = b2 >> 2;
+            tri_add(tri32, tri_cell(a0, b0));
+            atomicAdd(&m32[32 + a0 + b0], 2u);
+            atomicAdd(&m32[96 + abs(a0 - b0)], 2u);
         }
+        np_local = __reduce_add_sync(0xffffffffu, np_local);
+        if (lane == 0 && np_local) atomicAdd(&s_np[oi], np_local);
         __syncthreads();
-        const int npairs = s_np[oi];
         // ---- pass 2: per-pair cell counts (entropy, ASM) for the four levels ----
         uint32_t sg[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0};
-        for (int k = tid; k < npairs; k += kG64Threads) {
-            const uint32_t rec = pairs[k];
-            const int a3 = rec & 0xff, b3 = (rec >> 8) & 0xff, a2 = (rec >> 16) & 0xff, b2 = rec >> 24;
+        for (int j = tid; j < K; j += kG64Threads) {
+            const uint32_t rc = list[j];
+            const int r = rc >> 8, c = rc & 255, r2 = r + dy, c2 = c + dx;
+            if (!((r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u))) continue;
+            const int src = r * P + c;
+            const int a3 = q254[src], b3 = q254[src + dpos], a2 = q128[src], b2 = q128[src + dpos];
             const int a1 = a2 >> 1, b1 = b2 >> 1, a0 = a2 >> 2, b0 = b2 >> 2;
             uint32_t g[4];
             g[3] = hash_get(hash, lg, (uint32_t)(min(a3, b3) * 256 + max(a3, b3))) << (a3 == b3 ? 1 : 0);
