@@ -60,8 +60,7 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     uint32_t* rows = reinterpret_cast<uint32_t*>(plane + ((P * P + 15) & ~15));
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
-    __shared__ uint32_t s_R[kRlCells];
-    __shared__ float s_red[16 * NW];
+    __shared__ uint32_t s_R[4 * kRlCells];   // one 24 x 16 histogram per direction
     __shared__ int s_scan[NW + 1];
 
     const NucInfo inf = p.info[i];
@@ -135,28 +134,32 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     auto masked = [&](int r, int c) -> bool {
         return (unsigned)r < (unsigned)P && (unsigned)c < (unsigned)P && ((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u);
     };
-    for (int d = 0; d < 4; ++d) {
-        const int dx = c_dirs[d][0], dy = c_dirs[d][1];
-        for (int k = tid; k < kRlCells; k += kTexThreads) s_R[k] = 0u;
-        __syncthreads();
-        for (int j = tid; j < K; j += kTexThreads) {
-            const uint32_t rc = list[j];
-            const int r = rc >> 8, c = rc & 255;
-            const int lv = plane[r * P + c];
+    // ---- run detection for the four directions: one sweep per direction, four histograms ----
+    for (int k = tid; k < 4 * kRlCells; k += kTexThreads) s_R[k] = 0u;
+    __syncthreads();
+    for (int j = tid; j < K; j += kTexThreads) {
+        const uint32_t rc = list[j];
+        const int r = rc >> 8, c = rc & 255;
+        const int lv = plane[r * P + c];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int dx = c_dirs[d][0], dy = c_dirs[d][1];
             if (masked(r - dy, c - dx) && plane[(r - dy) * P + (c - dx)] == lv) continue;   // not a run start
             int len = 1, r2 = r + dy, c2 = c + dx;
             while (masked(r2, c2) && plane[r2 * P + c2] == lv) { ++len; r2 += dy; c2 += dx; }
-            atomicAdd(&s_R[lv * kRlMax + min(len, kRlMax) - 1], 1u);
+            atomicAdd(&s_R[d * kRlCells + lv * kRlMax + min(len, kRlMax) - 1], 1u);
         }
-        __syncthreads();
-        // ---- 17 features: 14 weighted sums of the counts + squared row/column sums ----
+    }
+    __syncthreads();
+    // ---- 17 features per direction: warp d owns direction d (12 cells per lane, one shuffle tree) ----
+    if (warp < 4) {
+        const uint32_t* R4 = s_R + warp * kRlCells;
         float v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = 0.f;
-        for (int k = tid; k < kRlCells; k += kTexThreads) {
-            const float R = (float)s_R[k];
+        for (int k = lane; k < kRlCells; k += 32) {
+            const float R = (float)R4[k];
             if (R == 0.f) continue;
-            // weights computed in registers: a per-thread index into __constant__ memory would serialise
             const float fi = (float)(k / kRlMax + 1), fj = (float)(k % kRlMax + 1);
             const float ii = fi * fi, jj = fj * fj, ri = __fdiv_rn(1.0f, ii), rj = __fdiv_rn(1.0f, jj);
             const float u = (fi - 12.5f) * (1.0f / 11.5f), u2 = u * u, m2 = 1.0f - u2;
@@ -175,19 +178,20 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             v[12] = fmaf(R, u2 * jj, v[12]);
             v[13] = fmaf(R, fj, v[13]);
         }
-        if (tid < kRlLevels) {   // grey-level non-uniformity: squared row sums (exact integers)
+        if (lane < kRlLevels) {   // grey-level non-uniformity: squared row sums (exact integers)
             uint32_t rs = 0;
-            for (int j = 0; j < kRlMax; ++j) rs += s_R[tid * kRlMax + j];
+            for (int j = 0; j < kRlMax; ++j) rs += R4[lane * kRlMax + j];
             v[14] = (float)rs * (float)rs;
         }
-        if (tid < kRlMax) {      // run-length non-uniformity: squared column sums
+        if (lane < kRlMax) {      // run-length non-uniformity: squared column sums
             uint32_t cs = 0;
-            for (int l = 0; l < kRlLevels; ++l) cs += s_R[l * kRlMax + tid];
+            for (int l = 0; l < kRlLevels; ++l) cs += R4[l * kRlMax + lane];
             v[15] = (float)cs * (float)cs;
         }
-        block_sum<16>(v, s_red);
-        if (tid == 0) {
-            float* o_ = out + d * 17;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = warp_sum(v[q]);
+        if (lane == 0) {
+            float* o_ = out + warp * 17;
             const double nr = v[0], mean = (double)v[13] / nr;
             o_[0] = (float)(v[1] / nr);  o_[1] = (float)(v[2] / nr);
             o_[2] = (float)(v[14] / nr); o_[3] = (float)(v[15] / nr);
@@ -200,7 +204,6 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             o_[15] = (float)mean;                            // run length mean
             o_[16] = (float)((double)v[2] / nr - mean * mean);   // run length variance
         }
-        __syncthreads();
     }
 }
 
