@@ -147,6 +147,10 @@ const char* nfx_feature_set_name(uint32_t bit);
  * Returns the string length (excluding NUL) or NFX_ERR_INVALID if buf is too small. */
 int nfx_centroid_key(float x, float y, char* buf, int buflen);
 
+/* Rust `Display` of one f32 (shortest round-trip decimal, never an exponent): the formatting polars uses
+ * for the key and the CSV writer. Returns the length or NFX_ERR_INVALID if buf is too small. */
+int nfx_format_f32(float v, char* buf, int buflen);
+
 /* ---- multi-GPU partition ------------------------------------------------------ */
 /* Contiguous index ranges, one per part, boundaries rounded to multiples of batch_size so that
  * every reference chunk [k*B,(k+1)*B) (src/main.rs:148) lives on one GPU. bounds: [parts+1]. */

@@ -20,7 +20,9 @@ def _stale() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+    if not os.path.exists(os.path.join(HERE, "nfx-cli")):
+        return True
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))] + [
         os.path.join(HERE, "..", "include", "nfx.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -52,7 +54,23 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    build_cli()
     return OUT
+
+
+CLI = os.path.join(HERE, "nfx-cli")
+
+
+def build_cli() -> str:
+    """The C++ host driver (host/*.cpp) linked against libnfx.so."""
+    srcs = [os.path.join(HERE, "host", f) for f in ("nfx_host.cpp", "cli.cpp")]
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(HERE, "..", "include"), *srcs, "-o", CLI,
+           "-L", HERE, "-lnfx", "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building nfx-cli failed")
+    return CLI
 
 
 if __name__ == "__main__":

@@ -176,6 +176,13 @@ int nfx_centroid_key(float x, float y, char* buf, int buflen) {
     return (int)s.size();
 }
 
+int nfx_format_f32(float v, char* buf, int buflen) {
+    const std::string s = nfx::rust_f32_display(v);
+    if (!buf || (int)s.size() + 1 > buflen) return NFX_ERR_INVALID;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
 int nfx_partition(int64_t n, int32_t batch_size, int32_t parts, int64_t* bounds) {
     if (n < 0 || batch_size <= 0 || parts <= 0 || !bounds) return NFX_ERR_INVALID;
     const int64_t chunks = (n + batch_size - 1) / batch_size;

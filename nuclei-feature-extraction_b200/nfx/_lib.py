@@ -48,6 +48,7 @@ SYMBOLS = {
     "nfx_parse_feature_set": (_i, [C.c_char_p, C.POINTER(_u32)]),
     "nfx_feature_set_name": (C.c_char_p, [_u32]),
     "nfx_centroid_key": (_i, [_f, _f, C.c_char_p, _i]),
+    "nfx_format_f32": (_i, [_f, C.c_char_p, _i]),
     "nfx_partition": (_i, [_i64, C.c_int32, C.c_int32, C.POINTER(_i64)]),
     "nfx_profile_enable": (_i, [_vp, _i]),
     "nfx_profile_reset": (_i, [_vp]),
