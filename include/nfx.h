@@ -151,6 +151,28 @@ int nfx_centroid_key(float x, float y, char* buf, int buflen);
  * for the key and the CSV writer. Returns the length or NFX_ERR_INVALID if buf is too small. */
 int nfx_format_f32(float v, char* buf, int buflen);
 
+/* ---- GeoJSON -> CSR polygon packing ------------------------------------- */
+/* Replaces `serde_json::from_reader::<FeatureCollection>` (src/main.rs:37-42) for the model of
+ * src/geojson.rs:8-24 (`features[].bbox` required, `features[].geometry.{type,coordinates}`, unknown
+ * keys ignored, duplicate or missing fields rejected) and keeps ring 0 of every feature, which is all
+ * preprocess_polygon reads (src/utils.rs:54-60). The text is scanned and parsed by `threads` host
+ * threads (<= 0: all cores); the result is the CSR the other entry points take. Numbers are
+ * deserialised like serde_json 1.0.107 without `float_roundtrip` does for an f32 field (u64
+ * significand, one power-of-ten multiply/divide in f64, then `as f32`), so the coordinates and hence
+ * the centroid keys are the reference's bit for bit. On error: NFX_ERR_INVALID, message with line and
+ * column through nfx_last_error(NULL). */
+typedef struct nfx_geojson nfx_geojson;
+int nfx_geojson_parse(const char* text, int64_t len, int32_t threads, nfx_geojson** out);
+int64_t nfx_geojson_count(const nfx_geojson* g);          /* features */
+int64_t nfx_geojson_vertices(const nfx_geojson* g);       /* stored vertices of all rings 0 */
+const float* nfx_geojson_xy(const nfx_geojson* g);        /* [vertices][2] f32 */
+const int64_t* nfx_geojson_offsets(const nfx_geojson* g); /* [features+1] */
+const float* nfx_geojson_bbox(const nfx_geojson* g);      /* [features][4], NaN where the array is shorter */
+const int32_t* nfx_geojson_rings(const nfx_geojson* g);   /* [features] ring count (only ring 0 is kept) */
+void nfx_geojson_free(nfx_geojson* g);
+/* One JSON number token deserialised as an f32 field (the rule above); NFX_ERR_INVALID if it is not a number. */
+int nfx_parse_f32(const char* token, int32_t len, float* out);
+
 /* ---- multi-GPU partition ------------------------------------------------------ */
 /* Contiguous index ranges, one per part, boundaries rounded to multiples of batch_size so that
  * every reference chunk [k*B,(k+1)*B) (src/main.rs:148) lives on one GPU. bounds: [parts+1]. */

@@ -161,125 +161,23 @@ std::vector<std::unique_ptr<FeatureSet>> to_fs(const std::vector<FeatureSetKind>
 }
 
 // ------------------------------------------------------------------------------------------------
-// GeoJSON (geojson.rs:8-24): a small recursive-descent JSON reader that keeps only what serde keeps
+// GeoJSON (geojson.rs:8-24, main.rs:37-42): the library's multi-threaded packer
 // ------------------------------------------------------------------------------------------------
-namespace {
-struct Json {
-    const char* p;
-    const char* end;
-    explicit Json(const std::string& s) : p(s.data()), end(s.data() + s.size()) {}
-    void ws() { while (p < end && std::isspace((unsigned char)*p)) ++p; }
-    [[noreturn]] void fail(const char* what) { throw Error(std::string("geojson: ") + what); }
-    bool eat(char c) { ws(); if (p < end && *p == c) { ++p; return true; } return false; }
-    void expect(char c) { if (!eat(c)) fail("unexpected character"); }
-    std::string str() {
-        expect('"');
-        std::string s;
-        while (p < end && *p != '"') {
-            if (*p == '\\' && p + 1 < end) { ++p; s.push_back(*p == 'n' ? '\n' : *p); ++p; }
-            else s.push_back(*p++);
-        }
-        expect('"');
-        return s;
-    }
-    double num() {
-        ws();
-        char* e = nullptr;
-        const double v = std::strtod(p, &e);
-        if (e == p) fail("number expected");
-        p = e;
-        return v;
-    }
-    void skip() {   // any value
-        ws();
-        if (p >= end) fail("truncated");
-        if (*p == '"') { str(); return; }
-        if (*p == '{') { ++p; if (eat('}')) return; do { str(); expect(':'); skip(); } while (eat(',')); expect('}'); return; }
-        if (*p == '[') { ++p; if (eat(']')) return; do { skip(); } while (eat(',')); expect(']'); return; }
-        while (p < end && (std::isalnum((unsigned char)*p) || *p == '-' || *p == '+' || *p == '.')) ++p;
-    }
-    std::vector<float> floats() {
-        std::vector<float> v;
-        expect('[');
-        if (eat(']')) return v;
-        do { v.push_back((float)num()); } while (eat(','));   // serde: f64 -> `as f32`
-        expect(']');
-        return v;
-    }
-};
-}  // namespace
-
-FeatureCollection load_geometry(const std::string& path) {
-    std::ifstream f(path, std::ios::binary);
+FeatureCollection load_geometry(const std::string& path, int threads) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f) throw Error("cannot open " + path);
-    std::stringstream ss;
-    ss << f.rdbuf();
-    const std::string text = ss.str();
-    Json j(text);
+    const std::streamsize len = f.tellg();
+    f.seekg(0);
+    std::vector<char> text((size_t)len);
+    if (len && !f.read(text.data(), len)) throw Error("cannot read " + path);
+    nfx_geojson* g = nullptr;
+    if (nfx_geojson_parse(text.data(), (int64_t)len, threads, &g) != NFX_OK) throw Error(nfx_last_error(nullptr));
     FeatureCollection fc;
-    bool have_features = false;
-    j.expect('{');
-    if (!j.eat('}')) {
-        do {
-            const std::string key = j.str();
-            j.expect(':');
-            if (key != "features") { j.skip(); continue; }
-            have_features = true;
-            j.expect('[');
-            if (j.eat(']')) continue;
-            do {
-                Feature ft;
-                bool have_bbox = false, have_geom = false;
-                j.expect('{');
-                if (!j.eat('}')) {
-                    do {
-                        const std::string k2 = j.str();
-                        j.expect(':');
-                        if (k2 == "bbox") { ft.bbox = j.floats(); have_bbox = true; }
-                        else if (k2 == "geometry") {
-                            have_geom = true;
-                            j.expect('{');
-                            if (!j.eat('}')) {
-                                do {
-                                    const std::string k3 = j.str();
-                                    j.expect(':');
-                                    if (k3 == "type") ft.geometry_type = j.str();
-                                    else if (k3 == "coordinates") {   // Vec<Vec<Vec<f32>>>
-                                        j.expect('[');
-                                        if (!j.eat(']')) {
-                                            do {
-                                                std::vector<Point> ring;
-                                                j.expect('[');
-                                                if (!j.eat(']')) {
-                                                    do {
-                                                        const std::vector<float> pt = j.floats();
-                                                        if (pt.size() < 2) j.fail("a position needs two numbers");
-                                                        ring.push_back({pt[0], pt[1]});
-                                                    } while (j.eat(','));
-                                                    j.expect(']');
-                                                }
-                                                ft.coordinates.push_back(std::move(ring));
-                                            } while (j.eat(','));
-                                            j.expect(']');
-                                        }
-                                    } else j.skip();
-                                } while (j.eat(','));
-                                j.expect('}');
-                            }
-                        } else j.skip();
-                    } while (j.eat(','));
-                    j.expect('}');
-                }
-                if (!have_bbox) throw Error("geojson: missing field `bbox`");         // geojson.rs:18 (not an Option)
-                if (!have_geom) throw Error("geojson: missing field `geometry`");
-                if (ft.coordinates.empty()) throw Error("geojson: feature without a ring");   // utils.rs:55 coordinates[0]
-                fc.features.push_back(std::move(ft));
-            } while (j.eat(','));
-            j.expect(']');
-        } while (j.eat(','));
-        j.expect('}');
-    }
-    if (!have_features) throw Error("geojson: missing field `features`");
+    const size_t n = (size_t)nfx_geojson_count(g), nv = (size_t)nfx_geojson_vertices(g);
+    fc.xy.assign(nfx_geojson_xy(g), nfx_geojson_xy(g) + 2 * nv);
+    fc.off.assign(nfx_geojson_offsets(g), nfx_geojson_offsets(g) + n + 1);
+    fc.bbox.assign(nfx_geojson_bbox(g), nfx_geojson_bbox(g) + 4 * n);
+    nfx_geojson_free(g);
     return fc;
 }
 
@@ -464,17 +362,14 @@ std::string validate_paths(const Args& a) {
 // pipeline (main.rs:146-158)
 // ------------------------------------------------------------------------------------------------
 static void csr_of(const FeatureCollection& g, size_t lo, size_t hi, std::vector<float>& xy, std::vector<int64_t>& off) {
-    xy.clear();
-    off.assign(1, 0);
-    for (size_t i = lo; i < hi; ++i) {
-        for (auto& p : g.features[i].coordinates[0]) { xy.push_back(p[0]); xy.push_back(p[1]); }   // ring 0 as stored
-        off.push_back((int64_t)xy.size() / 2);
-    }
+    xy.assign(g.xy.begin() + 2 * g.off[lo], g.xy.begin() + 2 * g.off[hi]);   // ring 0 as stored
+    off.resize(hi - lo + 1);
+    for (size_t i = lo; i <= hi; ++i) off[i - lo] = g.off[i] - g.off[lo];
 }
 
 DataFrame extract(const FeatureCollection& geometry, const Image& image, const Args& args) {
     const uint32_t mask = feature_mask(args.feature_sets);
-    const size_t n = geometry.features.size();
+    const size_t n = geometry.size();
     const int F = nfx_feature_count(mask);
     std::vector<float> cent(2 * n), feat((size_t)F * n);
     std::vector<int64_t> bounds(args.gpus.size() + 1);
@@ -511,7 +406,7 @@ DataFrame extract_via_trait(const FeatureCollection& geometry, const Image& imag
     Context ctx(args.gpus[0], args.patch_size, args.batch_size);
     auto sets = to_fs(args.feature_sets, ctx);
     const int P = args.patch_size;
-    const size_t n = geometry.features.size(), plane = (size_t)P * P;
+    const size_t n = geometry.size(), plane = (size_t)P * P;
     DataFrame all;
     for (size_t lo = 0; lo < n; lo += (size_t)args.batch_size) {   // par_chunks(batch_size), main.rs:148
         const size_t hi = std::min(n, lo + (size_t)args.batch_size), m = hi - lo;
@@ -532,8 +427,9 @@ DataFrame extract_via_trait(const FeatureCollection& geometry, const Image& imag
         std::vector<Points> polygons(m);
         for (size_t i = 0; i < m; ++i) {
             centroids[i] = {cent[2 * i], cent[2 * i + 1]};
-            for (auto& p : geometry.features[lo + i].coordinates[0])   // utils.rs:65-72: centred ring
-                polygons[i].push_back({p[0] - centroids[i][0], p[1] - centroids[i][1]});
+            const float* ring = geometry.ring(lo + i);
+            for (size_t k = 0; k < geometry.ring_len(lo + i); ++k)   // utils.rs:65-72: centred ring
+                polygons[i].push_back({ring[2 * k] - centroids[i][0], ring[2 * k + 1] - centroids[i][1]});
             for (size_t px = 0; px < plane; ++px) {
                 masks.data[i * plane + px] = mask_u8[i * plane + px] ? 1.0f : 0.0f;
                 for (int ch = 0; ch < 3; ++ch)   // utils.rs:172: u8 as f32 / 255

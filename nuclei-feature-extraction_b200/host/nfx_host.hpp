@@ -80,15 +80,17 @@ struct GaborFilterFeatureSet : FeatureSet { explicit GaborFilterFeatureSet(Conte
 std::vector<std::unique_ptr<FeatureSet>> to_fs(const std::vector<FeatureSetKind>& s, Context& ctx);   // args.rs:51-73
 
 // ---- geojson.rs:8-24, main.rs:37-42 ------------------------------------------------------------
-struct Feature {
-    std::vector<float> bbox;                     // required
-    std::string geometry_type;
-    std::vector<std::vector<Point>> coordinates; // rings, parsed as f32
-};
+// The collection is kept as the CSR nfx_geojson_parse produces (ring 0 of every feature; the reference keeps
+// all rings but reads only coordinates[0], utils.rs:55).
 struct FeatureCollection {
-    std::vector<Feature> features;
+    std::vector<float> xy;        // [vertices][2], f32 as serde parses them
+    std::vector<int64_t> off;     // [features+1]
+    std::vector<float> bbox;      // [features][4] (required field of Feature, unused downstream)
+    size_t size() const { return off.empty() ? 0 : off.size() - 1; }
+    const float* ring(size_t i) const { return xy.data() + 2 * off[i]; }
+    size_t ring_len(size_t i) const { return (size_t)(off[i + 1] - off[i]); }
 };
-FeatureCollection load_geometry(const std::string& path);
+FeatureCollection load_geometry(const std::string& path, int threads = 0);   // multi-threaded, nfx_geojson_parse
 
 // ---- main.rs:20-35 ------------------------------------------------------------------------------
 struct Image {

@@ -70,6 +70,38 @@ def pack_polygons(rings):
     return xy, off
 
 
+def parse_f32(token: str) -> np.float32:
+    """One JSON number token as the reference's serde_json hands it to an f32 field (nfx_parse_f32)."""
+    o = C.c_float()
+    b = token.encode()
+    if lib().nfx_parse_f32(b, len(b), C.byref(o)) != NFX_OK:
+        raise NfxError(-1, (lib().nfx_last_error(None) or b"").decode())
+    return np.float32(o.value)
+
+
+def geojson_pack(text, threads: int = 0):
+    """GeoJSON text (bytes / str / mmap-able buffer) -> CSR of ring 0 of every feature, parsed by `threads`
+    host threads (src/main.rs:37-42, src/geojson.rs:8-24): (poly_xy f32 [nv,2], poly_off i64 [n+1],
+    bbox f32 [n,4], rings i32 [n])."""
+    if isinstance(text, str):
+        text = text.encode()
+    buf = np.frombuffer(text, dtype=np.uint8)
+    h = C.c_void_p()
+    rc = lib().nfx_geojson_parse(C.cast(buf.ctypes.data, C.c_char_p), buf.size, threads, C.byref(h))
+    if rc != NFX_OK:
+        raise NfxError(rc, (lib().nfx_last_error(None) or b"").decode())
+    try:
+        n = lib().nfx_geojson_count(h)
+        nv = lib().nfx_geojson_vertices(h)
+        xy = np.ctypeslib.as_array(lib().nfx_geojson_xy(h), shape=(nv, 2)).copy() if nv else np.zeros((0, 2), np.float32)
+        off = np.ctypeslib.as_array(lib().nfx_geojson_offsets(h), shape=(n + 1,)).copy()
+        bbox = np.ctypeslib.as_array(lib().nfx_geojson_bbox(h), shape=(n, 4)).copy() if n else np.zeros((0, 4), np.float32)
+        rings = np.ctypeslib.as_array(lib().nfx_geojson_rings(h), shape=(n,)).copy() if n else np.zeros(0, np.int32)
+    finally:
+        lib().nfx_geojson_free(h)
+    return xy, off, bbox, rings
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

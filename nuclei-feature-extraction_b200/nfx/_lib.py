@@ -49,6 +49,15 @@ SYMBOLS = {
     "nfx_feature_set_name": (C.c_char_p, [_u32]),
     "nfx_centroid_key": (_i, [_f, _f, C.c_char_p, _i]),
     "nfx_format_f32": (_i, [_f, C.c_char_p, _i]),
+    "nfx_geojson_parse": (_i, [C.c_char_p, _i64, C.c_int32, C.POINTER(_vp)]),
+    "nfx_geojson_count": (_i64, [_vp]),
+    "nfx_geojson_vertices": (_i64, [_vp]),
+    "nfx_geojson_xy": (C.POINTER(_f), [_vp]),
+    "nfx_geojson_offsets": (C.POINTER(_i64), [_vp]),
+    "nfx_geojson_bbox": (C.POINTER(_f), [_vp]),
+    "nfx_geojson_rings": (C.POINTER(C.c_int32), [_vp]),
+    "nfx_geojson_free": (None, [_vp]),
+    "nfx_parse_f32": (_i, [C.c_char_p, C.c_int32, C.POINTER(_f)]),
     "nfx_partition": (_i, [_i64, C.c_int32, C.c_int32, C.POINTER(_i64)]),
     "nfx_profile_enable": (_i, [_vp, _i]),
     "nfx_profile_reset": (_i, [_vp]),

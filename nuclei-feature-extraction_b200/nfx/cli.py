@@ -61,24 +61,15 @@ def validate_paths(a):
     return ext
 
 
-def load_geometry(path):
+def load_geometry(path, threads: int = 0):
     """load_geometry (src/main.rs:37-42) + the serde model of src/geojson.rs:8-24: every feature
-    needs `bbox` and `geometry.coordinates`; ring 0 is taken as stored (closing duplicate kept) and
-    parsed to f32. Returns CSR (poly_xy f32 [sum V, 2], poly_off int64 [n+1])."""
-    with open(path, "r") as f:
-        fc = json.load(f)
-    feats = fc["features"]
-    off = np.zeros(len(feats) + 1, dtype=np.int64)
-    rings = []
-    for i, ft in enumerate(feats):
-        if "bbox" not in ft:
-            raise KeyError(f"missing field `bbox` in feature {i}")          # serde: required field
-        ring = np.asarray(ft["geometry"]["coordinates"][0], dtype=np.float64)
-        ring = ring.reshape(-1, ring.shape[-1])[:, :2].astype(np.float32)   # Vec<Vec<Vec<f32>>>
-        rings.append(ring)
-        off[i + 1] = off[i] + len(ring)
-    xy = np.concatenate(rings, 0) if rings else np.zeros((0, 2), np.float32)
-    return np.ascontiguousarray(xy, dtype=np.float32), off
+    needs `bbox` and `geometry.{type,coordinates}`; ring 0 is taken as stored (closing duplicate kept)
+    and parsed to f32 with serde_json's number rule by the library's multi-threaded packer
+    (nfx_geojson_parse). Returns CSR (poly_xy f32 [sum V, 2], poly_off int64 [n+1])."""
+    import nfx
+    text = np.fromfile(path, dtype=np.uint8)
+    xy, off, _bbox, _rings = nfx.geojson_pack(text, threads)
+    return xy, off
 
 
 def load_input_image(path):

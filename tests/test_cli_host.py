@@ -58,7 +58,7 @@ def test_geojson_model_f32_ring0_bbox_required(tmp_path):
     assert xy.dtype == np.float32 and off.tolist() == [0, 4]
     assert np.array_equal(xy, rings[0].astype(np.float32))          # parsed AS f32, closing duplicate kept
     _write_geojson(p, rings, with_bbox=False)
-    with pytest.raises(KeyError):
+    with pytest.raises(nfx.NfxError, match="missing field `bbox`"):
         cli.load_geometry(p)                                        # src/geojson.rs:18: bbox is not Option
 
 
