@@ -173,6 +173,21 @@ void nfx_geojson_free(nfx_geojson* g);
 /* One JSON number token deserialised as an f32 field (the rule above); NFX_ERR_INVALID if it is not a number. */
 int nfx_parse_f32(const char* token, int32_t len, float* out);
 
+/* ---- output assembly ----------------------------------------------------- */
+/* The text polars' CsvWriter writes for the reference's output DataFrame (src/main.rs:76-89 hstack behind
+ * the `centroid` key of src/utils.rs:226-232; writer at src/main.rs:163-166): a header line, then per
+ * nucleus `"cx,cy",f0,...,f{F-1}\n`, every f32 in Rust `Display` form (shortest round-trip digits, no
+ * exponent, NaN / inf / -inf). Cells are formatted ON THE GPU from the resident result of nfx_compute
+ * (k_csv_measure, scan, k_csv_write) and only the text crosses PCIe; call it per row range to stream a
+ * large table through a fixed host buffer. *len receives the byte count (also when NFX_ERR_INVALID
+ * reports that cap is too small; nothing is written then). `out` is a host pointer (pinned is faster). */
+int nfx_csv_header(uint32_t feature_mask, char* out, int64_t cap, int64_t* len);
+int nfx_csv_rows(nfx_ctx* ctx, int64_t row_lo, int64_t row_hi, char* out, int64_t cap, int64_t* len);
+/* Same formatter for a caller-held DataFrame (host pointers: centroids [n][2], features [n][cols] f32), e.g.
+ * the frames returned by nfx_compute_features_batched after the host's hstack. */
+int nfx_csv_format(nfx_ctx* ctx, int64_t n, int32_t cols, const float* centroids, const float* features,
+                   char* out, int64_t cap, int64_t* len);
+
 /* ---- multi-GPU partition ------------------------------------------------------ */
 /* Contiguous index ranges, one per part, boundaries rounded to multiples of batch_size so that
  * every reference chunk [k*B,(k+1)*B) (src/main.rs:148) lives on one GPU. bounds: [parts+1]. */

@@ -95,6 +95,12 @@ struct nfx_ctx {
     DevBuf<uint8_t> flush;
     int* d_bad = nullptr;
 
+    // output assembly (csv.cu)
+    DevBuf<int64_t> csv_len, csv_off;
+    DevBuf<uint8_t> csv_tmp;
+    DevBuf<char> csv_text;
+    DevBuf<float> csv_in;
+
     // measurement
     bool profile = false;
     std::vector<ProfRec> recs;
@@ -354,6 +360,7 @@ int nfx_destroy(nfx_ctx* ctx) {
     ctx->tile.release(); ctx->xy.release(); ctx->off.release(); ctx->centroid.release(); ctx->info.release();
     ctx->bitmask.release(); ctx->out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->gabor_part.release(); ctx->patches.release();
     ctx->scratch8.release(); ctx->scratchf.release(); ctx->scratch32.release(); ctx->flush.release();
+    ctx->csv_len.release(); ctx->csv_off.release(); ctx->csv_tmp.release(); ctx->csv_text.release(); ctx->csv_in.release();
     if (ctx->d_bad) cudaFree(ctx->d_bad);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
@@ -474,6 +481,59 @@ int nfx_download(nfx_ctx* ctx, float* centroids, float* features) {
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return NFX_OK;
+}
+
+// ---- output assembly ----------------------------------------------------------
+namespace {
+int csv_format_device(nfx_ctx* ctx, const float2* d_centroids, const float* d_features, int F, int64_t row_lo,
+                      int64_t rows, char* out, int64_t cap, int64_t* len) {
+    *len = 0;
+    if (rows == 0) return NFX_OK;
+    CK(ctx->csv_len.ensure((size_t)rows + 1));
+    CK(ctx->csv_off.ensure((size_t)rows + 1));
+    size_t tmp = 0;
+    CK(csv_scan_bytes(rows, &tmp));
+    CK(ctx->csv_tmp.ensure(tmp));
+    CsvParams p{d_centroids, d_features, F, row_lo, rows, ctx->csv_len.p, ctx->csv_off.p, nullptr};
+    CK(cudaMemsetAsync(ctx->csv_len.p + rows, 0, sizeof(int64_t), ctx->stream));
+    CK(timed(ctx, "k_csv_measure", 1, [&] { return launch_csv_measure(p, ctx->csv_tmp.p, tmp, ctx->stream); }));
+    ctx->launches += 2;   // cub's two scan kernels
+    int64_t total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->csv_off.p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *len = total;
+    if (total > cap || !out) return fail(ctx, NFX_ERR_INVALID, "csv: output buffer too small, need " + std::to_string(total) + " bytes");
+    CK(ctx->csv_text.ensure((size_t)total));
+    p.text = ctx->csv_text.p;
+    CK(timed(ctx, "k_csv_write", 1, [&] { return launch_csv_write(p, ctx->stream); }));
+    CK(cudaMemcpyAsync(out, ctx->csv_text.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+}  // namespace
+
+int nfx_csv_rows(nfx_ctx* ctx, int64_t row_lo, int64_t row_hi, char* out, int64_t cap, int64_t* len) {
+    if (!ctx || !len) return NFX_ERR_INVALID;
+    if (!ctx->computed_mask) return fail(ctx, NFX_ERR_STATE, "nothing computed: call nfx_compute first");
+    if (row_lo < 0 || row_hi < row_lo || row_hi > ctx->n) return fail(ctx, NFX_ERR_INVALID, "nfx_csv_rows: bad row range");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    return csv_format_device(ctx, ctx->centroid.p, ctx->out.p, ctx->out_cols, row_lo, row_hi - row_lo, out, cap, len);
+}
+
+int nfx_csv_format(nfx_ctx* ctx, int64_t n, int32_t cols, const float* centroids, const float* features, char* out,
+                   int64_t cap, int64_t* len) {
+    if (!ctx || !len || n < 0 || cols < 0 || (n > 0 && (!centroids || (cols > 0 && !features))))
+        return ctx ? fail(ctx, NFX_ERR_INVALID, "nfx_csv_format: bad arguments") : NFX_ERR_INVALID;
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    *len = 0;
+    if (n == 0) return NFX_OK;
+    const size_t nc = 2 * (size_t)n, nf = (size_t)n * (size_t)cols;
+    CK(ctx->csv_in.ensure(nc + nf + 4));
+    CK(cudaMemcpyAsync(ctx->csv_in.p, centroids, nc * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (nf) CK(cudaMemcpyAsync(ctx->csv_in.p + nc, features, nf * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return csv_format_device(ctx, reinterpret_cast<const float2*>(ctx->csv_in.p), ctx->csv_in.p + nc, cols, 0, n, out, cap, len);
 }
 
 int nfx_extract(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* poly_off, uint32_t mask,

@@ -109,4 +109,18 @@ cudaError_t launch_pack_batch(int64_t n, int P, const float* patchs, const float
                               uint8_t* patches_u8, int64_t pitch, uint32_t* bitmask, NucInfo* info,
                               int* bad_count, cudaStream_t s);
 
+// ---- csv.cu: output assembly -----------------------------------------------
+struct CsvParams {
+    const float2* centroids;   // [n] all rows of the context
+    const float* features;     // [n][F]
+    int F;
+    int64_t row_lo, rows;      // the rows to format
+    int64_t* row_len;          // [rows+1] scratch, entry `rows` must be zero
+    int64_t* row_off;          // [rows+1] exclusive scan: byte offset of every row, total at [rows]
+    char* text;                // output (k_csv_write)
+};
+cudaError_t csv_scan_bytes(int64_t rows, size_t* bytes);
+cudaError_t launch_csv_measure(const CsvParams& p, void* scan_tmp, size_t scan_bytes, cudaStream_t s);
+cudaError_t launch_csv_write(const CsvParams& p, cudaStream_t s);
+
 }  // namespace nfx

@@ -11,43 +11,20 @@
 #include <vector>
 
 #include "../../include/nfx.h"
+#include "f32_display.h"
 #include "nfx_host.h"
 
 namespace nfx {
 
-// Rust `impl Display for f32`: shortest decimal that round-trips, never an exponent, no ".0".
+// Rust `impl Display for f32` (f32_display.h): shortest round-trip digits, never an exponent, no ".0".
+static const uint64_t kPow5Inv[] = NFX_POW5_INV_SPLIT;
+static const uint64_t kPow5[] = NFX_POW5_SPLIT;
 std::string rust_f32_display(float x) {
-    if (x != x) return "NaN";
-    if (isinf(x)) return x > 0 ? "inf" : "-inf";
-    if (x == 0.0f) return signbit(x) ? "-0" : "0";
-    char buf[64];
-    int p = 0;
-    for (; p <= 9; ++p) {
-        snprintf(buf, sizeof buf, "%.*e", p, (double)x);
-        if (strtof(buf, nullptr) == x) break;
-    }
-    // buf = [-]d[.ddd]e[+-]XX
-    std::string s(buf);
-    const bool neg = s[0] == '-';
-    if (neg) s.erase(0, 1);
-    const size_t epos = s.find('e');
-    const int E = atoi(s.c_str() + epos + 1);
-    std::string digits;
-    for (size_t k = 0; k < epos; ++k)
-        if (s[k] != '.') digits.push_back(s[k]);
-    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
-    std::string out = neg ? "-" : "";
-    if (E >= 0) {
-        const size_t ip = (size_t)E + 1;
-        if (digits.size() <= ip) {
-            out += digits + std::string(ip - digits.size(), '0');
-        } else {
-            out += digits.substr(0, ip) + "." + digits.substr(ip);
-        }
-    } else {
-        out += "0." + std::string((size_t)(-E - 1), '0') + digits;
-    }
-    return out;
+    uint32_t bits;
+    memcpy(&bits, &x, 4);
+    char buf[NFX_F32_MAX_CHARS];
+    const int n = f32_display(bits, buf, kPow5Inv, kPow5);
+    return std::string(buf, (size_t)n);
 }
 
 namespace {
@@ -181,6 +158,18 @@ int nfx_format_f32(float v, char* buf, int buflen) {
     if (!buf || (int)s.size() + 1 > buflen) return NFX_ERR_INVALID;
     memcpy(buf, s.c_str(), s.size() + 1);
     return (int)s.size();
+}
+
+int nfx_csv_header(uint32_t mask, char* out, int64_t cap, int64_t* len) {
+    if (!len) return NFX_ERR_INVALID;
+    std::string h = "centroid";                       // main.rs:80-88: the key column, then the sets in flat() order
+    const int f = nfx_feature_count(mask);
+    for (int j = 0; j < f; ++j) { h += ','; h += nfx_feature_name(mask, j); }
+    h += '\n';
+    *len = (int64_t)h.size();
+    if (!out || cap < (int64_t)h.size()) { nfx::g_thread_error = "csv: header buffer too small"; return NFX_ERR_INVALID; }
+    memcpy(out, h.data(), h.size());
+    return NFX_OK;
 }
 
 int nfx_partition(int64_t n, int32_t batch_size, int32_t parts, int64_t* bounds) {

@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
         const Image image = load_input_image(args.slide);
         std::fprintf(stderr, "INFO Extracting features\n");      // main.rs:143
         const DataFrame df = args.via_trait ? extract_via_trait(geometry, image, args) : extract(geometry, image, args);
-        write_output(args.output, ext, df);
+        write_output(args.output, ext, df, args.host_csv || args.gpus.empty() ? -1 : args.gpus[0]);
         return 0;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "ERROR %s\n", e.what());

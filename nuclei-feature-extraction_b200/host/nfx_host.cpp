@@ -33,6 +33,7 @@ void DataFrame::vstack(const DataFrame& o) {
     if (names.empty() && centroid.empty()) { *this = o; return; }
     if (o.names != names) throw Error("vstack: schemas differ");
     centroid.insert(centroid.end(), o.centroid.begin(), o.centroid.end());
+    centroid_xy.insert(centroid_xy.end(), o.centroid_xy.begin(), o.centroid_xy.end());
     for (size_t j = 0; j < columns.size(); ++j) columns[j].insert(columns[j].end(), o.columns[j].begin(), o.columns[j].end());
 }
 
@@ -103,9 +104,10 @@ static std::string key_of(float x, float y) {
     nfx_centroid_key(x, y, b, sizeof b);   // utils.rs:226-228
     return b;
 }
-static DataFrame frame_from(uint32_t mask, const std::vector<std::string>& keys, const std::vector<float>& feat) {
+static DataFrame frame_from(uint32_t mask, const std::vector<std::string>& keys, const float* cent_xy, const std::vector<float>& feat) {
     DataFrame df;
     df.centroid = keys;
+    df.centroid_xy.assign(cent_xy, cent_xy + 2 * keys.size());
     const int F = nfx_feature_count(mask);
     const size_t n = keys.size();
     for (int j = 0; j < F; ++j) {
@@ -142,7 +144,7 @@ DataFrame FeatureSet::compute_features_batched(const std::vector<Point>& centroi
                                             masks.data.data(), out.data()));
     std::vector<std::string> keys;
     for (auto& c : centroids) keys.push_back(key_of(c[0], c[1]));
-    return frame_from(bit_, keys, out);
+    return frame_from(bit_, keys, centroids.empty() ? nullptr : &centroids[0][0], out);
 }
 
 std::vector<std::unique_ptr<FeatureSet>> to_fs(const std::vector<FeatureSetKind>& s, Context& ctx) {
@@ -322,6 +324,7 @@ Args parse_args(int argc, char** argv) {
         else if (s == "-o" || s == "--overwrite") a.overwrite = true;
         else if (s == "-v" || s == "--verbose") a.verbose = true;
         else if (s == "--via-trait") a.via_trait = true;
+        else if (s == "--host-csv") a.host_csv = true;
         else if (s == "-p" || s == "--patch-size") a.patch_size = need_int(i);
         else if (s == "-t" || s == "--thread-count") a.thread_count = need_int(i);
         else if (s == "-b" || s == "--batch-size") a.batch_size = need_int(i);
@@ -398,7 +401,7 @@ DataFrame extract(const FeatureCollection& geometry, const Image& image, const A
         if (!e.empty()) throw Error(e);
     std::vector<std::string> keys(n);
     for (size_t i = 0; i < n; ++i) keys[i] = key_of(cent[2 * i], cent[2 * i + 1]);
-    return frame_from(mask, keys, feat);
+    return frame_from(mask, keys, cent.data(), feat);
 }
 
 DataFrame extract_via_trait(const FeatureCollection& geometry, const Image& image, const Args& args) {
@@ -452,22 +455,45 @@ static std::string f32s(float v) {
     return b;
 }
 
-void write_output(const std::string& path, const std::string& ext, const DataFrame& df) {
+// CSV through the device formatter (nfx_csv_format): row-major blocks of the frame go up, text comes back.
+static void write_csv_device(std::ofstream& f, const DataFrame& df, int device) {
+    Context ctx(device, 64, 100);
+    const size_t n = df.height(), F = df.columns.size();
+    const size_t block = std::max<size_t>(1, std::min<size_t>(n, (64u << 20) / (4 * (F + 2))));   // ~64 MB of cells per call
+    std::vector<float> feat(block * F);
+    std::vector<char> text(block * (F + 2) * 12 + 64);
+    for (size_t lo = 0; lo < n; lo += block) {
+        const size_t m = std::min(block, n - lo);
+        for (size_t j = 0; j < F; ++j)
+            for (size_t i = 0; i < m; ++i) feat[i * F + j] = df.columns[j][lo + i];
+        int64_t len = 0;
+        int rc = nfx_csv_format(ctx.raw(), (int64_t)m, (int32_t)F, &df.centroid_xy[2 * lo], feat.data(), text.data(), (int64_t)text.size(), &len);
+        if (rc != NFX_OK && len > (int64_t)text.size()) {
+            text.resize((size_t)len);
+            rc = nfx_csv_format(ctx.raw(), (int64_t)m, (int32_t)F, &df.centroid_xy[2 * lo], feat.data(), text.data(), (int64_t)text.size(), &len);
+        }
+        ctx.check(rc);
+        f.write(text.data(), len);
+    }
+}
+
+void write_output(const std::string& path, const std::string& ext, const DataFrame& df, int device) {
     if (ext != "csv" && ext != "json")
         throw Error("nfx-cli writes csv and json; parquet / ipc need the polars writers of the Rust host (or `python -m nfx.cli`)");
     std::ofstream f(path, std::ios::binary);
     if (!f) throw Error("cannot create " + path);
-    if (ext == "csv") {
+    if (ext == "csv") {   // polars 0.32 CsvWriter (oracle/SPEC.md B12)
         f << "centroid";
         for (auto& nme : df.names) f << ',' << nme;
         f << '\n';
-        for (size_t i = 0; i < df.height(); ++i) {
-            f << '"' << df.centroid[i] << '"';   // the key holds a comma: quoted like polars' CsvWriter does
-            for (auto& col : df.columns) {
-                f << ',';
-                if (!std::isnan(col[i])) f << f32s(col[i]);   // null/NaN -> empty field
+        if (device >= 0 && df.centroid_xy.size() == 2 * df.height()) {
+            write_csv_device(f, df, device);
+        } else {
+            for (size_t i = 0; i < df.height(); ++i) {
+                f << '"' << df.centroid[i] << '"';   // the key holds a comma: quoted like polars' CsvWriter does
+                for (auto& col : df.columns) f << ',' << f32s(col[i]);   // NaN is a value, not a null, in polars
+                f << '\n';
             }
-            f << '\n';
         }
     } else {   // JSON lines
         for (size_t i = 0; i < df.height(); ++i) {

@@ -31,7 +31,8 @@ struct Tensor {
 
 // polars DataFrame subset: one Utf8 key column + f32 feature columns
 struct DataFrame {
-    std::vector<std::string> centroid;
+    std::vector<std::string> centroid;           // key column (utils.rs:226-232)
+    std::vector<float> centroid_xy;              // the same centroids as numbers, [row][2] (for the device CSV formatter)
     std::vector<std::string> names;
     std::vector<std::vector<float>> columns;     // columns[j][row]
     size_t height() const { return centroid.size(); }
@@ -103,7 +104,7 @@ Image load_input_image(const std::string& path);   // png (8-bit, non-interlaced
 struct Args {
     std::string geometry, slide, output;
     std::vector<FeatureSetKind> feature_sets;
-    bool overwrite = false, verbose = false, via_trait = false;
+    bool overwrite = false, verbose = false, via_trait = false, host_csv = false;
     int patch_size = 64;
     int thread_count = 0;
     std::vector<int> gpus;
@@ -120,6 +121,7 @@ DataFrame extract(const FeatureCollection& geometry, const Image& image, const A
 DataFrame extract_via_trait(const FeatureCollection& geometry, const Image& image, const Args& args);
 
 // ---- main.rs:160-189 ----------------------------------------------------------------------------
-void write_output(const std::string& path, const std::string& ext, const DataFrame& df);   // csv, json; others -> Error
+// csv (cells formatted on GPU `device` when >= 0, else on the host: same bytes), json; others -> Error
+void write_output(const std::string& path, const std::string& ext, const DataFrame& df, int device = -1);
 
 }  // namespace nfxhost

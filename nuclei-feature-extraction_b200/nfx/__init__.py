@@ -51,6 +51,25 @@ def centroid_key(x, y) -> str:
     return buf.value.decode()
 
 
+def format_f32(v) -> str:
+    """Rust `Display` of one f32 (nfx_format_f32): what polars writes into CSV cells and the key."""
+    buf = C.create_string_buffer(80)
+    n = lib().nfx_format_f32(C.c_float(float(np.float32(v))), buf, 80)
+    if n < 0:
+        raise NfxError(n, "format buffer too small")
+    return buf.value.decode()
+
+
+def csv_header(mask: int) -> bytes:
+    """`centroid,<columns>\\n` (src/main.rs:80-88, 163-166)."""
+    n = C.c_int64()
+    lib().nfx_csv_header(mask, None, 0, C.byref(n))
+    buf = C.create_string_buffer(n.value)
+    if lib().nfx_csv_header(mask, buf, n.value, C.byref(n)) != NFX_OK:
+        raise NfxError(-1, "csv header")
+    return buf.raw[:n.value]
+
+
 def partition(n: int, batch_size: int, parts: int):
     b = (C.c_int64 * (parts + 1))()
     rc = lib().nfx_partition(n, batch_size, parts, b)
@@ -180,6 +199,35 @@ class Extractor:
             features = np.empty((self.n, F), dtype=np.float32)
         self._ck(lib().nfx_download(self._h, _ptr(centroids), _ptr(features)))
         return centroids, features
+
+    def csv_rows(self, lo: int = 0, hi: int | None = None, buf=None, view: bool = False):
+        """CSV text of rows [lo, hi) of the resident result, formatted on the GPU (nfx_csv_rows). `buf` is an
+        optional reusable (pinned) uint8 array; it is grown when the text does not fit."""
+        hi = self.n if hi is None else hi
+        if buf is None:
+            buf = np.empty(max(1 << 16, (hi - lo) * 64), dtype=np.uint8)
+        n = C.c_int64()
+        rc = lib().nfx_csv_rows(self._h, lo, hi, _ptr(buf), buf.size, C.byref(n))
+        if rc != NFX_OK and n.value > buf.size:
+            buf = np.empty(n.value, dtype=np.uint8)
+            rc = lib().nfx_csv_rows(self._h, lo, hi, _ptr(buf), buf.size, C.byref(n))
+        self._ck(rc)
+        return buf[:n.value] if view else buf[:n.value].tobytes()
+
+    def csv_format(self, centroids, features) -> bytes:
+        """CSV rows of a caller-held frame (centroids [n,2], features [n,F] f32), formatted on the GPU."""
+        centroids = np.ascontiguousarray(centroids, dtype=np.float32).reshape(-1, 2)
+        n = len(centroids)
+        features = np.ascontiguousarray(features, dtype=np.float32)
+        features = features.reshape(n, features.shape[-1] if features.ndim == 2 else (features.size // max(n, 1)))
+        need = C.c_int64()
+        rc = lib().nfx_csv_format(self._h, n, features.shape[1], _ptr(centroids), _ptr(features), None, 0, C.byref(need))
+        if need.value == 0:
+            self._ck(rc)
+            return b""
+        buf = np.empty(need.value, dtype=np.uint8)
+        self._ck(lib().nfx_csv_format(self._h, n, features.shape[1], _ptr(centroids), _ptr(features), _ptr(buf), buf.size, C.byref(need)))
+        return buf[:need.value].tobytes()
 
     def extract(self, poly_xy, poly_off, feature_sets):
         """chunk(s) -> features, rows in input order. Returns (keys, centroids, features, names)."""

@@ -58,6 +58,9 @@ SYMBOLS = {
     "nfx_geojson_rings": (C.POINTER(C.c_int32), [_vp]),
     "nfx_geojson_free": (None, [_vp]),
     "nfx_parse_f32": (_i, [C.c_char_p, C.c_int32, C.POINTER(_f)]),
+    "nfx_csv_header": (_i, [_u32, _vp, _i64, C.POINTER(_i64)]),
+    "nfx_csv_rows": (_i, [_vp, _i64, _i64, _vp, _i64, C.POINTER(_i64)]),
+    "nfx_csv_format": (_i, [_vp, _i64, C.c_int32, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "nfx_partition": (_i, [_i64, C.c_int32, C.c_int32, C.POINTER(_i64)]),
     "nfx_profile_enable": (_i, [_vp, _i]),
     "nfx_profile_reset": (_i, [_vp]),

@@ -115,3 +115,16 @@ def test_cli_json_writer(inputs):
     assert r.returncode == 0, r.stderr
     rows = [json.loads(ln) for ln in open(out)]
     assert len(rows) == len(inputs["rings"]) and list(rows[0])[:3] == ["centroid", "mean_r", "mean_g"]
+
+
+@pytest.mark.gpu
+def test_cli_csv_device_formatter_equals_host_writer(inputs):
+    """The CSV cells formatted on the GPU (nfx_csv_format) are byte-identical to the host writer's."""
+    d = inputs["dir"]
+    a, b = d / "dev.csv", d / "host.csv"
+    for out, extra in ((a, []), (b, ["--host-csv"])):
+        r = _run(["-o", *extra, "--", d / "cells.geojson", d / "slide.png", out, "all"])
+        assert r.returncode == 0, r.stderr
+    ta, tb = open(a, "rb").read(), open(b, "rb").read()
+    assert ta == tb and ta.count(b"\n") == len(inputs["rings"]) + 1
+    assert ta.split(b"\n")[1].startswith(b'"')
