@@ -262,39 +262,32 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        double v[19];
-        v[0] = (double)K;
+    // ---- 17 columns, one lane each (out[6] = mean_h belongs to k_hue_finalize). Same f64 expressions for
+    //      every column: m = s/K ; mean = (pivot + m)/den ; std = sqrt(max(ss/K - m^2, 0))/den ----
+    if (warp == 0 && lane < 18 && lane != 6) {
+        // column -> index of its sum and of its sum of squares in v[] (0 = unused), v = [K, 8 integer sums, s1[5], s2[5]]
+        //              mean_r g  b  std_r g  b  -  mean_s mean_v std_h std_s std_v mean_hed0 1   2  std_hed0 1   2
+        static const int ia[18] = {1, 2, 3, 1, 2, 3, 0, 12, 7, 13, 12, 7, 9, 10, 11, 9, 10, 11};
+        static const int ib[18] = {0, 0, 0, 4, 5, 6, 0, 0, 0, 18, 17, 8, 0, 0, 0, 14, 15, 16};
+        auto fetch = [&](int q) -> double {   // q in 1..18
+            if (q <= 8) {
+                unsigned long long t = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            unsigned long long t = 0;
-            for (int w = 0; w < NW; ++w) t += s_ri[w][q];
-            v[1 + q] = (double)t;
-        }
-#pragma unroll
-        for (int q = 0; q < 10; ++q) v[9 + q] = (double)s_rf[0][q];
+                for (int w = 0; w < NW; ++w) t += s_ri[w][q - 1];
+                return (double)t;
+            }
+            return (double)s_rf[0][q - 9];
+        };
+        const int a = ia[lane], b = ib[lane];
+        const bool is_std = b != 0;
+        const bool is8 = a <= 8;                                   // u8-valued channel: scale by 1/255
+        const float pivf = lane == 7 ? pv.s : (lane == 12 ? pv.hed[0] : (lane == 13 ? pv.hed[1] : (lane == 14 ? pv.hed[2] : 0.f)));
+        const double Kd = (double)K;
+        const double m = fetch(a) / Kd;
+        double val = (double)pivf + m;
+        if (is_std) val = sqrt(fmax(fetch(b) / Kd - m * m, 0.0));
         float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
-        const double Kd = v[0];
-        auto mean8 = [&](double s) { return (float)(s / Kd / 255.0); };
-        auto std8 = [&](double s, double ss) {
-            const double m = s / Kd;
-            return (float)(sqrt(fmax(ss / Kd - m * m, 0.0)) / 255.0);
-        };
-        auto meanp = [&](int q, float pivot) { return (float)((double)pivot + v[9 + q] / Kd); };
-        auto stdp = [&](int q) {
-            const double m = v[9 + q] / Kd;
-            return (float)sqrt(fmax(v[14 + q] / Kd - m * m, 0.0));
-        };
-        out[0] = mean8(v[1]); out[1] = mean8(v[2]); out[2] = mean8(v[3]);
-        out[3] = std8(v[1], v[4]); out[4] = std8(v[2], v[5]); out[5] = std8(v[3], v[6]);
-        // out[6] = mean_h: k_hue_finalize
-        out[7] = meanp(3, pv.s);
-        out[8] = mean8(v[7]);
-        out[9] = stdp(4);
-        out[10] = stdp(3);
-        out[11] = std8(v[7], v[8]);
-        out[12] = meanp(0, pv.hed[0]); out[13] = meanp(1, pv.hed[1]); out[14] = meanp(2, pv.hed[2]);
-        out[15] = stdp(0); out[16] = stdp(1); out[17] = stdp(2);
+        out[lane] = (float)(is8 ? val / 255.0 : val);
     }
 }
 

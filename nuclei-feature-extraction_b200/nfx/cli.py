@@ -119,6 +119,15 @@ def extract_multi_gpu(image, xy, off, mask, gpus, patch_size, batch_size):
     return cents, feats
 
 
+def write_csv_device(path, cents, feats, mask, device, rows_per_call=65536):
+    """polars' CsvWriter output (oracle/SPEC.md B12) with the cells formatted on the GPU (nfx_csv_format)."""
+    import nfx
+    with open(path, "wb") as f, nfx.Extractor(device) as ex:
+        f.write(nfx.csv_header(mask))
+        for lo in range(0, len(cents), rows_per_call):
+            f.write(ex.csv_format(cents[lo:lo + rows_per_call], feats[lo:lo + rows_per_call]))
+
+
 def write_output(path, ext, keys, feats, names):
     """The writers of src/main.rs:160-189: first column `centroid` (Utf8), then one f32 column per feature."""
     import pyarrow as pa
@@ -165,7 +174,10 @@ def main(argv=None) -> int:
     except nfx.NfxError as e:
         die(str(e))
     keys = [nfx.centroid_key(c[0], c[1]) for c in cents]
-    write_output(a.output, ext, keys, feats, nfx.feature_names(mask))
+    if ext == "csv":
+        write_csv_device(a.output, cents, feats, mask, gpus[0])
+    else:
+        write_output(a.output, ext, keys, feats, nfx.feature_names(mask))
     return 0
 
 
