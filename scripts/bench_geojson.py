@@ -14,6 +14,12 @@ from nfx import synth
 
 def make_text(n, seed=4):
     xy, off = synth.synth_polygons(n, 100_000, 100_000, seed)
+    return make_text_from(xy, off)
+
+
+def make_text_from(xy, off):
+    """A QuPath-like export of these rings (coordinates printed as shortest-repr doubles)."""
+    n = len(off) - 1
     parts = ['{"type":"FeatureCollection","features":[']
     xs = xy.astype(np.float64)
     for i in range(n):

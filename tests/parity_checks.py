@@ -1,0 +1,66 @@
+"""Comparison rules shared by the GPU parity tests: which rows of the REFERENCE's own arithmetic are
+ill-conditioned (and are therefore compared on a coarser footing) for the shape and colour sets."""
+import numpy as np
+import torch
+
+import nfx_oracle as o
+from tolerances import mismatches
+
+
+def _report(bad, limit=12):
+    return "\n".join(f"row {r} {c}: got {g!r} want {w!r}" for r, c, g, w in bad[:limit]) + f"\n({len(bad)} mismatches)"
+
+
+def check_shape(got, want, dbg, names):
+    """got [n,12] from the kernels, (want, dbg) = o.shape_features(polys, masks, return_debug=True)."""
+    _ = o
+    # ill-conditioned rows: rank-1 masks (lambda_min ~ 0) -> compare minor axis relative to major
+    got = got.astype(np.float64).copy()
+    w2 = want.copy()
+    j_min, j_maj, j_ecc, j_ori, j_dev = 2, 1, 3, 4, 8
+    with np.errstate(invalid="ignore"):
+        degenerate = ~(w2[:, j_min] > 1e-2 * w2[:, j_maj])
+    for j in (j_min, j_ecc, j_ori, j_dev):
+        got[degenerate, j] = 0
+        w2[degenerate, j] = 0
+    # near-isotropic masks: the eigenvector direction is ill-conditioned in the reference's own f32
+    with np.errstate(invalid="ignore"):
+        iso = (w2[:, j_maj] - w2[:, j_min]) < 1e-3 * w2[:, j_maj]
+    for j in (j_ori, j_dev):
+        got[iso, j] = 0
+        w2[iso, j] = 0
+    # orientation is an angle: compare modulo pi-wrap at +-pi
+    d = np.abs(got[:, j_ori] - w2[:, j_ori])
+    wrap = np.isclose(d, 2 * np.pi, atol=1e-3)
+    got[wrap, j_ori] = w2[wrap, j_ori]
+    bad = mismatches(got, w2, names, "geometry")
+    # the deviation is a ratio of two integer counts: f32 noise upstream of the ellipse parameters may
+    # flip a boundary pixel in the REFERENCE's own arithmetic; allow +-2 px on <1% of the nuclei ...
+    dev_bad = [b for b in bad if b[1] == "eliptic_deviation"]
+    other = [b for b in bad if b[1] != "eliptic_deviation"]
+    assert not other, _report(other)
+    for r, _, g, w in dev_bad:
+        K = dbg[r]["area_px"]
+        assert abs(g * K - w * K) <= 2.5, f"row {r}: deviation count {g*K} vs {w*K}"
+    assert len(dev_bad) <= max(2, len(want) // 100), _report(dev_bad)
+
+
+def check_color(got, want, names, patches, masks, batch):
+    got = got.astype(np.float64).copy()
+    want = want.astype(np.float64).copy()
+    j = names.index("mean_h")
+    # hue mean: compare as an angle (wrap) and skip rows whose resultant vector is ~0 (atan2 of noise)
+    n = len(want)
+    for k in range(0, n, batch):
+        hsv = o.hsv_from_rgb(patches[k:k + batch])
+        s, c = o.circular_mean_vectors(hsv[:, 0], masks[k:k + batch])
+        area = masks[k:k + batch].sum(dim=[1, 2, 3]) * len(hsv)
+        R = (torch.sqrt(s * s + c * c) / area).numpy()
+        illc = ~(R > 1e-2)
+        got[k:k + batch][illc, j] = 0
+        want[k:k + batch][illc, j] = 0
+    d = np.abs(got[:, j] - want[:, j])
+    wrap = np.abs(d - 360.0) < 0.05
+    got[wrap, j] = want[wrap, j]
+    bad = mismatches(got, want, names, "color")
+    assert not bad, _report(bad)
