@@ -81,13 +81,16 @@ __device__ __forceinline__ void haralick_write(float* o_, double T, double sg, d
                                                double idm_sum) {
     const double lnT = log(T);
     const double asm_ = 2.0 * sg / (T * T);
-    const double hxy = lnT - 2.0 * slg / T;
+    // Entropies are >= 0; the logarithmic sums arrive in fixed point (2^-16 quantum), so a matrix with ONE occupied
+    // cell (asm == 1 exactly: the moments are exact integers) is pinned to its exact entropy 0 (-> IMC1 = 0/0 = NaN).
+    const bool one_cell = asm_ == 1.0;
+    const double hxy = one_cell ? 0.0 : fmax(lnT - 2.0 * slg / T, 0.0);
     const double mu = x1 / T, ei2 = x2 / T;
     const double var = ei2 - mu * mu;
-    const double hxm = lnT - cx / T;
+    const double hxm = one_cell ? 0.0 : fmax(lnT - cx / T, 0.0);
     const double dav = d1 / T, contrast = d2 / T, idm = idm_sum / T;
     const double sav = s1 / T, es2 = s2 / T;
-    const double sent = lnT - cs / T;
+    const double sent = one_cell ? 0.0 : fmax(lnT - cs / T, 0.0);
     const double eij = 0.5 * (es2 - 2.0 * ei2);
     o_[0] = (float)((eij - mu * mu) / var);            // correlation
     o_[1] = (float)contrast;

@@ -69,8 +69,10 @@ def test_constant_tile_closed_forms(full):
         for d in ("0_1", "1_1", "1_0", "1_-1"):
             g = lambda f: feats[ok, names.index(f"{f}_{d}_{L}")]
             assert np.all(g("contrast") == 0) and np.all(g("dissimilarity") == 0) and np.all(g("difference_variance") == 0)
-            assert np.allclose(g("angular_second_moment"), 1.0, atol=1e-6) and np.allclose(g("entropy"), 0.0, atol=1e-6)
-            assert np.allclose(g("inverse_difference_moment"), 1.0, atol=1e-6)
+            assert np.all(g("angular_second_moment") == 1.0) and np.all(g("entropy") == 0.0) and np.all(g("sum_entropy") == 0.0)
+            assert np.allclose(g("inverse_difference_moment"), 1.0, atol=1e-6) and np.all(g("sum_of_squares") == 0.0)
+            assert np.all(np.isnan(g("correlation"))) and np.all(np.isnan(g("information_measure_correlation1")))   # 0/0 like the reference
+            assert np.all(g("information_measure_correlation2") == 0.0)
 
 
 def test_chunk_permutation_is_bit_exact(full):
