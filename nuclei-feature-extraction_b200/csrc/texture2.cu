@@ -17,6 +17,8 @@
 #include <math.h>
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "nfx_kernels.h"
 
 namespace nfx {
@@ -247,12 +249,11 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     float* B = A + ((PH * PS + 31) & ~31);
     uint8_t* patch = reinterpret_cast<uint8_t*>(A);   // the fetched pixels are consumed before A is written
     uint32_t* rows = reinterpret_cast<uint32_t*>(B + ((PH * PS + 31) & ~31));
-    uint16_t* list = reinterpret_cast<uint16_t*>(rows + P * wpr);
+    // (the bytes after `rows` are slack: the strip loads of the last rows may run up to 4 plane rows past B)
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
-    __shared__ int s_scan[NW + 1];
-    __shared__ int s_box[4];
-    __shared__ double s_red[12 * NW];
+    __shared__ int s_box[5];
+    __shared__ double s_part[NW][2 * 24];   // per warp: (sum, sum of squares) of the 24 distinct filters
 
     const NucInfo inf = p.info[i];
     // fetched region: rows/cols [f0, f0 + fetch) of the window, f0 = -14 relative to the tile when TILED
@@ -265,60 +266,37 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         const int fw = TILED ? kGaborFetch : P;
         mbar_expect_tx(&bar, (uint32_t)(patch_panels(fw) * kPanelBytes * frows));
         tma_load_window(patch, &map, inf.left + fx, inf.top + fy, fw, frows, &bar);
-        s_box[0] = P; s_box[1] = -1; s_box[2] = P; s_box[3] = -1;
+        s_box[0] = P; s_box[1] = -1; s_box[2] = P; s_box[3] = -1; s_box[4] = 0;
     }
     s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
     for (int k = tid; k < PH * GS; k += kTexThreads) G[k] = 0.f;
     __syncthreads();
-    // ---- mask rows of the tile, bounding box, pixel list (tile-local coordinates) ----
+    // ---- mask rows of the tile, bounding box, pixel count (tile-local coordinates) ----
     const int gwpr = mask_wpr(WP);
     const uint32_t* gm = p.bitmask + i * (int64_t)WP * gwpr;
-    int K = 0;
     {
-        int rmin = P, rmax = -1, cmin = P, cmax = -1;
-        for (int base = 0; base < P * wpr; base += kTexThreads) {
-            const int k = base + tid;
+        int rmin = P, rmax = -1, cmin = P, cmax = -1, cnt = 0;
+        for (int k = tid; k < P * wpr; k += kTexThreads) {
             const int r = k / wpr, w = k - r * wpr, cb = w * 32;
             uint32_t bits = 0u;
-            if (k < P * wpr && oy + r < WP && (ox >> 5) + w < gwpr) bits = gm[(oy + r) * gwpr + (ox >> 5) + w];
-            if (k < P * wpr) rows[k] = bits;
+            if (oy + r < WP && (ox >> 5) + w < gwpr) bits = gm[(oy + r) * gwpr + (ox >> 5) + w];
+            rows[k] = bits;
             if (bits) {
                 rmin = min(rmin, r); rmax = max(rmax, r);
                 cmin = min(cmin, cb + __ffs(bits) - 1); cmax = max(cmax, cb + 31 - __clz(bits));
             }
-            const int cnt = __popc(bits);
-            int incl = cnt;
-#pragma unroll
-            for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o2);
-                if (lane >= o2) incl += t;
-            }
-            __syncthreads();
-            if (lane == 31) s_scan[warp] = incl;
-            __syncthreads();
-            int wbase = 0, total = 0;
-#pragma unroll
-            for (int t = 0; t < NW; ++t) {
-                const int v = s_scan[t];
-                wbase += (t < warp) ? v : 0;
-                total += v;
-            }
-            int pos = K + wbase + incl - cnt;
-            while (bits) {
-                const int c = cb + __ffs(bits) - 1;
-                bits &= bits - 1;
-                list[pos++] = (uint16_t)((r << 8) | c);
-            }
-            K += total;
+            cnt += __popc(bits);
         }
         rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) {
             atomicMin(&s_box[0], rmin); atomicMax(&s_box[1], rmax);
             atomicMin(&s_box[2], cmin); atomicMax(&s_box[3], cmax);
+            atomicAdd(&s_box[4], cnt);
         }
     }
     __syncthreads();
-    const int rmin = s_box[0], rmax = s_box[1], cmin = s_box[2], cmax = s_box[3];
+    const int rmin = s_box[0], rmax = s_box[1], cmin = s_box[2], cmax = s_box[3], K = s_box[4];
     float* out = p.out + i * (int64_t)p.out_stride + p.col_gabor;
     double* part = TILED ? p.gabor_partial + (i * (int64_t)gridDim.y + blockIdx.y) * kGaborPartial : nullptr;
     mbar_wait(&bar, 0);   // never leave the CTA with a TMA still writing its shared memory
@@ -349,12 +327,22 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 
     const int cq0 = cmin & ~3, nquad = ((cmax - cq0) >> 2) + 1;   // column quads of the bounding box
     const int nrow = rmax - rmin + kGaborK;                       // padded rows rmin .. rmax+29
-    // Row pass, 4 outputs per thread: out[c0+m] = sum_t G[pr][c0+m+t] * tap[t], m = 0..3.
-    // MODE 0: B <- envelope (the theta = 90 plane); MODE 1: A <- profile 0 (cos w); MODE 2: A,B <- profiles 2,3.
-    auto row_pass = [&](int mode, int q) {
-        for (int k = tid; k < nrow * nquad; k += kTexThreads) {
-            const int pr = rmin + k % nrow, c0 = cq0 + 4 * (k / nrow);   // row index fastest across the lanes
-            const float4* g4 = reinterpret_cast<const float4*>(G + pr * GS + c0);
+    const int rh = rmax - rmin + 1, ncol = cmax - cmin + 1;
+    auto mbit = [&](int r, int c) -> bool { return (rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u; };
+    // warp partials of NV doubles -> s_part[warp][slot0 ..): every slot is written by exactly one phase
+    auto stash2 = [&](double a, double b, int slot0) {
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) { s_part[warp][slot0] = a; s_part[warp][slot0 + 1] = b; }
+    };
+
+    // Horizontal FIR, 4 outputs per thread from 9 float4 loads (row index fastest across the lanes):
+    //   dA[pr][c0+m] = sum_t src[pr][c0+m+t] * ta[t]   (and dB with tb when TWO), pr = row_lo .. row_lo+nr-1.
+    auto h_store = [&](const float* src, int ss, float* dA, float* dB, int ds, bool env, int q, int row_lo, int nr) {
+        const bool two = !env;
+        for (int k = tid; k < nr * nquad; k += kTexThreads) {
+            const int pr = row_lo + k % nr, c0 = cq0 + 4 * (k / nr);
+            const float4* g4 = reinterpret_cast<const float4*>(src + pr * ss + c0);
             float x[36];
 #pragma unroll
             for (int m = 0; m < 9; ++m) {
@@ -364,103 +352,198 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int t = 0; t < kGaborK; ++t) {
-                const float ta = mode == 0 ? c_genv[t] : (mode == 1 ? c_gtap[q][0][t] : c_gtap[q][2][t]);
-                const float tb = c_gtap[q][3][t];
+                const float wa = env ? c_genv[t] : c_gtap[q][2][t], wb = c_gtap[q][3][t];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    a[m] = fmaf(x[m + t], ta, a[m]);
-                    if (mode == 2) b[m] = fmaf(x[m + t], tb, b[m]);
+                    a[m] = fmaf(x[m + t], wa, a[m]);
+                    if (two) b[m] = fmaf(x[m + t], wb, b[m]);
                 }
             }
-            float4* da = reinterpret_cast<float4*>((mode == 0 ? B : A) + pr * PS + c0);
-            *da = make_float4(a[0], a[1], a[2], a[3]);
-            if (mode == 2) *reinterpret_cast<float4*>(B + pr * PS + c0) = make_float4(b[0], b[1], b[2], b[3]);
-        }
-    };
-    // masked sums of NF filter outputs -> (mean, variance) columns of filters f0 + h*fstep (and + 24)
-    auto finish = [&](double* s, int nf, int f0, int fstep) {
-        double v[12];
-#pragma unroll
-        for (int h = 0; h < 12; ++h) v[h] = h < 2 * nf ? s[h] : 0.0;
-        block_sum<12>(v, s_red);   // also orders this pass before the planes are overwritten
-        if (tid == 0 && TILED) {
-            for (int h = 0; h < nf; ++h) {
-                const int f = f0 + h * fstep;
-                part[2 * f] = v[2 * h];
-                part[2 * f + 1] = v[2 * h + 1];
-            }
-        } else if (tid == 0) {
-            const double Kd = (double)K;
-            for (int h = 0; h < nf; ++h) {
-                const int f = f0 + h * fstep;
-                const double mean = v[2 * h] / Kd;
-                const float mf = (float)mean, vf = (float)fmax(v[2 * h + 1] / Kd - mean * mean, 0.0);
-                out[2 * f] = mf; out[2 * f + 1] = vf;
-                out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf;   // theta + 180 degrees: same kernel
-            }
+            *reinterpret_cast<float4*>(dA + pr * ds + c0) = make_float4(a[0], a[1], a[2], a[3]);
+            if (two) *reinterpret_cast<float4*>(dB + pr * ds + c0) = make_float4(b[0], b[1], b[2], b[3]);
         }
     };
 
-    // ---- theta = 90 (filters 12..17): one envelope-filtered plane, six column profiles ----
-    row_pass(0, 0);
+    // ======== theta = 90 (filters 12..17): rows with the envelope (ONE plane), then a vertical pass with the six
+    // cos(w v) profiles. The profiles are even (tap[t] = tap[29-t]): the 15 pair sums x[t] + x[29-t] are shared by
+    // the six filters (15 adds + 6 x 15 FMAs instead of 180 FMAs). SH output rows per thread share their loads. ====
+    h_store(G, GS, B, B, PS, true, 0, rmin, nrow);
+    __syncthreads();
+    auto v_six = [&](auto sh_tag) {
+        constexpr int SH = decltype(sh_tag)::value;
+        double s[12];
+#pragma unroll
+        for (int h = 0; h < 12; ++h) s[h] = 0.0;
+        const int nstrip = (rh + SH - 1) / SH;
+        for (int k = tid; k < nstrip * ncol; k += kTexThreads) {
+            const int c = cmin + k % ncol, r0 = rmin + SH * (k / ncol);
+            const float* src = B + r0 * PS + c;
+            float x[kGaborK - 1 + SH];
+#pragma unroll
+            for (int j = 0; j < kGaborK - 1 + SH; ++j) x[j] = src[j * PS];
+#pragma unroll
+            for (int m = 0; m < SH; ++m) {
+                float e[15];
+#pragma unroll
+                for (int t = 0; t < 15; ++t) e[t] = x[m + t] + x[m + 29 - t];
+                const bool in = (r0 + m <= rmax) && mbit(r0 + m, c);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 15; ++t) {
+                        if (t & 1) v1 = fmaf(e[t], c_gtap[q][0][t], v1);
+                        else v0 = fmaf(e[t], c_gtap[q][0][t], v0);
+                    }
+                    const double v = in ? (double)(v0 + v1) : 0.0;
+                    s[2 * q] += v; s[2 * q + 1] += v * v;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) stash2(s[2 * q], s[2 * q + 1], 2 * (12 + q));
+    };
+    // strip height: 4 rows halve the shared-memory traffic, 2 rows fill the 256 threads better on small boxes
+    const auto rounds = [&](int sh) { return (((rh + sh - 1) / sh) * ncol + kTexThreads - 1) / kTexThreads; };
+    const bool tall = rounds(4) * (kGaborK + 3 + 4 * kGaborK) <= rounds(2) * (kGaborK + 1 + 2 * kGaborK);
+    if (tall) v_six(std::integral_constant<int, 4>{}); else v_six(std::integral_constant<int, 2>{});
+    __syncthreads();
+
+    // ======== theta = 0 (filters 0..5): columns with the envelope first (one plane over the padded columns the box
+    // can reach, stride GS, spanning the A and B regions), then a horizontal pass with the six cos(w u) profiles. ====
+    float* V = A;
+    {
+        const int npc = ncol + kGaborK - 1;   // padded columns cmin .. cmax+29
+        const int nstrip = (rh + 3) / 4;
+        for (int k = tid; k < nstrip * npc; k += kTexThreads) {
+            const int pc = cmin + k % npc, r0 = rmin + 4 * (k / npc);
+            const float* src = G + r0 * GS + pc;
+            float x[kGaborK + 3];
+#pragma unroll
+            for (int j = 0; j < kGaborK + 3; ++j) x[j] = src[j * GS];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                for (int t = 0; t < kGaborK; ++t) {
+                    if (t & 1) v1 = fmaf(x[m + t], c_genv[t], v1);
+                    else v0 = fmaf(x[m + t], c_genv[t], v0);
+                }
+                V[(r0 + m) * GS + pc] = v0 + v1;
+            }
+        }
+    }
     __syncthreads();
     {
         double s[12];
 #pragma unroll
         for (int h = 0; h < 12; ++h) s[h] = 0.0;
-        for (int j = tid; j < K; j += kTexThreads) {
-            const uint32_t rc = list[j];
-            const float* a0 = B + (rc >> 8) * PS + (rc & 255);   // padded rows r .. r+29
-            float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = tid; k < rh * nquad; k += kTexThreads) {
+            const int r = rmin + k % rh, c0 = cq0 + 4 * (k / rh);
+            const float4* g4 = reinterpret_cast<const float4*>(V + r * GS + c0);
+            float x[36];
 #pragma unroll
-            for (int t = 0; t < kGaborK; ++t) {
-                const float x = a0[t * PS];
-#pragma unroll
-                for (int q = 0; q < 6; ++q) v[q] = fmaf(x, c_gtap[q][0][t], v[q]);
+            for (int m = 0; m < 9; ++m) {
+                const float4 v = g4[m];
+                x[4 * m] = v.x; x[4 * m + 1] = v.y; x[4 * m + 2] = v.z; x[4 * m + 3] = v.w;
             }
 #pragma unroll
-            for (int q = 0; q < 6; ++q) { s[2 * q] += (double)v[q]; s[2 * q + 1] += (double)v[q] * (double)v[q]; }
-        }
-        finish(s, 6, 12, 1);
-    }
-    for (int q = 0; q < 6; ++q) {
-        // ---- theta = 0 (filter q): rows cos(w u) -> A, columns envelope ----
-        row_pass(1, q);
-        __syncthreads();
-        {
-            double s[2] = {0.0, 0.0};
-            for (int j = tid; j < K; j += kTexThreads) {
-                const uint32_t rc = list[j];
-                const float* a = A + (rc >> 8) * PS + (rc & 255);
-                float w0[3] = {0.f, 0.f, 0.f};   // three partial sums: break the 30-deep FMA dependency chain
+            for (int m = 0; m < 4; ++m) {
+                float e[15];
 #pragma unroll
-                for (int t = 0; t < kGaborK; ++t) w0[t % 3] = fmaf(a[t * PS], c_genv[t], w0[t % 3]);
-                const float v0 = (w0[0] + w0[1]) + w0[2];
-                s[0] += (double)v0; s[1] += (double)v0 * (double)v0;
-            }
-            finish(s, 1, q, 1);
-        }
-        // ---- theta = 45 (filter 6+q) and 135 (filter 18+q): p -/+ q ----
-        row_pass(2, q);
-        __syncthreads();
-        {
-            double s[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int j = tid; j < K; j += kTexThreads) {
-                const uint32_t rc = list[j];
-                const float* a = A + (rc >> 8) * PS + (rc & 255);
-                const float* b = B + (rc >> 8) * PS + (rc & 255);
-                float pw[2] = {0.f, 0.f}, qw[2] = {0.f, 0.f};   // two partial sums each: four independent chains
+                for (int t = 0; t < 15; ++t) e[t] = x[m + t] + x[m + 29 - t];
+                const bool in = mbit(r, c0 + m);
 #pragma unroll
-                for (int t = 0; t < kGaborK; ++t) {
-                    pw[t & 1] = fmaf(a[t * PS], c_gtap[q][2][t], pw[t & 1]);
-                    qw[t & 1] = fmaf(b[t * PS], c_gtap[q][3][t], qw[t & 1]);
+                for (int q = 0; q < 6; ++q) {
+                    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 15; ++t) {
+                        if (t & 1) v1 = fmaf(e[t], c_gtap[q][0][t], v1);
+                        else v0 = fmaf(e[t], c_gtap[q][0][t], v0);
+                    }
+                    const double v = in ? (double)(v0 + v1) : 0.0;
+                    s[2 * q] += v; s[2 * q + 1] += v * v;
                 }
-                const float pp = pw[0] + pw[1], qq = qw[0] + qw[1];
-                const float v45 = pp - qq, v135 = pp + qq;
-                s[0] += (double)v45;  s[1] += (double)v45 * (double)v45;
-                s[2] += (double)v135; s[3] += (double)v135 * (double)v135;
             }
-            finish(s, 2, 6 + q, 12);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) stash2(s[2 * q], s[2 * q + 1], 2 * q);
+    }
+    __syncthreads();
+
+    // ======== theta = 45 (filter 6+q) and 135 (filter 18+q): rows with cos(w'u) -> A and sin(w'u) -> B in one pass,
+    // then p = (A columns, cos w'v), q = (B columns, sin w'v): the two filters are p - q and p + q. ========
+    auto v_diag = [&](auto sh_tag, int q) {
+        constexpr int SH = decltype(sh_tag)::value;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        const int nstrip = (rh + SH - 1) / SH;
+        for (int k = tid; k < nstrip * ncol; k += kTexThreads) {
+            const int c = cmin + k % ncol, r0 = rmin + SH * (k / ncol);
+            float pp[SH], qq[SH];
+            {
+                const float* src = A + r0 * PS + c;
+                float x[kGaborK - 1 + SH];
+#pragma unroll
+                for (int j = 0; j < kGaborK - 1 + SH; ++j) x[j] = src[j * PS];
+#pragma unroll
+                for (int m = 0; m < SH; ++m) {
+                    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < kGaborK; ++t) {
+                        if (t & 1) v1 = fmaf(x[m + t], c_gtap[q][2][t], v1);
+                        else v0 = fmaf(x[m + t], c_gtap[q][2][t], v0);
+                    }
+                    pp[m] = v0 + v1;
+                }
+            }
+            {
+                const float* src = B + r0 * PS + c;
+                float x[kGaborK - 1 + SH];
+#pragma unroll
+                for (int j = 0; j < kGaborK - 1 + SH; ++j) x[j] = src[j * PS];
+#pragma unroll
+                for (int m = 0; m < SH; ++m) {
+                    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < kGaborK; ++t) {
+                        if (t & 1) v1 = fmaf(x[m + t], c_gtap[q][3][t], v1);
+                        else v0 = fmaf(x[m + t], c_gtap[q][3][t], v0);
+                    }
+                    qq[m] = v0 + v1;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < SH; ++m) {
+                const bool in = (r0 + m <= rmax) && mbit(r0 + m, c);
+                const double v45 = in ? (double)(pp[m] - qq[m]) : 0.0, v135 = in ? (double)(pp[m] + qq[m]) : 0.0;
+                s[0] += v45;  s[1] += v45 * v45;
+                s[2] += v135; s[3] += v135 * v135;
+            }
+        }
+        stash2(s[0], s[1], 2 * (6 + q));
+        stash2(s[2], s[3], 2 * (18 + q));
+    };
+    for (int q = 0; q < 6; ++q) {
+        h_store(G, GS, A, B, PS, false, q, rmin, nrow);
+        __syncthreads();
+        if (tall) v_diag(std::integral_constant<int, 4>{}, q); else v_diag(std::integral_constant<int, 2>{}, q);
+        __syncthreads();
+    }
+
+    // ---- fold the warp partials in a fixed order: one thread per distinct filter ----
+    if (tid < 24) {
+        const int f = tid;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { s0 += s_part[w][2 * f]; s1 += s_part[w][2 * f + 1]; }
+        if (TILED) {
+            part[2 * f] = s0;
+            part[2 * f + 1] = s1;
+        } else {
+            const double Kd = (double)K, mean = s0 / Kd;
+            const float mf = (float)mean, vf = (float)fmax(s1 / Kd - mean * mean, 0.0);
+            out[2 * f] = mf; out[2 * f + 1] = vf;
+            out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf;   // theta + 180 degrees: same kernel
         }
     }
 }
