@@ -314,9 +314,11 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const int gr0 = rmin - kGaborLo, gr1 = rmax + (kGaborK - 1 - kGaborLo);   // tile-local rows, may leave [0,P)
     const int gc0 = cmin - kGaborLo, gc1 = cmax + (kGaborK - 1 - kGaborLo);
     const int gw = gc1 - gc0 + 1;
+    const float inv_gw = 1.0f / (float)gw;
     const int wr_lim = min(WP, inf.nvr), wc_lim = min(WP, inf.nvc);
     for (int k = tid; k < (gr1 - gr0 + 1) * gw; k += kTexThreads) {
-        const int r = gr0 + k / gw, c = gc0 + k % gw;          // tile-local
+        const int kr = __float2int_rz(((float)k + 0.5f) * inv_gw);   // = k / gw exactly (see fdiv below)
+        const int r = gr0 + kr, c = gc0 + (k - kr * gw);       // tile-local
         const int wr = oy + r, wc = ox + c;                    // window coordinates
         if (wr >= 0 && wr < wr_lim && wc >= 0 && wc < wc_lim) {
             const int a = patch_addr(frows, o, wr - fy, wc - fx);
@@ -329,6 +331,11 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const int nrow = rmax - rmin + kGaborK;                       // padded rows rmin .. rmax+29
     const int rh = rmax - rmin + 1, ncol = cmax - cmin + 1;
     auto mbit = [&](int r, int c) -> bool { return (rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u; };
+    // k / d for the item loops (k < 2^12, d < 2^7) without the integer-division sequence: exact, because
+    // (k + 0.5) / d is at least 0.5/d away from an integer while the f32 product is off by < 2^-10.
+    auto fdiv = [](int k, float inv) -> int { return __float2int_rz(((float)k + 0.5f) * inv); };
+    const float inv_nrow = 1.0f / (float)nrow, inv_rh = 1.0f / (float)rh, inv_ncol = 1.0f / (float)ncol,
+                inv_npc = 1.0f / (float)(ncol + kGaborK - 1);
     // warp partials of NV doubles -> s_part[warp][slot0 ..): every slot is written by exactly one phase
     auto stash2 = [&](double a, double b, int slot0) {
         a = warp_sum(a);
@@ -338,10 +345,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 
     // Horizontal FIR, 4 outputs per thread from 9 float4 loads (row index fastest across the lanes):
     //   dA[pr][c0+m] = sum_t src[pr][c0+m+t] * ta[t]   (and dB with tb when TWO), pr = row_lo .. row_lo+nr-1.
-    auto h_store = [&](const float* src, int ss, float* dA, float* dB, int ds, bool env, int q, int row_lo, int nr) {
+    auto h_store = [&](const float* src, int ss, float* dA, float* dB, int ds, bool env, int q, int row_lo, int nr, float inv_nr) {
         const bool two = !env;
         for (int k = tid; k < nr * nquad; k += kTexThreads) {
-            const int pr = row_lo + k % nr, c0 = cq0 + 4 * (k / nr);
+            const int kq = fdiv(k, inv_nr), pr = row_lo + (k - kq * nr), c0 = cq0 + 4 * kq;
             const float4* g4 = reinterpret_cast<const float4*>(src + pr * ss + c0);
             float x[36];
 #pragma unroll
@@ -367,7 +374,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     // ======== theta = 90 (filters 12..17): rows with the envelope (ONE plane), then a vertical pass with the six
     // cos(w v) profiles. The profiles are even (tap[t] = tap[29-t]): the 15 pair sums x[t] + x[29-t] are shared by
     // the six filters (15 adds + 6 x 15 FMAs instead of 180 FMAs). SH output rows per thread share their loads. ====
-    h_store(G, GS, B, B, PS, true, 0, rmin, nrow);
+    h_store(G, GS, B, B, PS, true, 0, rmin, nrow, inv_nrow);
     __syncthreads();
     auto v_six = [&](auto sh_tag) {
         constexpr int SH = decltype(sh_tag)::value;
@@ -376,7 +383,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         for (int h = 0; h < 12; ++h) s[h] = 0.0;
         const int nstrip = (rh + SH - 1) / SH;
         for (int k = tid; k < nstrip * ncol; k += kTexThreads) {
-            const int c = cmin + k % ncol, r0 = rmin + SH * (k / ncol);
+            const int ks = fdiv(k, inv_ncol), c = cmin + (k - ks * ncol), r0 = rmin + SH * ks;
             const float* src = B + r0 * PS + c;
             float x[kGaborK - 1 + SH];
 #pragma unroll
@@ -416,7 +423,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         const int npc = ncol + kGaborK - 1;   // padded columns cmin .. cmax+29
         const int nstrip = (rh + 3) / 4;
         for (int k = tid; k < nstrip * npc; k += kTexThreads) {
-            const int pc = cmin + k % npc, r0 = rmin + 4 * (k / npc);
+            const int ks = fdiv(k, inv_npc), pc = cmin + (k - ks * npc), r0 = rmin + 4 * ks;
             const float* src = G + r0 * GS + pc;
             float x[kGaborK + 3];
 #pragma unroll
@@ -439,7 +446,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 #pragma unroll
         for (int h = 0; h < 12; ++h) s[h] = 0.0;
         for (int k = tid; k < rh * nquad; k += kTexThreads) {
-            const int r = rmin + k % rh, c0 = cq0 + 4 * (k / rh);
+            const int kq = fdiv(k, inv_rh), r = rmin + (k - kq * rh), c0 = cq0 + 4 * kq;
             const float4* g4 = reinterpret_cast<const float4*>(V + r * GS + c0);
             float x[36];
 #pragma unroll
@@ -478,7 +485,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         double s[4] = {0.0, 0.0, 0.0, 0.0};
         const int nstrip = (rh + SH - 1) / SH;
         for (int k = tid; k < nstrip * ncol; k += kTexThreads) {
-            const int c = cmin + k % ncol, r0 = rmin + SH * (k / ncol);
+            const int ks = fdiv(k, inv_ncol), c = cmin + (k - ks * ncol), r0 = rmin + SH * ks;
             float pp[SH], qq[SH];
             {
                 const float* src = A + r0 * PS + c;
@@ -524,7 +531,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         stash2(s[2], s[3], 2 * (18 + q));
     };
     for (int q = 0; q < 6; ++q) {
-        h_store(G, GS, A, B, PS, false, q, rmin, nrow);
+        h_store(G, GS, A, B, PS, false, q, rmin, nrow, inv_nrow);
         __syncthreads();
         if (tall) v_diag(std::integral_constant<int, 4>{}, q); else v_diag(std::integral_constant<int, 2>{}, q);
         __syncthreads();
