@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -30,11 +31,21 @@
 #include "../../include/nfx.h"
 #include "nfx_host.h"
 
+// A buffer that is filled by the parser threads: no value-initialisation pass over it.
+template <typename T>
+struct RawBuf {
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void resize(size_t m) { p.reset(new T[m]); n = m; }
+    T* data() const { return p.get(); }
+    size_t size() const { return n; }
+    T& operator[](size_t i) const { return p[i]; }
+};
 struct nfx_geojson {
-    std::vector<float> xy;        // ring 0 of every feature, [nv][2]
-    std::vector<int64_t> off;     // [n+1]
-    std::vector<float> bbox;      // [n][4], NaN where the bbox array is shorter
-    std::vector<int32_t> rings;   // [n] number of rings of the feature (only ring 0 is kept, utils.rs:55)
+    RawBuf<float> xy;        // ring 0 of every feature, [nv][2]
+    RawBuf<int64_t> off;     // [n+1]
+    RawBuf<float> bbox;      // [n][4], NaN where the bbox array is shorter
+    RawBuf<int32_t> rings;   // [n] number of rings of the feature (only ring 0 is kept, utils.rs:55)
 };
 
 namespace {

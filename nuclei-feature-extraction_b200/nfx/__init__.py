@@ -98,10 +98,33 @@ def parse_f32(token: str) -> np.float32:
     return np.float32(o.value)
 
 
+class _GeojsonHandle:
+    """Owns an nfx_geojson; the arrays returned by geojson_pack are views into it and keep it alive."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        if self.h:
+            lib().nfx_geojson_free(self.h)
+            self.h = None
+
+
+def _view(ptr, shape, dtype, owner):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape, dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(C.addressof(ptr.contents))
+    a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    a.flags.writeable = False
+    buf._owner = owner               # the ctypes array is the numpy base: tie the handle's lifetime to it
+    return a
+
+
 def geojson_pack(text, threads: int = 0):
-    """GeoJSON text (bytes / str / mmap-able buffer) -> CSR of ring 0 of every feature, parsed by `threads`
-    host threads (src/main.rs:37-42, src/geojson.rs:8-24): (poly_xy f32 [nv,2], poly_off i64 [n+1],
-    bbox f32 [n,4], rings i32 [n])."""
+    """GeoJSON text (bytes / str / uint8 array) -> CSR of ring 0 of every feature, parsed by `threads` host threads
+    (src/main.rs:37-42, src/geojson.rs:8-24): (poly_xy f32 [nv,2], poly_off i64 [n+1], bbox f32 [n,4], rings i32 [n]).
+    The arrays are read-only views into the library's result (no copy); it is freed with the last of them."""
     if isinstance(text, str):
         text = text.encode()
     buf = np.frombuffer(text, dtype=np.uint8)
@@ -109,15 +132,13 @@ def geojson_pack(text, threads: int = 0):
     rc = lib().nfx_geojson_parse(C.cast(buf.ctypes.data, C.c_char_p), buf.size, threads, C.byref(h))
     if rc != NFX_OK:
         raise NfxError(rc, (lib().nfx_last_error(None) or b"").decode())
-    try:
-        n = lib().nfx_geojson_count(h)
-        nv = lib().nfx_geojson_vertices(h)
-        xy = np.ctypeslib.as_array(lib().nfx_geojson_xy(h), shape=(nv, 2)).copy() if nv else np.zeros((0, 2), np.float32)
-        off = np.ctypeslib.as_array(lib().nfx_geojson_offsets(h), shape=(n + 1,)).copy()
-        bbox = np.ctypeslib.as_array(lib().nfx_geojson_bbox(h), shape=(n, 4)).copy() if n else np.zeros((0, 4), np.float32)
-        rings = np.ctypeslib.as_array(lib().nfx_geojson_rings(h), shape=(n,)).copy() if n else np.zeros(0, np.int32)
-    finally:
-        lib().nfx_geojson_free(h)
+    own = _GeojsonHandle(h)
+    n = lib().nfx_geojson_count(h)
+    nv = lib().nfx_geojson_vertices(h)
+    xy = _view(lib().nfx_geojson_xy(h), (nv, 2), np.float32, own)
+    off = _view(lib().nfx_geojson_offsets(h), (n + 1,), np.int64, own)
+    bbox = _view(lib().nfx_geojson_bbox(h), (n, 4), np.float32, own)
+    rings = _view(lib().nfx_geojson_rings(h), (n,), np.int32, own)
     return xy, off, bbox, rings
 
 
