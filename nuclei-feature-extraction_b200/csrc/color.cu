@@ -308,22 +308,62 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     __shared__ __align__(8) uint64_t full[kHueStages], empty[kHueStages];
     __shared__ NucInfo s_info[kHueChunk];
 
+    // ---- union of the chunk's masks over this slab: mean_h only ever reads C, S under some mask of the batch, so
+    //      pixel quads outside the union are never evaluated (44 % of a 64 x 64 window for the bench's nuclei,
+    //      far more for small nuclei). Active quads are compacted and dealt to the consumer threads. ----
+    __shared__ uint32_t s_union[64];
+    __shared__ uint16_t s_qlist[kHueQpt * kHueConsumers];
+    __shared__ int s_nact;
+    const int qpr = P >> 2, nquads = R * qpr;
+    const int nrows_u = min(R, P - row0), words_u = nrows_u * wpr;
+    if (tid < 64) s_union[tid] = 0u;
+    __syncthreads();
+    for (int idx = tid; idx < nb * words_u; idx += kHueThreads) {
+        const int j = idx / words_u, w = idx - j * words_u;
+        const uint32_t v = p.bitmask[((b0 + j) * (int64_t)P + row0) * wpr + w];
+        if (v) atomicOr(&s_union[w], v);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int cnt = 0;
+        for (int base = 0; base < nquads; base += 32) {
+            const int q = base + lane, r = q / qpr, c = (q - r * qpr) * 4;
+            const bool act = q < nquads && r < nrows_u && ((s_union[r * wpr + (c >> 5)] >> (c & 31)) & 0xFu) != 0u;
+            const uint32_t b = __ballot_sync(0xffffffffu, act);
+            if (act) s_qlist[cnt + __popc(b & ((1u << lane) - 1u))] = (uint16_t)q;
+            cnt += __popc(b);
+        }
+        if (lane == 0) s_nact = cnt;
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    if (nact == 0) {   // no nucleus of the chunk has a masked pixel in this slab
+        for (int i = tid; i < nb; i += kHueThreads) {
+            float* hp = p.hue_partial + ((b0 + i) * (int64_t)p.slabs + slab) * 2;
+            hp[0] = 0.f;
+            hp[1] = 0.f;
+        }
+        return;
+    }
+    const int nwarps_act = min(kHueConsumers / 32, (nact + 31) / 32);   // consumer warps that own at least one quad
     if (tid == 0) {
-        for (int s = 0; s < kHueStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kHueConsumers / 32); }
+        for (int s = 0; s < kHueStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps_act); }
         mbar_fence_init();
     }
-    // consumer pixel ownership: quads tid and tid + 128 of the slab (4 px each)
-    const int qpr = P >> 2, nquads = R * qpr;
+    // consumer pixel ownership: active quads tid and tid + 128 of the compacted list (4 px each)
     bool owner[kHueQpt];
     int rr[kHueQpt], c0[kHueQpt], soff[kHueQpt];
 #pragma unroll
     for (int u = 0; u < kHueQpt; ++u) {
-        const int q = tid + u * kHueConsumers;
+        const int k = tid + u * kHueConsumers;
+        owner[u] = (tid < kHueConsumers) && (k < nact);
+        const int q = owner[u] ? (int)s_qlist[k] : 0;
         rr[u] = q / qpr;
         c0[u] = (q - rr[u] * qpr) * 4;
-        owner[u] = (tid < kHueConsumers) && (q < nquads) && (row0 + rr[u] < P);
         soff[u] = (c0[u] >> 6) * panel_stride(R) + rr[u] * kPanelBytes + (c0[u] & 63) * 3;   // + o per nucleus
+        asm volatile("" : "+r"(soff[u]));   // keep it in a register: recomputing it costs 12 instructions per patch
     }
+    const int nq_w = (warp < kHueConsumers / 32) ? ((warp * 32 < nact) + (kHueConsumers + warp * 32 < nact)) : 0;   // warp-uniform
     float C[kHueQpt][4], S[kHueQpt][4];
 #pragma unroll
     for (int u = 0; u < kHueQpt; ++u)
@@ -347,17 +387,26 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                     tma_load_window(ring + (size_t)s * stage_bytes, &map, inf.left, inf.top + row0, P, R, &full[s]);
                 }
             }
-        } else {
+        } else if (nq_w > 0) {
             for (int j = 0; j < cnt; ++j) {
                 const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
                 mbar_wait(&full[s], ph);
                 const NucInfo inf = s_info[j];
+                // soff is a multiple of 4, so the word alignment and the funnel shift depend on the nucleus only
                 const int ob = patch_byte_offset(inf.left);
+                const uint8_t* sb = ring + (size_t)s * stage_bytes + (ob & ~3);
+                const uint32_t sh = (uint32_t)(ob & 3) * 8u;
                 uint32_t w[kHueQpt][3];
 #pragma unroll
                 for (int u = 0; u < kHueQpt; ++u) {
                     w[u][0] = w[u][1] = w[u][2] = 0u;
-                    if (owner[u]) load_quad(ring + (size_t)s * stage_bytes, soff[u] + ob, w[u][0], w[u][1], w[u][2]);
+                    if (owner[u]) {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sb + soff[u]);   // 4-byte aligned
+                        const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3];
+                        w[u][0] = __funnelshift_r(a0, a1, sh);
+                        w[u][1] = __funnelshift_r(a1, a2, sh);
+                        w[u][2] = __funnelshift_r(a2, a3, sh);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
@@ -374,6 +423,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                 }
 #pragma unroll
                 for (int u = 0; u < kHueQpt; ++u) {
+                    if (u >= nq_w) break;   // warp-uniform: this warp has no second quad
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const Px px = quad_px(w[u][0], w[u][1], w[u][2], k);
