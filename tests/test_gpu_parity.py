@@ -190,6 +190,27 @@ def test_errors_do_not_abort(case):
         nfx.Extractor(99)                      # args.rs:176-180 "GPU {} does not exist"
 
 
+def test_empty_single_and_ragged_inputs(case):
+    """n = 0 (an empty FeatureCollection), one nucleus, a last chunk shorter than batch_size, rings of 0..2 vertices."""
+    with nfx.Extractor(0, 64, 100) as e:
+        e.upload_tile(case["tile"])
+        keys, cents, feats, names = e.extract(np.zeros((0, 2), np.float32), np.zeros(1, np.int64), ["all"])
+        assert keys == [] and cents.shape == (0, 2) and feats.shape == (0, 418)
+        assert e.csv_rows() == b""
+        one = case["rings"][3]
+        keys, cents, feats, names = e.extract(*nfx.pack_polygons([one]), ["geometry", "color"])
+        wk, wc, want, wn = o.extract([one], case["tile"], ["geometry", "color"], 64, 100)
+        assert keys == wk and np.allclose(feats[0, [0, 5, 12, 13, 18, 19]], want[0, [0, 5, 12, 13, 18, 19]], rtol=1e-4, atol=1e-6)
+        # degenerate rings: a point, a segment, an empty ring (centroid 0/0 = NaN in the reference, utils.rs:56-64)
+        rings = [np.array([[50.5, 60.5]], np.float32), np.array([[70, 80], [90, 80]], np.float32), np.zeros((0, 2), np.float32),
+                 case["rings"][5]]
+        keys, cents, feats, names = e.extract(*nfx.pack_polygons(rings), ["geometry", "color", "glcm"])
+        assert keys[0] == "50.5,60.5" and keys[1] == "80,80" and keys[2] == "NaN,NaN"
+        assert np.isnan(feats[:3, names.index("mean_r")]).all()          # no sample point inside -> empty masks
+        assert feats[0, names.index("area")] == 0 and feats[1, names.index("area")] == 0
+        assert np.isfinite(feats[3, names.index("mean_r")])
+
+
 # ---- config-5-like stress shapes: 256x256 windows, 500-vertex polygons -------------------------------
 @pytest.fixture(scope="module")
 def stress(libnfx):
