@@ -699,7 +699,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
 // 64-row slabs (aliased with the histogram region), co-occurring pairs are enumerated straight from
 // the mask words, G is a dense triangular u16 histogram (counts <= 65 280 fit), moments are u64.
 // =================================================================================================
-constexpr int kLargeThreads = 512;
+constexpr int kLargeThreads = 1024;
 constexpr int kLNW = kLargeThreads / 32;
 struct GlcmLargeSmem {
     int plane, region_t, rows, hist, part_i, part_f, total;
@@ -707,7 +707,7 @@ struct GlcmLargeSmem {
 __host__ __device__ inline GlcmLargeSmem glcm_large_layout(int P) {
     GlcmLargeSmem L;
     L.plane = 0;
-    L.region_t = (P * P + 127) & ~127;
+    L.region_t = (P * (P + 4) + 127) & ~127;   // plane rows are P + 4 bytes apart: a 256-byte pitch would put every row on the same banks
     int t = window_smem_bytes(P, 64) > kTriBytes ? window_smem_bytes(P, 64) : kTriBytes;
     L.rows = L.region_t + ((t + 127) & ~127);
     L.hist = L.rows + P * mask_wpr(P) * 4;
@@ -724,6 +724,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
     const int64_t i = blockIdx.x;
     const GlcmLargeSmem L = glcm_large_layout(P);
     uint8_t* plane = smem_raw + L.plane;
+    const int PP = P + 4;   // plane pitch
     uint8_t* slab = smem_raw + L.region_t;
     uint32_t* tri32 = reinterpret_cast<uint32_t*>(smem_raw + L.region_t);
     uint16_t* tri16 = reinterpret_cast<uint16_t*>(smem_raw + L.region_t);
@@ -770,7 +771,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                     pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
                 }
                 const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
-                plane[r * P + c] = round == 0 ? (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253)
+                plane[r * PP + c] = round == 0 ? (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253)
                                               : (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
             }
         }
@@ -779,7 +780,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
             const int lvd = p.dbg_levels == 32 ? 0 : (p.dbg_levels == 64 ? 1 : (p.dbg_levels == 128 ? 2 : 3));
             if ((round == 0) == (lvd == 3))
                 for (int k = tid; k < P * P; k += kLargeThreads)
-                    p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)(lvd == 3 ? plane[k] : (plane[k] >> (2 - lvd)));
+                    p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)(lvd == 3 ? plane[(k / P) * PP + k % P] : (plane[(k / P) * PP + k % P] >> (2 - lvd)));
         }
         for (int k = tid; k < kTriBytes / 16; k += kLargeThreads)
             reinterpret_cast<uint4*>(smem_raw + L.region_t)[k] = make_uint4(0, 0, 0, 0);
@@ -788,7 +789,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
 
         const int lv_hi = round == 0 ? 3 : 2, lv_lo = round == 0 ? 3 : 0;
         for (int oi = 0; oi < kGlcmOffsets; ++oi) {
-            const int dy = c_off[oi][0], dx = c_off[oi][1], dpos = dy * P + dx;
+            const int dy = c_off[oi][0], dx = c_off[oi][1], dpos = dy * PP + dx;
             for (int lv = lv_hi; lv >= lv_lo; --lv) {
                 const int NL = c_levels[lv], sh = lv == 3 ? 0 : 2 - lv, combo = lv * kGlcmOffsets + oi;
                 const int tri_words = ((NL * (NL + 1) / 2) + 1) / 2;
@@ -807,7 +808,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                         while (pb) {
                             const int c = 32 * w + __ffs(pb) - 1;
                             pb &= pb - 1;
-                            const int src = r * P + c;
+                            const int src = r * PP + c;
                             const int a = plane[src] >> sh, b = plane[src + dpos] >> sh;
                             const int lo = min(a, b), hi = max(a, b);
                             const int cell = ((hi * (hi + 1)) >> 1) + lo;

@@ -47,11 +47,14 @@ constexpr int kRlCells = kRlLevels * kRlMax;
 static_assert(kRlLevels == 24, "u = (i - 12.5)/11.5 below assumes 24 levels");
 
 // Dynamic smem: region X (slab, later the pixel list u16 (row << 8) | col) | plane[P*P] u8 | rows[P*wpr] u32
-__global__ void __launch_bounds__(kTexThreads)
+// THREADS = 256 for P <= 128 (several CTAs per SM); 1024 for larger windows, whose 204 KB of shared memory leave
+// room for one CTA per SM only (8 warps per SM measured 25 % issue-active at P = 256).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, CS rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kTexThreads / 32;
+    constexpr int NW = THREADS / 32;
     const int CS = p.slab_rows, nslab = (P + CS - 1) / CS;
     const int64_t i = blockIdx.x;
     // region X = slab buffer while the window streams in, pixel list afterwards
@@ -74,15 +77,15 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         mbar_expect_tx(&bar, slab_tx);
         tma_load_window(slab, &map, inf.left, inf.top, P, CS, &bar);
     }
-    s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (tid < 256) s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
-    for (int k = tid; k < P * wpr; k += kTexThreads) rows[k] = gm[k];
+    for (int k = tid; k < P * wpr; k += THREADS) rows[k] = gm[k];
     __syncthreads();
     // ---- 24-level plane (texture.rs:189 + SPEC.md B9), rows that hold mask bits only ----
     for (int sidx = 0; sidx < nslab; ++sidx) {
         const int row0 = sidx * CS, nrows = min(CS, P - row0);
         mbar_wait(&bar, sidx & 1);
-        for (int k = tid; k < nrows * P; k += kTexThreads) {
+        for (int k = tid; k < nrows * P; k += THREADS) {
             const int lr = k / P, c = k - lr * P, r = row0 + lr;
             uint32_t any = 0;
             for (int w = 0; w < wpr; ++w) any |= rows[r * wpr + w];
@@ -102,7 +105,7 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     }
     // ---- compacted list of the masked pixels (overwrites the slab buffer) ----
     int K = 0;
-    for (int base = 0; base < P * wpr; base += kTexThreads) {
+    for (int base = 0; base < P * wpr; base += THREADS) {
         const int k = base + tid;
         uint32_t bits = (k < P * wpr) ? rows[k] : 0u;
         const int cnt = __popc(bits);
@@ -137,9 +140,9 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         return (unsigned)r < (unsigned)P && (unsigned)c < (unsigned)P && ((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u);
     };
     // ---- run detection for the four directions: one sweep per direction, four histograms ----
-    for (int k = tid; k < 4 * kRlCells; k += kTexThreads) s_R[k] = 0u;
+    for (int k = tid; k < 4 * kRlCells; k += THREADS) s_R[k] = 0u;
     __syncthreads();
-    for (int j = tid; j < K; j += kTexThreads) {
+    for (int j = tid; j < K; j += THREADS) {
         const uint32_t rc = list[j];
         const int r = rc >> 8, c = rc & 255;
         const int lv = plane[r * P + c];
@@ -616,9 +619,15 @@ cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaS
     cudaError_t e;
     const int rx = window_smem_bytes(p.P, p.slab_rows) > ((p.P * p.P * 2 + 127) & ~127) ? window_smem_bytes(p.P, p.slab_rows) : ((p.P * p.P * 2 + 127) & ~127);
     const int smem = rx + ((p.P * p.P + 15) & ~15) + p.P * mask_wpr(p.P) * 4;
-    e = cudaFuncSetAttribute(k_glrlm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (p.P > 128) {
+        e = cudaFuncSetAttribute(k_glrlm<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        k_glrlm<1024><<<(unsigned)p.n, 1024, smem, s>>>(p, *map_cslab);
+        return cudaGetLastError();
+    }
+    e = cudaFuncSetAttribute(k_glrlm<kTexThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k_glrlm<<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_cslab);
+    k_glrlm<kTexThreads><<<(unsigned)p.n, kTexThreads, smem, s>>>(p, *map_cslab);
     return cudaGetLastError();
 }
 
