@@ -711,7 +711,7 @@ __host__ __device__ inline GlcmLargeSmem glcm_large_layout(int P) {
     int t = window_smem_bytes(P, 64) > kTriBytes ? window_smem_bytes(P, 64) : kTriBytes;
     L.rows = L.region_t + ((t + 127) & ~127);
     L.hist = L.rows + P * mask_wpr(P) * 4;
-    L.part_i = L.hist + 1024 * 4;
+    L.part_i = L.hist + 3 * 1024 * 4;   // hx[256] hs[512] hd[256] for each of the (up to) three levels of a round
     L.part_f = L.part_i + kCombos * kLNW * kNI * 8;
     L.total = L.part_f + kCombos * kLNW * kNF * 4;
     return L;
@@ -730,8 +730,6 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
     uint16_t* tri16 = reinterpret_cast<uint16_t*>(smem_raw + L.region_t);
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + L.rows);
     uint32_t* hx = reinterpret_cast<uint32_t*>(smem_raw + L.hist);
-    uint32_t* hs = hx + 256;
-    uint32_t* hd = hs + 512;
     unsigned long long* part_i = reinterpret_cast<unsigned long long*>(smem_raw + L.part_i);
     float* part_f = reinterpret_cast<float*>(smem_raw + L.part_f);
     __shared__ __align__(8) uint64_t bar;
@@ -784,46 +782,57 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
         }
         for (int k = tid; k < kTriBytes / 16; k += kLargeThreads)
             reinterpret_cast<uint4*>(smem_raw + L.region_t)[k] = make_uint4(0, 0, 0, 0);
-        for (int k = tid; k < 1024; k += kLargeThreads) hx[k] = 0u;
+        for (int k = tid; k < 3 * 1024; k += kLargeThreads) hx[k] = 0u;
         __syncthreads();
 
-        const int lv_hi = round == 0 ? 3 : 2, lv_lo = round == 0 ? 3 : 0;
+        // Levels of this round: 254 alone (round 0), or 128 / 64 / 32 together (round 1: q64 = q128 >> 1, q32 = q128 >> 2,
+        // so ONE enumeration of the co-occurring pairs feeds the three matrices: 15 atomics per pair in the first
+        // sweep, three cell look-ups in the second). Slot s of the round holds level lv_hi - s.
+        const int lv_hi = round == 0 ? 3 : 2, lv_lo = round == 0 ? 3 : 0, nlev = lv_hi - lv_lo + 1;
+        // triangular u16 histograms of the slots, packed two cells per u32 word, back to back in region T
+        int tri_off[3], tri_words_tot = 0;
+        for (int s = 0; s < 3; ++s) {
+            tri_off[s] = tri_words_tot;
+            if (s < nlev) { const int NL = c_levels[lv_hi - s]; tri_words_tot += ((NL * (NL + 1) / 2) + 1) / 2; }
+        }
         for (int oi = 0; oi < kGlcmOffsets; ++oi) {
             const int dy = c_off[oi][0], dx = c_off[oi][1], dpos = dy * PP + dx;
-            for (int lv = lv_hi; lv >= lv_lo; --lv) {
-                const int NL = c_levels[lv], sh = lv == 3 ? 0 : 2 - lv, combo = lv * kGlcmOffsets + oi;
-                const int tri_words = ((NL * (NL + 1) / 2) + 1) / 2;
-                unsigned long long vl[kNI] = {0, 0, 0, 0, 0, 0, 0}, np_local = 0;
-                float vf[kNF] = {0.f, 0.f, 0.f, 0.f};
-                const bool dbg = p.dbg_counts && p.dbg_levels == NL && p.dbg_dy == dy && p.dbg_dx == dx;
-                for (int pass = 0; pass < 2; ++pass) {
-                    for (int k = tid; k < P * wpr; k += kLargeThreads) {
-                        const int r = k / wpr, w = k - r * wpr, r2 = r + dy;
-                        if (r2 >= P) continue;
-                        const uint32_t* nr = rows + r2 * wpr;
-                        uint32_t nb = nr[w];
-                        if (dx == 1) nb = (nb >> 1) | ((w + 1 < wpr) ? (nr[w + 1] << 31) : 0u);
-                        else if (dx == -1) nb = (nb << 1) | ((w > 0) ? (nr[w - 1] >> 31) : 0u);
-                        uint32_t pb = rows[k] & nb;
-                        while (pb) {
-                            const int c = 32 * w + __ffs(pb) - 1;
-                            pb &= pb - 1;
-                            const int src = r * PP + c;
-                            const int a = plane[src] >> sh, b = plane[src + dpos] >> sh;
+            unsigned long long g2[3] = {0, 0, 0}, np_local = 0;   // sum of the cell counts met (= sum of squares of the cells)
+            float glg[3] = {0.f, 0.f, 0.f};                       // sum of ln(cell count)
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int k = tid; k < P * wpr; k += kLargeThreads) {
+                    const int r = k / wpr, w = k - r * wpr, r2 = r + dy;
+                    if (r2 >= P) continue;
+                    const uint32_t* nr = rows + r2 * wpr;
+                    uint32_t nb = nr[w];
+                    if (dx == 1) nb = (nb >> 1) | ((w + 1 < wpr) ? (nr[w + 1] << 31) : 0u);
+                    else if (dx == -1) nb = (nb << 1) | ((w > 0) ? (nr[w - 1] >> 31) : 0u);
+                    uint32_t pb = rows[k] & nb;
+                    while (pb) {
+                        const int c = 32 * w + __ffs(pb) - 1;
+                        pb &= pb - 1;
+                        const int src = r * PP + c;
+                        const int a0 = plane[src], b0 = plane[src + dpos];
+                        if (pass == 0) ++np_local;
+#pragma unroll
+                        for (int s = 0; s < 3; ++s) {
+                            if (s >= nlev) break;
+                            const int a = a0 >> s, b = b0 >> s;
                             const int lo = min(a, b), hi = max(a, b);
                             const int cell = ((hi * (hi + 1)) >> 1) + lo;
+                            uint32_t* hxs = hx + s * 1024;
                             if (pass == 0) {
-                                atomicAdd(&tri32[cell >> 1], 1u << ((cell & 1) * 16));
-                                atomicAdd(&hx[a], 1u);
-                                atomicAdd(&hx[b], 1u);
-                                atomicAdd(&hs[a + b], 2u);
-                                atomicAdd(&hd[hi - lo], 2u);
-                                ++np_local;
+                                atomicAdd(&tri32[tri_off[s] + (cell >> 1)], 1u << ((cell & 1) * 16));
+                                atomicAdd(&hxs[a], 1u);
+                                atomicAdd(&hxs[b], 1u);
+                                atomicAdd(&hxs[256 + a + b], 2u);
+                                atomicAdd(&hxs[768 + hi - lo], 2u);
                             } else {
-                                const uint32_t g = (uint32_t)tri16[cell] << (a == b ? 1 : 0);
-                                vl[0] += g;
-                                vf[0] += __logf((float)g);
-                                if (dbg) {
+                                const uint32_t g = (uint32_t)tri16[2 * tri_off[s] + cell] << (a == b ? 1 : 0);
+                                g2[s] += g;
+                                glg[s] += __logf((float)g);
+                                const int NL = c_levels[lv_hi - s];
+                                if (p.dbg_counts && p.dbg_levels == NL && p.dbg_dy == dy && p.dbg_dx == dx) {
                                     uint32_t* dc = p.dbg_counts + i * (int64_t)NL * NL;
                                     dc[a * NL + b] = g;
                                     dc[b * NL + a] = g;
@@ -831,15 +840,28 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                             }
                         }
                     }
-                    __syncthreads();
                 }
+                __syncthreads();
+            }
+            np_local = warp_sum(np_local);
+            if (tid == 0) s_npairs[oi] = 0ull;
+            __syncthreads();
+            if (lane == 0 && np_local) atomicAdd(&s_npairs[oi], np_local);
+            // ---- marginal sums of every slot, partials per warp ----
+            for (int s = 0; s < nlev; ++s) {
+                const int lv = lv_hi - s, NL = c_levels[lv], combo = lv * kGlcmOffsets + oi;
+                const uint32_t* hxs = hx + s * 1024;
+                const uint32_t* hss = hxs + 256;
+                const uint32_t* hds = hxs + 768;
+                unsigned long long vl[kNI] = {s == 0 ? g2[0] : (s == 1 ? g2[1] : g2[2]), 0, 0, 0, 0, 0, 0};
+                float vf[kNF] = {s == 0 ? glg[0] : (s == 1 ? glg[1] : glg[2]), 0.f, 0.f, 0.f};
                 for (int k = tid; k < 2 * NL - 1; k += kLargeThreads) {
-                    const unsigned long long c = hs[k], kk = (unsigned long long)k;
+                    const unsigned long long c = hss[k], kk = (unsigned long long)k;
                     vl[5] += kk * c;
                     vl[6] += kk * kk * c;
                     if (c) vf[2] += (float)c * __logf((float)c);
                     if (k < NL) {
-                        const unsigned long long cx = hx[k], cd = hd[k];
+                        const unsigned long long cx = hxs[k], cd = hds[k];
                         vl[1] += kk * cx;
                         vl[2] += kk * kk * cx;
                         vl[3] += kk * cd;
@@ -858,17 +880,11 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                     const float t = warp_sum(vf[q]);
                     if (lane == 0) part_f[(combo * kLNW + warp) * kNF + q] = t;
                 }
-                np_local = warp_sum(np_local);
-                if (lv == lv_hi) {
-                    if (tid == 0) s_npairs[oi] = 0ull;
-                    __syncthreads();
-                    if (lane == 0 && np_local) atomicAdd(&s_npairs[oi], np_local);
-                }
-                __syncthreads();
-                for (int k = tid; k < tri_words; k += kLargeThreads) tri32[k] = 0u;
-                for (int k = tid; k < 1024; k += kLargeThreads) hx[k] = 0u;
-                __syncthreads();
             }
+            __syncthreads();
+            for (int k = tid; k < tri_words_tot; k += kLargeThreads) tri32[k] = 0u;
+            for (int k = tid; k < nlev * 1024; k += kLargeThreads) hx[k] = 0u;
+            __syncthreads();
         }
         // ---- features of this round's levels ----
         if (tid < kCombos && p.out) {
