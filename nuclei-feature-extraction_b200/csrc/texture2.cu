@@ -11,9 +11,10 @@
 //
 // k_gabor: one CTA per nucleus (P <= 64). The isotropic-envelope Gabor kernel factorises exactly:
 //   g(u,v) = G(u)G(v)cos(a u + b v) = [G(u)cos(a u)][G(v)cos(b v)] - [G(u)sin(a u)][G(v)sin(b v)]
-// so each of the 48 filters is two separable passes (30 taps each instead of 900): a row pass over the
-// mask's bounding box (+29 halo rows) into two shared-memory planes, and a column pass at the masked
-// pixels only. Taps live in constant memory (warp-uniform index -> FFMA with a constant operand).
+// so each of the 48 filters is two separable passes (30 taps each instead of 900): a first pass over the
+// mask's bounding box plus its 29-pixel halo into shared-memory planes, and a second, register-tiled pass
+// over the bounding box whose outputs are summed under the mask. Taps live in constant memory
+// (warp-uniform index -> FFMA with a uniform-register operand).
 #include <math.h>
 #include <math_constants.h>
 
@@ -215,14 +216,16 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 // ------------------------------------------------------------------------------------------------
 // k_gabor. cos is even, so the kernels of theta and theta + 180 degrees are identical: 24 distinct
 // filters. Per frequency f (w = 2 pi f, w' = w cos 45):
-//   theta =   0: cos(w u)          -> rows with G cos(w u),  columns with G          (1 plane)
+//   theta =   0: cos(w u)          -> columns with G (ONE plane for all six f), rows with G cos(w u)
 //   theta =  90: cos(w v)          -> rows with G (ONE plane for all six f), columns with G cos(w v)
+//                  (G cos is even: the 15 pair sums x[t] + x[29-t] are shared by the six profiles of a pass)
 //   theta =  45: cos(w'u + w'v)    -> p - q   where p = (G cos w'u rows)(G cos w'v cols),
 //   theta = 135: cos(-w'u + w'v)   -> p + q         q = (G sin w'u rows)(G sin w'v cols)
-// Row passes are register tiled (4 outputs per thread from 9 float4 loads, row index fastest across
+// Horizontal passes are register tiled (4 outputs per thread from 9 float4 loads, row index fastest across
 // the lanes; the plane strides are 4 (mod 32) floats so that float4 loads and stores are bank-conflict
-// free); column passes run at the masked pixels only.
-// Dynamic smem: G[(P+29)][GS] | A[(P+29)][PS] (the TMA window lands here first) | B[(P+29)][PS] | rows | list.
+// free); vertical passes produce 2 or 4 outputs per thread from 31 or 33 loads down one column.
+// Dynamic smem: G[(P+29)][GS] | A[(P+29)][PS] (the TMA window lands here first) | B[(P+29)][PS] | rows | slack
+// (A and B together also hold the theta = 0 plane, stride GS; the slack absorbs strip loads past the last row).
 __host__ __device__ constexpr int gabor_gs(int P) { return ((P + kGaborK + 31) & ~31) + 4; }   // >= P+34, = 4 mod 32
 __host__ __device__ constexpr int gabor_ps(int P) { return ((P + 27) & ~31) + 4; }             // >= P,    = 4 mod 32
 
