@@ -22,7 +22,12 @@ namespace {
 
 // The raster-only variant runs one warp per nucleus (a ring has ~30 edges: a second warp only doubles the
 // issue slots of the serial parts); the shape variant keeps two warps for its two hull chains.
-template <bool SHAPE> struct GeomCfg { static constexpr int kThreads = SHAPE ? 64 : 32; };
+// A raster-only CTA carries four independent nuclei (one warp each, warp-level synchronisation only): one-warp CTAs are
+// capped at 32 resident warps per SM by the CTA limit, and the kernel is latency bound (serial centroid fold, f64 divides).
+template <bool SHAPE> struct GeomCfg {
+    static constexpr int kThreads = SHAPE ? 64 : 32;   // threads per nucleus
+    static constexpr int kNpc = SHAPE ? 1 : 4;         // nuclei per CTA
+};
 
 // first index k in [0,P] such that (k - P/2) >= v   (exact; v may be any double)
 __device__ __forceinline__ int first_index_geq(double v, int P) {
@@ -55,11 +60,15 @@ __device__ __forceinline__ double cross3(double2 o, double2 a, double2 b) {
 }
 
 template <bool RASTER, bool SHAPE>
-__global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads) k_geom(const GeomParams p) {
-    constexpr int kGeomThreads = GeomCfg<SHAPE>::kThreads;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x;
-    const int64_t i = blockIdx.x;
+__global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNpc) k_geom(const GeomParams p, const int nuc_smem) {
+    constexpr int kGeomThreads = GeomCfg<SHAPE>::kThreads, kNpc = GeomCfg<SHAPE>::kNpc;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int sub = kNpc > 1 ? (int)(threadIdx.x / kGeomThreads) : 0;            // which nucleus of the CTA
+    unsigned char* smem_raw = smem_all + (size_t)sub * nuc_smem;
+    const int P = p.P, wpr = mask_wpr(P), tid = kNpc > 1 ? (int)(threadIdx.x % kGeomThreads) : (int)threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kNpc + sub;
+    if (kNpc > 1 && i >= p.n) return;   // whole warp; the multi-nucleus variant only uses warp-level barriers
+    auto sync = [] { if (kNpc > 1) __syncwarp(); else __syncthreads(); };
     const int64_t o0 = p.poly_off[i];
     const int V = (int)(p.poly_off[i + 1] - o0);
 
@@ -69,15 +78,16 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads) k_geom(const GeomPar
     double2* sorted = reinterpret_cast<double2*>(pts + ((p.vmax + 1) & ~1));   // 16-byte aligned
     int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? p.vmax : 0));
     __shared__ double s_red[16];
-    __shared__ float s_c[2];
+    __shared__ float s_c_all[kNpc][2];
     __shared__ int s_hull[2];
+    float* s_c = s_c_all[sub];
 
     for (int k = tid; k < V; k += kGeomThreads) pts[k] = p.poly_xy[o0 + k];
     if (RASTER)
         for (int k = tid; k < P * wpr; k += kGeomThreads) rows[k] = 0u;
     else
         for (int k = tid; k < P * wpr; k += kGeomThreads) rows[k] = p.bitmask[i * P * wpr + k];
-    __syncthreads();
+    sync();
 
     if (RASTER) {
         if (tid == 0) {
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads) k_geom(const GeomPar
             inf.nvr = (int)max(0ll, min((long long)P, bottom - top));
             p.info[i] = inf;
         }
-        __syncthreads();
+        sync();
         const float cx = s_c[0], cy = s_c[1];
         for (int k = tid; k < V; k += kGeomThreads) {   // utils.rs:65-72
             float2 v = pts[k];
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads) k_geom(const GeomPar
             v.y = __fsub_rn(v.y, cy);
             pts[k] = v;
         }
-        __syncthreads();
+        sync();
 
         // ---- SPEC.md B1: edge-parallel scanline, float64 crossing abscissa ----
         const double half = 0.5 * (double)P;
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads) k_geom(const GeomPar
                 }
             }
         }
-        __syncthreads();
+        sync();
         for (int k = tid; k < P * wpr; k += kGeomThreads) p.bitmask[i * P * wpr + k] = rows[k];
     }
 
@@ -315,18 +325,22 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads) k_geom(const GeomPar
 cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     const int wpr = mask_wpr(p.P);
-    size_t smem = (size_t)((p.P * wpr + 3) & ~3) * 4 + (size_t)((p.vmax + 1) & ~1) * 8;
-    if (shape) smem += (size_t)p.vmax * 16 + (size_t)p.vmax * 2 * 4;
-    auto go = [&](auto kern, int threads) -> cudaError_t {
+    size_t nuc = (size_t)((p.P * wpr + 3) & ~3) * 4 + (size_t)((p.vmax + 1) & ~1) * 8;
+    if (shape) nuc += (size_t)p.vmax * 16 + (size_t)p.vmax * 2 * 4;
+    nuc = (nuc + 15) & ~(size_t)15;
+    auto go = [&](auto kern, int threads, int npc) -> cudaError_t {
+        const size_t smem = nuc * npc;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<(unsigned)p.n, threads, smem, s>>>(p);
+        kern<<<(unsigned)((p.n + npc - 1) / npc), threads * npc, smem, s>>>(p, (int)nuc);
         return cudaGetLastError();
     };
-    if (raster) return shape ? go(k_geom<true, true>, GeomCfg<true>::kThreads) : go(k_geom<true, false>, GeomCfg<false>::kThreads);
-    return shape ? go(k_geom<false, true>, GeomCfg<true>::kThreads) : cudaSuccess;
+    if (raster)
+        return shape ? go(k_geom<true, true>, GeomCfg<true>::kThreads, GeomCfg<true>::kNpc)
+                     : go(k_geom<true, false>, GeomCfg<false>::kThreads, GeomCfg<false>::kNpc);
+    return shape ? go(k_geom<false, true>, GeomCfg<true>::kThreads, GeomCfg<true>::kNpc) : cudaSuccess;
 }
 
 }  // namespace nfx
