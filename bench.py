@@ -322,6 +322,35 @@ def cpu_workers():
     return max(1, min(os.cpu_count() or 1, 16))   # bounded: each colour chunk holds ~1 GB of [N,N,P,P] f32
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned buffer is allocated, so that first-touch
+    places the staging memory next to the GPU's PCIe root (matters for the end-to-end number at N > 1, where eight
+    H2D streams otherwise cross the socket interconnect). Returns what it did (for the JSON line)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        cpulist = open(dev + "/local_cpulist").read().strip()
+        node = open(dev + "/numa_node").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": int(node), "cpus": len(cpus)}
+    except Exception as e:  # no NVML, no sysfs entry, single-node box: nothing to do
+        return {"numa_node": None, "note": str(e)[:80]}
+    return {"numa_node": None}
+
+
 def run_pipeline(args, local_rank):
     """The reference's whole main() minus file I/O (src/main.rs:110-190) on one GPU: GeoJSON text in host memory ->
     CSR polygons (nfx_geojson_parse, host threads) -> features (tile uploaded from pinned host memory every step) ->
@@ -458,6 +487,7 @@ def main():
         return
     mask = nfx.parse_feature_sets(sets)
     F = len(nfx.feature_names(mask))
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
     tile, xy, off = make_inputs(args.workload, nuclei, side, P, 2 + rank, pinned=True)
     ex = nfx.Extractor(local_rank, P, args.batch_size)
     ex.upload_tile(tile)
@@ -593,6 +623,8 @@ def main():
             "cpu_baseline": cpu,
             "checksum": checksum,
         }
+        if numa is not None:
+            line["host_numa_binding_rank0"] = numa
         print(json.dumps(line))
     ex.close()
     if dist is not None:
