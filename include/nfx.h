@@ -151,6 +151,28 @@ int nfx_centroid_key(float x, float y, char* buf, int buflen);
  * for the key and the CSV writer. Returns the length or NFX_ERR_INVALID if buf is too small. */
 int nfx_format_f32(float v, char* buf, int buflen);
 
+/* ---- slide decode -------------------------------------------------------- */
+/* The reference opens `.svs` slides with OpenSlide and reads one region per nucleus (src/utils.rs:79-139,
+ * src/main.rs:20-35). An Aperio .svs is a TIFF / BigTIFF whose directory 0 is the full-resolution image in
+ * JPEG-compressed tiles sharing one JPEGTables blob. nfx_slide_load_tiff parses that container (baseline TIFF
+ * 6.0 + BigTIFF, either byte order, tiles or strips, 8-bit 3-sample, compression 7), allocates the slide
+ * (origin 0,0) and decodes every block with nvJPEG straight into HBM on `threads` host threads (<= 0: all
+ * cores); only compressed bytes cross PCIe. Photometric = RGB blocks are taken as R,G,B components (no colour
+ * transform, as libtiff / OpenSlide do), Photometric = YCbCr blocks are converted. Real .svs files could not
+ * be tested in this environment; the container and decode paths are tested on synthetic
+ * files against libjpeg-turbo. `file` is the whole file in host memory (e.g. an mmap). */
+typedef struct nfx_tiff_level {
+    int64_t width, height;
+    int32_t block_width, block_height;   /* tile size, or (width, rows per strip) */
+    int64_t blocks;
+    int32_t compression, photometric;    /* TIFF tags 259, 262 */
+    int32_t jpeg_tables_bytes;           /* tag 347 */
+} nfx_tiff_level;
+int nfx_tiff_info(const uint8_t* file, int64_t len, nfx_tiff_level* out);   /* host only: no GPU needed */
+int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads);
+/* parity tap: a region of the resident slide back to the host, interleaved u8 RGB [h][w][3] */
+int nfx_debug_slide_read(nfx_ctx* ctx, int64_t x0, int64_t y0, int64_t w, int64_t h, uint8_t* rgb);
+
 /* ---- GeoJSON -> CSR polygon packing ------------------------------------- */
 /* Replaces `serde_json::from_reader::<FeatureCollection>` (src/main.rs:37-42) for the model of
  * src/geojson.rs:8-24 (`features[].bbox` required, `features[].geometry.{type,coordinates}`, unknown

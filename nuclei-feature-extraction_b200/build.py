@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnfx.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "geom.cu", "color.cu", "glcm.cu", "texture2.cu", "staged.cu", "csv.cu", "schema.cpp", "geojson.cpp"]
+SOURCES = ["api.cu", "geom.cu", "color.cu", "glcm.cu", "texture2.cu", "staged.cu", "csv.cu", "slide_decode.cu", "schema.cpp", "geojson.cpp", "tiff.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
@@ -49,7 +49,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+    r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lnvjpeg"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -410,6 +410,33 @@ int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h, int6
     return nfx_slide_write_tile(ctx, rgb, 0, 0, w, h, row_stride_bytes);
 }
 
+int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads) {
+    if (!ctx) return NFX_ERR_INVALID;
+    TiffLevel L;
+    std::string err;
+    if (!tiff_parse(file, len, L, err)) return fail(ctx, NFX_ERR_INVALID, "tiff: " + err);
+    int rc = nfx_slide_alloc(ctx, L.width, L.height, 0, 0);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->tile.p, 0, (size_t)ctx->tpitch * L.height, ctx->stream));   // sparse blocks stay black
+    CK(cudaStreamSynchronize(ctx->stream));
+    err = decode_tiff_level(file, L, ctx->tile.p, ctx->tpitch, ctx->device, threads);
+    if (!err.empty()) { ctx->have_tile = false; return fail(ctx, NFX_ERR_UNSUPPORTED, "tiff: " + err); }
+    return NFX_OK;
+}
+
+int nfx_debug_slide_read(nfx_ctx* ctx, int64_t x0, int64_t y0, int64_t w, int64_t h, uint8_t* rgb) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (!ctx->have_tile) return fail(ctx, NFX_ERR_STATE, "no slide resident");
+    if (!rgb || w <= 0 || h <= 0 || x0 < 0 || y0 < 0 || x0 + w > ctx->tw || y0 + h > ctx->th)
+        return fail(ctx, NFX_ERR_INVALID, "nfx_debug_slide_read: region outside the slide");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(rgb, (size_t)3 * w, ctx->tile.p + (size_t)y0 * ctx->tpitch + 3 * x0, ctx->tpitch, (size_t)3 * w, h,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NFX_OK;
+}
+
 int nfx_polygons_upload(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* poly_off) {
     if (!ctx) return NFX_ERR_INVALID;
     if (n < 0 || (n > 0 && (!poly_xy || !poly_off))) return fail(ctx, NFX_ERR_INVALID, "nfx_polygons_upload: bad arguments");

@@ -3,10 +3,24 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 namespace nfx {
 std::string rust_f32_display(float x);
 int set_cols(int set_index);                         // columns of set 0..4 (flat() order)
 int column_offset(uint32_t mask, uint32_t bit);      // first column of `bit` within `mask`, or -1
 extern thread_local std::string g_thread_error;      // last error without a context
+
+// Directory 0 of a TIFF / BigTIFF as a flat table of compressed blocks (tiles, or full-width strips). tiff.cpp
+struct TiffLevel {
+    int64_t width = 0, height = 0;
+    int block_w = 0, block_h = 0;
+    int64_t across = 0, down = 0;            // blocks per row / per column, row-major table
+    int compression = 1, photometric = 2, samples = 1;
+    std::vector<int64_t> offsets, counts;    // byte range of every block inside the file
+    std::vector<uint8_t> jpeg_tables;        // tag 347: SOI DQT DHT EOI shared by abbreviated block streams (may be empty)
+};
+bool tiff_parse(const uint8_t* file, int64_t len, TiffLevel& out, std::string& err);
+// slide_decode.cu: every block of L through nvJPEG into the slide (device pointer); "" on success
+std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* slide, int64_t pitch, int device, int threads);
 }  // namespace nfx

@@ -282,7 +282,17 @@ static Image load_png(const std::vector<uint8_t>& buf) {
 
 Image load_input_image(const std::string& path) {
     const std::string ext = ext_of(path);
-    if (ext == "svs") throw Error("OpenSlide input (.svs) is host-side decode and out of scope here: export the region to png");
+    if (ext == "svs" || ext == "tif" || ext == "tiff") {   // main.rs:21-24 (InputImage::Slide): level 0 of the TIFF container, decoded on the GPU
+        Image im;
+        std::ifstream tf(path, std::ios::binary);
+        if (!tf) throw Error("cannot open " + path);
+        im.tiff.assign((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
+        nfx_tiff_level lv;
+        if (nfx_tiff_info(im.tiff.data(), (int64_t)im.tiff.size(), &lv) != NFX_OK) throw Error(nfx_last_error(nullptr));
+        im.w = lv.width;
+        im.h = lv.height;
+        return im;
+    }
     if (ext == "jpg" || ext == "jpeg") throw Error("JPEG decode is not built into nfx-cli (no libjpeg in the image): convert to png, or use `python -m nfx.cli`");
     if (ext != "png" && ext != "ppm")
         throw Error("Unsupported input format. Please use one of the following : svs, png, jpg, jpeg");   // main.rs:29-31
@@ -291,6 +301,11 @@ Image load_input_image(const std::string& path) {
     std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     if (buf.size() >= 2 && buf[0] == 'P' && buf[1] == '6') return load_ppm(buf);
     return load_png(buf);
+}
+
+void upload_image(Context& ctx, const Image& image) {
+    if (!image.tiff.empty()) ctx.check(nfx_slide_load_tiff(ctx.raw(), image.tiff.data(), (int64_t)image.tiff.size(), 0));
+    else ctx.check(nfx_tile_upload(ctx.raw(), image.rgb.data(), image.w, image.h, 3 * image.w, 0, 0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,7 +400,7 @@ DataFrame extract(const FeatureCollection& geometry, const Image& image, const A
                 const size_t lo = (size_t)bounds[g], hi = (size_t)bounds[g + 1];
                 if (hi <= lo) return;
                 Context ctx(args.gpus[g], args.patch_size, args.batch_size);
-                ctx.check(nfx_tile_upload(ctx.raw(), image.rgb.data(), image.w, image.h, 3 * image.w, 0, 0));
+                upload_image(ctx, image);
                 std::vector<float> xy;
                 std::vector<int64_t> off;
                 csr_of(geometry, lo, hi, xy, off);
@@ -414,7 +429,7 @@ DataFrame extract_via_trait(const FeatureCollection& geometry, const Image& imag
     for (size_t lo = 0; lo < n; lo += (size_t)args.batch_size) {   // par_chunks(batch_size), main.rs:148
         const size_t hi = std::min(n, lo + (size_t)args.batch_size), m = hi - lo;
         // the Batch of utils.rs:17, built by kernels (2) and (1) instead of the host loader
-        ctx.check(nfx_tile_upload(ctx.raw(), image.rgb.data(), image.w, image.h, 3 * image.w, 0, 0));
+        upload_image(ctx, image);
         std::vector<float> xy;
         std::vector<int64_t> off;
         csr_of(geometry, lo, hi, xy, off);

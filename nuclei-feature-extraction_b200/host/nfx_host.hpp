@@ -96,9 +96,11 @@ FeatureCollection load_geometry(const std::string& path, int threads = 0);   // 
 // ---- main.rs:20-35 ------------------------------------------------------------------------------
 struct Image {
     int64_t w = 0, h = 0;
-    std::vector<uint8_t> rgb;                    // [h][w][3]
+    std::vector<uint8_t> rgb;                    // [h][w][3] (png / ppm)
+    std::vector<uint8_t> tiff;                   // or: the bytes of a JPEG-compressed TIFF / .svs, decoded on the GPU (nvJPEG)
 };
-Image load_input_image(const std::string& path);   // png (8-bit, non-interlaced) and binary ppm; svs/jpg -> Error
+Image load_input_image(const std::string& path);   // png (8-bit, non-interlaced), binary ppm, svs / tif / tiff (JPEG blocks); jpg -> Error
+void upload_image(Context& ctx, const Image& image);   // tile upload, or nvJPEG decode straight into the resident slide
 
 // ---- args.rs:76-183 -----------------------------------------------------------------------------
 struct Args {

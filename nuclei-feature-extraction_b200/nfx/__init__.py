@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import (FS_ALL, FS_COLOR, FS_GABOR, FS_GEOMETRY, FS_GLCM, FS_GLRLM, FS_TEXTURE, NFX_OK,
-                   NfxConfig, NfxError, NfxKernelTime, lib)
+                   NfxConfig, NfxError, NfxKernelTime, NfxTiffLevel, lib)
 
 _FLAT_BITS = (FS_GEOMETRY, FS_COLOR, FS_GLCM, FS_GLRLM, FS_GABOR)
 
@@ -87,6 +87,15 @@ def pack_polygons(rings):
     for i, r in enumerate(rings):
         xy[off[i]:off[i + 1]] = np.asarray(r, dtype=np.float32).reshape(-1, 2)
     return xy, off
+
+
+def tiff_info(data) -> dict:
+    """Directory 0 of a TIFF / BigTIFF held in memory (nfx_tiff_info): size, block size, compression."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    lv = NfxTiffLevel()
+    if lib().nfx_tiff_info(buf.ctypes.data, buf.size, C.byref(lv)) != NFX_OK:
+        raise NfxError(-1, (lib().nfx_last_error(None) or b"").decode())
+    return {f: getattr(lv, f) for f, _ in NfxTiffLevel._fields_}
 
 
 def parse_f32(token: str) -> np.float32:
@@ -186,6 +195,16 @@ class Extractor:
         self._tile_ref = rgb
         self._ck(lib().nfx_tile_upload(self._h, _ptr(rgb), rgb.shape[1], rgb.shape[0], rgb.strides[0],
                                        int(origin[0]), int(origin[1])))
+
+    def load_tiff(self, data, threads: int = 0):
+        """Level 0 of a JPEG-compressed TIFF / .svs held in memory -> the resident slide, decoded by nvJPEG."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        self._ck(lib().nfx_slide_load_tiff(self._h, buf.ctypes.data, buf.size, threads))
+
+    def slide_read(self, x0, y0, w, h):
+        out = np.empty((h, w, 3), dtype=np.uint8)
+        self._ck(lib().nfx_debug_slide_read(self._h, x0, y0, w, h, _ptr(out)))
+        return out
 
     def slide_alloc(self, w, h, origin=(0, 0)):
         """Reserve a W x H slide in HBM; fill it with write_tile (tiles / row bands, any order)."""

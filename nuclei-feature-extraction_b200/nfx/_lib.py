@@ -18,6 +18,11 @@ class NfxConfig(C.Structure):
     _fields_ = [("patch_size", C.c_int32), ("batch_size", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
+class NfxTiffLevel(C.Structure):
+    _fields_ = [("width", C.c_int64), ("height", C.c_int64), ("block_width", C.c_int32), ("block_height", C.c_int32),
+                ("blocks", C.c_int64), ("compression", C.c_int32), ("photometric", C.c_int32), ("jpeg_tables_bytes", C.c_int32)]
+
+
 class NfxKernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
@@ -49,6 +54,9 @@ SYMBOLS = {
     "nfx_feature_set_name": (C.c_char_p, [_u32]),
     "nfx_centroid_key": (_i, [_f, _f, C.c_char_p, _i]),
     "nfx_format_f32": (_i, [_f, C.c_char_p, _i]),
+    "nfx_tiff_info": (_i, [_vp, _i64, _vp]),
+    "nfx_slide_load_tiff": (_i, [_vp, _vp, _i64, C.c_int32]),
+    "nfx_debug_slide_read": (_i, [_vp, _i64, _i64, _i64, _i64, _vp]),
     "nfx_geojson_parse": (_i, [C.c_char_p, _i64, C.c_int32, C.POINTER(_vp)]),
     "nfx_geojson_count": (_i64, [_vp]),
     "nfx_geojson_vertices": (_i64, [_vp]),

@@ -75,8 +75,8 @@ def load_geometry(path, threads: int = 0):
 def load_input_image(path):
     """load_input_image (src/main.rs:20-35): png/jpg/jpeg -> [H,W,3] u8."""
     ext = os.path.splitext(path)[1].lstrip(".")
-    if ext == "svs":
-        die("OpenSlide input (.svs) is host-side decode and out of scope here: convert the region to png")
+    if ext in ("svs", "tif", "tiff"):     # InputImage::Slide (main.rs:21-24): the file bytes; level 0 is decoded on the GPU
+        return np.fromfile(path, dtype=np.uint8)
     if ext not in ("png", "jpg", "jpeg"):
         die("Unsupported input format. Please use one of the following : svs, png, jpg, jpeg")
     from PIL import Image
@@ -101,7 +101,10 @@ def extract_multi_gpu(image, xy, off, mask, gpus, patch_size, batch_size):
             return
         try:
             with nfx.Extractor(gpu, patch_size, batch_size) as ex:
-                ex.upload_tile(image)
+                if image.ndim == 1:
+                    ex.load_tiff(image)
+                else:
+                    ex.upload_tile(image)
                 ex.upload_polygons(xy[off[lo]:off[hi]], off[lo:hi + 1] - off[lo])
                 ex.compute(mask)
                 ex.download(cents[lo:hi], feats[lo:hi])
