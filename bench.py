@@ -351,6 +351,53 @@ def bind_to_gpu_numa(local_rank: int):
     return {"numa_node": None}
 
 
+def run_trait(args, local_rank):
+    """The drop-in route that keeps the reference's loader: `FeatureSet::compute_features_batched` per chunk of
+    `batch_size` nuclei with the reference's own Batch layout (patchs [n,3,P,P] f32, masks [n,1,P,P] f32 in host memory,
+    src/utils.rs:17, src/features/mod.rs:12-28) through nfx_compute_features_batched. Wall clock over whole chunks."""
+    import nfx
+    sets = args.sets.split(",") if args.sets else ["color"]
+    P, B = 64, args.batch_size
+    nchunks = max(1, (args.nuclei or 20_000) // B)
+    tile, xy, off = make_inputs("color", B, 2048, P, 2, pinned=False)
+    ex = nfx.Extractor(local_rank, P, B)
+    ex.upload_tile(tile)
+    ex.upload_polygons(xy, off)
+    masks_u8 = ex.rasterize()
+    patch_u8 = ex.gather_patches()
+    cents = np.zeros((B, 2), np.float32)   # only used for the key column, which the host formats
+    patchs = nfx.pinned_empty((B, 3, P, P), np.float32)
+    masks = nfx.pinned_empty((B, 1, P, P), np.float32)
+    patchs[:] = np.transpose(patch_u8.reshape(B, P, P, 3), (0, 3, 1, 2)).astype(np.float32) / np.float32(255.0)
+    masks[:, 0] = masks_u8.reshape(B, P, P)
+    rings = synth_rings(xy, off)
+    bits = {"geometry": nfx.FS_GEOMETRY, "color": nfx.FS_COLOR, "glcm": nfx.FS_GLCM, "glrlm": nfx.FS_GLRLM, "gabor": nfx.FS_GABOR}
+    todo = [nfx.FS_ALL] if sets == ["union"] else [bits[s] for s in sets]   # "union": all five sets in ONE call (one upload)
+    def chunk():
+        return [ex.compute_features_batched(b, cents, rings, patchs, masks) for b in todo]
+    for _ in range(max(args.warmup, 3)):
+        chunk()
+    t0 = time.perf_counter()
+    for _ in range(nchunks):
+        chunk()
+    dt = time.perf_counter() - t0
+    h2d = patchs.nbytes + masks.nbytes
+    print(json.dumps({
+        "metric": "nuclei/sec", "value": nchunks * B / dt, "unit": "nuclei/s", "n_gpus": 1, "steps": nchunks, "warmup": max(args.warmup, 3),
+        "ms_per_step": dt / nchunks * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 in, u8/f32 inside",
+        "data": "synthetic",
+        "config": {"workload": f"trait: compute_features_batched({'+'.join(sets)}) per chunk of {B} nuclei, {P}x{P} f32 patches and masks from pinned host "
+                               f"memory ({h2d / 1e6:.1f} MB per call and set), {nchunks} chunks", "timing": "host wall clock"},
+        "e2e": {"value": nchunks * B / dt, "unit": "nuclei/s", "h2d_bytes_per_step": h2d * len(todo), "d2h_bytes_per_step": 4 * B * sum(len(nfx.feature_names(b)) for b in todo)},
+        "gpu_launches": int(ex.launch_count()),
+    }))
+    ex.close()
+
+
+def synth_rings(xy, off):
+    return [xy[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
 def run_pipeline(args, local_rank):
     """The reference's whole main() minus file I/O (src/main.rs:110-190) on one GPU: GeoJSON text in host memory ->
     CSR polygons (nfx_geojson_parse, host threads) -> features (tile uploaded from pinned host memory every step) ->
@@ -410,7 +457,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nfx", choices=["nfx", "reference"])
-    ap.add_argument("--workload", default="color", choices=sorted(WORKLOADS) + ["staged", "pipeline"])
+    ap.add_argument("--workload", default="color", choices=sorted(WORKLOADS) + ["staged", "pipeline", "trait"])
     ap.add_argument("--sets", default="", help="pipeline workload: comma separated feature sets (default color)")
     ap.add_argument("--nuclei", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
@@ -430,6 +477,10 @@ def main():
     if args.workload == "pipeline":
         if rank == 0:
             run_pipeline(args, local_rank)
+        return
+    if args.workload == "trait":
+        if rank == 0:
+            run_trait(args, local_rank)
         return
     sets, nuclei, side, P, _ = WORKLOADS[args.workload]
     nuclei = args.nuclei or nuclei

@@ -110,8 +110,10 @@ int nfx_sync(nfx_ctx* ctx);
 /* FeatureSet::compute_features_batched(centroids, polygons, patchs, masks) (src/features/mod.rs:
  * 12-28) for ONE batch built by the reference's own loader: patchs [n,3,P,P] f32 with values k/255
  * (utils.rs:172), masks [n,1,P,P] f32 in {0,1}, polygons = CENTRED rings (utils.rs:65-72) in CSR.
- * `feature_set` is exactly one NFX_FS_* bit. All pointers are HOST pointers.
- * out: [n][nfx_feature_count(feature_set)] f32. The whole call is one chunk for mean_h. */
+ * `feature_set` is one NFX_FS_* bit (the trait call), or a union of bits: the batch is then uploaded
+ * once and the columns of the sets follow each other in flat() order (src/args.rs:38-45), which saves
+ * the 65 KB per nucleus of PCIe traffic each further per-set call would repeat. All pointers are HOST
+ * pointers. out: [n][nfx_feature_count(feature_set)] f32. The whole call is one chunk for mean_h. */
 int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t feature_set, int64_t n,
                                  const float* centroids, const float* poly_xy,
                                  const int64_t* poly_off, const float* patchs, const float* masks,

@@ -576,15 +576,15 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
                                  const float* masks, float* out) {
     if (!ctx) return NFX_ERR_INVALID;
     (void)centroids;   // only used for the key column, which the host formats (utils.rs:226-232)
-    if (fs != NFX_FS_GEOMETRY && fs != NFX_FS_COLOR && fs != NFX_FS_GLCM && fs != NFX_FS_GLRLM && fs != NFX_FS_GABOR)
-        return fail(ctx, NFX_ERR_INVALID, "feature_set must be exactly one NFX_FS_* bit");
+    if (fs == 0 || (fs & ~(uint32_t)NFX_FS_ALL))
+        return fail(ctx, NFX_ERR_INVALID, "feature_set must be one NFX_FS_* bit (the trait call) or a union of them (one upload, columns in flat() order)");
     int rc = check_patch_size(ctx, fs);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!patchs || !masks || !out))) return fail(ctx, NFX_ERR_INVALID, "nfx_compute_features_batched: bad arguments");
     if (n == 0) return NFX_OK;
     if ((rc = set_device(ctx))) return rc;
     // the asserts of shape.rs:23-47 / color.rs:18-42 become argument checks on the CSR
-    if (fs == NFX_FS_GEOMETRY)
+    if (fs & NFX_FS_GEOMETRY)
         if ((rc = nfx_polygons_upload(ctx, n, poly_xy, poly_off))) return rc;   // centred rings
     const int P = ctx->P, wpr = mask_wpr(P);
     const size_t plane = (size_t)P * P;
@@ -602,21 +602,22 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
         return launch_pack_batch(n, P, d_patchs, d_masks, ctx->patches.p, ctx->ppitch, ctx->bitmask.p,
                                  ctx->info.p, ctx->d_bad, ctx->stream);
     }));
-    const int cols = nfx_feature_count(fs);
+    const Cols c = columns(fs);
+    const int cols = c.total;
     CK(ctx->out.ensure((size_t)n * cols));
-    if (fs == NFX_FS_GEOMETRY) {
+    if (fs & NFX_FS_GEOMETRY) {
         GeomParams g;
         g.poly_xy = ctx->xy.p; g.poly_off = ctx->off.p; g.n = n; g.P = P; g.tile_ox = 0; g.tile_oy = 0;
         g.vmax = std::max(ctx->vmax, 1); g.centroid = ctx->centroid.p; g.info = ctx->info.p;
-        g.bitmask = ctx->bitmask.p; g.out = ctx->out.p; g.out_stride = cols; g.col_shape = 0; g.ellipse_bits = nullptr;
+        g.bitmask = ctx->bitmask.p; g.out = ctx->out.p; g.out_stride = cols; g.col_shape = c.shape; g.ellipse_bits = nullptr;
         CK(timed(ctx, "k_geom<shape>", 1, [&] { return launch_geom(g, false, true, ctx->stream); }));
-    } else if (fs == NFX_FS_COLOR) {
-        if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_cslab, &ctx->map_pat_slab, ctx->out.p, cols, 0))) return rc;
-    } else if (fs == NFX_FS_GLCM) {
-        if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_pat_cslab : &ctx->map_pat_patch, ctx->out.p, cols, 0, nullptr, 0, 0, 0, nullptr))) return rc;
-    } else {
-        if ((rc = run_tex2(ctx, n, fs, &ctx->map_pat_cslab, &ctx->map_pat_patch, &ctx->map_pat_gabor, ctx->out.p, cols, 0, 0))) return rc;
     }
+    if (fs & NFX_FS_COLOR)
+        if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_cslab, &ctx->map_pat_slab, ctx->out.p, cols, c.color))) return rc;
+    if (fs & NFX_FS_GLCM)
+        if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_pat_cslab : &ctx->map_pat_patch, ctx->out.p, cols, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
+    if (fs & (NFX_FS_GLRLM | NFX_FS_GABOR))
+        if ((rc = run_tex2(ctx, n, fs, &ctx->map_pat_cslab, &ctx->map_pat_patch, &ctx->map_pat_gabor, ctx->out.p, cols, c.glrlm, c.gabor))) return rc;
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(out, ctx->out.p, (size_t)n * cols * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -173,6 +173,13 @@ def test_trait_level_compute_features_batched(case, ex):
             want = o.glcm_feature_set(case["patches"][:n], case["masks"][:n])
             sel = [k * 14 + f for k in range(16) for f in (1, 2, 3, 4, 5, 9)]
             assert np.allclose(got[:, sel], want[:, sel], rtol=1e-4, atol=1e-6, equal_nan=True)
+    # a union of sets in ONE call: one upload of the batch, columns in flat() order, same bits as the per-set calls
+    parts = [ex.compute_features_batched(b, cents, polys, patches, masks)
+             for b in (nfx.FS_GEOMETRY, nfx.FS_COLOR, nfx.FS_GLCM, nfx.FS_GLRLM, nfx.FS_GABOR)]
+    both = ex.compute_features_batched(nfx.FS_ALL, cents, polys, patches, masks)
+    assert both.shape == (n, 418) and both.tobytes() == np.concatenate(parts, 1).tobytes()
+    with pytest.raises(nfx.NfxError):
+        ex.compute_features_batched(0x40, cents, polys, patches, masks)
     ex.upload_tile(case["tile"])
 
 
