@@ -451,27 +451,39 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
         }
     }
     __syncthreads();
-    // ---- masked sums of the slab's (S, C) image under each nucleus' mask ----
+    // ---- masked sums of the slab's (S, C) image under each nucleus' mask. Four nuclei per warp pass: their mask words
+    //      are fetched together, so the L2 latency of the (cold) bitmask is paid once per four nuclei ----
     const int nrows = min(R, P - row0), words = nrows * wpr;
-    for (int i = warp; i < nb; i += kHueThreads / 32) {
-        const uint32_t* gm = p.bitmask + ((b0 + i) * (int64_t)P + row0) * wpr;
-        float ss = 0.f, sc = 0.f;
+    constexpr int NWARP = kHueThreads / 32, UN = 4;
+    for (int i0 = warp * UN; i0 < nb; i0 += NWARP * UN) {
+        float ss[UN], sc[UN];
+#pragma unroll
+        for (int q = 0; q < UN; ++q) { ss[q] = 0.f; sc[q] = 0.f; }
         for (int w = lane; w < words; w += 32) {
-            uint32_t bits = gm[w];
+            uint32_t bits[UN];
+#pragma unroll
+            for (int q = 0; q < UN; ++q)
+                bits[q] = (i0 + q < nb) ? p.bitmask[((b0 + i0 + q) * (int64_t)P + row0) * wpr + w] : 0u;
             const int r = w / wpr, cb = (w - r * wpr) * 32;
-            while (bits) {
-                const int c = cb + __ffs(bits) - 1;
-                bits &= bits - 1;
-                ss += Ss[r * P + c];
-                sc += Cs[r * P + c];
+#pragma unroll
+            for (int q = 0; q < UN; ++q) {
+                uint32_t b = bits[q];
+                while (b) {
+                    const int c = cb + __ffs(b) - 1;
+                    b &= b - 1;
+                    ss[q] += Ss[r * P + c];
+                    sc[q] += Cs[r * P + c];
+                }
             }
         }
-        ss = warp_sum(ss);
-        sc = warp_sum(sc);
-        if (lane == 0) {
-            float* hp = p.hue_partial + ((b0 + i) * (int64_t)p.slabs + slab) * 2;
-            hp[0] = ss;
-            hp[1] = sc;
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            const float s1 = warp_sum(ss[q]), c1 = warp_sum(sc[q]);
+            if (lane == 0 && i0 + q < nb) {
+                float* hp = p.hue_partial + ((b0 + i0 + q) * (int64_t)p.slabs + slab) * 2;
+                hp[0] = s1;
+                hp[1] = c1;
+            }
         }
     }
 }
