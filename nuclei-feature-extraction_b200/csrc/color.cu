@@ -26,9 +26,12 @@ namespace nfx {
 namespace {
 
 constexpr int kColorThreads = 128;
-constexpr int kHueConsumers = 128;               // 4 consumer warps, 2 pixel quads (8 px) per thread
-constexpr int kHueThreads = kHueConsumers + 32;  // + 1 TMA producer warp
-constexpr int kHueQpt = 2;                       // quads per consumer thread: slab holds <= 256 quads
+// k_hue_batch<NCW>: NCW consumer warps + 1 TMA producer warp; a slab holds <= 256 pixel quads. NCW = 4 (2 quads = 8 px per
+// thread) is the throughput shape: 6 CTAs share an SM. NCW = 8 (1 quad per thread) is used when there are too few
+// (chunk, slab) CTAs to give an SM more than one -- a trait-level call is ONE chunk -- where a lone warp per
+// scheduler issues only every fourth cycle (ncu: 24 % issue-active, 85 us per 100 patches): twice the warps
+// halve that. Every pixel still adds its patches in the same order, so both shapes give the same bits.
+constexpr int kHueMaxQuads = 256;
 constexpr int kHueStages = 8;
 constexpr int kHueChunk = 128;                   // nuclei whose NucInfo is staged in smem at a time
 
@@ -293,8 +296,10 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
 
 // ------------------------------------------------------------------------------------------------
 // grid = (n_batches, slabs). Dynamic smem: ring[kHueStages][panels*192*R] | Cs[R*P] | Ss[R*P] f32.
-__global__ void __launch_bounds__(kHueThreads)
+template <int NCW>
+__global__ void __launch_bounds__(32 * NCW + 32)
 k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R) {
+    constexpr int kHueConsumers = 32 * NCW, kHueThreads = kHueConsumers + 32, kHueQpt = kHueMaxQuads / kHueConsumers;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stage_bytes = window_smem_bytes(P, R);
@@ -312,7 +317,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     //      pixel quads outside the union are never evaluated (44 % of a 64 x 64 window for the bench's nuclei,
     //      far more for small nuclei). Active quads are compacted and dealt to the consumer threads. ----
     __shared__ uint32_t s_union[64];
-    __shared__ uint16_t s_qlist[kHueQpt * kHueConsumers];
+    __shared__ uint16_t s_qlist[kHueMaxQuads];
     __shared__ int s_nact;
     const int qpr = P >> 2, nquads = R * qpr;
     const int nrows_u = min(R, P - row0), words_u = nrows_u * wpr;
@@ -363,7 +368,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
         soff[u] = (c0[u] >> 6) * panel_stride(R) + rr[u] * kPanelBytes + (c0[u] & 63) * 3;   // + o per nucleus
         asm volatile("" : "+r"(soff[u]));   // keep it in a register: recomputing it costs 12 instructions per patch
     }
-    const int nq_w = (warp < kHueConsumers / 32) ? ((warp * 32 < nact) + (kHueConsumers + warp * 32 < nact)) : 0;   // warp-uniform
+    const int nq_w = (warp < NCW) ? ((warp * 32 < nact) + (kHueQpt > 1 && kHueConsumers + warp * 32 < nact)) : 0;   // warp-uniform
     float C[kHueQpt][4], S[kHueQpt][4];
 #pragma unroll
     for (int u = 0; u < kHueQpt; ++u)
@@ -541,12 +546,20 @@ cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, 
     if (p.n <= 0) return cudaSuccess;
     const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
     const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * p.P * 4;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_hue_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-    }
     dim3 grid((unsigned)nbatch, (unsigned)p.slabs);
-    k_hue_batch<<<grid, kHueThreads, smem, s>>>(p, *map_slab, R);
+    if (nbatch * p.slabs < 2 * 148) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_hue_batch<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R);
+    } else {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_hue_batch<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_hue_batch<4><<<grid, 32 * 4 + 32, smem, s>>>(p, *map_slab, R);
+    }
     return cudaGetLastError();
 }
 
