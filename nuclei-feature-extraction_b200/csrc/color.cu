@@ -26,11 +26,11 @@ namespace nfx {
 namespace {
 
 constexpr int kColorThreads = 128;
-// k_hue_batch<NCW>: NCW consumer warps + 1 TMA producer warp; a slab holds <= 256 pixel quads. NCW = 4 (2 quads = 8 px per
-// thread) is the throughput shape: 6 CTAs share an SM. NCW = 8 (1 quad per thread) is used when there are too few
-// (chunk, slab) CTAs to give an SM more than one -- a trait-level call is ONE chunk -- where a lone warp per
-// scheduler issues only every fourth cycle (ncu: 24 % issue-active, 85 us per 100 patches): twice the warps
-// halve that. Every pixel still adds its patches in the same order, so both shapes give the same bits.
+// k_hue_batch<NCW>: NCW consumer warps + 1 TMA producer warp; a slab holds <= 256 pixel quads. NCW = 8 (one quad =
+// 4 px per thread, 40 registers) is what is launched: 54 warps per SM instead of the 30 of NCW = 4 (0.665 -> 0.637 ms per
+// 100 000 nuclei), and a lone (chunk, slab) CTA on an SM -- a trait-level call is ONE chunk -- no longer leaves each
+// scheduler with a single warp that issues every fourth cycle (86 -> 66 us per 100 patches). Every pixel adds its
+// patches in the same order whatever NCW is, so the results do not depend on it.
 constexpr int kHueMaxQuads = 256;
 constexpr int kHueStages = 8;
 constexpr int kHueChunk = 128;                   // nuclei whose NucInfo is staged in smem at a time
@@ -547,19 +547,11 @@ cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, 
     const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
     const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * p.P * 4;
     dim3 grid((unsigned)nbatch, (unsigned)p.slabs);
-    if (nbatch * p.slabs < 2 * 148) {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-        }
-        k_hue_batch<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R);
-    } else {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_hue_batch<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-        }
-        k_hue_batch<4><<<grid, 32 * 4 + 32, smem, s>>>(p, *map_slab, R);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
     }
+    k_hue_batch<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R);
     return cudaGetLastError();
 }
 
