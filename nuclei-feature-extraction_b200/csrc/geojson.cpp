@@ -244,7 +244,20 @@ struct Reader {
         *esc = false;
         while (p < end && *p != '"') {
             if ((unsigned char)*p < 0x20) fail("control character in string");
-            if (*p == '\\') { *esc = true; ++p; if (p >= end) break; }
+            if (*p == '\\') {   // serde_json checks the escape even in strings it skips (ignore_str / ignore_escape)
+                *esc = true;
+                ++p;
+                if (p >= end) break;
+                const char e2 = *p;
+                if (e2 == 'u') {
+                    if (end - p < 5) fail("EOF while parsing a string");
+                    for (int k = 1; k <= 4; ++k)
+                        if (!isxdigit((unsigned char)p[k])) fail("invalid escape");
+                    p += 4;
+                } else if (e2 != '"' && e2 != '\\' && e2 != '/' && e2 != 'b' && e2 != 'f' && e2 != 'n' && e2 != 'r' && e2 != 't') {
+                    fail("invalid escape");
+                }
+            }
             ++p;
         }
         if (p >= end) fail("EOF while parsing a string");

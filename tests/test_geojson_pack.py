@@ -150,3 +150,40 @@ def test_pack_error_position_and_order(libnfx):
             nfx.geojson_pack(text, t)
         msgs.add(str(e.value))
     assert len(msgs) == 1 and "fewer than two" in msgs.pop()      # the first error in input order, whatever the thread count
+
+
+def test_pack_fuzz_accepts_and_rejects_like_the_reference_reader(libnfx):
+    """Random one- and two-byte mutations of a valid document: the packer must accept exactly what the restated
+    serde reader accepts, and produce the same arrays when both accept (strings with escapes, nested unknown values,
+    holes, 3-D positions and an empty bbox are all in the seed document)."""
+    base = ('{"type":"FeatureCollection","features":[{"type":"Feature","id":"a","bbox":[1.5,2,3e1,4],"geometry":{"type":"Polygon",'
+            '"coordinates":[[[10.25,20.5],[30,20.125],[25.5,40],[10.25,20.5]],[[1,2],[3,4],[1,2]]]},"properties":{"name":"x \\"q\\" [{",'
+            '"v":[1,{"k":null},true]}},{"bbox":[],"geometry":{"coordinates":[[[0.1,0.2],[3,4,5]]],"type":"Polygon"}}],"extra":{"a":[1,2,{"b":"]"}]}}')
+    rng = np.random.default_rng(123)
+    alphabet = list('{}[]",:.-+eE0123456789 \n\\tnulrfas')
+    accepted = 0
+    for _ in range(2500):
+        s = list(base)
+        for _ in range(rng.integers(1, 3)):
+            k = rng.integers(0, len(s))
+            op = rng.integers(0, 3)
+            if op == 0:
+                del s[k]
+            elif op == 1:
+                s.insert(k, alphabet[rng.integers(0, len(alphabet))])
+            else:
+                s[k] = alphabet[rng.integers(0, len(alphabet))]
+        t = "".join(s)
+        try:
+            want = gr.load_text(t)
+        except Exception:
+            want = None
+        try:
+            got = nfx.geojson_pack(t, 2)
+        except nfx.NfxError:
+            got = None
+        assert (want is None) == (got is None), t
+        if want is not None:
+            accepted += 1
+            assert all(_same(g, w) for g, w in zip(got, want)), t
+    assert accepted > 300
