@@ -391,7 +391,7 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
 //     2^-16 quantum, far below the 1e-4 tolerance) so that warp reduction is one REDUX each;
 //   * tables are cleared densely with 128-bit stores. 3 block barriers per offset.
 // =================================================================================================
-constexpr int kG64Threads = 256, kG64NW = kG64Threads / 32;   // 512 threads measured slower (22.6 vs 20.2 ms / 200k)
+constexpr int kG64Threads = 256, kG64NW = kG64Threads / 32;   // 384 / 512 threads measured slower (17.4 / 22.6 vs 16.2 / 20.2 ms per 200k)
 constexpr int kTri32 = 32 * 33 / 2, kTri64 = 64 * 65 / 2, kTri128 = 128 * 129 / 2;
 constexpr int kOffTri128 = 0;                                  // bytes inside region A
 constexpr int kOffTri64 = kOffTri128 + kTri128 * 2;            // 16512
