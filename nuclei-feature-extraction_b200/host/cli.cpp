@@ -19,6 +19,10 @@ int main(int argc, char** argv) {
         const FeatureCollection geometry = load_geometry(args.geometry);
         const Image image = load_input_image(args.slide);
         std::fprintf(stderr, "INFO Extracting features\n");      // main.rs:143
+        if (ext == "csv" && !args.via_trait && !args.host_csv) {
+            extract_to_csv(geometry, image, args, args.output);   // rows formatted on each GPU, no DataFrame in between
+            return 0;
+        }
         const DataFrame df = args.via_trait ? extract_via_trait(geometry, image, args) : extract(geometry, image, args);
         write_output(args.output, ext, df, args.host_csv || args.gpus.empty() ? -1 : args.gpus[0]);
         return 0;

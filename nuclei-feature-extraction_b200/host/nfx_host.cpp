@@ -419,6 +419,59 @@ DataFrame extract(const FeatureCollection& geometry, const Image& image, const A
     return frame_from(mask, keys, cent.data(), feat);
 }
 
+void extract_to_csv(const FeatureCollection& geometry, const Image& image, const Args& args, const std::string& path) {
+    const uint32_t mask = feature_mask(args.feature_sets);
+    const size_t n = geometry.size();
+    std::vector<int64_t> bounds(args.gpus.size() + 1);
+    if (nfx_partition((int64_t)n, args.batch_size, (int)args.gpus.size(), bounds.data()) != NFX_OK) throw Error("bad partition");
+    std::vector<std::string> errors(args.gpus.size());
+    std::vector<std::vector<char>> text(args.gpus.size());   // the rows of each range; ranges are contiguous and ordered
+    std::vector<std::thread> threads;
+    for (size_t g = 0; g < args.gpus.size(); ++g) {
+        threads.emplace_back([&, g] {
+            try {
+                const size_t lo = (size_t)bounds[g], hi = (size_t)bounds[g + 1];
+                if (hi <= lo) return;
+                Context ctx(args.gpus[g], args.patch_size, args.batch_size);
+                upload_image(ctx, image);
+                std::vector<float> xy;
+                std::vector<int64_t> off;
+                csr_of(geometry, lo, hi, xy, off);
+                ctx.check(nfx_polygons_upload(ctx.raw(), (int64_t)(hi - lo), xy.data(), off.data()));
+                ctx.check(nfx_compute(ctx.raw(), mask));
+                const int64_t m = (int64_t)(hi - lo), F = nfx_feature_count(mask);
+                const int64_t block = std::max<int64_t>(1, std::min<int64_t>(m, (64ll << 20) / (4 * (F + 2))));
+                std::vector<char> buf((size_t)block * (F + 2) * 12 + 64);
+                for (int64_t r = 0; r < m; r += block) {
+                    const int64_t r1 = std::min(m, r + block);
+                    int64_t len = 0;
+                    int rc = nfx_csv_rows(ctx.raw(), r, r1, buf.data(), (int64_t)buf.size(), &len);
+                    if (rc != NFX_OK && len > (int64_t)buf.size()) {
+                        buf.resize((size_t)len);
+                        rc = nfx_csv_rows(ctx.raw(), r, r1, buf.data(), (int64_t)buf.size(), &len);
+                    }
+                    ctx.check(rc);
+                    text[g].insert(text[g].end(), buf.begin(), buf.begin() + len);
+                }
+                if (args.verbose) std::fprintf(stderr, "INFO Extracted features for %zu/%zu patches\n", hi, n);   // main.rs:152-157
+            } catch (const std::exception& e) {
+                errors[g] = e.what();
+            }
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (auto& e : errors)
+        if (!e.empty()) throw Error(e);
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot create " + path);
+    int64_t hl = 0;
+    nfx_csv_header(mask, nullptr, 0, &hl);
+    std::vector<char> header((size_t)hl);
+    if (nfx_csv_header(mask, header.data(), hl, &hl) != NFX_OK) throw Error("csv header");
+    f.write(header.data(), hl);
+    for (auto& t : text) f.write(t.data(), (std::streamsize)t.size());
+}
+
 DataFrame extract_via_trait(const FeatureCollection& geometry, const Image& image, const Args& args) {
     feature_mask(args.feature_sets);   // duplicate / empty checks
     Context ctx(args.gpus[0], args.patch_size, args.batch_size);

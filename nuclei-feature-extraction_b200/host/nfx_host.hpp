@@ -118,6 +118,9 @@ std::string validate_paths(const Args& a);         // returns the output extensi
 // ---- main.rs:146-158 ----------------------------------------------------------------------------
 // Contiguous index ranges per GPU (nfx_partition), one host thread + context each, merged in input order.
 DataFrame extract(const FeatureCollection& geometry, const Image& image, const Args& args);
+// The csv arm of main.rs:163-166 without a DataFrame in between: every GPU formats the rows of its own range from the
+// result that is still resident (nfx_csv_rows) and only text comes back; the ranges are written in input order.
+void extract_to_csv(const FeatureCollection& geometry, const Image& image, const Args& args, const std::string& path);
 // Same result through the trait objects: masks and patches come back from kernels (1) and (2) as the
 // reference's Batch tensors (utils.rs:17) and go through FeatureSet::compute_features_batched chunk by chunk.
 DataFrame extract_via_trait(const FeatureCollection& geometry, const Image& image, const Args& args);
