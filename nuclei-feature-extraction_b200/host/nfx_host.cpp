@@ -1,10 +1,14 @@
 // nfx_host.cpp -- implementation of the C++ host mirror (see nfx_host.hpp for the reference citations).
 #include "nfx_host.hpp"
 
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -166,14 +170,18 @@ std::vector<std::unique_ptr<FeatureSet>> to_fs(const std::vector<FeatureSetKind>
 // GeoJSON (geojson.rs:8-24, main.rs:37-42): the library's multi-threaded packer
 // ------------------------------------------------------------------------------------------------
 FeatureCollection load_geometry(const std::string& path, int threads) {
-    std::ifstream f(path, std::ios::binary | std::ios::ate);
-    if (!f) throw Error("cannot open " + path);
-    const std::streamsize len = f.tellg();
-    f.seekg(0);
-    std::vector<char> text((size_t)len);
-    if (len && !f.read(text.data(), len)) throw Error("cannot read " + path);
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw Error("cannot open " + path);
+    struct stat st;
+    if (::fstat(fd, &st) != 0) { ::close(fd); throw Error("cannot stat " + path); }
+    const size_t len = (size_t)st.st_size;
+    void* map = len ? ::mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;   // parsed in place: no copy of the text
+    ::close(fd);
+    if (len && map == MAP_FAILED) throw Error("cannot map " + path);
     nfx_geojson* g = nullptr;
-    if (nfx_geojson_parse(text.data(), (int64_t)len, threads, &g) != NFX_OK) throw Error(nfx_last_error(nullptr));
+    const int rc = nfx_geojson_parse(len ? (const char*)map : "", (int64_t)len, threads, &g);
+    if (len) ::munmap(map, len);
+    if (rc != NFX_OK) throw Error(nfx_last_error(nullptr));
     FeatureCollection fc;
     const size_t n = (size_t)nfx_geojson_count(g), nv = (size_t)nfx_geojson_vertices(g);
     fc.xy.assign(nfx_geojson_xy(g), nfx_geojson_xy(g) + 2 * nv);
@@ -284,9 +292,12 @@ Image load_input_image(const std::string& path) {
     const std::string ext = ext_of(path);
     if (ext == "svs" || ext == "tif" || ext == "tiff") {   // main.rs:21-24 (InputImage::Slide): level 0 of the TIFF container, decoded on the GPU
         Image im;
-        std::ifstream tf(path, std::ios::binary);
+        std::ifstream tf(path, std::ios::binary | std::ios::ate);
         if (!tf) throw Error("cannot open " + path);
-        im.tiff.assign((std::istreambuf_iterator<char>(tf)), std::istreambuf_iterator<char>());
+        const std::streamsize tlen = tf.tellg();
+        tf.seekg(0);
+        im.tiff.resize((size_t)tlen);
+        if (tlen && !tf.read((char*)im.tiff.data(), tlen)) throw Error("cannot read " + path);
         nfx_tiff_level lv;
         if (nfx_tiff_info(im.tiff.data(), (int64_t)im.tiff.size(), &lv) != NFX_OK) throw Error(nfx_last_error(nullptr));
         im.w = lv.width;
@@ -425,34 +436,68 @@ void extract_to_csv(const FeatureCollection& geometry, const Image& image, const
     std::vector<int64_t> bounds(args.gpus.size() + 1);
     if (nfx_partition((int64_t)n, args.batch_size, (int)args.gpus.size(), bounds.data()) != NFX_OK) throw Error("bad partition");
     std::vector<std::string> errors(args.gpus.size());
-    std::vector<std::vector<char>> text(args.gpus.size());   // the rows of each range; ranges are contiguous and ordered
+    std::vector<std::vector<char>> text(args.gpus.size());   // rows of the ranges after the first, kept until their turn
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot create " + path);
+    {
+        int64_t hl = 0;
+        nfx_csv_header(mask, nullptr, 0, &hl);
+        std::vector<char> header((size_t)hl);
+        if (nfx_csv_header(mask, header.data(), hl, &hl) != NFX_OK) throw Error("csv header");
+        f.write(header.data(), hl);
+    }
     std::vector<std::thread> threads;
     for (size_t g = 0; g < args.gpus.size(); ++g) {
         threads.emplace_back([&, g] {
             try {
                 const size_t lo = (size_t)bounds[g], hi = (size_t)bounds[g + 1];
                 if (hi <= lo) return;
+                const bool timing = std::getenv("NFX_CLI_TIMING") != nullptr;
+                auto t0 = std::chrono::steady_clock::now();
+                auto lap = [&](const char* what) {
+                    const auto t1 = std::chrono::steady_clock::now();
+                    if (timing) std::fprintf(stderr, "[nfx-cli]   gpu %d %-10s %.1f ms\n", args.gpus[g], what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+                    t0 = t1;
+                };
                 Context ctx(args.gpus[g], args.patch_size, args.batch_size);
+                lap("context");
                 upload_image(ctx, image);
+                lap("image->HBM");
                 std::vector<float> xy;
                 std::vector<int64_t> off;
                 csr_of(geometry, lo, hi, xy, off);
                 ctx.check(nfx_polygons_upload(ctx.raw(), (int64_t)(hi - lo), xy.data(), off.data()));
                 ctx.check(nfx_compute(ctx.raw(), mask));
+                ctx.check(nfx_sync(ctx.raw()));
+                lap("kernels");
                 const int64_t m = (int64_t)(hi - lo), F = nfx_feature_count(mask);
                 const int64_t block = std::max<int64_t>(1, std::min<int64_t>(m, (64ll << 20) / (4 * (F + 2))));
-                std::vector<char> buf((size_t)block * (F + 2) * 12 + 64);
+                // pinned staging for the text (the D2H runs at PCIe speed); the first range streams straight into the file
+                struct Pinned {
+                    char* p = nullptr; int64_t cap = 0;
+                    void ensure(int64_t need) {
+                        if (need <= cap) return;
+                        if (p) nfx_host_free(p);
+                        void* q = nullptr;
+                        if (nfx_host_alloc(&q, need) != NFX_OK) throw Error("cannot allocate pinned host memory");
+                        p = (char*)q; cap = need;
+                    }
+                    ~Pinned() { if (p) nfx_host_free(p); }
+                } buf;
+                buf.ensure(block * (F + 2) * 12 + 64);
                 for (int64_t r = 0; r < m; r += block) {
                     const int64_t r1 = std::min(m, r + block);
                     int64_t len = 0;
-                    int rc = nfx_csv_rows(ctx.raw(), r, r1, buf.data(), (int64_t)buf.size(), &len);
-                    if (rc != NFX_OK && len > (int64_t)buf.size()) {
-                        buf.resize((size_t)len);
-                        rc = nfx_csv_rows(ctx.raw(), r, r1, buf.data(), (int64_t)buf.size(), &len);
+                    int rc = nfx_csv_rows(ctx.raw(), r, r1, buf.p, buf.cap, &len);
+                    if (rc != NFX_OK && len > buf.cap) {
+                        buf.ensure(len);
+                        rc = nfx_csv_rows(ctx.raw(), r, r1, buf.p, buf.cap, &len);
                     }
                     ctx.check(rc);
-                    text[g].insert(text[g].end(), buf.begin(), buf.begin() + len);
+                    if (g == 0) f.write(buf.p, len);
+                    else text[g].insert(text[g].end(), buf.p, buf.p + len);
                 }
+                lap("csv rows");
                 if (args.verbose) std::fprintf(stderr, "INFO Extracted features for %zu/%zu patches\n", hi, n);   // main.rs:152-157
             } catch (const std::exception& e) {
                 errors[g] = e.what();
@@ -462,13 +507,6 @@ void extract_to_csv(const FeatureCollection& geometry, const Image& image, const
     for (auto& t : threads) t.join();
     for (auto& e : errors)
         if (!e.empty()) throw Error(e);
-    std::ofstream f(path, std::ios::binary);
-    if (!f) throw Error("cannot create " + path);
-    int64_t hl = 0;
-    nfx_csv_header(mask, nullptr, 0, &hl);
-    std::vector<char> header((size_t)hl);
-    if (nfx_csv_header(mask, header.data(), hl, &hl) != NFX_OK) throw Error("csv header");
-    f.write(header.data(), hl);
     for (auto& t : text) f.write(t.data(), (std::streamsize)t.size());
 }
 
