@@ -534,7 +534,7 @@ cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStrea
     cudaError_t e = ensure_lut(s);
     if (e != cudaSuccess) return e;
     const int smem = color_smem_bytes(p.P);
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
         e = cudaFuncSetAttribute(k_color, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
@@ -547,7 +547,7 @@ cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, 
     const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
     const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * p.P * 4;
     dim3 grid((unsigned)nbatch, (unsigned)p.slabs);
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
         cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }

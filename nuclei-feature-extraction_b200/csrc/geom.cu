@@ -330,7 +330,7 @@ cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream
     nuc = (nuc + 15) & ~(size_t)15;
     auto go = [&](auto kern, int threads, int npc) -> cudaError_t {
         const size_t smem = nuc * npc;
-        if (smem > 48 * 1024) {
+        if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }

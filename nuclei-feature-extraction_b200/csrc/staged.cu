@@ -119,7 +119,7 @@ cudaError_t launch_gather(int64_t n, int P, const NucInfo* info, const CUtensorM
                           uint8_t* patches, int64_t pitch, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     const int smem = patch_smem_bytes(P) + 16;   // the re-alignment reads one word past the payload
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
         cudaError_t e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }

@@ -282,6 +282,35 @@ def test_mid_p128_all_sets(libnfx):
     assert ok.all(), f"{(~ok).sum()} mismatches at P=128: {np.argwhere(~ok)[:5]}"
 
 
+@pytest.mark.parametrize("P,scale", [(16, 0.05), (20, 0.07), (48, 0.17), (80, 0.28), (96, 0.34), (200, 0.75)])
+def test_odd_patch_sizes_all_sets(libnfx, P, scale):
+    """patch_size is any multiple of 4 in [16, 256]: sizes that are not powers of two leave partial mask words, partial
+    hue slabs (1024 / P rows), partial Gabor tiles (P = 80, 96, 200) and take each of the three GLCM kernels."""
+    tile, rings = stress_case(n=10, size=640, seed=P, patch=256)
+    rings = [((r - r.mean(0)) * scale + r.mean(0)).astype(np.float32) for r in rings]
+    xy, off = nfx.pack_polygons(rings)
+    with nfx.Extractor(0, P, 4) as e:
+        e.upload_tile(tile)
+        keys, cents, got, names = e.extract(xy, off, ["all"])
+        masks = e.rasterize()
+    cents_o, polys, patches, pmasks = o.load_image_dataset(rings, tile, P)
+    assert np.array_equal(masks != 0, pmasks[:, 0].numpy() != 0), f"masks differ at P={P}"
+    wkeys, wc, want, wnames = o.extract(rings, tile, ["all"], P, 4)
+    assert names == wnames and keys == wkeys
+    cols = ["area", "perimeter", "convex_hull_area", "mean_r", "std_g", "mean_s", "std_v", "mean_eosin", "std_dab", "contrast_0_1_32",
+            "entropy_1_1_64", "angular_second_moment_1_0_128", "sum_entropy_1_-1_254", "sum_variance_0_1_254", "short_run_emphasis_1_0",
+            "run_percentage_0_1", "long_run_emphasis_-1_1", "gabor_angle_0_frequency_0.5_mean", "gabor_angle_45_frequency_2_variance",
+            "gabor_angle_90_frequency_8_mean", "gabor_angle_135_frequency_1_variance"]
+    sel = [names.index(c) for c in cols]
+    atol = np.array([2e-4 if c.startswith("gabor") else 2e-6 for c in cols])
+    d = np.abs(got[:, sel].astype(np.float64) - want[:, sel])
+    ok = (d <= atol + 1e-4 * np.abs(want[:, sel])) | (np.isnan(got[:, sel]) & np.isnan(want[:, sel]))
+    assert ok.all(), f"P={P}: {[(cols[j], float(got[i, sel[j]]), float(want[i, sel[j]])) for i, j in np.argwhere(~ok)[:6]]}"
+    j = names.index("mean_h")
+    dh = np.abs(got[:, j] - want[:, j])
+    assert np.nanmax(np.minimum(dh, 360 - dh)) < 0.05
+
+
 def test_slide_streamed_as_tiles_equals_single_upload(case):
     """BASELINE config 4 mechanics: the slide is written tile by tile (and band by band) into HBM."""
     tile = case["tile"]
