@@ -73,6 +73,52 @@ __device__ __forceinline__ Px quad_px(uint32_t w0, uint32_t w1, uint32_t w2, int
     return p;
 }
 
+// The same four pixels through PRMT (one instruction per byte instead of shift + mask): k_hue_batch's inner loop.
+__device__ __forceinline__ Px quad_px_prmt(uint32_t w0, uint32_t w1, uint32_t w2, int k) {
+    Px p;
+    switch (k) {
+        case 0: p.r = __byte_perm(w0, 0, 0x4440); p.g = __byte_perm(w0, 0, 0x4441); p.b = __byte_perm(w0, 0, 0x4442); break;
+        case 1: p.r = __byte_perm(w0, 0, 0x4443); p.g = __byte_perm(w1, 0, 0x4440); p.b = __byte_perm(w1, 0, 0x4441); break;
+        case 2: p.r = __byte_perm(w1, 0, 0x4442); p.g = __byte_perm(w1, 0, 0x4443); p.b = __byte_perm(w2, 0, 0x4440); break;
+        default: p.r = __byte_perm(w2, 0, 0x4441); p.g = __byte_perm(w2, 0, 0x4442); p.b = __byte_perm(w2, 0, 0x4443); break;
+    }
+    return p;
+}
+
+// Shared-memory loads from a 32-bit shared address kept in a register (a generic pointer to a static __shared__ array is
+// re-derived from SR_CgaCtaId inside the loop otherwise).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));   // read-only table: may be scheduled freely
+    return v;
+}
+__device__ __forceinline__ NucInfo lds_info(uint32_t a) {
+    NucInfo v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.left), "=r"(v.top), "=r"(v.nvc), "=r"(v.nvr) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, ~1 ulp
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -295,7 +341,7 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// grid = (n_batches, slabs). Dynamic smem: ring[kHueStages][panels*192*R] | Cs[R*P] | Ss[R*P] f32.
+// grid = (n_batches, slabs). Dynamic smem: ring[kHueStages][panels*208*R] | Cs[R*wpr*33] | Ss[R*wpr*33] f32.
 template <int NCW>
 __global__ void __launch_bounds__(32 * NCW + 32)
 k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R) {
@@ -309,7 +355,9 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     const int slab = blockIdx.y, row0 = slab * R;
     uint8_t* ring = smem_raw;
     float* Cs = reinterpret_cast<float*>(smem_raw + (size_t)kHueStages * stage_bytes);
-    float* Ss = Cs + R * P;
+    // (C, S) images: one 33-float row per 32-pixel mask word, so that the fold's lanes (one mask word each) hit
+    // different banks when they read the same bit position (a P-float pitch put them all on one bank)
+    float* Ss = Cs + R * wpr * 33;
     __shared__ __align__(8) uint64_t full[kHueStages], empty[kHueStages];
     __shared__ NucInfo s_info[kHueChunk];
 
@@ -319,6 +367,10 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     __shared__ uint32_t s_union[64];
     __shared__ uint16_t s_qlist[kHueMaxQuads];
     __shared__ int s_nact;
+    // (pi/3) / d for d = max - min in 1..255 ([0] is never multiplied by a non-zero numerator): one LDS instead of
+    // I2FP + MUFU.RCP + FMUL per pixel
+    __shared__ float s_rcp[256];
+    for (int k = tid; k < 256; k += kHueThreads) s_rcp[k] = k ? __fdiv_rn(1.0471975511965976f, (float)k) : 0.f;
     const int qpr = P >> 2, nquads = R * qpr;
     const int nrows_u = min(R, P - row0), words_u = nrows_u * wpr;
     if (tid < 64) s_union[tid] = 0u;
@@ -375,6 +427,11 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
 #pragma unroll
         for (int k = 0; k < 4; ++k) { C[u][k] = 0.f; S[u][k] = 0.f; }
 
+    // 32-bit shared addresses of everything the consumer loop touches, pinned in registers
+    uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), info_a = smem_u32(s_info), ring_a = smem_u32(ring),
+             rcp_a = smem_u32(s_rcp);
+    asm volatile("" : "+r"(full_a), "+r"(empty_a), "+r"(info_a), "+r"(ring_a), "+r"(rcp_a));
+
     int it = 0;   // global iteration counter over the batch's nuclei (ring position)
     for (int base = 0; base < nb; base += kHueChunk) {
         const int cnt = min(kHueChunk, nb - base);
@@ -393,28 +450,30 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                 }
             }
         } else if (nq_w > 0) {
-            for (int j = 0; j < cnt; ++j) {
-                const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
-                mbar_wait(&full[s], ph);
-                const NucInfo inf = s_info[j];
+            uint32_t g = (uint32_t)it, ia = info_a;
+            for (int j = 0; j < cnt; ++j, ++g, ia += (uint32_t)sizeof(NucInfo)) {
+                const uint32_t s = g % kHueStages, ph = (g / kHueStages) & 1u;
+                while (!mbar_try_wait_a(full_a + s * 8u, ph)) {
+                }
+                const NucInfo inf = lds_info(ia);
                 // soff is a multiple of 4, so the word alignment and the funnel shift depend on the nucleus only
-                const int ob = patch_byte_offset(inf.left);
-                const uint8_t* sb = ring + (size_t)s * stage_bytes + (ob & ~3);
-                const uint32_t sh = (uint32_t)(ob & 3) * 8u;
+                const uint32_t ob = (uint32_t)patch_byte_offset(inf.left);
+                const uint32_t sb = ring_a + s * (uint32_t)stage_bytes + (ob & ~3u);
+                const uint32_t sh = (ob & 3u) * 8u;
                 uint32_t w[kHueQpt][3];
 #pragma unroll
                 for (int u = 0; u < kHueQpt; ++u) {
                     w[u][0] = w[u][1] = w[u][2] = 0u;
                     if (owner[u]) {
-                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sb + soff[u]);   // 4-byte aligned
-                        const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3];
+                        const uint32_t wa = sb + (uint32_t)soff[u];   // 4-byte aligned
+                        const uint32_t a0 = lds_u32(wa), a1 = lds_u32(wa + 4), a2 = lds_u32(wa + 8), a3 = lds_u32(wa + 12);
                         w[u][0] = __funnelshift_r(a0, a1, sh);
                         w[u][1] = __funnelshift_r(a1, a2, sh);
                         w[u][2] = __funnelshift_r(a2, a3, sh);
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) mbar_arrive_a(empty_a + s * 8u);
                 if (inf.nvc < P || inf.nvr < P) {   // rare: window partly never copied (NucInfo)
 #pragma unroll
                     for (int u = 0; u < kHueQpt; ++u) {
@@ -431,10 +490,14 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
                     if (u >= nq_w) break;   // warp-uniform: this warp has no second quad
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const Px px = quad_px(w[u][0], w[u][1], w[u][2], k);
+                        const Px px = quad_px_prmt(w[u][0], w[u][1], w[u][2], k);
                         const uint32_t mx = max(px.r, max(px.g, px.b)), mn = min(px.r, min(px.g, px.b));
-                        // h = 60 t degrees = t * pi/3 radians (no wrap needed under sin/cos); d = 0 -> t = 0
-                        const float ang = hue_sextant<false>(px, mx, mx - mn) * 1.0471975511965976f;
+                        // h = 60 t degrees = t * pi/3 radians (no wrap needed under sin/cos); d = 0 -> numerator 0 -> angle 0
+                        const bool isr = (mx == px.r), isg = (mx == px.g);
+                        const int gb = (int)px.g - (int)px.b, br = (int)px.b - (int)px.r, rg = (int)px.r - (int)px.g;
+                        const int num = isr ? gb : (isg ? br : rg);
+                        const float offs = isr ? 0.0f : (isg ? 2.0943951023931953f : 4.1887902047863905f);
+                        const float ang = fmaf((float)num, lds_f32(rcp_a + (mx - mn) * 4u), offs);
                         C[u][k] += __cosf(ang);
                         S[u][k] += __sinf(ang);
                     }
@@ -450,8 +513,9 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (c0[u] + k < P) {
-                Cs[rr[u] * P + c0[u] + k] = C[u][k];
-                Ss[rr[u] * P + c0[u] + k] = S[u][k];
+                const int a = (rr[u] * wpr + (c0[u] >> 5)) * 33 + (c0[u] & 31) + k;
+                Cs[a] = C[u][k];
+                Ss[a] = S[u][k];
             }
         }
     }
@@ -469,15 +533,15 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
 #pragma unroll
             for (int q = 0; q < UN; ++q)
                 bits[q] = (i0 + q < nb) ? p.bitmask[((b0 + i0 + q) * (int64_t)P + row0) * wpr + w] : 0u;
-            const int r = w / wpr, cb = (w - r * wpr) * 32;
+            const float *Sw = Ss + w * 33, *Cw = Cs + w * 33;
 #pragma unroll
             for (int q = 0; q < UN; ++q) {
                 uint32_t b = bits[q];
                 while (b) {
-                    const int c = cb + __ffs(b) - 1;
+                    const int c = __ffs(b) - 1;
                     b &= b - 1;
-                    ss[q] += Ss[r * P + c];
-                    sc[q] += Cs[r * P + c];
+                    ss[q] += Sw[c];
+                    sc[q] += Cw[c];
                 }
             }
         }
@@ -545,7 +609,7 @@ cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStrea
 cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int R, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
-    const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * p.P * 4;
+    const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * mask_wpr(p.P) * 33 * 4;
     dim3 grid((unsigned)nbatch, (unsigned)p.slabs);
     if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
         cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
