@@ -380,13 +380,14 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
 // k_glcm64: P <= 64. All four levels of one offset are processed in ONE sweep over the pairs:
 //   * the masked pixels are compacted once into a coordinate list (shared by the 4 offsets);
 //   * pass 1 walks that list, tests the neighbour bit and issues the shared-memory atomics of all 4
-//     levels (17 per pair); pass 2 walks it again for the cell counts. No pair list is kept: with a
+//     levels (13 per pair); pass 2 walks it again for the cell counts. No pair list is kept: with a
 //     4096-slot hash that brings the CTA to 69 KB of shared memory = 3 CTAs per SM (the kernel is
 //     bound by shared-memory latency, so residency matters more than the re-derived pair);
 //   * G for 32/64/128 levels lives in dense triangular u16 histograms (22 KB together); G for 254
 //     levels (32 385 cells, <= K occupied) lives in an open-addressing hash table of 4096 slots
 //     (linear probing; a 64 x 64 mask has at most 4032 pairs, so it can never fill up);
 //   * p_x of 32 and 64 levels is the 128-level histogram folded by 4 / 2 (exact: q32 = q128 >> 2);
+//   * p_{x-y} is never built: its three moments are linear in the pairs and live in registers;
 //   * every partial sum is an integer (moments exactly, logarithmic terms in fixed point with a
 //     2^-16 quantum, far below the 1e-4 tolerance) so that warp reduction is one REDUX each;
 //   * tables are cleared densely with 128-bit stores. 3 block barriers per offset.
@@ -402,7 +403,6 @@ constexpr int kRegionA64 = kOffHash + kHashMax * 4;            // 54528
 constexpr int kMargWords = 2048;                               // m32 @0, m64 @128, m128 @384, m254 @896
 constexpr int kNP = 11;                                        // partial sums per (level, offset)
 constexpr float kLnFix = 0.6931471805599453f * 65536.0f;      // log2 -> ln, 16 fractional bits
-constexpr float kIdmFix = 262144.0f;                           // 18 fractional bits
 
 struct Glcm64Smem {
     int rows, q128, q254, list, marg, parts, total;
@@ -480,6 +480,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     __shared__ float s_lut[256];
     __shared__ int s_scan[kG64NW + 1];
     __shared__ int s_np[kGlcmOffsets];
+    __shared__ float s_idm[256];   // 2 / (1 + k^2): a pair adds 2 to G at distance k from the diagonal
 
     const NucInfo inf = p.info[i];
     if (tid == 0) {
@@ -489,7 +490,10 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
     }
     if (tid < kGlcmOffsets) s_np[tid] = 0;
-    if (tid < 256) s_lut[tid] = __fdiv_rn((float)tid, 255.0f);   // utils.rs:172  u8 -> f32 / 255.0
+    if (tid < 256) {
+        s_lut[tid] = __fdiv_rn((float)tid, 255.0f);   // utils.rs:172  u8 -> f32 / 255.0
+        s_idm[tid] = __fdiv_rn(2.0f, 1.0f + (float)(tid * tid));
+    }
     // ---- mask rows -> shared memory + compacted pixel list ((row << 8) | col) ----
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
     int K = 0;
@@ -564,7 +568,12 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         const int dy = c_off[oi][0], dx = c_off[oi][1];
         const int dpos = dy * P + dx;
         // ---- pass 1: neighbour test, atomics of all four levels ----
+        // The difference histogram p_{x-y} only ever enters through its moments sum k c, sum k^2 c and sum c / (1 + k^2),
+        // which are linear in the pairs: they are accumulated in registers (its atomics were the most conflicted of all:
+        // |a - b| is 0, 1 or 2 for most pairs, so up to 15 lanes of a warp hit the same word).
         int np_local = 0;
+        uint32_t d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+        float fi[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = tid; j < K; j += kG64Threads) {
             const uint32_t rc = list[j];
             const int r = rc >> 8, c = rc & 255, r2 = r + dy, c2 = c + dx;
@@ -577,26 +586,37 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
             atomicAdd(&m254[a3], 1u);
             atomicAdd(&m254[b3], 1u);
             atomicAdd(&m254[256 + a3 + b3], 2u);
-            atomicAdd(&m254[768 + abs(a3 - b3)], 2u);
+            { const int k = abs(a3 - b3); d1[3] += k; d2[3] += k * k; fi[3] += s_idm[k]; }
             // 128 levels
             tri_add(tri128, tri_cell(a2, b2));
             atomicAdd(&m128[a2], 1u);
             atomicAdd(&m128[b2], 1u);
             atomicAdd(&m128[128 + a2 + b2], 2u);
-            atomicAdd(&m128[384 + abs(a2 - b2)], 2u);
+            { const int k = abs(a2 - b2); d1[2] += k; d2[2] += k * k; fi[2] += s_idm[k]; }
             // 64 levels (p_x is folded from the 128-level histogram later)
             const int a1 = a2 >> 1, b1 = b2 >> 1;
             tri_add(tri64, tri_cell(a1, b1));
             atomicAdd(&m64[64 + a1 + b1], 2u);
-            atomicAdd(&m64[192 + abs(a1 - b1)], 2u);
+            { const int k = abs(a1 - b1); d1[1] += k; d2[1] += k * k; fi[1] += s_idm[k]; }
             // 32 levels
             const int a0 = a2 >> 2, b0 = b2 >> 2;
             tri_add(tri32, tri_cell(a0, b0));
             atomicAdd(&m32[32 + a0 + b0], 2u);
-            atomicAdd(&m32[96 + abs(a0 - b0)], 2u);
+            { const int k = abs(a0 - b0); d1[0] += k; d2[0] += k * k; fi[0] += s_idm[k]; }
         }
         np_local = __reduce_add_sync(0xffffffffu, np_local);
         if (lane == 0 && np_local) atomicAdd(&s_np[oi], np_local);
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {   // parked now: keeps the twelve accumulators out of pass 2's register budget
+            const uint32_t t1 = __reduce_add_sync(0xffffffffu, d1[lv]), t2 = __reduce_add_sync(0xffffffffu, d2[lv]);
+            const float tf = warp_sum(fi[lv]);
+            if (lane == 0) {
+                uint32_t* pp = parts + ((lv * kGlcmOffsets + oi) * kG64NW + warp) * kNP;
+                pp[3] = 2u * t1;   // every pair counts twice in the symmetric matrix
+                pp[4] = 2u * t2;
+                pp[10] = __float_as_uint(tf);
+            }
+        }
         __syncthreads();
         // ---- pass 2: per-pair cell counts (entropy, ASM) for the four levels ----
         uint32_t sg[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0};
@@ -646,18 +666,15 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
                     if (lv >= 2) cx = m[k];
                     else if (lv == 1) cx = m128[2 * k] + m128[2 * k + 1];
                     else cx = m128[4 * k] + m128[4 * k + 1] + m128[4 * k + 2] + m128[4 * k + 3];
-                    const uint32_t cd = m[3 * NL + k];                      // p_{x-y}
                     v[1] += kk * cx;
                     v[2] += kk * kk * cx;
-                    v[3] += kk * cd;
-                    v[4] += kk * kk * cd;
                     v[8] += fix_clnc(cx);
-                    v[10] += __float2uint_rn(__fdividef((float)cd, 1.0f + (float)(kk * kk)) * kIdmFix);
                 }
             }
             const int combo = lv * kGlcmOffsets + oi;
 #pragma unroll
             for (int q = 0; q < kNP; ++q) {
+                if (q == 3 || q == 4 || q == 10) continue;   // difference moments: written after pass 1
                 const uint32_t t = __reduce_add_sync(0xffffffffu, v[q]);
                 if (lane == 0) parts[(combo * kG64NW + warp) * kNP + q] = t;
             }
@@ -683,11 +700,16 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
             double acc[kNP];
             for (int q = 0; q < kNP; ++q) {
                 unsigned long long t = 0;
-                for (int w = 0; w < kG64NW; ++w) t += parts[(combo * kG64NW + w) * kNP + q];
-                acc[q] = (double)t;
+                double tf = 0.0;
+                for (int w = 0; w < kG64NW; ++w) {
+                    const uint32_t v = parts[(combo * kG64NW + w) * kNP + q];
+                    t += v;
+                    tf += (double)__uint_as_float(v);   // q == 10 only: f32 partial sums of 2 / (1 + k^2)
+                }
+                acc[q] = q == 10 ? tf : (double)t;
             }
             haralick_write(o_, 2.0 * (double)npairs, acc[0], acc[7] / 65536.0, acc[1], acc[2], acc[3], acc[4], acc[5], acc[6],
-                           acc[8] / 32768.0, acc[9] / 32768.0, acc[10] / 262144.0);
+                           acc[8] / 32768.0, acc[9] / 32768.0, acc[10]);
         }
     }
 }
