@@ -92,7 +92,7 @@ def _check_color(got, want, names, case, batch):
     check_color(got, want, names, case["patches"], case["masks"], batch)
 
 
-@pytest.mark.parametrize("batch", [100, 37])
+@pytest.mark.parametrize("batch", [100, 37, 200])   # 200 > the 128 nuclei k_hue_batch stages at a time
 def test_color_features(case, batch):
     with nfx.Extractor(0, 64, batch) as e:
         e.upload_tile(case["tile"])
