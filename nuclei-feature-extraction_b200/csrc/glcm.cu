@@ -769,6 +769,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
     __shared__ unsigned long long s_npairs[kGlcmOffsets];
+    __shared__ float s_idm[256];   // 2 / (1 + k^2): a pair adds 2 to G at distance k from the diagonal
 
     const NucInfo inf = p.info[i];
     const int o = patch_byte_offset(inf.left);
@@ -776,7 +777,10 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
-    if (tid < 256) s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (tid < 256) {
+        s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
+        s_idm[tid] = __fdiv_rn(2.0f, 1.0f + (float)(tid * tid));
+    }
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
     for (int k = tid; k < P * wpr; k += kLargeThreads) rows[k] = gm[k];
     __syncthreads();
@@ -820,7 +824,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
         __syncthreads();
 
         // Levels of this round: 254 alone (round 0), or 128 / 64 / 32 together (round 1: q64 = q128 >> 1, q32 = q128 >> 2,
-        // so ONE enumeration of the co-occurring pairs feeds the three matrices: 15 atomics per pair in the first
+        // so ONE enumeration of the co-occurring pairs feeds the three matrices: 12 atomics per pair in the first
         // sweep, three cell look-ups in the second). Slot s of the round holds level lv_hi - s.
         const int lv_hi = round == 0 ? 3 : 2, lv_lo = round == 0 ? 3 : 0, nlev = lv_hi - lv_lo + 1;
         // triangular u16 histograms of the slots, packed two cells per u32 word, back to back in region T
@@ -833,6 +837,10 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
             const int dy = c_off[oi][0], dx = c_off[oi][1], dpos = dy * PP + dx;
             unsigned long long g2[3] = {0, 0, 0}, np_local = 0;   // sum of the cell counts met (= sum of squares of the cells)
             float glg[3] = {0.f, 0.f, 0.f};                       // sum of ln(cell count)
+            // moments of the difference histogram p_{x-y}: linear in the pairs, kept in registers (its atomics were the
+            // most conflicted ones: |a - b| is 0, 1 or 2 for most pairs)
+            uint32_t d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};        // <= 128 pairs per thread: 128 * 253^2 < 2^32
+            float fi[3] = {0.f, 0.f, 0.f};
             for (int pass = 0; pass < 2; ++pass) {
                 for (int k = tid; k < P * wpr; k += kLargeThreads) {
                     const int r = k / wpr, w = k - r * wpr, r2 = r + dy;
@@ -860,7 +868,10 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                                 atomicAdd(&hxs[a], 1u);
                                 atomicAdd(&hxs[b], 1u);
                                 atomicAdd(&hxs[256 + a + b], 2u);
-                                atomicAdd(&hxs[768 + hi - lo], 2u);
+                                const uint32_t kd = (uint32_t)(hi - lo);
+                                d1[s] += kd;
+                                d2[s] += kd * kd;
+                                fi[s] += s_idm[kd];
                             } else {
                                 const uint32_t g = (uint32_t)tri16[2 * tri_off[s] + cell] << (a == b ? 1 : 0);
                                 g2[s] += g;
@@ -886,22 +897,21 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                 const int lv = lv_hi - s, NL = c_levels[lv], combo = lv * kGlcmOffsets + oi;
                 const uint32_t* hxs = hx + s * 1024;
                 const uint32_t* hss = hxs + 256;
-                const uint32_t* hds = hxs + 768;
                 unsigned long long vl[kNI] = {s == 0 ? g2[0] : (s == 1 ? g2[1] : g2[2]), 0, 0, 0, 0, 0, 0};
                 float vf[kNF] = {s == 0 ? glg[0] : (s == 1 ? glg[1] : glg[2]), 0.f, 0.f, 0.f};
+                vl[3] = 2ull * (s == 0 ? d1[0] : (s == 1 ? d1[1] : d1[2]));   // every pair counts twice in the symmetric matrix
+                vl[4] = 2ull * (s == 0 ? d2[0] : (s == 1 ? d2[1] : d2[2]));
+                vf[3] = s == 0 ? fi[0] : (s == 1 ? fi[1] : fi[2]);
                 for (int k = tid; k < 2 * NL - 1; k += kLargeThreads) {
                     const unsigned long long c = hss[k], kk = (unsigned long long)k;
                     vl[5] += kk * c;
                     vl[6] += kk * kk * c;
                     if (c) vf[2] += (float)c * __logf((float)c);
                     if (k < NL) {
-                        const unsigned long long cx = hxs[k], cd = hds[k];
+                        const unsigned long long cx = hxs[k];
                         vl[1] += kk * cx;
                         vl[2] += kk * kk * cx;
-                        vl[3] += kk * cd;
-                        vl[4] += kk * kk * cd;
                         if (cx) vf[1] += (float)cx * __logf((float)cx);
-                        vf[3] += __fdividef((float)cd, 1.0f + (float)(kk * kk));
                     }
                 }
 #pragma unroll
