@@ -35,6 +35,9 @@ WORKLOADS = {
     "shape": (["geometry"], 10_000, 4096, 64, {}),
     "glcm": (["glcm"], 1_000_000, 49152, 64, {}),
     "all": (["all"], 100_000, 16384, 64, {}),
+    # the two remaining sets of `texture` / `all` on their own (BASELINE metric: nuclei/s PER feature set)
+    "glrlm": (["glrlm"], 100_000, 16384, 64, {}),
+    "gabor": (["gabor"], 100_000, 16384, 64, {}),
     # BASELINE config 5: large irregular nuclei, 256x256 windows, 500-vertex polygons
     "stress": (["all"], 20_000, 16384, 256,
                dict(r0_range=(40.0, 110.0), v_range=(500, 500), harmonics=(3, 7, 19))),
