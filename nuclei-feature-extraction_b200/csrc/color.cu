@@ -171,7 +171,7 @@ __device__ __forceinline__ void zero_uncopied(uint8_t* patch, int P, int o, int 
 
 // ------------------------------------------------------------------------------------------------
 // The window is processed in row slabs of CS = min(P, 64) rows (one slab for the default P = 64):
-// dynamic smem = slab[panels*208*CS] | rows[P*wpr] u32 | lut[256] f32 | list[CS*P] u16 ((row << 8) | col).
+// dynamic smem = slab[panels*208*CS] | rows[P*wpr] u32 | lut[256] f32 | list[CS*P] u16 (byte address of the pixel in the slab).
 // The slab holding the patch centre goes first because its centre pixel provides the pivots.
 __global__ void __launch_bounds__(kColorThreads, 8)
 k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
@@ -190,6 +190,7 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
     __shared__ int s_scan[NW + 1];
     __shared__ uint32_t s_ri[NW][9];
     __shared__ float s_rf[NW][10];
+    __shared__ float s_pv[5];
 
     const NucInfo inf = p.info[i];
     const int o = patch_byte_offset(inf.left);
@@ -240,10 +241,11 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
             }
             int pos = K + wbase + incl - cnt;
             const int r = k / wpr, cb = (k - r * wpr) * 32;
+            const int abase = patch_addr(CS, 0, r, cb);   // a mask word never straddles a 64-pixel panel
             while (bits) {
-                const int c = cb + __ffs(bits) - 1;
+                const int c = __ffs(bits) - 1;
                 bits &= bits - 1;
-                list[pos++] = (uint16_t)((r << 8) | c);
+                list[pos++] = (uint16_t)(abase + 3 * c);   // byte address of the pixel in the slab (without o): < 53 KB
             }
             K += total;
         }
@@ -260,15 +262,20 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
             }
             __syncthreads();
         }
-        if (it == 0) {   // pivots (any value of the right magnitude removes the one-pass cancellation)
-            const int a = patch_addr(CS, o, P / 2 - row0, P / 2);
-            Px c = {patch[a], patch[a + 1], patch[a + 2]};
-            pv = convert(c, lut);
+        if (it == 0) {   // pivots (any value of the right magnitude removes the one-pass cancellation): one thread converts
+            if (tid == 0) {
+                const int a = patch_addr(CS, o, P / 2 - row0, P / 2);
+                Px c = {patch[a], patch[a + 1], patch[a + 2]};
+                const HsvHed t = convert(c, lut);
+                s_pv[0] = t.h; s_pv[1] = t.s; s_pv[2] = t.hed[0]; s_pv[3] = t.hed[1]; s_pv[4] = t.hed[2];
+            }
+            __syncthreads();
+            pv.h = s_pv[0]; pv.s = s_pv[1]; pv.hed[0] = s_pv[2]; pv.hed[1] = s_pv[3]; pv.hed[2] = s_pv[4];
         }
+        const uint8_t* pbase = patch + o;
         for (int j = tid; j < K; j += kColorThreads) {
-            const uint32_t rc = list[j];
-            const int a = patch_addr(CS, o, rc >> 8, rc & 255);
-            const Px px = {patch[a], patch[a + 1], patch[a + 2]};
+            const uint8_t* pp = pbase + list[j];
+            const Px px = {pp[0], pp[1], pp[2]};
             const HsvHed c = convert(px, lut);
             sr += px.r; sg += px.g; sb += px.b;
             srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
