@@ -348,6 +348,153 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_color_warp: P = 64 (the reference's default patch size and every BASELINE configuration but the stress one). ONE WARP
+// per nucleus, four nuclei per CTA, no block barrier after the table load. k_color spends more than a third of its
+// instructions in per-warp fixed work (block scan, cross-warp reductions, barriers) that four warps repeat for ~7 pixels per
+// thread; here one warp pays it once for ~29 pixels per lane:
+//   * the window is taken in four 16-row sub-slabs (one TMA box {208 B, 16 rows} each = 32 mask words = one per lane);
+//     sub-slabs without a mask bit are never fetched (a third of the DRAM traffic for the bench's nuclei);
+//   * while a sub-slab is in flight its mask words are compacted into a list of byte addresses (warp scan);
+//   * pivots come from the first masked pixel; sums are reduced with REDUX / one shuffle tree, the 17 columns are finished by
+//     17 lanes exactly like k_color does.
+// Dynamic smem: per warp { slab[16 * 208] | list[1024] u16 } | lut[256] f32.
+constexpr int kCwWarps = 4, kCwRows = 16;
+constexpr int kCwSlabBytes = kCwRows * kPanelBytes;              // 3328, a multiple of 128
+constexpr int kCwWarpBytes = kCwSlabBytes + kCwRows * 64 * 2;    // + list: 5376
+static_assert(kCwSlabBytes % 128 == 0 && kCwWarpBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
+
+__global__ void __launch_bounds__(32 * kCwWarps, 9)
+k_color_warp(const ColorParams p, const __grid_constant__ CUtensorMap map /* box {208, 16 rows} */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int P = 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* lut = reinterpret_cast<float*>(smem_raw + kCwWarps * kCwWarpBytes);
+    __shared__ __align__(8) uint64_t s_bar[kCwWarps];
+    for (int k = tid; k < 256; k += 32 * kCwWarps) lut[k] = g_od_lut[k];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kCwWarps + warp;
+    if (i >= p.n) return;
+
+    uint8_t* slab = smem_raw + warp * kCwWarpBytes;
+    uint16_t* list = reinterpret_cast<uint16_t*>(slab + kCwSlabBytes);
+    uint64_t* bar = &s_bar[warp];
+    const NucInfo inf = p.info[i];
+    const int o = patch_byte_offset(inf.left);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    const uint32_t* gm = p.bitmask + i * (int64_t)(P * 2);
+    uint32_t w[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) w[s] = gm[s * 32 + lane];
+    __syncwarp();
+
+    HsvHed pv;
+    pv.h = 0.f; pv.s = 0.f; pv.hed[0] = 0.f; pv.hed[1] = 0.f; pv.hed[2] = 0.f; pv.mx = 0u;
+    bool first = true;
+    uint32_t phase = 0;
+    int Ktot = 0;
+    uint32_t sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
+    float s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};   // hed0, hed1, hed2, s, h (pivoted)
+    const int abase = (lane >> 1) * kPanelBytes + (lane & 1) * 96;   // patch_addr(16, 0, lane / 2, 32 * (lane & 1))
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        uint32_t bits = w[s];
+        if (!__any_sync(0xffffffffu, bits != 0u)) continue;   // warp-uniform: no masked pixel in these 16 rows
+        const int row0 = s * kCwRows;
+        if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)kCwSlabBytes);
+            tma_load_window(slab, &map, inf.left, inf.top + row0, P, kCwRows, bar);
+        }
+        // ---- while the sub-slab is in flight: compact its 32 mask words into a list of byte addresses ----
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+            if (lane >= o2) incl += t;
+        }
+        const int K = __shfl_sync(0xffffffffu, incl, 31);
+        int pos = incl - cnt;
+        while (bits) {
+            const int c = __ffs(bits) - 1;
+            bits &= bits - 1;
+            list[pos++] = (uint16_t)(abase + 3 * c);
+        }
+        Ktot += K;
+        __syncwarp();   // list visible
+        while (!mbar_try_wait(bar, phase)) {
+        }
+        phase ^= 1u;
+        if (inf.nvc < P || inf.nvr < row0 + kCwRows) {   // rare: part of the window is never copied (NucInfo)
+            for (int k = lane; k < kCwRows * P; k += 32) {
+                const int r = k >> 6, c = k & 63;
+                if (row0 + r >= inf.nvr || c >= inf.nvc) {
+                    const int a = patch_addr(kCwRows, o, r, c);
+                    slab[a] = 0; slab[a + 1] = 0; slab[a + 2] = 0;
+                }
+            }
+            __syncwarp();
+        }
+        const uint8_t* pbase = slab + o;
+        if (first) {   // pivots (any value of the right magnitude removes the one-pass cancellation): the first masked pixel
+            const uint8_t* pp = pbase + list[0];
+            const Px c = {pp[0], pp[1], pp[2]};
+            pv = convert(c, lut);
+            first = false;
+        }
+        for (int j = lane; j < K; j += 32) {
+            const uint8_t* pp = pbase + list[j];
+            const Px px = {pp[0], pp[1], pp[2]};
+            const HsvHed c = convert(px, lut);
+            sr += px.r; sg += px.g; sb += px.b;
+            srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
+            sv += c.mx; svv += c.mx * c.mx;
+            float d;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { d = c.hed[q] - pv.hed[q]; s1[q] += d; s2[q] = fmaf(d, d, s2[q]); }
+            d = c.s - pv.s; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
+            d = c.h - pv.h; s1[4] += d; s2[4] = fmaf(d, d, s2[4]);
+        }
+        __syncwarp();   // slab and list are reused by the next sub-slab
+    }
+    // ---- sums: every lane ends up with every total; lane 0 parks them in the (dead) list for the column lanes ----
+    uint32_t* fi = reinterpret_cast<uint32_t*>(list);
+    float* ff = reinterpret_cast<float*>(list) + 8;
+    {
+        const uint32_t vi[8] = {sr, sg, sb, srr, sgg, sbb, sv, svv};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t t = __reduce_add_sync(0xffffffffu, vi[q]);
+            if (lane == 0) fi[q] = t;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float a = warp_sum(s1[q]), b = warp_sum(s2[q]);
+            if (lane == 0) { ff[q] = a; ff[5 + q] = b; }
+        }
+    }
+    __syncwarp();
+    // ---- 17 columns, one lane each (out[6] = mean_h belongs to k_hue_finalize); same f64 expressions as k_color ----
+    if (lane < 18 && lane != 6) {
+        static const int ia[18] = {1, 2, 3, 1, 2, 3, 0, 12, 7, 13, 12, 7, 9, 10, 11, 9, 10, 11};
+        static const int ib[18] = {0, 0, 0, 4, 5, 6, 0, 0, 0, 18, 17, 8, 0, 0, 0, 14, 15, 16};
+        auto fetch = [&](int q) -> double { return q <= 8 ? (double)fi[q - 1] : (double)ff[q - 9]; };   // q in 1..18
+        const int a = ia[lane], b = ib[lane];
+        const bool is_std = b != 0;
+        const bool is8 = a <= 8;                                   // u8-valued channel: scale by 1/255
+        const float pivf = lane == 7 ? pv.s : (lane == 12 ? pv.hed[0] : (lane == 13 ? pv.hed[1] : (lane == 14 ? pv.hed[2] : 0.f)));
+        const double Kd = (double)Ktot;
+        const double m = fetch(a) / Kd;
+        double val = (double)pivf + m;
+        if (is_std) val = sqrt(fmax(fetch(b) / Kd - m * m, 0.0));
+        float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
+        out[lane] = (float)(is8 ? val / 255.0 : val);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // grid = (n_batches, slabs). Dynamic smem: ring[kHueStages][panels*208*R] | Cs[R*wpr*33] | Ss[R*wpr*33] f32.
 template <int NCW>
 __global__ void __launch_bounds__(32 * NCW + 32)
@@ -610,6 +757,17 @@ cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStrea
         if (e != cudaSuccess) return e;
     }
     k_color<<<(unsigned)p.n, kColorThreads, smem, s>>>(p, *map);
+    return cudaGetLastError();
+}
+
+// P = 64 only; `map_slab` is the {208 B, 16 rows} slab map (hue_slab_rows(64) == 16) that k_hue_batch uses too.
+cudaError_t launch_color_warp(const ColorParams& p, const CUtensorMap* map_slab, cudaStream_t s) {
+    if (p.n <= 0) return cudaSuccess;
+    if (p.P != 64 || hue_slab_rows(64) != kCwRows) return cudaErrorInvalidValue;
+    cudaError_t e = ensure_lut(s);
+    if (e != cudaSuccess) return e;
+    const int smem = kCwWarps * kCwWarpBytes + 256 * 4;
+    k_color_warp<<<(unsigned)((p.n + kCwWarps - 1) / kCwWarps), 32 * kCwWarps, smem, s>>>(p, *map_slab);
     return cudaGetLastError();
 }
 

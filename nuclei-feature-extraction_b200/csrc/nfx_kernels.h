@@ -53,6 +53,7 @@ struct ColorParams {
     int slab_rows;             // k_color row-slab height = color_slab_rows(P)
 };
 cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStream_t s);
+cudaError_t launch_color_warp(const ColorParams& p, const CUtensorMap* map_slab16, cudaStream_t s);   // P == 64
 cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int slab_rows,
                              cudaStream_t s);
 cudaError_t launch_hue_finalize(const ColorParams& p, cudaStream_t s);
