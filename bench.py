@@ -60,7 +60,7 @@ def algorithmic_bytes(workload: str, P: int, F: int) -> float:
 def kernel_bytes(name: str, P: int, slabs: int) -> float:
     """Per-nucleus compulsory traffic of one kernel."""
     px, bm, info = 3 * P * P, P * P / 8, 16
-    if name == "k_color":
+    if name in ("k_color", "k_color_warp"):
         return px + bm + info + 4 * 17
     if name == "k_hue_batch":
         return px + bm + info + 8 * slabs

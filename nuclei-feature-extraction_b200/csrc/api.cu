@@ -241,7 +241,8 @@ int run_color(nfx_ctx* ctx, int64_t n, int batch, const CUtensorMap* mp, const C
     c.slabs = slabs;
     c.slab_rows = color_slab_rows(ctx->P);
     // P == 64: one warp per nucleus over 16-row sub-slabs (the slab map); other sizes: one CTA per nucleus
-    CK(timed(ctx, "k_color", 1, [&] { return ctx->P == 64 ? launch_color_warp(c, ms, ctx->stream) : launch_color(c, mp, ctx->stream); }));
+    if (ctx->P == 64) CK(timed(ctx, "k_color_warp", 1, [&] { return launch_color_warp(c, ms, ctx->stream); }));
+    else CK(timed(ctx, "k_color", 1, [&] { return launch_color(c, mp, ctx->stream); }));
     CK(timed(ctx, "k_hue_batch", 1, [&] { return launch_hue_batch(c, ms, R, ctx->stream); }));
     CK(timed(ctx, "k_hue_finalize", 1, [&] { return launch_hue_finalize(c, ctx->stream); }));
     return NFX_OK;
