@@ -19,6 +19,8 @@
 // k_hue_finalize: sums slab partials in fixed order (bit-reproducible for any GPU count) + atan2.
 #include <math_constants.h>
 
+#include <mutex>
+
 #include "nfx_kernels.h"
 
 namespace nfx {
@@ -735,14 +737,20 @@ int color_smem_bytes(int P) {
     return window_smem_bytes(P, cs) + P * mask_wpr(P) * 4 + 256 * 4 + list_bytes;
 }
 
+// One table per device, shared by every context on it (the reference gives each rayon thread its own context and
+// several of them share a GPU, utils.rs:215-221): filled once under a lock and COMPLETED before the flag is set, because
+// the streams of other contexts are not ordered after `s`.
+static std::mutex g_lut_mu;
 static bool g_lut_ready[64] = {};
 static cudaError_t ensure_lut(cudaStream_t s) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_lut_mu);
     if (dev < 64 && g_lut_ready[dev]) return cudaSuccess;
     k_init_od_lut<<<1, 256, 0, s>>>();
     e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e == cudaSuccess && dev < 64) g_lut_ready[dev] = true;
     return e;
 }

@@ -15,6 +15,7 @@
 // mask's bounding box plus its 29-pixel halo into shared-memory planes, and a second, register-tiled pass
 // over the bounding box whose outputs are summed under the mask. Taps live in constant memory
 // (warp-uniform index -> FFMA with a uniform-register operand).
+#include <mutex>
 #include <math.h>
 #include <math_constants.h>
 
@@ -591,11 +592,15 @@ int gabor_max_patch() { return 256; }
 int gabor_tiles(int P) { return P <= kGaborTile ? 1 : ((P + kGaborTile - 1) / kGaborTile) * ((P + kGaborTile - 1) / kGaborTile); }
 int gabor_fetch_rows() { return kGaborFetch; }
 
+// One copy of the taps per device, shared by every context on it: written once under a lock and completed before the flag
+// is set (the streams of other contexts are not ordered after the copy).
+static std::mutex g_taps_mu;
 static bool g_taps_ready[64] = {};
 static cudaError_t ensure_gabor_taps() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_taps_mu);
     if (dev < 64 && g_taps_ready[dev]) return cudaSuccess;
     // oracle gabor_bank: taps on linspace(-1,1,30), theta = angle_idx*2*pi/8, sigma = 0.45 (texture.rs:319-334)
     static float h[6][4][kGaborK], env[kGaborK];
@@ -613,6 +618,7 @@ static cudaError_t ensure_gabor_taps() {
     }
     e = cudaMemcpyToSymbol(c_gtap, h, sizeof(h));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_genv, env, sizeof(env));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess && dev < 64) g_taps_ready[dev] = true;
     return e;
 }

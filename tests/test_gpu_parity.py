@@ -490,3 +490,40 @@ def test_gabor_tiled_p256_and_p128(stress):
     c, polys, patches, masks = o.load_image_dataset(rings, tile, 128)
     bad = mismatches(got, o.gabor_feature_set(patches, masks), names, "gabor")
     assert not bad, _report(bad)
+
+
+def test_contexts_of_several_host_threads_share_a_device():
+    """The reference gives every rayon worker its own context and several workers share a GPU (utils.rs:215-221).
+    Four host threads, one context each, started together in a FRESH process (the device-wide optical-density and
+    Gabor tap tables are not initialised yet): every thread must get the bytes of a lone run."""
+    import os
+    import subprocess
+    import sys
+    pkg = os.path.dirname(os.path.dirname(os.path.abspath(nfx.__file__)))
+    code = r"""
+import sys, threading
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import nfx
+from nfx import synth
+tile = synth.synth_tile(512, 512, 3)
+xy, off = synth.synth_polygons(200, 512, 512, 3)
+start = threading.Barrier(4)
+out = [None] * 4
+def work(k):
+    with nfx.Extractor(0, 64, 100) as e:
+        e.upload_tile(tile)
+        start.wait()
+        out[k] = e.extract(xy, off, ["color", "gabor"])[2].copy()
+ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+[t.start() for t in ts]
+[t.join() for t in ts]
+with nfx.Extractor(0, 64, 100) as e:
+    e.upload_tile(tile)
+    lone = e.extract(xy, off, ["color", "gabor"])[2]
+assert all(o is not None and np.array_equal(o, lone, equal_nan=True) for o in out), "contexts disagree"
+assert np.isfinite(lone[:, 12]).any()          # mean_haematoxylin: read through the shared table
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code, pkg], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
