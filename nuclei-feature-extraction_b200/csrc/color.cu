@@ -19,6 +19,8 @@
 // k_hue_finalize: sums slab partials in fixed order (bit-reproducible for any GPU count) + atan2.
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "nfx_kernels.h"
@@ -119,6 +121,19 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t a, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_arrive_a(uint32_t a) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+
+// one lane of the (converged) warp, without keeping the lane index in a register
+__device__ __forceinline__ bool elect_one() {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok));
+    return ok != 0;
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, ~1 ulp
@@ -497,6 +512,225 @@ k_color_warp(const ColorParams p, const __grid_constant__ CUtensorMap map /* box
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed f32x2 arithmetic (sm_100 FFMA2 / FADD2): one issue slot for two pixels. k_color_warp is issue bound (82 % issue
+// active, round-1 ncu), and 24 of the 74 instructions of its pixel loop are FADD / FMUL / FFMA.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 bcast2(float v) { return pack2(v, v); }
+
+// k_color_warp2: k_color_warp with TWO masked pixels per lane and loop step, so that every float operation of the loop is one
+// packed f32x2 instruction for both pixels (HED matrix, pivot subtraction, the ten running sums) and the integer sums
+// take both pixels in one IADD3. The pivot is folded into the HED chain (max(y, 0) - pv = max(y - pv, -pv)). A sub-slab with
+// an odd number of masked pixels gets one dummy list entry that points at a copy of the PIVOT pixel kept next to the slab:
+// its pivoted float terms are exactly zero and its integer terms are subtracted once at the end.
+// Dynamic smem: per warp { slab[16 * 208] | pivot pixel (16 B) | list[1024 + 2] u16 } | lut[256] f32.
+constexpr int kCw2PivBytes = 16;
+constexpr int kCw2WarpBytes = ((kCwSlabBytes + kCw2PivBytes + (kCwRows * 64 + 2) * 2) + 127) & ~127;
+static_assert(kCw2WarpBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
+
+__global__ void __launch_bounds__(32 * kCwWarps, 7)
+k_color_warp2(const ColorParams p, const __grid_constant__ CUtensorMap map /* box {208, 16 rows} */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int P = 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* lut = reinterpret_cast<float*>(smem_raw + kCwWarps * kCw2WarpBytes);
+    __shared__ __align__(8) uint64_t s_bar[kCwWarps];
+    for (int k = tid; k < 256; k += 32 * kCwWarps) lut[k] = g_od_lut[k];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kCwWarps + warp;
+    if (i >= p.n) return;
+
+    uint8_t* slab = smem_raw + warp * kCw2WarpBytes;
+    uint8_t* pivpx = slab + kCwSlabBytes;
+    uint16_t* list = reinterpret_cast<uint16_t*>(slab + kCwSlabBytes + kCw2PivBytes);   // 4-byte aligned
+    uint64_t* bar = &s_bar[warp];
+    const NucInfo inf = p.info[i];
+    const int o = patch_byte_offset(inf.left);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    const uint32_t* gm = p.bitmask + i * (int64_t)(P * 2);
+    uint32_t w[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) w[s] = gm[s * 32 + lane];
+    __syncwarp();
+
+    float pvh = 0.f, pvs = 0.f, pv0 = 0.f, pv1 = 0.f, pv2 = 0.f;
+    Px ppx = {0u, 0u, 0u};
+    uint32_t pmx = 0u;
+    bool first = true;
+    uint32_t phase = 0;
+    int Ktot = 0, ndummy = 0;
+    uint32_t sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
+    f32x2 a1[5], a2[5];   // hed0, hed1, hed2, s, h (pivoted), one running sum per pixel of the pair
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { a1[q] = 0ull; a2[q] = 0ull; }
+    const int abase = (lane >> 1) * kPanelBytes + (lane & 1) * 96;   // patch_addr(16, 0, lane / 2, 32 * (lane & 1))
+    const uint32_t lut_a = smem_u32(lut);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        uint32_t bits = w[s];
+        if (!__any_sync(0xffffffffu, bits != 0u)) continue;   // warp-uniform: no masked pixel in these 16 rows
+        const int row0 = s * kCwRows;
+        if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)kCwSlabBytes);
+            tma_load_window(slab, &map, inf.left, inf.top + row0, P, kCwRows, bar);
+        }
+        // ---- while the sub-slab is in flight: compact its 32 mask words into a list of byte addresses ----
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+            if (lane >= o2) incl += t;
+        }
+        const int K = __shfl_sync(0xffffffffu, incl, 31);
+        int pos = incl - cnt;
+        while (bits) {
+            const int c = __ffs(bits) - 1;
+            bits &= bits - 1;
+            list[pos++] = (uint16_t)(abase + 3 * c);
+        }
+        const int Kpad = (K + 1) & ~1;
+        if (lane == 0 && (K & 1)) list[K] = (uint16_t)(kCwSlabBytes - o);   // dummy entry: the pivot pixel's copy
+        ndummy += K & 1;
+        Ktot += K;
+        __syncwarp();   // list visible
+        while (!mbar_try_wait(bar, phase)) {
+        }
+        phase ^= 1u;
+        if (inf.nvc < P || inf.nvr < row0 + kCwRows) {   // rare: part of the window is never copied (NucInfo)
+            for (int k = lane; k < kCwRows * P; k += 32) {
+                const int r = k >> 6, c = k & 63;
+                if (row0 + r >= inf.nvr || c >= inf.nvc) {
+                    const int a = patch_addr(kCwRows, o, r, c);
+                    slab[a] = 0; slab[a + 1] = 0; slab[a + 2] = 0;
+                }
+            }
+            __syncwarp();
+        }
+        const uint8_t* pbase = slab + o;
+        if (first) {   // pivots (any value of the right magnitude removes the one-pass cancellation): the first masked pixel
+            const uint8_t* pp = pbase + list[0];
+            ppx.r = pp[0]; ppx.g = pp[1]; ppx.b = pp[2];
+            const HsvHed c = convert(ppx, lut);
+            pvh = c.h; pvs = c.s; pv0 = c.hed[0]; pv1 = c.hed[1]; pv2 = c.hed[2]; pmx = c.mx;
+            __syncwarp();
+            if (lane == 0) { pivpx[0] = (uint8_t)ppx.r; pivpx[1] = (uint8_t)ppx.g; pivpx[2] = (uint8_t)ppx.b; }
+            __syncwarp();
+            first = false;
+        }
+        const f32x2 npv0 = bcast2(-pv0), npv1 = bcast2(-pv1), npv2 = bcast2(-pv2), npvs = bcast2(-pvs), npvh = bcast2(-pvh);
+        const uint32_t pb_a = smem_u32(pbase);
+        for (int j = 2 * lane; j < Kpad; j += 64) {
+            const uint32_t le = *reinterpret_cast<const uint32_t*>(list + j);   // two byte addresses
+            const uint32_t aa = pb_a + (le & 0xffffu), ab = pb_a + (le >> 16);
+            uint32_t rA, gA, bA, rB, gB, bB;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(rA) : "r"(aa));
+            asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(gA) : "r"(aa));
+            asm volatile("ld.shared.u8 %0, [%1+2];" : "=r"(bA) : "r"(aa));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(rB) : "r"(ab));
+            asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(gB) : "r"(ab));
+            asm volatile("ld.shared.u8 %0, [%1+2];" : "=r"(bB) : "r"(ab));
+            // ---- exact integer sums ----
+            sr += rA + rB; sg += gA + gB; sb += bA + bB;
+            srr += rA * rA; srr += rB * rB; sgg += gA * gA; sgg += gB * gB; sbb += bA * bA; sbb += bB * bB;
+            // ---- HED: optical densities from the table, 3x3 matrix, clamp, pivoted sums ----
+            const f32x2 oa = pack2(lds_f32(lut_a + rA * 4u), lds_f32(lut_a + rB * 4u));
+            const f32x2 ob = pack2(lds_f32(lut_a + gA * 4u), lds_f32(lut_a + gB * 4u));
+            const f32x2 oc = pack2(lds_f32(lut_a + bA * 4u), lds_f32(lut_a + bB * 4u));
+            {
+                f32x2 t0 = fma2(oa, bcast2(HED_M00), npv0), t1 = fma2(oa, bcast2(HED_M01), npv1), t2 = fma2(oa, bcast2(HED_M02), npv2);
+                t0 = fma2(ob, bcast2(HED_M10), t0); t1 = fma2(ob, bcast2(HED_M11), t1); t2 = fma2(ob, bcast2(HED_M12), t2);
+                t0 = fma2(oc, bcast2(HED_M20), t0); t1 = fma2(oc, bcast2(HED_M21), t1); t2 = fma2(oc, bcast2(HED_M22), t2);
+                float x, y;
+                unpack2(t0, x, y); t0 = pack2(fmaxf(x, -pv0), fmaxf(y, -pv0));   // max(hed, 0) - pv
+                unpack2(t1, x, y); t1 = pack2(fmaxf(x, -pv1), fmaxf(y, -pv1));
+                unpack2(t2, x, y); t2 = pack2(fmaxf(x, -pv2), fmaxf(y, -pv2));
+                a1[0] = add2(a1[0], t0); a2[0] = fma2(t0, t0, a2[0]);
+                a1[1] = add2(a1[1], t1); a2[1] = fma2(t1, t1, a2[1]);
+                a1[2] = add2(a1[2], t2); a2[2] = fma2(t2, t2, a2[2]);
+            }
+            // ---- HSV ----
+            const uint32_t mxA = max(rA, max(gA, bA)), mnA = min(rA, min(gA, bA)), dA = mxA - mnA;
+            const uint32_t mxB = max(rB, max(gB, bB)), mnB = min(rB, min(gB, bB)), dB = mxB - mnB;
+            sv += mxA + mxB; svv += mxA * mxA; svv += mxB * mxB;
+            const f32x2 dd = pack2(u8f(dA), u8f(dB));
+            const f32x2 rmx = pack2(rcp_approx(u8f(max(mxA, 1u))), rcp_approx(u8f(max(mxB, 1u))));
+            const f32x2 ds = fma2(dd, rmx, npvs);
+            a1[3] = add2(a1[3], ds); a2[3] = fma2(ds, ds, a2[3]);
+            const Px pA = {rA, gA, bA}, pB = {rB, gB, bB};
+            // 60 * hue_sextant<true>: t = num / d + offs, wrapped into [0, 6)
+            float tA = hue_sextant<true>(pA, mxA, dA), tB = hue_sextant<true>(pB, mxB, dB);
+            const f32x2 dh = fma2(pack2(tA, tB), bcast2(60.0f), npvh);
+            a1[4] = add2(a1[4], dh); a2[4] = fma2(dh, dh, a2[4]);
+        }
+        __syncwarp();   // slab and list are reused by the next sub-slab
+    }
+    // ---- sums: every lane ends up with every total; lane 0 parks them in the (dead) list for the column lanes ----
+    uint32_t* fi = reinterpret_cast<uint32_t*>(list);
+    float* ff = reinterpret_cast<float*>(list) + 8;
+    {
+        const uint32_t vi[8] = {sr, sg, sb, srr, sgg, sbb, sv, svv};
+        // the dummy entries added the pivot pixel ndummy times
+        const uint32_t dm[8] = {ppx.r, ppx.g, ppx.b, ppx.r * ppx.r, ppx.g * ppx.g, ppx.b * ppx.b, pmx, pmx * pmx};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t t = __reduce_add_sync(0xffffffffu, vi[q]);
+            if (lane == 0) fi[q] = t - (uint32_t)ndummy * dm[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            float x, y, u, v;
+            unpack2(a1[q], x, y);
+            unpack2(a2[q], u, v);
+            const float a = warp_sum(x + y), b = warp_sum(u + v);
+            if (lane == 0) { ff[q] = a; ff[5 + q] = b; }
+        }
+    }
+    __syncwarp();
+    // ---- 17 columns, one lane each (out[6] = mean_h belongs to k_hue_finalize); same f64 expressions as k_color ----
+    if (lane < 18 && lane != 6) {
+        static const int ia[18] = {1, 2, 3, 1, 2, 3, 0, 12, 7, 13, 12, 7, 9, 10, 11, 9, 10, 11};
+        static const int ib[18] = {0, 0, 0, 4, 5, 6, 0, 0, 0, 18, 17, 8, 0, 0, 0, 14, 15, 16};
+        auto fetch = [&](int q) -> double { return q <= 8 ? (double)fi[q - 1] : (double)ff[q - 9]; };   // q in 1..18
+        const int a = ia[lane], b = ib[lane];
+        const bool is_std = b != 0;
+        const bool is8 = a <= 8;                                   // u8-valued channel: scale by 1/255
+        const float pivf = lane == 7 ? pvs : (lane == 12 ? pv0 : (lane == 13 ? pv1 : (lane == 14 ? pv2 : 0.f)));
+        const double Kd = (double)Ktot;
+        const double m = fetch(a) / Kd;
+        double val = (double)pivf + m;
+        if (is_std) val = sqrt(fmax(fetch(b) / Kd - m * m, 0.0));
+        float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
+        out[lane] = (float)(is8 ? val / 255.0 : val);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // grid = (n_batches, slabs). Dynamic smem: ring[kHueStages][panels*208*R] | Cs[R*wpr*33] | Ss[R*wpr*33] f32.
 template <int NCW>
 __global__ void __launch_bounds__(32 * NCW + 32)
@@ -713,6 +947,286 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_hue_batch2: same decomposition as k_hue_batch (one CTA per (chunk, row slab), a TMA producer warp, 8 consumer warps that
+// own one pixel quad of the union each), with the per-patch fixed work cut down (ncu, round 2: 44 of the 139 instructions per
+// patch and warp were ring / barrier / address work, the masked fold was 12.5 % of the kernel, producer spinning 4.4 %):
+//   * a ring stage holds TWO patches: one mbarrier wait, one arrive and one loop step per pair of patches;
+//   * the per-patch constants of the quad loads (word offset, funnel shift, "window partly uncopied") are packed into one
+//     u32 when the chunk's NucInfo is staged; every lane of an active warp computes (lanes without a quad re-read quad 0
+//     and are dropped at the end), so the loop body has no ownership branches;
+//   * the fold under each nucleus' mask uses ROW PREFIX SUMS of the (S, C) image in fixed point (exact integer differences,
+//     no cancellation, any order gives the same bits): a mask word is walked run by run -- two 64-bit loads per run of
+//     set bits instead of two loads and two adds per set bit. `fix_shift` keeps batch * P * 2^shift below 2^31;
+//   * the producer lane sleeps between polls of the `empty` barrier.
+// Dynamic smem: ring[kHue2Stages][2][stage_bytes] | pre[R][P + 2] int2 {S, C} (entry k = sum of the first k pixels).
+constexpr int kHue2Stages = 4;
+template <int NCW>
+__global__ void __launch_bounds__(32 * NCW + 32, 5)
+k_hue_batch2(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R, const int fix_shift) {
+    constexpr int kConsumers = 32 * NCW, kThreads = kConsumers + 32;
+    static_assert(kConsumers == kHueMaxQuads, "one quad per consumer thread");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stage_bytes = window_smem_bytes(P, R);
+    const uint32_t stage_tx = (uint32_t)(patch_panels(P) * kPanelBytes * R);
+    const int64_t b0 = (int64_t)blockIdx.x * p.batch_size;
+    const int nb = (int)min((int64_t)p.batch_size, p.n - b0);
+    const int slab = blockIdx.y, row0 = slab * R;
+    uint8_t* ring = smem_raw;
+    const int ppitch = P + 2;
+    int2* pre = reinterpret_cast<int2*>(smem_raw + (size_t)kHue2Stages * 2 * stage_bytes);
+    __shared__ __align__(8) uint64_t full[kHue2Stages], empty[kHue2Stages];
+    __shared__ NucInfo s_info[kHueChunk];
+    __shared__ __align__(8) uint32_t s_pinfo[kHueChunk + 2];
+    __shared__ uint32_t s_union[64];
+    __shared__ uint16_t s_qlist[kHueMaxQuads];
+    __shared__ int s_nact;
+    __shared__ float s_rcp[256];   // (pi/3) / d
+    for (int k = tid; k < 256; k += kThreads) s_rcp[k] = k ? __fdiv_rn(1.0471975511965976f, (float)k) : 0.f;
+    const int qpr = P >> 2, nquads = R * qpr;
+    const int nrows_u = min(R, P - row0), words_u = nrows_u * wpr;
+    if (tid < 64) s_union[tid] = 0u;
+    for (int k = tid; k < R * ppitch; k += kThreads) pre[k] = make_int2(0, 0);
+    __syncthreads();
+    {   // union of the chunk's masks over this slab (thread t walks words t, t + T, ... of the [nb][words_u] block)
+        int j = tid / words_u, w = tid - j * words_u;
+        const int dj = kThreads / words_u, dw = kThreads - dj * words_u;
+        while (j < nb) {
+            const uint32_t v = p.bitmask[((b0 + j) * (int64_t)P + row0) * wpr + w];
+            if (v) atomicOr(&s_union[w], v);
+            j += dj; w += dw;
+            if (w >= words_u) { w -= words_u; ++j; }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int cnt = 0;
+        for (int base = 0; base < nquads; base += 32) {
+            const int q = base + lane, r = q / qpr, c = (q - r * qpr) * 4;
+            const bool act = q < nquads && r < nrows_u && ((s_union[r * wpr + (c >> 5)] >> (c & 31)) & 0xFu) != 0u;
+            const uint32_t b = __ballot_sync(0xffffffffu, act);
+            if (act) s_qlist[cnt + __popc(b & ((1u << lane) - 1u))] = (uint16_t)q;
+            cnt += __popc(b);
+        }
+        if (lane == 0) s_nact = cnt;
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    if (nact == 0) {   // no nucleus of the chunk has a masked pixel in this slab
+        for (int i = tid; i < nb; i += kThreads) {
+            float* hp = p.hue_partial + ((b0 + i) * (int64_t)p.slabs + slab) * 2;
+            hp[0] = 0.f;
+            hp[1] = 0.f;
+        }
+        return;
+    }
+    const int nwarps_act = min(NCW, (nact + 31) / 32);   // consumer warps that own at least one quad
+    if (tid == 0) {
+        for (int s = 0; s < kHue2Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps_act); }
+        mbar_fence_init();
+    }
+    const bool owner = (tid < kConsumers) && (tid < nact);
+    const int q = (int)s_qlist[owner ? tid : 0];
+    const int rr = q / qpr, c0 = (q - rr * qpr) * 4;
+    uint32_t soff = (uint32_t)((c0 >> 6) * panel_stride(R) + rr * kPanelBytes + (c0 & 63) * 3);   // + word offset per patch
+    const bool active = warp < nwarps_act;   // warp-uniform
+    float C[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};
+
+    uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), pinfo_a = smem_u32(s_pinfo), ring_a = smem_u32(ring),
+             rcp_a = smem_u32(s_rcp);
+    asm volatile("" : "+r"(full_a), "+r"(empty_a), "+r"(pinfo_a), "+r"(ring_a), "+r"(rcp_a), "+r"(soff));
+
+    // four pixels of one patch: words w0..w2 hold r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3.
+    // B200 issues FADD / FMUL / FFMA every cycle but ALU-pipe instructions (PRMT, VIMNMX, ISETP, SEL, IADD3, LEA, I2FP) and
+    // IMAD only every second cycle (scripts/f32x2_probe.cu), and the integer form of this loop was ALU-pipe bound (ncu: 68 %
+    // ALU, 23 % FMA). So the pixel is unpacked straight into FLOATS (PRMT against 0x4B000000 gives 2^23 + byte, exact), the
+    // channel differences are FADDs (the bias cancels), and the sextant select is three predicated FFMA/FMULs instead of
+    // integer subtractions, two selects and a conversion. The table index d = max - min is the difference of the bit patterns.
+    auto hue_angle = [&](float fr, float fg, float fb) -> float {
+        const float mx = fmaxf(fr, fmaxf(fg, fb)), mn = fminf(fr, fminf(fg, fb));
+        const uint32_t d = (uint32_t)(__float_as_int(mx) - __float_as_int(mn));
+        const float rd = lds_f32(rcp_a + d * 4u);   // (pi/3) / d, 0 for d = 0 (then every difference is 0 too)
+        // h = 60 t degrees = t * pi/3 radians (no wrap needed under sin/cos): max = r -> (g-b)/d ; g -> 2 + (b-r)/d ; b -> 4 + (r-g)/d
+        float ang;
+        asm("{\n"
+            ".reg .pred pr, pg;\n"
+            ".reg .f32 gb, br, rg;\n"
+            "sub.f32 gb, %2, %3;\n"
+            "sub.f32 br, %3, %1;\n"
+            "sub.f32 rg, %1, %2;\n"
+            "setp.eq.f32 pr, %4, %1;\n"
+            "setp.eq.f32 pg, %4, %2;\n"
+            "fma.rn.f32 %0, rg, %5, 0f40860A92;\n"        // 4 pi / 3
+            "@pg fma.rn.f32 %0, br, %5, 0f40060A92;\n"    // 2 pi / 3
+            "@pr mul.f32 %0, gb, %5;\n"
+            "}\n"
+            : "=&f"(ang)
+            : "f"(fr), "f"(fg), "f"(fb), "f"(mx), "f"(rd));
+        return ang;
+    };
+    auto accumulate = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
+        constexpr uint32_t kBias = 0x4B000000u;   // 2^23: PRMT picks one byte of w and the three upper bytes of kBias
+#define NFX_BF(w, k) __uint_as_float(__byte_perm((w), kBias, 0x7540 + (k)))
+        const float a0 = hue_angle(NFX_BF(w0, 0), NFX_BF(w0, 1), NFX_BF(w0, 2));
+        const float a1 = hue_angle(NFX_BF(w0, 3), NFX_BF(w1, 0), NFX_BF(w1, 1));
+        const float a2 = hue_angle(NFX_BF(w1, 2), NFX_BF(w1, 3), NFX_BF(w2, 0));
+        const float a3 = hue_angle(NFX_BF(w2, 1), NFX_BF(w2, 2), NFX_BF(w2, 3));
+#undef NFX_BF
+        C[0] += __cosf(a0); S[0] += __sinf(a0);
+        C[1] += __cosf(a1); S[1] += __sinf(a1);
+        C[2] += __cosf(a2); S[2] += __sinf(a2);
+        C[3] += __cosf(a3); S[3] += __sinf(a3);
+    };
+    // bytes of the quad that the reference never copies (NucInfo) read as zero
+    auto mask_uncopied = [&](const NucInfo& inf, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+        const bool rowdead = (row0 + rr) >= inf.nvr;
+        const int nlive = rowdead ? 0 : min(max(inf.nvc - c0, 0), 4);   // live pixels of the quad
+        const int nbytes = 3 * nlive;                                    // pixel k occupies bytes 3k..3k+2 of the 12-byte quad
+        w0 = nbytes >= 4 ? w0 : (nbytes > 0 ? (w0 & ((1u << (8 * nbytes)) - 1u)) : 0u);
+        w1 = nbytes >= 8 ? w1 : (nbytes > 4 ? (w1 & ((1u << (8 * (nbytes - 4))) - 1u)) : 0u);
+        w2 = nbytes >= 12 ? w2 : (nbytes > 8 ? (w2 & ((1u << (8 * (nbytes - 8))) - 1u)) : 0u);
+    };
+
+    uint32_t gq = 0;   // pair counter over the whole batch (ring position)
+    for (int base = 0; base < nb; base += kHueChunk) {
+        const int cnt = min(kHueChunk, nb - base);
+        __syncthreads();   // previous chunk fully consumed before the staged records are overwritten
+        for (int k = tid; k < cnt + 1; k += kThreads) {
+            uint32_t pi = 0u;
+            if (k < cnt) {
+                const NucInfo inf = p.info[b0 + base + k];
+                s_info[k] = inf;
+                const uint32_t ob = (uint32_t)patch_byte_offset(inf.left);
+                pi = (ob & ~3u) | ((ob & 3u) << 11) | ((inf.nvc < P || inf.nvr < P) ? 0x10000u : 0u);
+            }
+            s_pinfo[k] = pi;
+        }
+        __syncthreads();
+        const int npairs = (cnt + 1) >> 1;
+        if (warp == NCW) {
+            // ---- TMA producer warp (one elected lane) ----
+            if (lane == 0) {
+                for (int jp = 0; jp < npairs; ++jp) {
+                    const uint32_t g = gq + (uint32_t)jp, s = g % kHue2Stages, ph = (g / kHue2Stages) & 1u;
+                    if (g >= (uint32_t)kHue2Stages)
+                        while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(40);
+                    const int two = (2 * jp + 1 < cnt);
+                    mbar_expect_tx(&full[s], stage_tx * (two ? 2u : 1u));
+                    uint8_t* dst = ring + (size_t)s * 2 * stage_bytes;
+                    const NucInfo i0 = s_info[2 * jp];
+                    tma_load_window(dst, &map, i0.left, i0.top + row0, P, R, &full[s]);
+                    if (two) {
+                        const NucInfo i1 = s_info[2 * jp + 1];
+                        tma_load_window(dst + stage_bytes, &map, i1.left, i1.top + row0, P, R, &full[s]);
+                    }
+                }
+            }
+        } else if (active) {
+            uint32_t g = gq, pa = pinfo_a;
+            for (int jp = 0; jp < npairs; ++jp, ++g, pa += 8u) {
+                const uint32_t s = g % kHue2Stages, ph = (g / kHue2Stages) & 1u;
+                while (!mbar_try_wait_a(full_a + s * 8u, ph)) {
+                }
+                uint32_t pi0, pi1;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pi0), "=r"(pi1) : "r"(pa) : "memory");
+                // soff is a multiple of 4, so the word alignment and the funnel shift depend on the patch only
+                const uint32_t sb = ring_a + s * (uint32_t)(2 * stage_bytes) + soff;
+                const uint32_t wa = sb + (pi0 & 0xffu), wb = sb + (uint32_t)stage_bytes + (pi1 & 0xffu);
+                const uint32_t a0 = lds_u32(wa), a1 = lds_u32(wa + 4), a2 = lds_u32(wa + 8), a3 = lds_u32(wa + 12);
+                const uint32_t b0w = lds_u32(wb), b1 = lds_u32(wb + 4), b2 = lds_u32(wb + 8), b3 = lds_u32(wb + 12);
+                const uint32_t sha = pi0 >> 8, shb = pi1 >> 8;   // the funnel shift uses the low five bits
+                uint32_t u0 = __funnelshift_r(a0, a1, sha), u1 = __funnelshift_r(a1, a2, sha), u2 = __funnelshift_r(a2, a3, sha);
+                uint32_t v0 = __funnelshift_r(b0w, b1, shb), v1 = __funnelshift_r(b1, b2, shb), v2 = __funnelshift_r(b2, b3, shb);
+                __syncwarp();
+                if (elect_one()) mbar_arrive_a(empty_a + s * 8u);
+                const bool two = 2 * jp + 1 < cnt;   // warp-uniform: the last pair of an odd chunk holds one patch
+                if ((pi0 | pi1) & 0x10000u) {   // rare: a window partly never copied (NucInfo); own copy of the arithmetic
+                    if (pi0 & 0x10000u) mask_uncopied(s_info[2 * jp], u0, u1, u2);
+                    if (pi1 & 0x10000u) mask_uncopied(s_info[2 * jp + 1], v0, v1, v2);
+                    accumulate(u0, u1, u2);
+                    if (two) accumulate(v0, v1, v2);
+                } else {
+                    accumulate(u0, u1, u2);
+                    if (two) accumulate(v0, v1, v2);
+                }
+            }
+        }
+        gq += (uint32_t)npairs;
+    }
+    __syncthreads();
+    // ---- the slab's (S, C) image in fixed point, then inclusive row prefix sums: pre[r][k] = sum of pixels 0..k-1 ----
+    if (owner) {
+        const float scale = (float)(1u << fix_shift);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c0 + k < P) pre[rr * ppitch + 1 + c0 + k] = make_int2(__float2int_rn(S[k] * scale), __float2int_rn(C[k] * scale));
+    }
+    __syncthreads();
+    constexpr int NWARP = kThreads / 32;
+    const int nrows = min(R, P - row0), words = nrows * wpr;
+    for (int r = warp; r < nrows; r += NWARP) {
+        int2* row = pre + r * ppitch;
+        int cx = 0, cy = 0;
+        for (int c = 0; c < P; c += 64) {
+            const int e0 = 1 + c + 2 * lane;
+            int2 a = (e0 <= P) ? row[e0] : make_int2(0, 0), b = (e0 + 1 <= P) ? row[e0 + 1] : make_int2(0, 0);
+            const int lx = a.x + b.x, ly = a.y + b.y;
+            int ix = lx, iy = ly;
+#pragma unroll
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int tx = __shfl_up_sync(0xffffffffu, ix, o2), ty = __shfl_up_sync(0xffffffffu, iy, o2);
+                if (lane >= o2) { ix += tx; iy += ty; }
+            }
+            a.x += cx + ix - lx; a.y += cy + iy - ly;
+            b.x += a.x; b.y += a.y;
+            if (e0 <= P) row[e0] = a;
+            if (e0 + 1 <= P) row[e0 + 1] = b;
+            cx += __shfl_sync(0xffffffffu, ix, 31);
+            cy += __shfl_sync(0xffffffffu, iy, 31);
+        }
+    }
+    __syncthreads();
+    // ---- masked sums under each nucleus' mask, four nuclei per warp pass (their mask words are fetched together) ----
+    constexpr int UN = 4;
+    const float inv_scale = 1.0f / (float)(1u << fix_shift);
+    for (int i0 = warp * UN; i0 < nb; i0 += NWARP * UN) {
+        float ss[UN], sc[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) { ss[u] = 0.f; sc[u] = 0.f; }
+        for (int w = lane; w < words; w += 32) {
+            uint32_t bits[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                bits[u] = (i0 + u < nb) ? p.bitmask[((b0 + i0 + u) * (int64_t)P + row0) * wpr + w] : 0u;
+            const int r = w / wpr;
+            const int2* rowp = pre + r * ppitch + (w - r * wpr) * 32;
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                uint32_t b = bits[u];
+                while (b) {   // one iteration per run of set bits
+                    const int s = __ffs(b) - 1;
+                    const uint32_t nt = ~(b >> s);
+                    const int e = s + (nt ? __ffs(nt) - 1 : 32);   // run = bits [s, e)
+                    const int2 hi = rowp[e], lo = rowp[s];
+                    ss[u] += (float)(hi.x - lo.x);
+                    sc[u] += (float)(hi.y - lo.y);
+                    b = (e >= 32) ? 0u : (b & (0xffffffffu << e));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const float s1 = warp_sum(ss[u]), c1 = warp_sum(sc[u]);
+            if (lane == 0 && i0 + u < nb) {
+                float* hp = p.hue_partial + ((b0 + i0 + u) * (int64_t)p.slabs + slab) * 2;
+                hp[0] = s1 * inv_scale;
+                hp[1] = c1 * inv_scale;
+            }
+        }
+    }
+}
+
 __global__ void k_hue_finalize(const ColorParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
@@ -769,26 +1283,59 @@ cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStrea
 }
 
 // P = 64 only; `map_slab` is the {208 B, 16 rows} slab map (hue_slab_rows(64) == 16) that k_hue_batch uses too.
+static int color_warp_version() {
+    static const int v = [] { const char* e = getenv("NFX_CW_V"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
 cudaError_t launch_color_warp(const ColorParams& p, const CUtensorMap* map_slab, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     if (p.P != 64 || hue_slab_rows(64) != kCwRows) return cudaErrorInvalidValue;
     cudaError_t e = ensure_lut(s);
     if (e != cudaSuccess) return e;
-    const int smem = kCwWarps * kCwWarpBytes + 256 * 4;
-    k_color_warp<<<(unsigned)((p.n + kCwWarps - 1) / kCwWarps), 32 * kCwWarps, smem, s>>>(p, *map_slab);
+    const unsigned grid = (unsigned)((p.n + kCwWarps - 1) / kCwWarps);
+    if (color_warp_version() == 1) {
+        const int smem = kCwWarps * kCwWarpBytes + 256 * 4;
+        k_color_warp<<<grid, 32 * kCwWarps, smem, s>>>(p, *map_slab);
+    } else {
+        const int smem = kCwWarps * kCw2WarpBytes + 256 * 4;
+        k_color_warp2<<<grid, 32 * kCwWarps, smem, s>>>(p, *map_slab);
+    }
     return cudaGetLastError();
+}
+
+// Largest shift with batch * P * 2^shift < 2^31 (the row prefix sums of k_hue_batch2 are int32), at most 18.
+static int hue_fix_shift(int64_t nb, int P) {
+    int sh = 18;
+    while (sh > 0 && (double)nb * P * (double)(1u << sh) >= 2147483648.0) --sh;
+    return sh;
+}
+
+static int hue_version() {
+    static const int v = [] { const char* e = getenv("NFX_HUE_V"); return e ? atoi(e) : 2; }();
+    return v;
 }
 
 cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int R, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
-    const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * mask_wpr(p.P) * 33 * 4;
     dim3 grid((unsigned)nbatch, (unsigned)p.slabs);
-    if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
-        cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int64_t nbmax = p.n < p.batch_size ? p.n : p.batch_size;
+    if (hue_version() == 1 || (double)nbmax * p.P >= 2147483648.0) {
+        const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * mask_wpr(p.P) * 33 * 4;
+        if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
+            cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_hue_batch<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R);
+        return cudaGetLastError();
+    }
+    const int smem = kHue2Stages * 2 * window_smem_bytes(p.P, R) + R * (p.P + 2) * (int)sizeof(int2);
+    if (smem > 32 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_hue_batch2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    k_hue_batch<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R);
+    k_hue_batch2<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R, hue_fix_shift(nbmax, p.P));
     return cudaGetLastError();
 }
 

@@ -55,8 +55,94 @@ __device__ __forceinline__ bool ellipse_inside(double x, double y, double cx, do
     return val <= 1.0;
 }
 
+// ---- SPEC.md B1 raster, executed by ONE warp ---------------------------------------------------------------------------
+// Round 1 gave each lane one edge and let it walk that edge's rows (0 to ~10 of them, a float64 division per row): 13 of 32
+// lanes were active on average (ncu). Now the (edge, row) pairs of a block of 64 edges are flattened over the lanes: every
+// lane sets up at most two edges (row range, and ONE float64 reciprocal of dy), a warp scan of the row counts numbers the
+// pairs, and lane l takes pairs l, l + 32, ... (binary search of the pair number in the scanned counts).
+// Bit-exactness: the rule is X = xi + ((y - yi) * dx) / dy with every operation rounded to float64, and pixel c is toggled
+// iff c - P/2 < X. A pair first evaluates X' = xi + ((y - yi) * dx) * (1 / dy), which is within a few ulp of X; only when
+// X' + P/2 lies within 1e-9 (relative) of an integer -- where the two could fall on different sides of a pixel abscissa --
+// is the division carried out. Either way the toggled prefix is the one the per-pixel rule gives.
+constexpr int kEdgeBlock = 64;
+struct EdgeRecs {               // per nucleus, in shared memory
+    double xi[kEdgeBlock], yi[kEdgeBlock], dx[kEdgeBlock], dy[kEdgeBlock], rdy[kEdgeBlock];
+    int r0[kEdgeBlock];
+    int off[kEdgeBlock + 1];    // exclusive scan of the row counts
+};
+
+__device__ __forceinline__ void raster_warp(const float2* pts, int V, int P, uint32_t* rows, EdgeRecs* er, int lane) {
+    const int wpr = mask_wpr(P);
+    const double half = 0.5 * (double)P;
+    for (int e0 = 0; e0 < V; e0 += kEdgeBlock) {
+        int cnt[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = lane + 32 * u, k = e0 + j;
+            cnt[u] = 0;
+            if (k < V) {   // warp-uniform for u = 1 when the block holds <= 32 edges, divergent only in the last block
+                const float2 a = pts[k], b = pts[(k + 1 == V) ? 0 : k + 1];
+                if (!(a.y == b.y || !(a.y == a.y) || !(b.y == b.y))) {
+                    const double ylo = fmin((double)a.y, (double)b.y), yhi = fmax((double)a.y, (double)b.y);
+                    const int r0 = first_index_geq(ylo, P), r1 = first_index_geq(yhi, P);
+                    if (r1 > r0) {
+                        const double dye = __dsub_rn((double)b.y, (double)a.y);
+                        er->xi[j] = (double)a.x;
+                        er->yi[j] = (double)a.y;
+                        er->dx[j] = __dsub_rn((double)b.x, (double)a.x);
+                        er->dy[j] = dye;
+                        er->rdy[j] = __ddiv_rn(1.0, dye);
+                        er->r0[j] = r0;
+                        cnt[u] = r1 - r0;
+                    }
+                }
+            }
+        }
+        // exclusive scan over the 64 counts (lane l owns entries l and l + 32)
+        int i0 = cnt[0], i1 = cnt[1];
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const int t0 = __shfl_up_sync(0xffffffffu, i0, o2), t1 = __shfl_up_sync(0xffffffffu, i1, o2);
+            if (lane >= o2) { i0 += t0; i1 += t1; }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, i0, 31), T = tot0 + __shfl_sync(0xffffffffu, i1, 31);
+        er->off[lane] = i0 - cnt[0];
+        er->off[lane + 32] = tot0 + i1 - cnt[1];
+        if (lane == 0) er->off[kEdgeBlock] = T;
+        __syncwarp();
+        for (int t = lane; t < T; t += 32) {
+            int j = 0;   // largest j with off[j] <= t and a non-empty range: off[j] <= t < off[j + 1]
+#pragma unroll
+            for (int step = kEdgeBlock / 2; step > 0; step >>= 1)
+                if (er->off[j + step] <= t) j += step;
+            const int r = er->r0[j] + (t - er->off[j]);
+            const double y = (double)r - half;
+            const double xi = er->xi[j];
+            const double num = __dmul_rn(__dsub_rn(y, er->yi[j]), er->dx[j]);
+            double X = __dadd_rn(xi, __dmul_rn(num, er->rdy[j]));
+            const double tt = X + half, fr = tt - rint(tt);
+            if (!(fabs(fr) > 1e-9 * fmax(1.0, fabs(tt))))   // next to a pixel abscissa (or not finite): the rule's own division
+                X = __dadd_rn(xi, __ddiv_rn(num, er->dy[j]));
+            if (!(X == X)) continue;                          // `x < NaN` is false for every pixel: nothing toggled
+            const int nb = first_index_geq(X, P);             // pixels c < nb satisfy (c - P/2) < X
+            for (int w = 0; w < wpr; ++w) {
+                const uint32_t m = prefix_bits(nb - 32 * w);
+                if (m) atomicXor(&rows[r * wpr + w], m);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ double cross3(double2 o, double2 a, double2 b) {
     return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x);
+}
+
+// bytes of one nucleus' shared memory before the edge records (rows | pts | sorted | stk), 16-byte aligned
+__host__ __device__ __forceinline__ size_t geom_edge_offset(int P, int vmax, bool shape) {
+    size_t b = (size_t)((P * mask_wpr(P) + 3) & ~3) * 4 + (size_t)((vmax + 1) & ~1) * 8;
+    if (shape) b += (size_t)vmax * 16 + (size_t)vmax * 2 * 4;
+    return (b + 15) & ~(size_t)15;
 }
 
 template <bool RASTER, bool SHAPE>
@@ -77,6 +163,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
     float2* pts = reinterpret_cast<float2*>(rows + ((P * wpr + 3) & ~3));
     double2* sorted = reinterpret_cast<double2*>(pts + ((p.vmax + 1) & ~1));   // 16-byte aligned
     int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? p.vmax : 0));
+    EdgeRecs* erecs = reinterpret_cast<EdgeRecs*>(smem_raw + geom_edge_offset(P, p.vmax, SHAPE));   // RASTER only
     __shared__ double s_red[16];
     __shared__ float s_c_all[kNpc][2];
     __shared__ int s_hull[2];
@@ -126,26 +213,8 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
         }
         sync();
 
-        // ---- SPEC.md B1: edge-parallel scanline, float64 crossing abscissa ----
-        const double half = 0.5 * (double)P;
-        for (int k = tid; k < V; k += kGeomThreads) {
-            const float2 a = pts[k], b = pts[(k + 1 == V) ? 0 : k + 1];
-            if (a.y == b.y || !(a.y == a.y) || !(b.y == b.y)) continue;
-            const double ylo = fmin((double)a.y, (double)b.y), yhi = fmax((double)a.y, (double)b.y);
-            const int r0 = first_index_geq(ylo, P), r1 = first_index_geq(yhi, P);
-            const double xi = a.x, yi = a.y, dxe = __dsub_rn((double)b.x, xi),
-                         dye = __dsub_rn((double)b.y, yi);
-            for (int r = r0; r < r1; ++r) {
-                const double y = (double)r - half;
-                const double X =
-                    __dadd_rn(xi, __ddiv_rn(__dmul_rn(__dsub_rn(y, yi), dxe), dye));
-                const int nb = first_index_geq(X, P);   // pixels c < nb satisfy (c - P/2) < X
-                for (int w = 0; w < wpr; ++w) {
-                    const uint32_t m = prefix_bits(nb - 32 * w);
-                    if (m) atomicXor(&rows[r * wpr + w], m);
-                }
-            }
-        }
+        // ---- SPEC.md B1: scanline raster over flattened (edge, row) pairs, one warp ----
+        if (tid < 32) raster_warp(pts, V, P, rows, erecs, tid);
         sync();
         for (int k = tid; k < P * wpr; k += kGeomThreads) p.bitmask[i * P * wpr + k] = rows[k];
     }
@@ -324,9 +393,8 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
 
 cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
-    const int wpr = mask_wpr(p.P);
-    size_t nuc = (size_t)((p.P * wpr + 3) & ~3) * 4 + (size_t)((p.vmax + 1) & ~1) * 8;
-    if (shape) nuc += (size_t)p.vmax * 16 + (size_t)p.vmax * 2 * 4;
+    size_t nuc = geom_edge_offset(p.P, p.vmax, shape);
+    if (raster) nuc += sizeof(EdgeRecs);
     nuc = (nuc + 15) & ~(size_t)15;
     auto go = [&](auto kern, int threads, int npc) -> cudaError_t {
         const size_t smem = nuc * npc;
