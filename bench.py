@@ -134,17 +134,6 @@ def make_inputs(workload, nuclei, side, P, seed, pinned):
     return tile, xy, off
 
 
-def synth_polygons_chunked(nuclei, side, P, seed, kw, chunk=500_000):
-    from nfx import synth
-    xs, offs, base = [], [np.zeros(1, np.int64)], 0
-    for k in range(0, nuclei, chunk):
-        xy, off = synth.synth_polygons(min(chunk, nuclei - k), side, side, seed + 7919 * (k // chunk), patch=P, **kw)
-        xs.append(xy)
-        offs.append(off[1:] + base)
-        base += int(off[-1])
-    return np.concatenate(xs), np.concatenate(offs)
-
-
 def run_staged(args, local_rank):
     """North-star kernels (1) gather and (2) raster on their own: batched window gather tile -> u8 patch
     array (k_gather) and polygon -> 1-bit mask (k_geom<raster>), timed with CUDA events per launch."""
@@ -190,97 +179,6 @@ def run_staged(args, local_rank):
                      "frac": g["gbs"] / hbm_peak, "traffic": None},
         "kernels": kern, "gpu_launches": int(sum(v["launches"] for v in kern.values())),
     }))
-    ex.close()
-
-
-def run_slide(args, rank, local_rank, world, dist):
-    """BASELINE config 4: a side x side slide lives in HBM (30 GB at 100k x 100k), streamed from the host
-    as 8192^2 tiles through two pinned staging buffers; the nuclei are split over the ranks in
-    contiguous index ranges aligned to batch_size (every rank keeps the whole slide: index order is
-    not spatial order). A step = stream the tiles + upload the range's polygons + all kernels + D2H."""
-    import nfx
-    from nfx import synth
-    sets, nuclei, side, P, kw = WORKLOADS["slide"]
-    nuclei = args.nuclei or nuclei
-    side = args.tile or side
-    mask = nfx.parse_feature_sets(sets)
-    F = len(nfx.feature_names(mask))
-    T = 8192
-    block = synth.synth_tile(4096, 4096, 4)
-    stage = [nfx.pinned_empty((T, T, 3), np.uint8) for _ in range(2)]
-    for b in stage:
-        for r in range(0, T, 4096):
-            for c in range(0, T, 4096):
-                b[r:r + 4096, c:c + 4096] = block
-    xy, off = synth_polygons_chunked(nuclei, side, P, 4, kw)
-    bounds = nfx.partition(nuclei, args.batch_size, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
-    n = hi - lo
-    pxy = nfx.pinned_empty((int(off[hi] - off[lo]), 2), np.float32)
-    pxy[...] = xy[off[lo]:off[hi]]
-    poff = nfx.pinned_empty((n + 1,), np.int64)
-    poff[...] = off[lo:hi + 1] - off[lo]
-    cents = nfx.pinned_empty((n, 2), np.float32)
-    feats = nfx.pinned_empty((n, F), np.float32)
-    ex = nfx.Extractor(local_rank, P, args.batch_size)
-    ex.slide_alloc(side, side)
-
-    def stream_tiles():
-        k = 0
-        for y in range(0, side, T):
-            for x in range(0, side, T):
-                h, w = min(T, side - y), min(T, side - x)
-                ex.write_tile(stage[k & 1][:h, :w], x, y)
-                k += 1
-        return k
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    ntiles = stream_tiles()
-    ex.upload_polygons(pxy, poff)
-    for _ in range(max(args.warmup, 3) if n < 500_000 else 1):
-        ex.compute(mask)
-    ex.sync()
-    barrier()
-    K = max(1, min(args.steps, 3))
-    ex.profile(True)
-    ex.profile_reset()
-    l0 = ex.launch_count()
-    ex.timer_start()
-    for _ in range(K):
-        ex.compute(mask)
-    ms = ex.timer_stop() / K
-    launches = ex.launch_count() - l0
-    prof = ex.profile_get()
-    ex.profile(False)
-    barrier()
-    t0 = time.perf_counter()
-    stream_tiles()
-    ex.upload_polygons(pxy, poff)
-    ex.compute(mask)
-    ex.download(cents, feats)
-    e2e_ms = 1e3 * (time.perf_counter() - t0)
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms, e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
-    if rank == 0:
-        kern = {k: {"launches": v[0], "avg_ms": v[1] / max(v[0], 1)} for k, v in prof.items()}
-        print(json.dumps({
-            "metric": "nuclei/sec", "value": nuclei / (ms * 1e-3), "unit": "nuclei/s", "n_gpus": world, "steps": K,
-            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8/f32", "data": "synthetic",
-            "config": {"workload": f"slide: {'+'.join(sets)}, {nuclei} nuclei over a {side}x{side} u8 RGB slide resident in HBM "
-                                   f"({3 * side * side / 1e9:.1f} GB per GPU), streamed as {ntiles} tiles of {T}^2, P={P}, "
-                                   f"batch_size={args.batch_size}",
-                       "partition": f"contiguous index ranges aligned to batch_size, {n} nuclei on rank 0"},
-            "e2e": {"value": nuclei / (e2e_ms * 1e-3), "unit": "nuclei/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": 3 * side * side + pxy.nbytes + poff.nbytes, "d2h_bytes_per_step": cents.nbytes + feats.nbytes},
-            "gpu_launches": launches, "kernels": kern, "checksum": float(np.nansum(feats[:: max(1, n // 997)])),
-        }))
     ex.close()
 
 
@@ -454,6 +352,314 @@ def run_pipeline(args, local_rank):
     ex.close()
 
 
+# ======================================================================================================
+# Building blocks of the default run
+# ======================================================================================================
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def source_hash():
+    """sha256 (16 hex digits) over the kernel sources: ties the ncu-derived DRAM traffic in profiles/r2_traffic.json to the
+    kernels it was captured from (a stale entry reads as null, never as a number)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "nuclei-feature-extraction_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(workload, kernel, nuclei, P):
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if tj.get("csrc_sha16") != source_hash():
+            return None
+        ent = tj.get(workload, {}).get(kernel)
+        if ent and ent["nuclei"] == nuclei and ent["patch"] == P:
+            return ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
+def resident(ex, mask, K, W, min_s=0.0, barrier=lambda: None):
+    """W (or more, for >= min_s seconds under load) untimed steps, then exactly K timed steps with the inputs already in
+    HBM: CUDA events on the context stream around the K steps and around every kernel launch."""
+    t_w, nw = time.perf_counter(), 0
+    while nw < W or (time.perf_counter() - t_w < min_s and nw < 2000):
+        ex.compute(mask)
+        nw += 1
+        if nw % 8 == 0:
+            ex.sync()
+    ex.sync()
+    barrier()
+    ex.profile(True)
+    ex.profile_reset()
+    l0 = ex.launch_count()
+    ex.sync()
+    barrier()
+    ex.timer_start()
+    for _ in range(K):
+        ex.compute(mask)
+    ms = ex.timer_stop() / K
+    barrier()
+    launches = ex.launch_count() - l0
+    prof = ex.profile_get()
+    ex.profile(False)
+    kern = {k: {"launches": v[0], "avg_ms": v[1] / max(v[0], 1)} for k, v in prof.items()}
+    tot = sum(v["avg_ms"] for v in kern.values()) or 1.0
+    for v in kern.values():
+        v["share"] = v["avg_ms"] / tot
+    return {"ms": ms, "kern": kern, "launches": launches, "warmup_steps_run": nw}
+
+
+def roofline_of(run, workload, nuclei, P, F, peak, peak_kind, world=1):
+    """HBM roofline of the dominant kernel: algorithmic bytes per launch / its CUDA-event time."""
+    kern = run["kern"]
+    if not kern:
+        return None
+    R = max(1, min(P, 1024 // P))
+    slabs = (P + R - 1) // R
+    for k, v in kern.items():
+        v["gbs"] = kernel_bytes(k, P, slabs) * nuclei / (v["avg_ms"] * 1e-3) / 1e9 if v["avg_ms"] > 0 else 0.0
+    dom = max(kern, key=lambda k: kern[k]["avg_ms"])
+    value = nuclei / (run["ms"] * 1e-3)
+    return {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kern[dom]["gbs"] / peak, "traffic": measured_traffic(workload, dom, nuclei, P), "peak_source": peak_kind,
+            "bytes_per_nucleus": kernel_bytes(dom, P, slabs), "avg_launch_ms": kern[dom]["avg_ms"],
+            "pipeline_bytes_per_nucleus": algorithmic_bytes(workload, P, F),
+            "pipeline_frac": value * algorithmic_bytes(workload, P, F) / 1e9 / peak}
+
+
+def e2e_double_buffered(ctxs, outs, submit, n_steps):
+    """n_steps whole steps (pinned H2D of every input, kernels, D2H of the results) through two contexts used alternately,
+    like the reference's rayon workers overlap their batches: step k's copies overlap step k-1's kernels; the timed region
+    contains the full H2D + kernels + D2H of every step. Returns ms per step (host wall clock)."""
+    for c, (oc, of) in zip(ctxs, outs):     # warm both contexts
+        submit(c)
+        c.download(oc, of)
+    t0 = time.perf_counter()
+    submit(ctxs[0])
+    for k in range(1, n_steps):
+        submit(ctxs[k & 1])
+        ctxs[(k - 1) & 1].download(*outs[(k - 1) & 1])
+    ctxs[(n_steps - 1) & 1].download(*outs[(n_steps - 1) & 1])
+    return 1e3 * (time.perf_counter() - t0) / n_steps
+
+
+SET_NAMES = {"geometry": "shape", "color": "color", "glcm": "glcm", "glrlm": "glrlm", "gabor": "gabor", "all": "all"}
+
+
+def per_set_block(args, ex, ex2, tile, xy, off, nuclei, P, peak, peak_kind, cpu):
+    """BASELINE metric "nuclei/sec per feature set": every set on the headline's resident inputs (100 000 nuclei, 64 x 64
+    windows, 16384^2 tile): device-resident rate, dominant kernel and its HBM fraction, end-to-end rate, CPU oracle rate."""
+    import nfx
+    out = {}
+    for name in ("geometry", "color", "glcm", "glrlm", "gabor", "all"):
+        mask = nfx.parse_feature_sets([name])
+        F = len(nfx.feature_names(mask))
+        wl = SET_NAMES[name]
+        run = resident(ex, mask, 10 if name in ("geometry", "color") else 4, 3)
+        roof = roofline_of(run, wl, nuclei, P, F, peak, peak_kind)
+        rec = {"columns": F, "ms_per_step": run["ms"], "value": nuclei / (run["ms"] * 1e-3), "unit": "nuclei/s",
+               "dominant_kernel": roof["kernel"], "frac": roof["frac"], "pipeline_frac": roof["pipeline_frac"],
+               "kernels_ms": {k: v["avg_ms"] for k, v in run["kern"].items()}, "gpu_launches": run["launches"]}
+        if not args.no_e2e:
+            outs = [(nfx.pinned_empty((nuclei, 2), np.float32), nfx.pinned_empty((nuclei, F), np.float32)) for _ in range(2)]
+
+            def submit(c):
+                c.upload_tile(tile)
+                c.upload_polygons(xy, off)
+                c.compute(mask)
+            ms = e2e_double_buffered([ex, ex2], outs, submit, 4)
+            rec["e2e"] = {"value": nuclei / (ms * 1e-3), "unit": "nuclei/s", "ms_per_step": ms,
+                          "h2d_bytes_per_step": tile.nbytes + xy.nbytes + off.nbytes, "d2h_bytes_per_step": 8 * nuclei + 4 * F * nuclei}
+        if cpu:
+            workers = cpu_workers()
+            rate, dt, done = cpu_reference_rate([name], tile, xy, off, P, args.batch_size, workers * args.batch_size, workers, budget_s=5.0)
+            rec["cpu_baseline"] = {"value": rate, "unit": "nuclei/s", "cores": workers, "kind": "port",
+                                   "sample": f"first {done} nuclei ({dt:.1f} s), oracle on {workers} chunk-parallel host threads"}
+        out[name] = rec
+    return out
+
+
+def fill_slide(ex, side, stage, T, y_lo=0, y_hi=None):
+    """Stream rows [y_lo, y_hi) of a side x side slide from the two pinned staging tiles; returns the bytes sent."""
+    y_hi = side if y_hi is None else y_hi
+    k, sent = 0, 0
+    for y in range(y_lo, y_hi, T):
+        for x in range(0, side, T):
+            h, w = min(T, y_hi - y), min(T, side - x)
+            ex.write_tile(stage[k & 1][:h, :w], x, y)
+            sent += 3 * h * w
+            k += 1
+    return sent
+
+
+def staging_tiles(T, seed):
+    import nfx
+    from nfx import synth
+    block = synth.synth_tile(min(T, 4096), min(T, 4096), seed)
+    stage = [nfx.pinned_empty((T, T, 3), np.uint8) for _ in range(2)]
+    for b in stage:
+        for r in range(0, T, block.shape[0]):
+            for c in range(0, T, block.shape[1]):
+                b[r:r + block.shape[0], c:c + block.shape[1]] = block[:min(block.shape[0], T - r), :min(block.shape[1], T - c)]
+    return stage
+
+
+def slide_job(args, sets, nuclei, side, P, rank, local_rank, world, dist, seed, poly_kw, steps, label):
+    """One slide resident in HBM on every GPU, nuclei split over the ranks in contiguous index ranges aligned to batch_size
+    (index order is not spatial order, so every range touches every tile). Each rank receives only ITS 1/N of the rows
+    from the host; the rest comes from the peers over NVLink (nfx_slide_export / nfx_slide_import_rows).
+    Device-resident step = all kernels over the rank's range; end-to-end step = own rows H2D + peers' rows over NVLink +
+    polygons H2D + kernels + D2H of the features. Times are the max over ranks."""
+    import nfx
+    from nfx import synth
+    mask = nfx.parse_feature_sets(sets)
+    F = len(nfx.feature_names(mask))
+    T = min(8192, side)
+    stage = staging_tiles(T, seed)
+    xy, off = synth.synth_polygons_pool(nuclei, side, side, seed, patch=P, **poly_kw)
+    bounds = nfx.partition(nuclei, args.batch_size, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n = hi - lo
+    pxy = nfx.pinned_empty((int(off[hi] - off[lo]), 2), np.float32)
+    pxy[...] = xy[off[lo]:off[hi]]
+    poff = nfx.pinned_empty((n + 1,), np.int64)
+    poff[...] = off[lo:hi + 1] - off[lo]
+    del xy
+    cents = nfx.pinned_empty((n, 2), np.float32)
+    feats = nfx.pinned_empty((n, F), np.float32)
+    ex = nfx.Extractor(local_rank, P, args.batch_size)
+    ex.slide_alloc(side, side)
+    rows = [(side * r) // world for r in range(world + 1)]     # rank r owns rows [rows[r], rows[r+1])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def place_slide():
+        sent = fill_slide(ex, side, stage, T, rows[rank], rows[rank + 1])
+        nvl = 0
+        if world > 1:
+            ex.sync()
+            handles = [None] * world
+            dist.all_gather_object(handles, ex.slide_export())      # also the barrier: every rank's rows are in its HBM
+            for q in range(world):
+                if q != rank:
+                    ex.slide_import_rows(handles[q], rows[q], rows[q + 1] - rows[q])
+                    nvl += 3 * side * (rows[q + 1] - rows[q])
+        return sent, nvl
+
+    place_slide()
+    ex.upload_polygons(pxy, poff)
+    run = resident(ex, mask, steps, 1, barrier=barrier)
+    t0 = time.perf_counter()
+    sent, nvl = place_slide()
+    ex.upload_polygons(pxy, poff)
+    ex.compute(mask)
+    ex.download(cents, feats)
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        ex.sync()
+        barrier()           # peers may still be reading this rank's rows
+    ms = run["ms"]
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    checksum = float(np.nansum(feats[:: max(1, n // 997)]))
+    rec = {"workload": f"{label}: {'+'.join(sets)}, {nuclei} nuclei over a {side}x{side} u8 RGB slide resident in HBM "
+                       f"({3 * side * side / 1e9:.1f} GB per GPU), P={P}, batch_size={args.batch_size}",
+           "partition": f"contiguous index ranges aligned to batch_size ({n} nuclei on rank 0); slide rows split over the ranks "
+                        f"for the host upload, peers' rows fetched over NVLink" if world > 1 else "one GPU",
+           "n_gpus": world, "scaling": "strong", "nuclei": nuclei, "columns": F, "steps": steps,
+           "ms_per_step": ms, "value": nuclei / (ms * 1e-3), "unit": "nuclei/s",
+           "e2e": {"value": nuclei / (e2e_ms * 1e-3), "unit": "nuclei/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step_per_gpu": sent + pxy.nbytes + poff.nbytes, "nvlink_bytes_per_step_per_gpu": nvl,
+                   "d2h_bytes_per_step_per_gpu": cents.nbytes + feats.nbytes},
+           "kernels_ms": {k: v["avg_ms"] for k, v in run["kern"].items()}, "gpu_launches": run["launches"], "checksum": checksum}
+    if run["kern"]:
+        dom = max(run["kern"], key=lambda k: run["kern"][k]["avg_ms"])
+        rec["dominant_kernel"] = dom
+    ex.close()
+    return rec
+
+
+def config_records(args, local_rank, peak, peak_kind, cpu):
+    """BASELINE.json configs 1, 3, 4 and 5 at their stated sizes (config 2 is the headline)."""
+    import nfx
+    out = {}
+    # ---- config 1: shape set, 10k polygons, 4096^2 tile (the reference's own CPU-runnable case) ----
+    sets, nuclei, side, P, kw = WORKLOADS["shape"]
+    tile, xy, off = make_inputs("shape", nuclei, side, P, 1, pinned=True)
+    mask = nfx.parse_feature_sets(sets)
+    F = len(nfx.feature_names(mask))
+    ex, ex2 = nfx.Extractor(local_rank, P, args.batch_size), nfx.Extractor(local_rank, P, args.batch_size)
+    ex.upload_tile(tile)
+    ex.upload_polygons(xy, off)
+    run = resident(ex, mask, 20, 3)
+    roof = roofline_of(run, "shape", nuclei, P, F, peak, peak_kind)
+    rec = {"workload": f"shape: geometry set, {nuclei} nuclei, {P}x{P} windows, tile {side}x{side}", "ms_per_step": run["ms"],
+           "value": nuclei / (run["ms"] * 1e-3), "unit": "nuclei/s", "dominant_kernel": roof["kernel"], "frac": roof["frac"],
+           "note": "the geometry set reads no pixel: the HBM fraction is reported for completeness only",
+           "kernels_ms": {k: v["avg_ms"] for k, v in run["kern"].items()}, "gpu_launches": run["launches"]}
+    if not args.no_e2e:
+        outs = [(nfx.pinned_empty((nuclei, 2), np.float32), nfx.pinned_empty((nuclei, F), np.float32)) for _ in range(2)]
+
+        def submit(c):
+            c.upload_tile(tile)
+            c.upload_polygons(xy, off)
+            c.compute(mask)
+        ms = e2e_double_buffered([ex, ex2], outs, submit, 6)
+        rec["e2e"] = {"value": nuclei / (ms * 1e-3), "unit": "nuclei/s", "ms_per_step": ms,
+                      "h2d_bytes_per_step": tile.nbytes + xy.nbytes + off.nbytes, "d2h_bytes_per_step": 8 * nuclei + 4 * F * nuclei}
+    if cpu:
+        workers = cpu_workers()
+        rate, dt, done = cpu_reference_rate(sets, tile, xy, off, P, args.batch_size, min(nuclei, workers * args.batch_size * 2), workers, budget_s=8.0)
+        rec["cpu_baseline"] = {"value": rate, "unit": "nuclei/s", "cores": workers, "kind": "port",
+                               "sample": f"first {done} nuclei of the same workload ({dt:.1f} s), oracle = torch-CPU restatement of the tch path"}
+    out["1"] = rec
+    ex.close()
+    ex2.close()
+    # ---- config 3: GLCM set, 1M nuclei ----
+    sets, nuclei, side, P, kw = WORKLOADS["glcm"]
+    nuclei = int(os.environ.get("NFX_BENCH_C3_NUCLEI", nuclei))
+    out["3"] = slide_job(args, sets, nuclei, side, P, 0, local_rank, 1, None, 3, kw, 3, "glcm (config 3)")
+    out["3"]["note"] = ("BASELINE words the set as '32 grey levels, distances 1/2, 4 angles' (8 matrices); the reference's GlcmFeatureSet "
+                        "is levels {32,64,128,254} x 4 offsets at distance 1 = 16 matrices / 224 columns (src/features/texture.rs:19-20): "
+                        "the drop-in computes and this line times the reference's set, the larger of the two")
+    # ---- config 5: stress, 256x256 windows, 500-vertex polygons, all sets ----
+    sets, nuclei, side, P, kw = WORKLOADS["stress"]
+    nuclei = int(os.environ.get("NFX_BENCH_C5_NUCLEI", nuclei))
+    out["5"] = slide_job(args, sets, nuclei, side, P, 0, local_rank, 1, None, 5, kw, 2, "stress (config 5)")
+    # ---- config 4: all sets, 5M nuclei, 100k x 100k slide ----
+    sets, nuclei, side, P, kw = WORKLOADS["slide"]
+    nuclei = int(os.environ.get("NFX_BENCH_C4_NUCLEI", nuclei))
+    side = int(os.environ.get("NFX_BENCH_C4_SIDE", side))
+    out["4"] = slide_job(args, sets, nuclei, side, P, 0, local_rank, 1, None, 4, kw, 1, "slide (config 4)")
+    return out
+
+
+def h2d_rate(ex, tile, barrier):
+    """GB/s of ONE pinned upload of this rank's tile while every other rank does the same (what bounds the weak-scaling
+    end-to-end number: the ranks share the host's PCIe root complexes)."""
+    ex.sync()
+    barrier()
+    t0 = time.perf_counter()
+    ex.upload_tile(tile)
+    ex.sync()
+    return tile.nbytes / (time.perf_counter() - t0) / 1e9
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -468,6 +674,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="nuclei of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline only: no per_set / configs / strong blocks")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -485,12 +692,13 @@ def main():
         if rank == 0:
             run_trait(args, local_rank)
         return
-    sets, nuclei, side, P, _ = WORKLOADS[args.workload]
+    sets, nuclei, side, P, poly_kw = WORKLOADS[args.workload]
     nuclei = args.nuclei or nuclei
     side = args.tile or side
     W = max(args.warmup, 3) if args.impl == "nfx" else args.warmup
     K = max(args.steps, 1)
     cores = os.cpu_count() or 1
+    quick = args.quick or bool(os.environ.get("NFX_BENCH_QUICK")) or args.workload != "color" or bool(args.nuclei) or bool(args.tile)
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -498,7 +706,11 @@ def main():
             return
         workers = cpu_workers()
         sample = args.cpu_sample or workers * args.batch_size * {"color": 2, "shape": 4}.get(args.workload, 1)
-        tile, xy, off = make_inputs(args.workload, max(sample, 1000), min(side, 4096), P, 2, pinned=False)
+        if args.workload == "slide":       # the 100k^2 slide is never held on the host: same nuclei density on one 8192^2 tile
+            tile, xy, off = make_inputs(args.workload, max(sample, 1000), 8192, P, 4, pinned=False)
+        else:                              # exactly the GPU arm's rank-0 inputs; the oracle runs on their first `sample` nuclei
+            tile, xy, off = make_inputs(args.workload, nuclei, side, P, 2, pinned=False)
+        sample = min(sample, len(off) - 1)
         rates = []
         for it in range(args.warmup + K):
             r, dt, done = cpu_reference_rate(sets, tile, xy, off, P, args.batch_size, sample, workers)
@@ -512,8 +724,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, sets, nuclei, side, P),
             "cpu_baseline": {"value": value, "unit": "nuclei/s", "cores": workers, "kind": "port",
-                             "sample": f"{sample} nuclei of the workload per step on a {min(side, 4096)}^2 tile x {K} steps, oracle "
-                                       f"(torch-CPU restatement of the tch path), {workers} chunk-parallel host threads of {cores} cores"},
+                             "sample": f"each step = the first {sample} nuclei of that workload (same tile, same polygons, same seed as the "
+                                       f"GPU arm's rank 0) x {K} steps, oracle (torch-CPU restatement of the tch path), {workers} "
+                                       f"chunk-parallel host threads of {cores} cores"},
             "e2e": {"value": value, "unit": "nuclei/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -533,8 +746,15 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    peak, peak_kind = hbm_peak()
     if args.workload == "slide":
-        run_slide(args, rank, local_rank, world, dist)
+        rec = slide_job(args, sets, nuclei, side, P, rank, local_rank, world, dist, 4, poly_kw, max(1, min(args.steps, 3)), "slide (config 4)")
+        if rank == 0:
+            line = {"metric": "nuclei/sec", "value": rec["value"], "unit": "nuclei/s", "n_gpus": world, "steps": rec["steps"], "warmup": 1,
+                    "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "u8/f32", "data": "synthetic", "config": {"workload": rec["workload"], "partition": rec["partition"]},
+                    "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "kernels_ms": rec["kernels_ms"], "checksum": rec["checksum"]}
+            print(json.dumps(line))
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
@@ -552,44 +772,20 @@ def main():
     # ---- device-resident throughput ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    t_w = time.perf_counter()
-    nw = 0
     exact = bool(os.environ.get("NFX_BENCH_EXACT_WARMUP"))   # profiling runs: exactly W warm-up steps
-    while nw < W or (not exact and time.perf_counter() - t_w < 0.25 and nw < 2000):   # >= W steps, >= 0.25 s under load
-        ex.compute(mask)
-        nw += 1
-        if nw % 8 == 0:
-            ex.sync()
-    ex.sync()
-    barrier()
-    ex.profile(True)
-    ex.profile_reset()
-    l0 = ex.launch_count()
-    ex.sync()
-    barrier()
-    ex.timer_start()
-    for _ in range(K):
-        ex.compute(mask)
-    ms = ex.timer_stop()
-    barrier()
-    launches = ex.launch_count() - l0
-    prof = ex.profile_get()
-    ex.profile(False)
+    run = resident(ex, mask, K, W, min_s=0.0 if exact else 0.25, barrier=barrier)
     clocks = sampler.stop()
     ex.download(cents, feats)
     checksum = float(np.nansum(feats[:: max(1, nuclei // 997)]))
 
     # ---- end to end through the host API with host buffers ----
-    # Every step: pinned H2D of the tile and the polygons, all kernels, D2H of centroids + features.
-    # Two contexts are used alternately (double buffering, like the reference's rayon workers overlap
-    # their batches): step k's copies overlap step k-1's kernels; the timed region still contains the
-    # full H2D + kernels + D2H of every step.
     e2e_ms = None
     h2d = tile.nbytes + xy.nbytes + off.nbytes
     d2h = cents.nbytes + feats.nbytes
+    ex2 = None
+    h2d_gbs = None
     if not args.no_e2e:
         ex2 = nfx.Extractor(local_rank, P, args.batch_size)
-        ctxs = [ex, ex2]
         outs = [(cents, feats), (nfx.pinned_empty((nuclei, 2), np.float32), nfx.pinned_empty((nuclei, F), np.float32))]
 
         def submit(c):
@@ -597,62 +793,32 @@ def main():
             c.upload_polygons(xy, off)
             c.compute(mask)
 
-        for c, (oc, of) in zip(ctxs, outs):     # warm both contexts
-            submit(c)
-            c.download(oc, of)
         barrier()
-        n_e2e = max(4, min(K, 6))
-        t0 = time.perf_counter()
-        submit(ctxs[0])
-        for k in range(1, n_e2e):
-            submit(ctxs[k & 1])
-            ctxs[(k - 1) & 1].download(*outs[(k - 1) & 1])
-        ctxs[(n_e2e - 1) & 1].download(*outs[(n_e2e - 1) & 1])
-        e2e_ms = 1e3 * (time.perf_counter() - t0) / n_e2e
-        ex2.close()
+        e2e_ms = e2e_double_buffered([ex, ex2], outs, submit, max(4, min(K, 6)))
+        h2d_gbs = h2d_rate(ex, tile, barrier)
 
     # ---- max over ranks ----
-    step_ms = ms / K
+    step_ms = run["ms"]
     if dist is not None:
         import torch
         t = torch.tensor([step_ms, e2e_ms or 0.0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_max = float(t[0]), float(t[1])
         e2e_ms = e2e_max if e2e_ms is not None else None
+        if h2d_gbs is not None:
+            g = torch.tensor([h2d_gbs], device="cuda")
+            allg = [torch.zeros_like(g) for _ in range(world)]
+            dist.all_gather(allg, g)
+            h2d_gbs = [float(x[0]) for x in allg]
     total = nuclei * world
     value = total / (step_ms * 1e-3)
+    run["ms"] = step_ms
 
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        R = max(1, min(P, 1024 // P))
-        slabs = (P + R - 1) // R
-        kern = {k: {"launches": v[0], "avg_ms": v[1] / max(v[0], 1)} for k, v in prof.items()}
-        tot = sum(v["avg_ms"] for v in kern.values()) or 1.0
-        for k, v in kern.items():
-            v["share"] = v["avg_ms"] / tot
-            v["gbs"] = kernel_bytes(k, P, slabs) * nuclei / (v["avg_ms"] * 1e-3) / 1e9 if v["avg_ms"] > 0 else 0.0
-        dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            ent = tj.get(args.workload, {}).get(dom)
-            if ent and ent["nuclei"] == nuclei and ent["patch"] == P:
-                traffic = ent["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        roof = None
-        if dom:
-            roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
-                    "bytes_per_nucleus": kernel_bytes(dom, P, slabs), "avg_launch_ms": kern[dom]["avg_ms"],
-                    "pipeline_bytes_per_nucleus": algorithmic_bytes(args.workload, P, F),
-                    "pipeline_frac": value / world * algorithmic_bytes(args.workload, P, F) / 1e9 / hbm_peak}
+        roof = roofline_of(run, args.workload, nuclei, P, F, peak, peak_kind)
+        if roof:
+            roof["pipeline_frac"] = value / world * algorithmic_bytes(args.workload, P, F) / 1e9 / peak
         cpu = None
         if not args.no_cpu_baseline:
             workers = cpu_workers()
@@ -663,24 +829,46 @@ def main():
                    "sample": f"first {done} nuclei of the same workload ({dt:.1f} s), oracle = torch-CPU restatement of the "
                              f"tch path, {workers} chunk-parallel host threads of {cores} cores"}
         line = {
-            "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_steps_run": nw,
+            "metric": "nuclei/sec", "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_steps_run": run["warmup_steps_run"],
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/f32", "data": "synthetic",
             "config": workload_config(args, sets, nuclei, side, P),
             "e2e": None if e2e_ms is None else {"value": total / (e2e_ms * 1e-3), "unit": "nuclei/s",
                                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                                 "ms_per_step": e2e_ms},
-            "gpu_launches": launches,
+                                                 "ms_per_step": e2e_ms,
+                                                 "h2d_gbs_per_rank_all_ranks_uploading": h2d_gbs},
+            "gpu_launches": run["launches"],
             "clocks": clocks,
             "roofline": roof,
-            "kernels": kern,
+            "kernels": run["kern"],
             "cpu_baseline": cpu,
             "checksum": checksum,
+            "csrc_sha16": source_hash(),
         }
         if numa is not None:
             line["host_numa_binding_rank0"] = numa
-        print(json.dumps(line))
+    # ---- the other feature sets and BASELINE configs, measured in the same run (one GPU) ----
+    if not quick and world == 1:
+        if ex2 is None:
+            ex2 = nfx.Extractor(local_rank, P, args.batch_size)
+        line["per_set"] = per_set_block(args, ex, ex2, tile, xy, off, nuclei, P, peak, peak_kind, not args.no_cpu_baseline)
+    if ex2 is not None:
+        ex2.close()
     ex.close()
+    del tile, cents, feats
+    if not quick and world == 1:
+        line["configs"] = config_records(args, local_rank, peak, peak_kind, not args.no_cpu_baseline)
+        line["configs"]["2"] = "the headline of this line"
+    # ---- N > 1: BASELINE config 4 split over the ranks (strong scaling) ----
+    if not quick and world > 1:
+        s_sets, s_nuclei, s_side, s_P, s_kw = WORKLOADS["slide"]
+        s_nuclei = int(os.environ.get("NFX_BENCH_C4_NUCLEI", s_nuclei))
+        s_side = int(os.environ.get("NFX_BENCH_C4_SIDE", s_side))
+        rec = slide_job(args, s_sets, s_nuclei, s_side, s_P, rank, local_rank, world, dist, 4, s_kw, 1, "slide (config 4)")
+        if rank == 0:
+            line["strong"] = rec
+    if rank == 0:
+        print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

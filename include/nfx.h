@@ -79,6 +79,27 @@ int nfx_slide_alloc(nfx_ctx* ctx, int64_t w, int64_t h, int64_t origin_x, int64_
 int nfx_slide_write_tile(nfx_ctx* ctx, const uint8_t* rgb, int64_t x0, int64_t y0, int64_t w, int64_t h,
                          int64_t row_stride_bytes);
 
+/* ---- one slide on several GPUs (BASELINE config 4) ------------------------------------
+ * The reference gives every rayon worker the same slide and moves each batch's patches to
+ * gpus[worker % len] (src/utils.rs:211-224); GeoJSON index order is not spatial order, so every GPU's index range
+ * touches every tile. Here the slide is resident on EVERY GPU, but each of N GPUs receives only 1/N of it from the
+ * host over its own PCIe link and the rest from its peers over NVLink / NVSwitch:
+ *   rank r: nfx_slide_alloc(W, H) ; nfx_slide_write_tile(rows of r) ; nfx_sync ; nfx_slide_export(&handle[r])
+ *   all   : exchange the handles (any host mechanism) and make sure every rank has synchronised its upload
+ *   rank r: for every peer q != r: nfx_slide_import_rows(handle[q], first row of q, rows of q)
+ * nfx_slide_import_rows opens the peer's allocation with CUDA IPC (the peer is another PROCESS: one process per GPU)
+ * and copies the rows device to device on the context stream. nfx_slide_copy_rows is the same transfer between two
+ * contexts of ONE process (one host thread per GPU, like nfx-cli). Both slides must have the same size. */
+typedef struct nfx_slide_handle {
+    uint8_t ipc[64];      /* cudaIpcMemHandle_t of the slide allocation */
+    int64_t width, height, pitch;
+    int32_t device;
+    int32_t reserved;
+} nfx_slide_handle;
+int nfx_slide_export(nfx_ctx* ctx, nfx_slide_handle* out);
+int nfx_slide_import_rows(nfx_ctx* ctx, const nfx_slide_handle* peer, int64_t y0, int64_t rows);
+int nfx_slide_copy_rows(nfx_ctx* dst, nfx_ctx* src, int64_t y0, int64_t rows);
+
 /* Stage n polygons (GeoJSON ring 0 of each feature, closing duplicate included, exactly as
  * `geometry.coordinates[0]` parses to f32: src/geojson.rs:8-24) in CSR form:
  * poly_xy = [poly_off[n]][2] f32 (x,y) slide coordinates, poly_off = [n+1] vertex offsets.

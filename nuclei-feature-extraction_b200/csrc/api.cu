@@ -64,6 +64,8 @@ struct nfx_ctx {
     bool have_tile = false;
     CUtensorMap map_tile_patch, map_tile_slab, map_tile_cslab, map_tile_gabor;
 
+    std::vector<std::pair<std::string, void*>> peers;   // CUDA IPC mappings of peer slides (nfx_slide_import_rows)
+
     // polygons
     DevBuf<float2> xy;
     DevBuf<int64_t> off;
@@ -359,6 +361,8 @@ int nfx_destroy(nfx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& pr : ctx->peers) cudaIpcCloseMemHandle(pr.second);
+    ctx->peers.clear();
     ctx->tile.release(); ctx->xy.release(); ctx->off.release(); ctx->centroid.release(); ctx->info.release();
     ctx->bitmask.release(); ctx->out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->gabor_part.release(); ctx->patches.release();
     ctx->scratch8.release(); ctx->scratchf.release(); ctx->scratch32.release(); ctx->flush.release();
@@ -410,6 +414,61 @@ int nfx_tile_upload(nfx_ctx* ctx, const uint8_t* rgb, int64_t w, int64_t h, int6
     int rc = nfx_slide_alloc(ctx, w, h, origin_x, origin_y);
     if (rc) return rc;
     return nfx_slide_write_tile(ctx, rgb, 0, 0, w, h, row_stride_bytes);
+}
+
+int nfx_slide_export(nfx_ctx* ctx, nfx_slide_handle* out) {
+    if (!ctx || !out) return NFX_ERR_INVALID;
+    if (!ctx->have_tile) return fail(ctx, NFX_ERR_STATE, "no slide allocated: call nfx_slide_alloc first");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->tile.p));
+    static_assert(sizeof(h) == sizeof(out->ipc), "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out->ipc, &h, sizeof h);
+    out->width = ctx->tw; out->height = ctx->th; out->pitch = ctx->tpitch; out->device = ctx->device;
+    return NFX_OK;
+}
+
+static int check_rows(nfx_ctx* ctx, int64_t w, int64_t h, int64_t pitch, int64_t y0, int64_t rows) {
+    if (!ctx->have_tile) return fail(ctx, NFX_ERR_STATE, "no slide allocated: call nfx_slide_alloc first");
+    if (w != ctx->tw || h != ctx->th || pitch != ctx->tpitch) return fail(ctx, NFX_ERR_INVALID, "peer slide has a different size");
+    if (y0 < 0 || rows < 0 || y0 + rows > ctx->th) return fail(ctx, NFX_ERR_INVALID, "rows outside the slide");
+    return NFX_OK;
+}
+
+int nfx_slide_import_rows(nfx_ctx* ctx, const nfx_slide_handle* peer, int64_t y0, int64_t rows) {
+    if (!ctx || !peer) return NFX_ERR_INVALID;
+    int rc = check_rows(ctx, peer->width, peer->height, peer->pitch, y0, rows);
+    if (rc) return rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (rows == 0) return NFX_OK;
+    const std::string key(reinterpret_cast<const char*>(peer->ipc), sizeof peer->ipc);
+    void* base = nullptr;
+    for (auto& pr : ctx->peers)
+        if (pr.first == key) base = pr.second;
+    if (!base) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, peer->ipc, sizeof h);
+        CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peers.emplace_back(key, base);
+    }
+    // same pitch on both sides: the rows are one contiguous range (NVLink / NVSwitch when the peer is another GPU)
+    CK(cudaMemcpyAsync(ctx->tile.p + (size_t)y0 * ctx->tpitch, static_cast<const uint8_t*>(base) + (size_t)y0 * ctx->tpitch,
+                       (size_t)rows * ctx->tpitch, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NFX_OK;
+}
+
+int nfx_slide_copy_rows(nfx_ctx* ctx, nfx_ctx* src, int64_t y0, int64_t rows) {
+    if (!ctx || !src) return NFX_ERR_INVALID;
+    if (!src->have_tile) return fail(ctx, NFX_ERR_STATE, "source context has no slide");
+    int rc = check_rows(ctx, src->tw, src->th, src->tpitch, y0, rows);
+    if (rc) return rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (rows == 0) return NFX_OK;
+    CK(cudaMemcpyPeerAsync(ctx->tile.p + (size_t)y0 * ctx->tpitch, ctx->device, src->tile.p + (size_t)y0 * src->tpitch, src->device,
+                           (size_t)rows * ctx->tpitch, ctx->stream));
+    return NFX_OK;
 }
 
 int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads) {

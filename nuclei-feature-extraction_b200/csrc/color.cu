@@ -14,12 +14,12 @@
 //             sums the hue of EVERY patch of the batch under mask i. It factorises into one P x P
 //             image per batch, C[p] = sum_j cos h_j[p], S[p] = sum_j sin h_j[p], followed by masked
 //             sums. One CTA per (batch, row slab): a TMA producer warp streams the slab of each of
-//             the batch's patches through a 4-stage mbarrier ring, 8 consumer warps keep C,S in
-//             registers, then each warp folds the slab under the masks of its share of nuclei.
+//             the batch's patches through a 4-stage mbarrier ring (two patches per stage), 8 consumer
+//             warps keep C,S in registers, then each warp folds the slab under the masks of its share
+//             of nuclei (row prefix sums in fixed point, one step per run of mask bits).
+// k_color_warp: the P = 64 form of k_color, one warp per nucleus.
 // k_hue_finalize: sums slab partials in fixed order (bit-reproducible for any GPU count) + atan2.
 #include <math_constants.h>
-
-#include <stdlib.h>
 
 #include <mutex>
 
@@ -31,13 +31,12 @@ namespace {
 
 constexpr int kColorThreads = 128;   // 64 threads (18 warps per SM): 0.56 -> 0.66 ms per 100k nuclei
 // k_hue_batch<NCW>: NCW consumer warps + 1 TMA producer warp; a slab holds <= 256 pixel quads. NCW = 8 (one quad =
-// 4 px per thread, 40 registers) is what is launched: 54 warps per SM instead of the 30 of NCW = 4 (0.665 -> 0.637 ms per
-// 100 000 nuclei), and a lone (chunk, slab) CTA on an SM -- a trait-level call is ONE chunk -- no longer leaves each
-// scheduler with a single warp that issues every fourth cycle (86 -> 66 us per 100 patches). Every pixel adds its
+// 4 px per thread, 40 registers) is what is launched: 45 warps per SM instead of the 30 of NCW = 4 (0.665 -> 0.637 ms per
+// 100 000 nuclei in round 1), and a lone (chunk, slab) CTA on an SM -- a trait-level call is ONE chunk -- no longer leaves
+// each scheduler with a single warp that issues every fourth cycle (86 -> 66 us per 100 patches). Every pixel adds its
 // patches in the same order whatever NCW is, so the results do not depend on it.
 constexpr int kHueMaxQuads = 256;
-constexpr int kHueStages = 8;
-constexpr int kHueChunk = 128;                   // nuclei whose NucInfo is staged in smem at a time
+constexpr int kHueChunk = 128;                   // nuclei whose NucInfo is staged in smem at a time (even: pairs never straddle)
 
 // OD(v) = ln(max(v/255, 1e-6)) / ln(1e-6), f32 (SPEC.md B4); filled once per process.
 __device__ float g_od_lut[256];
@@ -66,29 +65,6 @@ __device__ __forceinline__ float u8f(uint32_t v) {   // exact; compiles to one I
 struct Px {
     uint32_t r, g, b;
 };
-__device__ __forceinline__ Px quad_px(uint32_t w0, uint32_t w1, uint32_t w2, int k) {
-    Px p;
-    switch (k) {
-        case 0: p.r = w0 & 0xff; p.g = (w0 >> 8) & 0xff; p.b = (w0 >> 16) & 0xff; break;
-        case 1: p.r = w0 >> 24; p.g = w1 & 0xff; p.b = (w1 >> 8) & 0xff; break;
-        case 2: p.r = (w1 >> 16) & 0xff; p.g = w1 >> 24; p.b = w2 & 0xff; break;
-        default: p.r = (w2 >> 8) & 0xff; p.g = (w2 >> 16) & 0xff; p.b = w2 >> 24; break;
-    }
-    return p;
-}
-
-// The same four pixels through PRMT (one instruction per byte instead of shift + mask): k_hue_batch's inner loop.
-__device__ __forceinline__ Px quad_px_prmt(uint32_t w0, uint32_t w1, uint32_t w2, int k) {
-    Px p;
-    switch (k) {
-        case 0: p.r = __byte_perm(w0, 0, 0x4440); p.g = __byte_perm(w0, 0, 0x4441); p.b = __byte_perm(w0, 0, 0x4442); break;
-        case 1: p.r = __byte_perm(w0, 0, 0x4443); p.g = __byte_perm(w1, 0, 0x4440); p.b = __byte_perm(w1, 0, 0x4441); break;
-        case 2: p.r = __byte_perm(w1, 0, 0x4442); p.g = __byte_perm(w1, 0, 0x4443); p.b = __byte_perm(w2, 0, 0x4440); break;
-        default: p.r = __byte_perm(w2, 0, 0x4441); p.g = __byte_perm(w2, 0, 0x4442); p.b = __byte_perm(w2, 0, 0x4443); break;
-    }
-    return p;
-}
-
 // Shared-memory loads from a 32-bit shared address kept in a register (a generic pointer to a static __shared__ array is
 // re-derived from SR_CgaCtaId inside the loop otherwise).
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -99,11 +75,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 __device__ __forceinline__ float lds_f32(uint32_t a) {
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));   // read-only table: may be scheduled freely
-    return v;
-}
-__device__ __forceinline__ NucInfo lds_info(uint32_t a) {
-    NucInfo v;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.left), "=r"(v.top), "=r"(v.nvc), "=r"(v.nvr) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t a, uint32_t parity) {
@@ -171,19 +142,6 @@ __device__ __forceinline__ HsvHed convert(const Px& p, const float* lut) {
     o.hed[1] = fmaxf(0.f, a * HED_M01 + b * HED_M11 + c * HED_M21);
     o.hed[2] = fmaxf(0.f, a * HED_M02 + b * HED_M12 + c * HED_M22);
     return o;
-}
-
-// Zero the part of the window the reference never copies (NucInfo comment): rare, warp-uniform.
-__device__ __forceinline__ void zero_uncopied(uint8_t* patch, int P, int o, int nvc, int nvr) {
-    if (nvc >= P && nvr >= P) return;
-    for (int k = threadIdx.x; k < P * P; k += blockDim.x) {
-        const int r = k / P, c = k - r * P;
-        if (r >= nvr || c >= nvc) {
-            const int a = patch_addr(P, o, r, c);
-            patch[a] = 0; patch[a + 1] = 0; patch[a + 2] = 0;
-        }
-    }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -277,6 +235,7 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
                     patch[a] = 0; patch[a + 1] = 0; patch[a + 2] = 0;
                 }
             }
+            fence_proxy_async();   // these generic-proxy stores precede the next slab's TMA (async proxy) write of the same bytes
             __syncthreads();
         }
         if (it == 0) {   // pivots (any value of the right magnitude removes the one-pass cancellation): one thread converts
@@ -374,20 +333,32 @@ k_color(const ColorParams p, const __grid_constant__ CUtensorMap map) {
 //   * while a sub-slab is in flight its mask words are compacted into a list of byte addresses (warp scan);
 //   * pivots come from the first masked pixel; sums are reduced with REDUX / one shuffle tree, the 17 columns are finished by
 //     17 lanes exactly like k_color does.
-// Dynamic smem: per warp { slab[16 * 208] | list[1024] u16 } | lut[256] f32.
 constexpr int kCwWarps = 4, kCwRows = 16;
 constexpr int kCwSlabBytes = kCwRows * kPanelBytes;              // 3328, a multiple of 128
 constexpr int kCwWarpBytes = kCwSlabBytes + kCwRows * 64 * 2;    // + list: 5376
 static_assert(kCwSlabBytes % 128 == 0 && kCwWarpBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
 
+// ------------------------------------------------------------------------------------------------
+// The pixel loop lives on the FMA pipe. On B200 FADD / FMUL / FFMA issue every cycle while
+// ALU-pipe instructions (VIMNMX, ISETP, SEL, IADD3, LEA, I2FP) and IMAD issue every second cycle
+// (scripts/f32x2_probe.cu, profiles/r2_f32x2_probe.txt); the round-1 integer form of this loop spent 50 ALU-pipe cycles per pixel.
+//   * the optical-density table holds {OD(v), (float)v}: one 64-bit load per channel gives both, no conversions;
+//   * max / min are FMNMX3, the sextant select is three predicated FFMAs (as in k_hue_batch), 1/d and 1/max are MUFU.RCP
+//     of the float value plus 1e-30 (d = 0 -> numerator 0 -> 0, the reference's rule for grey pixels);
+//   * the "integer" sums run in f32: a lane sees at most 128 pixels of a 64 x 64 window, so every partial sum stays below
+//     2^24 and is exact; they are converted once and reduced with REDUX as before;
+//   * the pivot is folded into the HED chain: max(y, 0) - pv = max(y - pv, -pv).
+// A packed f32x2 version (two pixels per lane and step, FFMA2 / FADD2) was 5 % SLOWER than the scalar loop: FFMA2 issues every
+// second cycle, so it saves issue slots but no FMA-pipe time, and the ALU pipe stayed the limit (profiles/README.md).
+// Dynamic smem: per warp { slab[16 * 208] | list[1024] u16 } | lut2[256] float2.
 __global__ void __launch_bounds__(32 * kCwWarps, 9)
 k_color_warp(const ColorParams p, const __grid_constant__ CUtensorMap map /* box {208, 16 rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int P = 64;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* lut = reinterpret_cast<float*>(smem_raw + kCwWarps * kCwWarpBytes);
+    float2* lut2 = reinterpret_cast<float2*>(smem_raw + kCwWarps * kCwWarpBytes);
     __shared__ __align__(8) uint64_t s_bar[kCwWarps];
-    for (int k = tid; k < 256; k += 32 * kCwWarps) lut[k] = g_od_lut[k];
+    for (int k = tid; k < 256; k += 32 * kCwWarps) lut2[k] = make_float2(g_od_lut[k], (float)k);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * kCwWarps + warp;
     if (i >= p.n) return;
@@ -406,15 +377,14 @@ k_color_warp(const ColorParams p, const __grid_constant__ CUtensorMap map /* box
 #pragma unroll
     for (int s = 0; s < 4; ++s) w[s] = gm[s * 32 + lane];
     __syncwarp();
-
-    HsvHed pv;
-    pv.h = 0.f; pv.s = 0.f; pv.hed[0] = 0.f; pv.hed[1] = 0.f; pv.hed[2] = 0.f; pv.mx = 0u;
+    float pvh = 0.f, pvs = 0.f, pv0 = 0.f, pv1 = 0.f, pv2 = 0.f;
     bool first = true;
     uint32_t phase = 0;
     int Ktot = 0;
-    uint32_t sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
+    float fr1 = 0.f, fg1 = 0.f, fb1 = 0.f, fr2 = 0.f, fg2 = 0.f, fb2 = 0.f, fv1 = 0.f, fv2 = 0.f;   // exact (< 2^24 per lane)
     float s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};   // hed0, hed1, hed2, s, h (pivoted)
     const int abase = (lane >> 1) * kPanelBytes + (lane & 1) * 96;   // patch_addr(16, 0, lane / 2, 32 * (lane & 1))
+    const uint32_t lut_a = smem_u32(lut2);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         uint32_t bits = w[s];
@@ -452,27 +422,59 @@ k_color_warp(const ColorParams p, const __grid_constant__ CUtensorMap map /* box
                     slab[a] = 0; slab[a + 1] = 0; slab[a + 2] = 0;
                 }
             }
+            fence_proxy_async();   // generic-proxy stores before the next sub-slab's TMA (async proxy) write of the same bytes
             __syncwarp();
         }
         const uint8_t* pbase = slab + o;
         if (first) {   // pivots (any value of the right magnitude removes the one-pass cancellation): the first masked pixel
             const uint8_t* pp = pbase + list[0];
             const Px c = {pp[0], pp[1], pp[2]};
-            pv = convert(c, lut);
+            const HsvHed t = convert(c, g_od_lut);
+            pvh = t.h; pvs = t.s; pv0 = t.hed[0]; pv1 = t.hed[1]; pv2 = t.hed[2];
             first = false;
         }
+        const float n0 = -pv0, n1 = -pv1, n2 = -pv2;
         for (int j = lane; j < K; j += 32) {
             const uint8_t* pp = pbase + list[j];
-            const Px px = {pp[0], pp[1], pp[2]};
-            const HsvHed c = convert(px, lut);
-            sr += px.r; sg += px.g; sb += px.b;
-            srr += px.r * px.r; sgg += px.g * px.g; sbb += px.b * px.b;
-            sv += c.mx; svv += c.mx * c.mx;
-            float d;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { d = c.hed[q] - pv.hed[q]; s1[q] += d; s2[q] = fmaf(d, d, s2[q]); }
-            d = c.s - pv.s; s1[3] += d; s2[3] = fmaf(d, d, s2[3]);
-            d = c.h - pv.h; s1[4] += d; s2[4] = fmaf(d, d, s2[4]);
+            const uint32_t r = pp[0], g = pp[1], b = pp[2];
+            float oa, fr, ob, fg, oc, fb;   // optical density and value of each channel
+            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oa), "=f"(fr) : "r"(lut_a + r * 8u));
+            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ob), "=f"(fg) : "r"(lut_a + g * 8u));
+            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oc), "=f"(fb) : "r"(lut_a + b * 8u));
+            fr1 += fr; fg1 += fg; fb1 += fb;
+            fr2 = fmaf(fr, fr, fr2); fg2 = fmaf(fg, fg, fg2); fb2 = fmaf(fb, fb, fb2);
+            // HED minus pivot: max(y, 0) - pv = max(y - pv, -pv)
+            float d0 = fmaxf(fmaf(oc, HED_M20, fmaf(ob, HED_M10, fmaf(oa, HED_M00, n0))), n0);
+            float d1 = fmaxf(fmaf(oc, HED_M21, fmaf(ob, HED_M11, fmaf(oa, HED_M01, n1))), n1);
+            float d2 = fmaxf(fmaf(oc, HED_M22, fmaf(ob, HED_M12, fmaf(oa, HED_M02, n2))), n2);
+            s1[0] += d0; s2[0] = fmaf(d0, d0, s2[0]);
+            s1[1] += d1; s2[1] = fmaf(d1, d1, s2[1]);
+            s1[2] += d2; s2[2] = fmaf(d2, d2, s2[2]);
+            // HSV
+            const float mx = fmaxf(fr, fmaxf(fg, fb)), mn = fminf(fr, fminf(fg, fb));
+            fv1 += mx; fv2 = fmaf(mx, mx, fv2);
+            const float d = mx - mn;
+            const float rd = rcp_approx(d + 1e-30f), rm = rcp_approx(mx + 1e-30f);
+            float t;   // hue in sextants, wrapped into [0, 6): max = r -> (g-b)/d (+6 if negative) ; g -> 2 + (b-r)/d ; b -> 4 + (r-g)/d
+            asm("{\n"
+                ".reg .pred pr, pg, pn;\n"
+                ".reg .f32 gb, br, rg;\n"
+                "sub.f32 gb, %2, %3;\n"
+                "sub.f32 br, %3, %1;\n"
+                "sub.f32 rg, %1, %2;\n"
+                "setp.eq.f32 pr, %4, %1;\n"
+                "setp.eq.f32 pg, %4, %2;\n"
+                "setp.lt.and.f32 pn, gb, 0f00000000, pr;\n"
+                "fma.rn.f32 %0, rg, %5, 0f40800000;\n"        // 4
+                "@pg fma.rn.f32 %0, br, %5, 0f40000000;\n"    // 2
+                "@pr mul.f32 %0, gb, %5;\n"
+                "@pn add.f32 %0, %0, 0f40C00000;\n"           // + 6
+                "}\n"
+                : "=&f"(t)
+                : "f"(fr), "f"(fg), "f"(fb), "f"(mx), "f"(rd));
+            const float dh = fmaf(t, 60.0f, -pvh), ds = fmaf(d, rm, -pvs);
+            s1[3] += ds; s2[3] = fmaf(ds, ds, s2[3]);
+            s1[4] += dh; s2[4] = fmaf(dh, dh, s2[4]);
         }
         __syncwarp();   // slab and list are reused by the next sub-slab
     }
@@ -480,234 +482,15 @@ k_color_warp(const ColorParams p, const __grid_constant__ CUtensorMap map /* box
     uint32_t* fi = reinterpret_cast<uint32_t*>(list);
     float* ff = reinterpret_cast<float*>(list) + 8;
     {
-        const uint32_t vi[8] = {sr, sg, sb, srr, sgg, sbb, sv, svv};
+        const float vf[8] = {fr1, fg1, fb1, fr2, fg2, fb2, fv1, fv2};
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint32_t t = __reduce_add_sync(0xffffffffu, vi[q]);
+            const uint32_t t = __reduce_add_sync(0xffffffffu, (uint32_t)__float2int_rn(vf[q]));
             if (lane == 0) fi[q] = t;
         }
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
             const float a = warp_sum(s1[q]), b = warp_sum(s2[q]);
-            if (lane == 0) { ff[q] = a; ff[5 + q] = b; }
-        }
-    }
-    __syncwarp();
-    // ---- 17 columns, one lane each (out[6] = mean_h belongs to k_hue_finalize); same f64 expressions as k_color ----
-    if (lane < 18 && lane != 6) {
-        static const int ia[18] = {1, 2, 3, 1, 2, 3, 0, 12, 7, 13, 12, 7, 9, 10, 11, 9, 10, 11};
-        static const int ib[18] = {0, 0, 0, 4, 5, 6, 0, 0, 0, 18, 17, 8, 0, 0, 0, 14, 15, 16};
-        auto fetch = [&](int q) -> double { return q <= 8 ? (double)fi[q - 1] : (double)ff[q - 9]; };   // q in 1..18
-        const int a = ia[lane], b = ib[lane];
-        const bool is_std = b != 0;
-        const bool is8 = a <= 8;                                   // u8-valued channel: scale by 1/255
-        const float pivf = lane == 7 ? pv.s : (lane == 12 ? pv.hed[0] : (lane == 13 ? pv.hed[1] : (lane == 14 ? pv.hed[2] : 0.f)));
-        const double Kd = (double)Ktot;
-        const double m = fetch(a) / Kd;
-        double val = (double)pivf + m;
-        if (is_std) val = sqrt(fmax(fetch(b) / Kd - m * m, 0.0));
-        float* out = p.out + i * (int64_t)p.out_stride + p.col_color;
-        out[lane] = (float)(is8 ? val / 255.0 : val);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Packed f32x2 arithmetic (sm_100 FFMA2 / FADD2): one issue slot for two pixels. k_color_warp is issue bound (82 % issue
-// active, round-1 ncu), and 24 of the 74 instructions of its pixel loop are FADD / FMUL / FFMA.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 bcast2(float v) { return pack2(v, v); }
-
-// k_color_warp2: k_color_warp with TWO masked pixels per lane and loop step, so that every float operation of the loop is one
-// packed f32x2 instruction for both pixels (HED matrix, pivot subtraction, the ten running sums) and the integer sums
-// take both pixels in one IADD3. The pivot is folded into the HED chain (max(y, 0) - pv = max(y - pv, -pv)). A sub-slab with
-// an odd number of masked pixels gets one dummy list entry that points at a copy of the PIVOT pixel kept next to the slab:
-// its pivoted float terms are exactly zero and its integer terms are subtracted once at the end.
-// Dynamic smem: per warp { slab[16 * 208] | pivot pixel (16 B) | list[1024 + 2] u16 } | lut[256] f32.
-constexpr int kCw2PivBytes = 16;
-constexpr int kCw2WarpBytes = ((kCwSlabBytes + kCw2PivBytes + (kCwRows * 64 + 2) * 2) + 127) & ~127;
-static_assert(kCw2WarpBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
-
-__global__ void __launch_bounds__(32 * kCwWarps, 7)
-k_color_warp2(const ColorParams p, const __grid_constant__ CUtensorMap map /* box {208, 16 rows} */) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int P = 64;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* lut = reinterpret_cast<float*>(smem_raw + kCwWarps * kCw2WarpBytes);
-    __shared__ __align__(8) uint64_t s_bar[kCwWarps];
-    for (int k = tid; k < 256; k += 32 * kCwWarps) lut[k] = g_od_lut[k];
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * kCwWarps + warp;
-    if (i >= p.n) return;
-
-    uint8_t* slab = smem_raw + warp * kCw2WarpBytes;
-    uint8_t* pivpx = slab + kCwSlabBytes;
-    uint16_t* list = reinterpret_cast<uint16_t*>(slab + kCwSlabBytes + kCw2PivBytes);   // 4-byte aligned
-    uint64_t* bar = &s_bar[warp];
-    const NucInfo inf = p.info[i];
-    const int o = patch_byte_offset(inf.left);
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
-    const uint32_t* gm = p.bitmask + i * (int64_t)(P * 2);
-    uint32_t w[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) w[s] = gm[s * 32 + lane];
-    __syncwarp();
-
-    float pvh = 0.f, pvs = 0.f, pv0 = 0.f, pv1 = 0.f, pv2 = 0.f;
-    Px ppx = {0u, 0u, 0u};
-    uint32_t pmx = 0u;
-    bool first = true;
-    uint32_t phase = 0;
-    int Ktot = 0, ndummy = 0;
-    uint32_t sr = 0, sg = 0, sb = 0, srr = 0, sgg = 0, sbb = 0, sv = 0, svv = 0;
-    f32x2 a1[5], a2[5];   // hed0, hed1, hed2, s, h (pivoted), one running sum per pixel of the pair
-#pragma unroll
-    for (int q = 0; q < 5; ++q) { a1[q] = 0ull; a2[q] = 0ull; }
-    const int abase = (lane >> 1) * kPanelBytes + (lane & 1) * 96;   // patch_addr(16, 0, lane / 2, 32 * (lane & 1))
-    const uint32_t lut_a = smem_u32(lut);
-#pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
-        uint32_t bits = w[s];
-        if (!__any_sync(0xffffffffu, bits != 0u)) continue;   // warp-uniform: no masked pixel in these 16 rows
-        const int row0 = s * kCwRows;
-        if (lane == 0) {
-            mbar_expect_tx(bar, (uint32_t)kCwSlabBytes);
-            tma_load_window(slab, &map, inf.left, inf.top + row0, P, kCwRows, bar);
-        }
-        // ---- while the sub-slab is in flight: compact its 32 mask words into a list of byte addresses ----
-        const int cnt = __popc(bits);
-        int incl = cnt;
-#pragma unroll
-        for (int o2 = 1; o2 < 32; o2 <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o2);
-            if (lane >= o2) incl += t;
-        }
-        const int K = __shfl_sync(0xffffffffu, incl, 31);
-        int pos = incl - cnt;
-        while (bits) {
-            const int c = __ffs(bits) - 1;
-            bits &= bits - 1;
-            list[pos++] = (uint16_t)(abase + 3 * c);
-        }
-        const int Kpad = (K + 1) & ~1;
-        if (lane == 0 && (K & 1)) list[K] = (uint16_t)(kCwSlabBytes - o);   // dummy entry: the pivot pixel's copy
-        ndummy += K & 1;
-        Ktot += K;
-        __syncwarp();   // list visible
-        while (!mbar_try_wait(bar, phase)) {
-        }
-        phase ^= 1u;
-        if (inf.nvc < P || inf.nvr < row0 + kCwRows) {   // rare: part of the window is never copied (NucInfo)
-            for (int k = lane; k < kCwRows * P; k += 32) {
-                const int r = k >> 6, c = k & 63;
-                if (row0 + r >= inf.nvr || c >= inf.nvc) {
-                    const int a = patch_addr(kCwRows, o, r, c);
-                    slab[a] = 0; slab[a + 1] = 0; slab[a + 2] = 0;
-                }
-            }
-            __syncwarp();
-        }
-        const uint8_t* pbase = slab + o;
-        if (first) {   // pivots (any value of the right magnitude removes the one-pass cancellation): the first masked pixel
-            const uint8_t* pp = pbase + list[0];
-            ppx.r = pp[0]; ppx.g = pp[1]; ppx.b = pp[2];
-            const HsvHed c = convert(ppx, lut);
-            pvh = c.h; pvs = c.s; pv0 = c.hed[0]; pv1 = c.hed[1]; pv2 = c.hed[2]; pmx = c.mx;
-            __syncwarp();
-            if (lane == 0) { pivpx[0] = (uint8_t)ppx.r; pivpx[1] = (uint8_t)ppx.g; pivpx[2] = (uint8_t)ppx.b; }
-            __syncwarp();
-            first = false;
-        }
-        const f32x2 npv0 = bcast2(-pv0), npv1 = bcast2(-pv1), npv2 = bcast2(-pv2), npvs = bcast2(-pvs), npvh = bcast2(-pvh);
-        const uint32_t pb_a = smem_u32(pbase);
-        for (int j = 2 * lane; j < Kpad; j += 64) {
-            const uint32_t le = *reinterpret_cast<const uint32_t*>(list + j);   // two byte addresses
-            const uint32_t aa = pb_a + (le & 0xffffu), ab = pb_a + (le >> 16);
-            uint32_t rA, gA, bA, rB, gB, bB;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(rA) : "r"(aa));
-            asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(gA) : "r"(aa));
-            asm volatile("ld.shared.u8 %0, [%1+2];" : "=r"(bA) : "r"(aa));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(rB) : "r"(ab));
-            asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(gB) : "r"(ab));
-            asm volatile("ld.shared.u8 %0, [%1+2];" : "=r"(bB) : "r"(ab));
-            // ---- exact integer sums ----
-            sr += rA + rB; sg += gA + gB; sb += bA + bB;
-            srr += rA * rA; srr += rB * rB; sgg += gA * gA; sgg += gB * gB; sbb += bA * bA; sbb += bB * bB;
-            // ---- HED: optical densities from the table, 3x3 matrix, clamp, pivoted sums ----
-            const f32x2 oa = pack2(lds_f32(lut_a + rA * 4u), lds_f32(lut_a + rB * 4u));
-            const f32x2 ob = pack2(lds_f32(lut_a + gA * 4u), lds_f32(lut_a + gB * 4u));
-            const f32x2 oc = pack2(lds_f32(lut_a + bA * 4u), lds_f32(lut_a + bB * 4u));
-            {
-                f32x2 t0 = fma2(oa, bcast2(HED_M00), npv0), t1 = fma2(oa, bcast2(HED_M01), npv1), t2 = fma2(oa, bcast2(HED_M02), npv2);
-                t0 = fma2(ob, bcast2(HED_M10), t0); t1 = fma2(ob, bcast2(HED_M11), t1); t2 = fma2(ob, bcast2(HED_M12), t2);
-                t0 = fma2(oc, bcast2(HED_M20), t0); t1 = fma2(oc, bcast2(HED_M21), t1); t2 = fma2(oc, bcast2(HED_M22), t2);
-                float x, y;
-                unpack2(t0, x, y); t0 = pack2(fmaxf(x, -pv0), fmaxf(y, -pv0));   // max(hed, 0) - pv
-                unpack2(t1, x, y); t1 = pack2(fmaxf(x, -pv1), fmaxf(y, -pv1));
-                unpack2(t2, x, y); t2 = pack2(fmaxf(x, -pv2), fmaxf(y, -pv2));
-                a1[0] = add2(a1[0], t0); a2[0] = fma2(t0, t0, a2[0]);
-                a1[1] = add2(a1[1], t1); a2[1] = fma2(t1, t1, a2[1]);
-                a1[2] = add2(a1[2], t2); a2[2] = fma2(t2, t2, a2[2]);
-            }
-            // ---- HSV ----
-            const uint32_t mxA = max(rA, max(gA, bA)), mnA = min(rA, min(gA, bA)), dA = mxA - mnA;
-            const uint32_t mxB = max(rB, max(gB, bB)), mnB = min(rB, min(gB, bB)), dB = mxB - mnB;
-            sv += mxA + mxB; svv += mxA * mxA; svv += mxB * mxB;
-            const f32x2 dd = pack2(u8f(dA), u8f(dB));
-            const f32x2 rmx = pack2(rcp_approx(u8f(max(mxA, 1u))), rcp_approx(u8f(max(mxB, 1u))));
-            const f32x2 ds = fma2(dd, rmx, npvs);
-            a1[3] = add2(a1[3], ds); a2[3] = fma2(ds, ds, a2[3]);
-            const Px pA = {rA, gA, bA}, pB = {rB, gB, bB};
-            // 60 * hue_sextant<true>: t = num / d + offs, wrapped into [0, 6)
-            float tA = hue_sextant<true>(pA, mxA, dA), tB = hue_sextant<true>(pB, mxB, dB);
-            const f32x2 dh = fma2(pack2(tA, tB), bcast2(60.0f), npvh);
-            a1[4] = add2(a1[4], dh); a2[4] = fma2(dh, dh, a2[4]);
-        }
-        __syncwarp();   // slab and list are reused by the next sub-slab
-    }
-    // ---- sums: every lane ends up with every total; lane 0 parks them in the (dead) list for the column lanes ----
-    uint32_t* fi = reinterpret_cast<uint32_t*>(list);
-    float* ff = reinterpret_cast<float*>(list) + 8;
-    {
-        const uint32_t vi[8] = {sr, sg, sb, srr, sgg, sbb, sv, svv};
-        // the dummy entries added the pivot pixel ndummy times
-        const uint32_t dm[8] = {ppx.r, ppx.g, ppx.b, ppx.r * ppx.r, ppx.g * ppx.g, ppx.b * ppx.b, pmx, pmx * pmx};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t t = __reduce_add_sync(0xffffffffu, vi[q]);
-            if (lane == 0) fi[q] = t - (uint32_t)ndummy * dm[q];
-        }
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            float x, y, u, v;
-            unpack2(a1[q], x, y);
-            unpack2(a2[q], u, v);
-            const float a = warp_sum(x + y), b = warp_sum(u + v);
             if (lane == 0) { ff[q] = a; ff[5 + q] = b; }
         }
     }
@@ -731,226 +514,11 @@ k_color_warp2(const ColorParams p, const __grid_constant__ CUtensorMap map /* bo
 }
 
 // ------------------------------------------------------------------------------------------------
-// grid = (n_batches, slabs). Dynamic smem: ring[kHueStages][panels*208*R] | Cs[R*wpr*33] | Ss[R*wpr*33] f32.
-template <int NCW>
-__global__ void __launch_bounds__(32 * NCW + 32)
-k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R) {
-    constexpr int kHueConsumers = 32 * NCW, kHueThreads = kHueConsumers + 32, kHueQpt = kHueMaxQuads / kHueConsumers;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int P = p.P, wpr = mask_wpr(P), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int stage_bytes = window_smem_bytes(P, R);
-    const uint32_t stage_tx = (uint32_t)(patch_panels(P) * kPanelBytes * R);
-    const int64_t b0 = (int64_t)blockIdx.x * p.batch_size;
-    const int nb = (int)min((int64_t)p.batch_size, p.n - b0);
-    const int slab = blockIdx.y, row0 = slab * R;
-    uint8_t* ring = smem_raw;
-    float* Cs = reinterpret_cast<float*>(smem_raw + (size_t)kHueStages * stage_bytes);
-    // (C, S) images: one 33-float row per 32-pixel mask word, so that the fold's lanes (one mask word each) hit
-    // different banks when they read the same bit position (a P-float pitch put them all on one bank)
-    float* Ss = Cs + R * wpr * 33;
-    __shared__ __align__(8) uint64_t full[kHueStages], empty[kHueStages];
-    __shared__ NucInfo s_info[kHueChunk];
-
-    // ---- union of the chunk's masks over this slab: mean_h only ever reads C, S under some mask of the batch, so
-    //      pixel quads outside the union are never evaluated (44 % of a 64 x 64 window for the bench's nuclei,
-    //      far more for small nuclei). Active quads are compacted and dealt to the consumer threads. ----
-    __shared__ uint32_t s_union[64];
-    __shared__ uint16_t s_qlist[kHueMaxQuads];
-    __shared__ int s_nact;
-    // (pi/3) / d for d = max - min in 1..255 ([0] is never multiplied by a non-zero numerator): one LDS instead of
-    // I2FP + MUFU.RCP + FMUL per pixel
-    __shared__ float s_rcp[256];
-    for (int k = tid; k < 256; k += kHueThreads) s_rcp[k] = k ? __fdiv_rn(1.0471975511965976f, (float)k) : 0.f;
-    const int qpr = P >> 2, nquads = R * qpr;
-    const int nrows_u = min(R, P - row0), words_u = nrows_u * wpr;
-    if (tid < 64) s_union[tid] = 0u;
-    __syncthreads();
-    for (int idx = tid; idx < nb * words_u; idx += kHueThreads) {
-        const int j = idx / words_u, w = idx - j * words_u;
-        const uint32_t v = p.bitmask[((b0 + j) * (int64_t)P + row0) * wpr + w];
-        if (v) atomicOr(&s_union[w], v);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int cnt = 0;
-        for (int base = 0; base < nquads; base += 32) {
-            const int q = base + lane, r = q / qpr, c = (q - r * qpr) * 4;
-            const bool act = q < nquads && r < nrows_u && ((s_union[r * wpr + (c >> 5)] >> (c & 31)) & 0xFu) != 0u;
-            const uint32_t b = __ballot_sync(0xffffffffu, act);
-            if (act) s_qlist[cnt + __popc(b & ((1u << lane) - 1u))] = (uint16_t)q;
-            cnt += __popc(b);
-        }
-        if (lane == 0) s_nact = cnt;
-    }
-    __syncthreads();
-    const int nact = s_nact;
-    if (nact == 0) {   // no nucleus of the chunk has a masked pixel in this slab
-        for (int i = tid; i < nb; i += kHueThreads) {
-            float* hp = p.hue_partial + ((b0 + i) * (int64_t)p.slabs + slab) * 2;
-            hp[0] = 0.f;
-            hp[1] = 0.f;
-        }
-        return;
-    }
-    const int nwarps_act = min(kHueConsumers / 32, (nact + 31) / 32);   // consumer warps that own at least one quad
-    if (tid == 0) {
-        for (int s = 0; s < kHueStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps_act); }
-        mbar_fence_init();
-    }
-    // consumer pixel ownership: active quads tid and tid + 128 of the compacted list (4 px each)
-    bool owner[kHueQpt];
-    int rr[kHueQpt], c0[kHueQpt], soff[kHueQpt];
-#pragma unroll
-    for (int u = 0; u < kHueQpt; ++u) {
-        const int k = tid + u * kHueConsumers;
-        owner[u] = (tid < kHueConsumers) && (k < nact);
-        const int q = owner[u] ? (int)s_qlist[k] : 0;
-        rr[u] = q / qpr;
-        c0[u] = (q - rr[u] * qpr) * 4;
-        soff[u] = (c0[u] >> 6) * panel_stride(R) + rr[u] * kPanelBytes + (c0[u] & 63) * 3;   // + o per nucleus
-        asm volatile("" : "+r"(soff[u]));   // keep it in a register: recomputing it costs 12 instructions per patch
-    }
-    const int nq_w = (warp < NCW) ? ((warp * 32 < nact) + (kHueQpt > 1 && kHueConsumers + warp * 32 < nact)) : 0;   // warp-uniform
-    float C[kHueQpt][4], S[kHueQpt][4];
-#pragma unroll
-    for (int u = 0; u < kHueQpt; ++u)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { C[u][k] = 0.f; S[u][k] = 0.f; }
-
-    // 32-bit shared addresses of everything the consumer loop touches, pinned in registers
-    uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), info_a = smem_u32(s_info), ring_a = smem_u32(ring),
-             rcp_a = smem_u32(s_rcp);
-    asm volatile("" : "+r"(full_a), "+r"(empty_a), "+r"(info_a), "+r"(ring_a), "+r"(rcp_a));
-
-    int it = 0;   // global iteration counter over the batch's nuclei (ring position)
-    for (int base = 0; base < nb; base += kHueChunk) {
-        const int cnt = min(kHueChunk, nb - base);
-        __syncthreads();   // previous chunk fully consumed before s_info is overwritten
-        for (int k = tid; k < cnt; k += kHueThreads) s_info[k] = p.info[b0 + base + k];
-        __syncthreads();
-        if (warp == kHueConsumers / 32) {
-            // ---- TMA producer warp (one elected lane) ----
-            if (lane == 0) {
-                for (int j = 0; j < cnt; ++j) {
-                    const int g = it + j, s = g % kHueStages, ph = (g / kHueStages) & 1;
-                    if (g >= kHueStages) mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], stage_tx);
-                    const NucInfo inf = s_info[j];
-                    tma_load_window(ring + (size_t)s * stage_bytes, &map, inf.left, inf.top + row0, P, R, &full[s]);
-                }
-            }
-        } else if (nq_w > 0) {
-            uint32_t g = (uint32_t)it, ia = info_a;
-            for (int j = 0; j < cnt; ++j, ++g, ia += (uint32_t)sizeof(NucInfo)) {
-                const uint32_t s = g % kHueStages, ph = (g / kHueStages) & 1u;
-                while (!mbar_try_wait_a(full_a + s * 8u, ph)) {
-                }
-                const NucInfo inf = lds_info(ia);
-                // soff is a multiple of 4, so the word alignment and the funnel shift depend on the nucleus only
-                const uint32_t ob = (uint32_t)patch_byte_offset(inf.left);
-                const uint32_t sb = ring_a + s * (uint32_t)stage_bytes + (ob & ~3u);
-                const uint32_t sh = (ob & 3u) * 8u;
-                uint32_t w[kHueQpt][3];
-#pragma unroll
-                for (int u = 0; u < kHueQpt; ++u) {
-                    w[u][0] = w[u][1] = w[u][2] = 0u;
-                    if (owner[u]) {
-                        const uint32_t wa = sb + (uint32_t)soff[u];   // 4-byte aligned
-                        const uint32_t a0 = lds_u32(wa), a1 = lds_u32(wa + 4), a2 = lds_u32(wa + 8), a3 = lds_u32(wa + 12);
-                        w[u][0] = __funnelshift_r(a0, a1, sh);
-                        w[u][1] = __funnelshift_r(a1, a2, sh);
-                        w[u][2] = __funnelshift_r(a2, a3, sh);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(empty_a + s * 8u);
-                if (inf.nvc < P || inf.nvr < P) {   // rare: window partly never copied (NucInfo)
-#pragma unroll
-                    for (int u = 0; u < kHueQpt; ++u) {
-                        const bool rowdead = (row0 + rr[u]) >= inf.nvr;
-                        const int nlive = rowdead ? 0 : min(max(inf.nvc - c0[u], 0), 4);   // live pixels of the quad
-                        const int nbytes = 3 * nlive;   // pixel k occupies bytes 3k..3k+2 of the 12-byte quad
-                        w[u][0] = nbytes >= 4 ? w[u][0] : (nbytes > 0 ? (w[u][0] & ((1u << (8 * nbytes)) - 1u)) : 0u);
-                        w[u][1] = nbytes >= 8 ? w[u][1] : (nbytes > 4 ? (w[u][1] & ((1u << (8 * (nbytes - 4))) - 1u)) : 0u);
-                        w[u][2] = nbytes >= 12 ? w[u][2] : (nbytes > 8 ? (w[u][2] & ((1u << (8 * (nbytes - 8))) - 1u)) : 0u);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kHueQpt; ++u) {
-                    if (u >= nq_w) break;   // warp-uniform: this warp has no second quad
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const Px px = quad_px_prmt(w[u][0], w[u][1], w[u][2], k);
-                        const uint32_t mx = max(px.r, max(px.g, px.b)), mn = min(px.r, min(px.g, px.b));
-                        // h = 60 t degrees = t * pi/3 radians (no wrap needed under sin/cos); d = 0 -> numerator 0 -> angle 0
-                        const bool isr = (mx == px.r), isg = (mx == px.g);
-                        const int gb = (int)px.g - (int)px.b, br = (int)px.b - (int)px.r, rg = (int)px.r - (int)px.g;
-                        const int num = isr ? gb : (isg ? br : rg);
-                        const float offs = isr ? 0.0f : (isg ? 2.0943951023931953f : 4.1887902047863905f);
-                        const float ang = fmaf((float)num, lds_f32(rcp_a + (mx - mn) * 4u), offs);
-                        C[u][k] += __cosf(ang);
-                        S[u][k] += __sinf(ang);
-                    }
-                }
-            }
-        }
-        it += cnt;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kHueQpt; ++u) {
-        if (!owner[u]) continue;   // non-owners accumulated cos(0) = 1 of zero words: never stored
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (c0[u] + k < P) {
-                const int a = (rr[u] * wpr + (c0[u] >> 5)) * 33 + (c0[u] & 31) + k;
-                Cs[a] = C[u][k];
-                Ss[a] = S[u][k];
-            }
-        }
-    }
-    __syncthreads();
-    // ---- masked sums of the slab's (S, C) image under each nucleus' mask. Four nuclei per warp pass: their mask words
-    //      are fetched together, so the L2 latency of the (cold) bitmask is paid once per four nuclei ----
-    const int nrows = min(R, P - row0), words = nrows * wpr;
-    constexpr int NWARP = kHueThreads / 32, UN = 4;
-    for (int i0 = warp * UN; i0 < nb; i0 += NWARP * UN) {
-        float ss[UN], sc[UN];
-#pragma unroll
-        for (int q = 0; q < UN; ++q) { ss[q] = 0.f; sc[q] = 0.f; }
-        for (int w = lane; w < words; w += 32) {
-            uint32_t bits[UN];
-#pragma unroll
-            for (int q = 0; q < UN; ++q)
-                bits[q] = (i0 + q < nb) ? p.bitmask[((b0 + i0 + q) * (int64_t)P + row0) * wpr + w] : 0u;
-            const float *Sw = Ss + w * 33, *Cw = Cs + w * 33;
-#pragma unroll
-            for (int q = 0; q < UN; ++q) {
-                uint32_t b = bits[q];
-                while (b) {
-                    const int c = __ffs(b) - 1;
-                    b &= b - 1;
-                    ss[q] += Sw[c];
-                    sc[q] += Cw[c];
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < UN; ++q) {
-            const float s1 = warp_sum(ss[q]), c1 = warp_sum(sc[q]);
-            if (lane == 0 && i0 + q < nb) {
-                float* hp = p.hue_partial + ((b0 + i0 + q) * (int64_t)p.slabs + slab) * 2;
-                hp[0] = s1;
-                hp[1] = c1;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_hue_batch2: same decomposition as k_hue_batch (one CTA per (chunk, row slab), a TMA producer warp, 8 consumer warps that
-// own one pixel quad of the union each), with the per-patch fixed work cut down (ncu, round 2: 44 of the 139 instructions per
-// patch and warp were ring / barrier / address work, the masked fold was 12.5 % of the kernel, producer spinning 4.4 %):
+// k_hue_batch: grid = (n_batches, slabs); one CTA per (chunk, row slab), a TMA producer warp, 8 consumer warps that own one
+// pixel quad of the union of the chunk's masks each (mean_h only ever reads C, S under some mask of the batch, so quads outside
+// the union are never evaluated: 44 % of a 64 x 64 window for the bench's nuclei). Round 2 cut the per-patch fixed work
+// (ncu: 44 of the 139 instructions per patch and warp were ring / barrier / address work, the masked fold was 12.5 % of the
+// kernel, producer spinning 4.4 %):
 //   * a ring stage holds TWO patches: one mbarrier wait, one arrive and one loop step per pair of patches;
 //   * the per-patch constants of the quad loads (word offset, funnel shift, "window partly uncopied") are packed into one
 //     u32 when the chunk's NucInfo is staged; every lane of an active warp computes (lanes without a quad re-read quad 0
@@ -963,7 +531,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
 constexpr int kHue2Stages = 4;
 template <int NCW>
 __global__ void __launch_bounds__(32 * NCW + 32, 5)
-k_hue_batch2(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R, const int fix_shift) {
+k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const int R, const int fix_shift) {
     constexpr int kConsumers = 32 * NCW, kThreads = kConsumers + 32;
     static_assert(kConsumers == kHueMaxQuads, "one quad per consumer thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1283,37 +851,21 @@ cudaError_t launch_color(const ColorParams& p, const CUtensorMap* map, cudaStrea
 }
 
 // P = 64 only; `map_slab` is the {208 B, 16 rows} slab map (hue_slab_rows(64) == 16) that k_hue_batch uses too.
-static int color_warp_version() {
-    static const int v = [] { const char* e = getenv("NFX_CW_V"); return e ? atoi(e) : 1; }();
-    return v;
-}
-
 cudaError_t launch_color_warp(const ColorParams& p, const CUtensorMap* map_slab, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
     if (p.P != 64 || hue_slab_rows(64) != kCwRows) return cudaErrorInvalidValue;
     cudaError_t e = ensure_lut(s);
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((p.n + kCwWarps - 1) / kCwWarps);
-    if (color_warp_version() == 1) {
-        const int smem = kCwWarps * kCwWarpBytes + 256 * 4;
-        k_color_warp<<<grid, 32 * kCwWarps, smem, s>>>(p, *map_slab);
-    } else {
-        const int smem = kCwWarps * kCw2WarpBytes + 256 * 4;
-        k_color_warp2<<<grid, 32 * kCwWarps, smem, s>>>(p, *map_slab);
-    }
+    const int smem = kCwWarps * kCwWarpBytes + 256 * 8;
+    k_color_warp<<<(unsigned)((p.n + kCwWarps - 1) / kCwWarps), 32 * kCwWarps, smem, s>>>(p, *map_slab);
     return cudaGetLastError();
 }
 
-// Largest shift with batch * P * 2^shift < 2^31 (the row prefix sums of k_hue_batch2 are int32), at most 18.
+// Largest shift with batch * P * 2^shift < 2^31 (the row prefix sums of k_hue_batch are int32), at most 18.
 static int hue_fix_shift(int64_t nb, int P) {
     int sh = 18;
     while (sh > 0 && (double)nb * P * (double)(1u << sh) >= 2147483648.0) --sh;
     return sh;
-}
-
-static int hue_version() {
-    static const int v = [] { const char* e = getenv("NFX_HUE_V"); return e ? atoi(e) : 2; }();
-    return v;
 }
 
 cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, int R, cudaStream_t s) {
@@ -1321,21 +873,13 @@ cudaError_t launch_hue_batch(const ColorParams& p, const CUtensorMap* map_slab, 
     const int64_t nbatch = (p.n + p.batch_size - 1) / p.batch_size;
     dim3 grid((unsigned)nbatch, (unsigned)p.slabs);
     const int64_t nbmax = p.n < p.batch_size ? p.n : p.batch_size;
-    if (hue_version() == 1 || (double)nbmax * p.P >= 2147483648.0) {
-        const int smem = kHueStages * window_smem_bytes(p.P, R) + 2 * R * mask_wpr(p.P) * 33 * 4;
-        if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
-            cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-        }
-        k_hue_batch<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R);
-        return cudaGetLastError();
-    }
+    if ((double)nbmax * p.P >= 2147483648.0) return cudaErrorInvalidValue;   // a chunk of > 2^31 / P nuclei
     const int smem = kHue2Stages * 2 * window_smem_bytes(p.P, R) + R * (p.P + 2) * (int)sizeof(int2);
-    if (smem > 32 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_hue_batch2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
+        cudaError_t e = cudaFuncSetAttribute(k_hue_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    k_hue_batch2<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R, hue_fix_shift(nbmax, p.P));
+    k_hue_batch<8><<<grid, 32 * 8 + 32, smem, s>>>(p, *map_slab, R, hue_fix_shift(nbmax, p.P));
     return cudaGetLastError();
 }
 

@@ -217,6 +217,22 @@ class Extractor:
         self._ck(lib().nfx_slide_write_tile(self._h, _ptr(rgb), int(x0), int(y0), rgb.shape[1], rgb.shape[0],
                                             rgb.strides[0]))
 
+    # -- one slide on several GPUs (include/nfx.h: nfx_slide_export / import_rows / copy_rows) --
+    def slide_export(self) -> bytes:
+        """Handle of this context's slide for another PROCESS (CUDA IPC): 96 bytes, send them by any host mechanism."""
+        h = np.zeros(96, dtype=np.uint8)
+        self._ck(lib().nfx_slide_export(self._h, _ptr(h)))
+        return h.tobytes()
+
+    def slide_import_rows(self, handle: bytes, y0: int, rows: int):
+        """Rows [y0, y0 + rows) of the peer's slide -> this context's slide, device to device (NVLink between GPUs)."""
+        h = np.frombuffer(handle, dtype=np.uint8).copy()
+        self._ck(lib().nfx_slide_import_rows(self._h, _ptr(h), int(y0), int(rows)))
+
+    def slide_copy_rows(self, src: "Extractor", y0: int, rows: int):
+        """Same transfer between two contexts of one process."""
+        self._ck(lib().nfx_slide_copy_rows(self._h, src._h, int(y0), int(rows)))
+
     def upload_polygons(self, poly_xy, poly_off):
         poly_xy = np.ascontiguousarray(poly_xy, dtype=np.float32)
         poly_off = np.ascontiguousarray(poly_off, dtype=np.int64)

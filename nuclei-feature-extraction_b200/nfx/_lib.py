@@ -37,6 +37,9 @@ SYMBOLS = {
     "nfx_tile_upload": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64]),
     "nfx_slide_alloc": (_i, [_vp, _i64, _i64, _i64, _i64]),
     "nfx_slide_write_tile": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64]),
+    "nfx_slide_export": (_i, [_vp, _vp]),
+    "nfx_slide_import_rows": (_i, [_vp, _vp, _i64, _i64]),
+    "nfx_slide_copy_rows": (_i, [_vp, _vp, _i64, _i64]),
     "nfx_polygons_upload": (_i, [_vp, _i64, _vp, _vp]),
     "nfx_compute": (_i, [_vp, _u32]),
     "nfx_download": (_i, [_vp, _vp, _vp]),

@@ -78,5 +78,29 @@ def synth_polygons(n: int, h: int, w: int, seed: int = 1, patch: int = 64, r0_ra
     return xy, off
 
 
+def synth_polygons_pool(n: int, h: int, w: int, seed: int = 1, patch: int = 64, pool: int = 200_000, **kw):
+    """Same rings as synth_polygons for the first `pool` nuclei; nucleus i >= pool re-uses the SHAPE of nucleus i % pool at
+    a fresh uniformly random centre (features are independent per nucleus, so millions of nuclei do not need millions of
+    distinct shapes: 5M rings take ~3 s instead of ~40 s of host time). Returns (poly_xy f32, poly_off int64)."""
+    if n <= pool:
+        return synth_polygons(n, h, w, seed, patch=patch, **kw)
+    bxy, boff = synth_polygons(pool, h, w, seed, patch=patch, **kw)
+    lens = np.diff(boff)
+    # shape relative to its first vertex-mean (float64), so that it can be moved
+    cen = np.add.reduceat(bxy.astype(np.float64), boff[:-1], axis=0) / lens[:, None]
+    rel = bxy.astype(np.float64) - np.repeat(cen, lens, axis=0)
+    rng = np.random.default_rng(seed + 104729)
+    m = patch / 2 + 1
+    blocks, offs, base = [bxy], [boff[1:]], int(boff[-1])
+    for k in range(pool, n, pool):
+        cnt = min(pool, n - k)
+        nv = int(boff[cnt])
+        c = np.stack([rng.uniform(m, max(w - m, m + 1), size=cnt), rng.uniform(m, max(h - m, m + 1), size=cnt)], axis=1)
+        blocks.append((rel[:nv] + np.repeat(c, lens[:cnt], axis=0)).astype(np.float32))
+        offs.append(boff[1:cnt + 1] + base)
+        base += nv
+    return np.concatenate(blocks), np.concatenate([np.zeros(1, np.int64)] + offs)
+
+
 def rings_of(poly_xy, poly_off):
     return [poly_xy[poly_off[i]:poly_off[i + 1]] for i in range(len(poly_off) - 1)]

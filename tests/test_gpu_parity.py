@@ -527,3 +527,71 @@ print("ok")
 """
     r = subprocess.run([sys.executable, "-c", code, pkg], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_slide_shared_between_contexts_is_byte_identical(case):
+    """BASELINE config 4 placement (include/nfx.h, nfx_slide_copy_rows): a context that received only the top rows of
+    the slide from the host and the rest from a peer context computes the same bytes as one that received all of it."""
+    tile = case["tile"]
+    H, W = tile.shape[:2]
+    cut = H // 3 + 5
+    sets = ["geometry", "color", "glcm"]
+    with nfx.Extractor(0, 64, 100) as a, nfx.Extractor(0, 64, 100) as b:
+        a.upload_tile(tile)
+        want = a.extract(case["xy"], case["off"], sets)
+        b.slide_alloc(W, H)
+        b.write_tile(np.ascontiguousarray(tile[:cut]), 0, 0)
+        a.sync()
+        b.slide_copy_rows(a, cut, H - cut)
+        got = b.extract(case["xy"], case["off"], sets)
+        assert np.array_equal(b.slide_read(0, 0, W, H), tile)
+        with pytest.raises(nfx.NfxError):
+            b.slide_copy_rows(a, H - 2, 5)            # rows outside the slide
+    assert got[0] == want[0]
+    assert got[2].tobytes() == want[2].tobytes()
+
+
+_IPC_CHILD = r"""
+import sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import numpy as np
+import nfx
+from cases import small_case
+tile, rings = small_case()
+e = nfx.Extractor(0, 64, 100)
+e.upload_tile(tile)
+e.sync()
+print(e.slide_export().hex(), flush=True)
+sys.stdin.readline()          # keep the allocation alive until the parent has copied from it
+e.close()
+"""
+
+
+def test_slide_rows_from_another_process_over_cuda_ipc(case):
+    """One process per GPU (torchrun): rank q's share of the slide reaches rank r through nfx_slide_export /
+    nfx_slide_import_rows. Two processes on the one GPU of the test box exercise the same calls."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.join(os.path.dirname(here), "nuclei-feature-extraction_b200")
+    child = subprocess.Popen([sys.executable, "-c", _IPC_CHILD, pkg, here], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+    try:
+        line = child.stdout.readline().strip()
+        assert len(line) == 192, f"child did not export a handle: {line!r}"
+        handle = bytes.fromhex(line)
+        tile = case["tile"]
+        H, W = tile.shape[:2]
+        cut = H // 2
+        with nfx.Extractor(0, 64, 100) as b:
+            b.slide_alloc(W, H)
+            b.write_tile(np.ascontiguousarray(tile[cut:]), 0, cut)
+            b.slide_import_rows(handle, 0, cut)
+            b.sync()
+            assert np.array_equal(b.slide_read(0, 0, W, H), tile)
+            with pytest.raises(nfx.NfxError):
+                b.slide_import_rows(handle, -1, 4)
+    finally:
+        child.stdin.write("\n")
+        child.stdin.flush()
+        child.wait(timeout=60)
