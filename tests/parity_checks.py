@@ -64,3 +64,28 @@ def check_color(got, want, names, patches, masks, batch):
     got[wrap, j] = want[wrap, j]
     bad = mismatches(got, want, names, "color")
     assert not bad, _report(bad)
+
+
+def check_all_columns(got, names, rings, tile, P, batch, sets=None):
+    """Every column of every requested set (flat() order, default all five = 418 columns) against the oracle on the same
+    rings / tile: geometry through check_shape, colour through check_color (chunk-coupled mean_h), the texture sets through
+    tolerances.mismatches. Returns the oracle's masks so that callers can compare rasters too."""
+    sets = list(o.FLAT_ORDER) if sets is None else sets
+    cents, polys, patches, masks = o.load_image_dataset(rings, tile, P)
+    assert list(names) == [c for s in sets for c in o.SET_COLUMNS[s]], "schema mismatch"
+    col = 0
+    for s in sets:
+        cols = o.SET_COLUMNS[s]
+        sub = np.asarray(got)[:, col:col + len(cols)]
+        col += len(cols)
+        if s == "geometry":
+            want, dbg = o.shape_features(polys, masks, return_debug=True)
+            check_shape(sub, want, dbg, cols)
+        elif s == "color":
+            want = np.concatenate([o.color_features(patches[k:k + batch].clone(), masks[k:k + batch]) for k in range(0, len(rings), batch)], 0)
+            check_color(sub, want, cols, patches, masks, batch)
+        else:
+            fn = {"glcm": o.glcm_feature_set, "glrlm": o.glrlm_feature_set, "gabor": o.gabor_feature_set}[s]
+            bad = mismatches(sub, fn(patches, masks), cols, s)
+            assert not bad, f"{s} at P={P}:\n" + _report(bad)
+    return masks

@@ -9,7 +9,7 @@ import torch
 import nfx
 import nfx_oracle as o
 from nfx import synth
-from parity_checks import check_color, check_shape
+from parity_checks import check_all_columns, check_color, check_shape
 
 pytestmark = pytest.mark.gpu
 
@@ -92,3 +92,59 @@ def test_chunk_permutation_is_bit_exact(full):
         e2.upload_tile(full["tile"])
         k2, c2, f2, _ = e2.extract(xy, off, ["geometry", "color"])
     assert f2.tobytes() == full["feats"].tobytes() and k2 == full["keys"]
+
+
+def test_sampled_chunks_of_the_texture_sets_match_oracle(full):
+    """GLCM, GLRLM and Gabor at the full size (100 000 nuclei in one launch): whole reference chunks sampled against the
+    oracle, every column."""
+    ex = full["ex"]
+    keys, cents, feats, names = ex.extract(full["xy"], full["off"], ["texture"])
+    assert keys == full["keys"]
+    rng = np.random.default_rng(3)
+    for k in sorted(rng.choice(N // B, size=2, replace=False).tolist() + [N // B - 1]):
+        lo, hi = k * B, (k + 1) * B
+        rings = [full["xy"][full["off"][i]:full["off"][i + 1]] for i in range(lo, hi)]
+        check_all_columns(feats[lo:hi], names, rings, full["tile"], P, B, sets=["glcm", "glrlm", "gabor"])
+
+
+class _PeriodicSlide:
+    """What the oracle's gather needs of an image (shape, 2-D slicing) for a slide that repeats one block: the 5 GB slide
+    of the test below never has to exist on the host."""
+
+    def __init__(self, block, side):
+        self.block, self.shape = block, (side, side, 3)
+
+    def __getitem__(self, idx):
+        rs, cs = idx
+        n = self.block.shape[0]
+        return self.block[np.ix_(np.arange(rs.start, rs.stop) % n, np.arange(cs.start, cs.stop) % n)]
+
+
+def test_slide_path_sampled_chunks_match_oracle(libnfx):
+    """BASELINE config 4 mechanics at a size the test box holds quickly: a 40 960^2 slide (5 GB in HBM) written as 8192^2
+    tiles from two pinned staging buffers, 400 000 nuclei over all of it, all five sets; whole chunks sampled against the oracle
+    (which reads its windows from a periodic view of the staging block)."""
+    side, T, n = 40960, 8192, 400_000
+    block = synth.synth_tile(4096, 4096, 4)
+    stage = [nfx.pinned_empty((T, T, 3), np.uint8) for _ in range(2)]
+    for b in stage:
+        for r in range(0, T, 4096):
+            for c in range(0, T, 4096):
+                b[r:r + 4096, c:c + 4096] = block
+    xy, off = synth.synth_polygons_pool(n, side, side, 4)
+    with nfx.Extractor(0, P, B) as ex:
+        ex.slide_alloc(side, side)
+        k = 0
+        for y in range(0, side, T):
+            for x in range(0, side, T):
+                ex.write_tile(stage[k & 1], x, y)
+                k += 1
+        keys, cents, feats, names = ex.extract(xy, off, ["all"])
+    assert feats.shape == (n, 418)
+    slide = _PeriodicSlide(block, side)
+    rng = np.random.default_rng(5)
+    for k in sorted(rng.choice(n // B, size=2, replace=False).tolist()):
+        lo, hi = k * B, (k + 1) * B
+        rings = [xy[off[i]:off[i + 1]] for i in range(lo, hi)]
+        assert keys[lo:hi] == [o.centroid_key(o.preprocess_polygon(r)[0]) for r in rings]
+        check_all_columns(feats[lo:hi], names, rings, slide, P, B)       # whole chunks (mean_h couples them), all 418 columns

@@ -8,7 +8,7 @@ import nfx
 import nfx_oracle as o
 from cases import small_case, stress_case
 from nfx import synth
-from parity_checks import _report, check_color, check_shape
+from parity_checks import _report, check_all_columns, check_color, check_shape
 from tolerances import mismatches
 
 pytestmark = pytest.mark.gpu
@@ -239,13 +239,19 @@ def test_stress_p256_masks_gather_shape_color(stress):
         assert np.array_equal(got, wantp), "P=256 patches differ"
         keys, cents, feats, names = e.extract(stress["xy"], stress["off"], ["geometry", "color"])
     assert np.array_equal(cents.view(np.uint32), stress["cents"].view(np.uint32))
-    wshape = o.shape_features(stress["polys"], stress["masks"])
-    sel = [0, 1, 2, 3, 5, 6, 7, 9, 10, 11]
-    bad = mismatches(feats[:, :12][:, sel], wshape[:, sel], [o.SHAPE_COLUMNS[j] for j in sel], "geometry")
-    assert not bad, _report(bad)
+    wshape, dbg = o.shape_features(stress["polys"], stress["masks"], return_debug=True)
+    check_shape(feats[:, :12], wshape, dbg, o.SHAPE_COLUMNS)          # all 12 columns, orientation and eliptic_deviation included
     n = len(stress["rings"])
     rows = [o.color_features(stress["patches"][k:k + 8].clone(), stress["masks"][k:k + 8]) for k in range(0, n, 8)]
     _check_color(feats[:, 12:], np.concatenate(rows, 0), o.COLOR_COLUMNS, stress, 8)
+
+
+def test_stress_p256_all_418_columns(stress):
+    """BASELINE config 5 geometry (256 x 256 windows, 500-vertex rings): every column of every set."""
+    with nfx.Extractor(0, 256, 8) as e:
+        e.upload_tile(stress["tile"])
+        keys, cents, got, names = e.extract(stress["xy"], stress["off"], ["all"])
+    check_all_columns(got, names, stress["rings"], stress["tile"], 256, 8)
 
 
 def test_stress_p256_glcm(stress):
@@ -273,13 +279,8 @@ def test_mid_p128_all_sets(libnfx):
     with nfx.Extractor(0, 128, 5) as e:
         e.upload_tile(tile)
         keys, cents, got, names = e.extract(xy, off, ["geometry", "color", "glcm"])
-    wkeys, wc, want, wnames = o.extract(rings, tile, ["geometry", "color", "glcm"], 128, 5)
-    assert names == wnames and keys == wkeys
-    sel = [names.index(c) for c in ("area", "major_axis", "perimeter", "convex_hull_area", "mean_r", "std_g", "mean_s",
-                                    "std_v", "mean_eosin", "std_dab", "contrast_0_1_32", "entropy_1_1_64",
-                                    "angular_second_moment_1_0_128", "sum_entropy_1_-1_254", "sum_variance_0_1_254")]
-    ok = np.isclose(got[:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-6, equal_nan=True)
-    assert ok.all(), f"{(~ok).sum()} mismatches at P=128: {np.argwhere(~ok)[:5]}"
+    assert keys == [o.centroid_key(o.preprocess_polygon(r)[0]) for r in rings]
+    check_all_columns(got, names, rings, tile, 128, 5, sets=["geometry", "color", "glcm"])      # every column, not a selection
 
 
 @pytest.mark.parametrize("P,scale", [(16, 0.05), (20, 0.07), (48, 0.17), (80, 0.28), (96, 0.34), (200, 0.75)])
@@ -293,105 +294,10 @@ def test_odd_patch_sizes_all_sets(libnfx, P, scale):
         e.upload_tile(tile)
         keys, cents, got, names = e.extract(xy, off, ["all"])
         masks = e.rasterize()
-    cents_o, polys, patches, pmasks = o.load_image_dataset(rings, tile, P)
+    assert keys == [o.centroid_key(o.preprocess_polygon(r)[0]) for r in rings]
+    pmasks = check_all_columns(got, names, rings, tile, P, 4)            # all 418 columns
     assert np.array_equal(masks != 0, pmasks[:, 0].numpy() != 0), f"masks differ at P={P}"
-    wkeys, wc, want, wnames = o.extract(rings, tile, ["all"], P, 4)
-    assert names == wnames and keys == wkeys
-    cols = ["area", "perimeter", "convex_hull_area", "mean_r", "std_g", "mean_s", "std_v", "mean_eosin", "std_dab", "contrast_0_1_32",
-            "entropy_1_1_64", "angular_second_moment_1_0_128", "sum_entropy_1_-1_254", "sum_variance_0_1_254", "short_run_emphasis_1_0",
-            "run_percentage_0_1", "long_run_emphasis_-1_1", "gabor_angle_0_frequency_0.5_mean", "gabor_angle_45_frequency_2_variance",
-            "gabor_angle_90_frequency_8_mean", "gabor_angle_135_frequency_1_variance"]
-    sel = [names.index(c) for c in cols]
-    atol = np.array([2e-4 if c.startswith("gabor") else 2e-6 for c in cols])
-    d = np.abs(got[:, sel].astype(np.float64) - want[:, sel])
-    ok = (d <= atol + 1e-4 * np.abs(want[:, sel])) | (np.isnan(got[:, sel]) & np.isnan(want[:, sel]))
-    assert ok.all(), f"P={P}: {[(cols[j], float(got[i, sel[j]]), float(want[i, sel[j]])) for i, j in np.argwhere(~ok)[:6]]}"
-    j = names.index("mean_h")
-    dh = np.abs(got[:, j] - want[:, j])
-    assert np.nanmax(np.minimum(dh, 360 - dh)) < 0.05
 
-
-def test_slide_streamed_as_tiles_equals_single_upload(case):
-    """BASELINE config 4 mechanics: the slide is written tile by tile (and band by band) into HBM."""
-    tile = case["tile"]
-    H, W = tile.shape[:2]
-    with nfx.Extractor(0, 64, 100) as e:
-        e.upload_tile(tile)
-        k0, c0, f0, _ = e.extract(case["xy"], case["off"], ["color", "glcm"])
-    with nfx.Extractor(0, 64, 100) as e:
-        e.slide_alloc(W, H)
-        ts = 256
-        for y in range(0, H, ts):
-            for x in range(0, W, ts):
-                e.write_tile(np.ascontiguousarray(tile[y:y + ts, x:x + ts]), x, y)
-        k1, c1, f1, _ = e.extract(case["xy"], case["off"], ["color", "glcm"])
-        with pytest.raises(nfx.NfxError):
-            e.write_tile(np.ascontiguousarray(tile[:64, :64]), W - 10, 0)
-    assert k0 == k1 and np.array_equal(f0, f1, equal_nan=True)
-
-
-def test_tile_origin_offsets_slide_coordinates(case):
-    """A tile with origin (ox, oy) serves polygons given in slide coordinates: same result as the
-    reference pipeline run on the whole slide with the tile embedded at (ox, oy)."""
-    tile = case["tile"]
-    H, W = tile.shape[:2]
-    ox, oy = 1000, 700
-    slide = np.zeros((oy + H + 64, ox + W + 64, 3), np.uint8)
-    slide[oy:oy + H, ox:ox + W] = tile
-    n = 120
-    rings = [(r + np.array([ox, oy], np.float32)).astype(np.float32) for r in case["rings"][:n]]
-    xy, off = nfx.pack_polygons(rings)
-    with nfx.Extractor(0, 64, 100) as e:
-        e.upload_tile(tile, origin=(ox, oy))
-        keys, cents, got, names = e.extract(xy, off, ["color"])
-        masks = e.rasterize()
-        patches = e.gather_patches()
-    wc, wpolys, wpatches, wmasks = o.load_image_dataset(rings, slide, 64)
-    assert keys == [o.centroid_key(c) for c in wc]
-    assert np.array_equal(masks != 0, wmasks[:, 0].numpy() != 0)
-    assert np.array_equal(patches, np.stack([o.gather_patch_u8(slide, c, 64) for c in wc]))
-    sub = dict(patches=wpatches, masks=wmasks, rings=rings)
-    rows = [o.color_features(wpatches[k:k + 100].clone(), wmasks[k:k + 100]) for k in range(0, n, 100)]
-    _check_color(got, np.concatenate(rows, 0), names, sub, 100)
-
-
-def test_glrlm_features(case, ex):
-    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["glrlm"])
-    want = o.glrlm_feature_set(case["patches"], case["masks"])
-    assert names == o.GLRLM_COLUMNS
-    bad = mismatches(got, want, names, "glrlm")
-    assert not bad, _report(bad)
-
-
-def test_gabor_features(case, ex):
-    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["gabor"])
-    want = o.gabor_feature_set(case["patches"], case["masks"])
-    assert names == o.GABOR_COLUMNS
-    bad = mismatches(got, want, names, "gabor")
-    assert not bad, _report(bad)
-
-
-def test_all_418_columns_in_flat_order(case, ex):
-    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["all"])
-    assert len(names) == 418 and names == [c for s_ in o.FLAT_ORDER for c in o.SET_COLUMNS[s_]]
-    n = 60
-    wkeys, wc, want, wnames = o.extract(case["rings"][:n], case["tile"], ["all"], 64, 100)
-    assert wnames == names and keys[:n] == wkeys
-    # chunk 0 is rows 0..99 in both runs only when n covers it: compare the batch-independent columns
-    sel = [names.index(c) for c in ("area", "mean_g", "std_eosin", "contrast_1_1_64", "short_run_emphasis_1_0",
-                                    "run_percentage_-1_1", "gabor_angle_0_frequency_0.5_mean",
-                                    "gabor_angle_90_frequency_2_variance", "gabor_angle_315_frequency_8_mean")]
-    ok = np.isclose(got[:n][:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-4, equal_nan=True)
-    assert ok.all(), f"{(~ok).sum()} mismatches: {np.argwhere(~ok)[:6]}"
-
-
-def test_glrlm_p256(stress):
-    with nfx.Extractor(0, 256, 8) as e:
-        e.upload_tile(stress["tile"])
-        keys, cents, got, names = e.extract(stress["xy"][:stress["off"][6]], stress["off"][:7], ["glrlm"])
-    want = o.glrlm_feature_set(stress["patches"][:6], stress["masks"][:6])
-    bad = mismatches(got, want, names, "glrlm")
-    assert not bad, _report(bad)
 
 
 def test_small_patch_p32_all_sets(libnfx):
@@ -403,15 +309,9 @@ def test_small_patch_p32_all_sets(libnfx):
         e.upload_tile(tile)
         keys, cents, got, names = e.extract(xy, off, ["all"])
         masks = e.rasterize()
-    wkeys, wc, want, wnames = o.extract(rings, tile, ["all"], 32, 25)
-    assert names == wnames and keys == wkeys
-    wm = np.stack([o.polygon_mask(32, 32, o.preprocess_polygon(r)[1].astype(np.float64)) for r in rings])
-    assert np.array_equal(masks != 0, wm)
-    sel = [names.index(c) for c in ("area", "perimeter", "mean_b", "std_r", "mean_v", "mean_haematoxylin", "contrast_0_1_32",
-                                    "entropy_1_-1_254", "long_run_emphasis_0_1", "run_percentage_1_1",
-                                    "gabor_angle_45_frequency_1_mean", "gabor_angle_270_frequency_6_variance")]
-    ok = np.isclose(got[:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-4, equal_nan=True)
-    assert ok.all(), f"{(~ok).sum()} mismatches at P=32: {np.argwhere(~ok)[:6]}"
+    assert keys == [o.centroid_key(o.preprocess_polygon(r)[0]) for r in rings]
+    pmasks = check_all_columns(got, names, rings, tile, 32, 25)          # all 418 columns
+    assert np.array_equal(masks != 0, pmasks[:, 0].numpy() != 0)
 
 
 # ---- size-independent properties ------------------------------------------------
