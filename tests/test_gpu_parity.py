@@ -300,6 +300,89 @@ def test_odd_patch_sizes_all_sets(libnfx, P, scale):
 
 
 
+def test_slide_streamed_as_tiles_equals_single_upload(case):
+    """BASELINE config 4 mechanics: the slide is written tile by tile (and band by band) into HBM."""
+    tile = case["tile"]
+    H, W = tile.shape[:2]
+    with nfx.Extractor(0, 64, 100) as e:
+        e.upload_tile(tile)
+        k0, c0, f0, _ = e.extract(case["xy"], case["off"], ["color", "glcm"])
+    with nfx.Extractor(0, 64, 100) as e:
+        e.slide_alloc(W, H)
+        ts = 256
+        for y in range(0, H, ts):
+            for x in range(0, W, ts):
+                e.write_tile(np.ascontiguousarray(tile[y:y + ts, x:x + ts]), x, y)
+        k1, c1, f1, _ = e.extract(case["xy"], case["off"], ["color", "glcm"])
+        with pytest.raises(nfx.NfxError):
+            e.write_tile(np.ascontiguousarray(tile[:64, :64]), W - 10, 0)
+    assert k0 == k1 and np.array_equal(f0, f1, equal_nan=True)
+
+
+def test_tile_origin_offsets_slide_coordinates(case):
+    """A tile with origin (ox, oy) serves polygons given in slide coordinates: same result as the
+    reference pipeline run on the whole slide with the tile embedded at (ox, oy)."""
+    tile = case["tile"]
+    H, W = tile.shape[:2]
+    ox, oy = 1000, 700
+    slide = np.zeros((oy + H + 64, ox + W + 64, 3), np.uint8)
+    slide[oy:oy + H, ox:ox + W] = tile
+    n = 120
+    rings = [(r + np.array([ox, oy], np.float32)).astype(np.float32) for r in case["rings"][:n]]
+    xy, off = nfx.pack_polygons(rings)
+    with nfx.Extractor(0, 64, 100) as e:
+        e.upload_tile(tile, origin=(ox, oy))
+        keys, cents, got, names = e.extract(xy, off, ["color"])
+        masks = e.rasterize()
+        patches = e.gather_patches()
+    wc, wpolys, wpatches, wmasks = o.load_image_dataset(rings, slide, 64)
+    assert keys == [o.centroid_key(c) for c in wc]
+    assert np.array_equal(masks != 0, wmasks[:, 0].numpy() != 0)
+    assert np.array_equal(patches, np.stack([o.gather_patch_u8(slide, c, 64) for c in wc]))
+    sub = dict(patches=wpatches, masks=wmasks, rings=rings)
+    rows = [o.color_features(wpatches[k:k + 100].clone(), wmasks[k:k + 100]) for k in range(0, n, 100)]
+    _check_color(got, np.concatenate(rows, 0), names, sub, 100)
+
+
+def test_glrlm_features(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["glrlm"])
+    want = o.glrlm_feature_set(case["patches"], case["masks"])
+    assert names == o.GLRLM_COLUMNS
+    bad = mismatches(got, want, names, "glrlm")
+    assert not bad, _report(bad)
+
+
+def test_gabor_features(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["gabor"])
+    want = o.gabor_feature_set(case["patches"], case["masks"])
+    assert names == o.GABOR_COLUMNS
+    bad = mismatches(got, want, names, "gabor")
+    assert not bad, _report(bad)
+
+
+def test_all_418_columns_in_flat_order(case, ex):
+    keys, cents, got, names = ex.extract(case["xy"], case["off"], ["all"])
+    assert len(names) == 418 and names == [c for s_ in o.FLAT_ORDER for c in o.SET_COLUMNS[s_]]
+    n = 60
+    wkeys, wc, want, wnames = o.extract(case["rings"][:n], case["tile"], ["all"], 64, 100)
+    assert wnames == names and keys[:n] == wkeys
+    # chunk 0 is rows 0..99 in both runs only when n covers it: compare the batch-independent columns
+    sel = [names.index(c) for c in ("area", "mean_g", "std_eosin", "contrast_1_1_64", "short_run_emphasis_1_0",
+                                    "run_percentage_-1_1", "gabor_angle_0_frequency_0.5_mean",
+                                    "gabor_angle_90_frequency_2_variance", "gabor_angle_315_frequency_8_mean")]
+    ok = np.isclose(got[:n][:, sel].astype(np.float64), want[:, sel], rtol=1e-4, atol=1e-4, equal_nan=True)
+    assert ok.all(), f"{(~ok).sum()} mismatches: {np.argwhere(~ok)[:6]}"
+
+
+def test_glrlm_p256(stress):
+    with nfx.Extractor(0, 256, 8) as e:
+        e.upload_tile(stress["tile"])
+        keys, cents, got, names = e.extract(stress["xy"][:stress["off"][6]], stress["off"][:7], ["glrlm"])
+    want = o.glrlm_feature_set(stress["patches"][:6], stress["masks"][:6])
+    bad = mismatches(got, want, names, "glrlm")
+    assert not bad, _report(bad)
+
+
 def test_small_patch_p32_all_sets(libnfx):
     """P = 32: single-word mask rows, the runtime-stride Gabor variant, small windows at tile borders."""
     tile = synth.synth_tile(200, 200, 13)
