@@ -448,6 +448,28 @@ def test_partitioned_run_is_byte_identical(case):
     assert merged.tobytes() == full.tobytes()
 
 
+def test_repeated_runs_are_bit_identical(case, stress):
+    """compute-sanitizer is closed on this pool (profiles/r2_sanitizer_closed.txt); a race in the shared-memory atomics
+    (XOR raster, GLCM tables), the mbarrier rings or the cross-warp reductions would make runs differ. Every kernel, eight
+    runs alternating between two contexts (two streams in flight), P = 64 and P = 256: identical bytes, NaNs included."""
+    for c, P, B in ((case, 64, 100), (stress, 256, 8)):
+        with nfx.Extractor(0, P, B) as a, nfx.Extractor(0, P, B) as b:
+            for e in (a, b):
+                e.upload_tile(c["tile"])
+                e.upload_polygons(c["xy"], c["off"])
+            mask = nfx.parse_feature_sets(["all"])
+            ref = None
+            for it in range(4):
+                a.compute(mask)
+                b.compute(mask)            # both contexts' kernels are queued before either is read back
+                for e in (a, b):
+                    f = e.download()[1].tobytes()
+                    ref = f if ref is None else ref
+                    assert f == ref, f"run {it} differs at P={P}"
+            m0 = a.rasterize().tobytes()
+            assert all(e.rasterize().tobytes() == m0 for e in (a, b, a))
+
+
 def test_recompute_is_deterministic(case, ex):
     a = ex.extract(case["xy"], case["off"], ["all"])[2]
     b = ex.extract(case["xy"], case["off"], ["all"])[2]
