@@ -47,8 +47,27 @@ typedef struct nfx_config {
     int32_t patch_size;   /* -p/--patch-size, default 64. A multiple of 4 in [16, 256]. */
     int32_t batch_size;   /* -b/--batch-size, default 100. mean_h couples the nuclei of one chunk
                              [k*B,(k+1)*B) (src/features/color.rs:50-51, 144-155; src/main.rs:148). */
-    int32_t reserved[6];  /* must be 0 */
+    int32_t rule_flags;   /* NFX_RULE_* bits below; 0 = the rules of oracle/SPEC.md */
+    int32_t reserved[5];  /* must be 0 */
 } nfx_config;
+
+/* Switches of the rules whose upstream source (tch-utils@d1c10c0) is not available (oracle/SPEC.md section B, "parity
+ * unpinned"): the adopted position is 0, the flag selects the most plausible alternative, in the kernels and -- under the
+ * same name -- in the oracle (oracle.RULES). tools/emit_reference_golden.rs + tests/test_reference_golden.py tell which
+ * position the reference takes once someone can run it. */
+#define NFX_RULE_RASTER_PIXEL_CENTRE 0x1  /* polygon / ellipse rasters sample the pixel CENTRE (c + 0.5 - P/2, r + 0.5 - P/2)
+                                             instead of (c - P/2, r - P/2)          (src/utils.rs:152-157, shape.rs:80-87) */
+#define NFX_RULE_GABOR_HALF_TURN     0x2  /* Gabor angles i * pi / 8 instead of i * 2 pi / 8 (texture.rs:333-334). The oracle has
+                                             both positions; the kernel bank is built for the full turn (24 distinct filters)
+                                             and nfx_compute refuses the Gabor set under this flag (NFX_ERR_UNSUPPORTED) */
+#define NFX_RULE_GLCM_254_U8         0x4  /* the 254-level GLCM quantises like an 8-bit image, q = min(floor(g * 255), 253), instead of
+                                             min(floor(g * 254), 253) (src/features/texture.rs:19, 40-46). The power-of-two level
+                                             counts keep floor(g * L): the kernels use floor(g*32) = floor(g*128) >> 2 */
+#define NFX_RULE_WINDOW_SLIDE        0x8  /* the slide path's window (src/utils.rs:96-126) instead of the image path's
+                                             (utils.rs:159-192): origin = ((cx - P/2) as u32, (cy - P/2) as u32) -- negative origins
+                                             saturate to 0, i.e. the window is SHIFTED, not zero padded, at the left / top edge --
+                                             and always P x P (OpenSlide returns black beyond the right / bottom edge). Set
+                                             automatically by nfx_slide_load_tiff (.svs / .tif input). */
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 /* Replaces Device::Cuda(gpus[idx]) selection (src/utils.rs:215-221). cfg may be NULL (defaults). */

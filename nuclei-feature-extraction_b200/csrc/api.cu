@@ -54,6 +54,7 @@ struct ProfRec {
 struct nfx_ctx {
     int device = 0;
     int P = 64, B = 100;
+    uint32_t rules = 0;   // NFX_RULE_* (nfx_config.rule_flags; NFX_RULE_WINDOW_SLIDE is also set by nfx_slide_load_tiff)
     cudaStream_t stream = nullptr;
     std::string err;
     EncodeTiledFn encode = nullptr;
@@ -195,6 +196,8 @@ Cols columns(uint32_t mask) {
 
 int check_patch_size(nfx_ctx* ctx, uint32_t mask) {
     if (mask == 0 || (mask & ~NFX_FS_ALL)) return fail(ctx, NFX_ERR_INVALID, "empty or unknown feature mask");
+    if ((mask & NFX_FS_GABOR) && (ctx->rules & NFX_RULE_GABOR_HALF_TURN))
+        return fail(ctx, NFX_ERR_UNSUPPORTED, "NFX_RULE_GABOR_HALF_TURN: the kernel bank is built for angles i * 2 pi / 8 (24 distinct filters); only the oracle has the half-turn bank");
     return NFX_OK;
 }
 
@@ -220,6 +223,8 @@ int run_geom(nfx_ctx* ctx, bool shape, float* out, int stride, int col, uint32_t
     g.out_stride = stride;
     g.col_shape = col;
     g.ellipse_bits = ellipse_bits;
+    g.sample_off = (ctx->rules & NFX_RULE_RASTER_PIXEL_CENTRE) ? 0.5f : 0.0f;
+    g.slide_window = (ctx->rules & NFX_RULE_WINDOW_SLIDE) ? 1 : 0;
     CK(timed(ctx, shape ? "k_geom<raster,shape>" : "k_geom<raster>", 1,
              [&] { return launch_geom(g, true, shape, ctx->stream); }));
     ctx->have_geom = true;
@@ -265,6 +270,7 @@ int run_glcm(nfx_ctx* ctx, int64_t n, const CUtensorMap* mp, float* out, int str
     g.dbg_dy = ddy;
     g.dbg_dx = ddx;
     g.dbg_grey = dbg_grey;
+    g.scale254 = (ctx->rules & NFX_RULE_GLCM_254_U8) ? 255.0f : 254.0f;
     CK(timed(ctx, "k_glcm", 1, [&] { return launch_glcm(g, mp, ctx->stream); }));
     return NFX_OK;
 }
@@ -324,10 +330,16 @@ int nfx_create(int device, const nfx_config* cfg, nfx_ctx** out) {
     if (!out) return fail(nullptr, NFX_ERR_INVALID, "nfx_create: out is NULL");
     *out = nullptr;
     int P = 64, B = 100;
+    uint32_t rules = 0;
     if (cfg) {
         if (cfg->patch_size) P = cfg->patch_size;
         if (cfg->batch_size) B = cfg->batch_size;
+        rules = (uint32_t)cfg->rule_flags;
+        for (int k = 0; k < 5; ++k)
+            if (cfg->reserved[k]) return fail(nullptr, NFX_ERR_INVALID, "nfx_config.reserved must be 0");
     }
+    if (rules & ~(uint32_t)(NFX_RULE_RASTER_PIXEL_CENTRE | NFX_RULE_GABOR_HALF_TURN | NFX_RULE_GLCM_254_U8 | NFX_RULE_WINDOW_SLIDE))
+        return fail(nullptr, NFX_ERR_INVALID, "unknown nfx_config.rule_flags bit");
     if (P < 16 || P > 256 || (P & 3)) return fail(nullptr, NFX_ERR_UNSUPPORTED, "patch_size must be a multiple of 4 in [16,256]");
     if (B < 1) return fail(nullptr, NFX_ERR_INVALID, "batch_size must be >= 1");
     int count = 0;
@@ -342,6 +354,7 @@ int nfx_create(int device, const nfx_config* cfg, nfx_ctx** out) {
     ctx->device = device;
     ctx->P = P;
     ctx->B = B;
+    ctx->rules = rules;
     auto bail = [&](int rc) { nfx_destroy(ctx); return rc; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(cuda_fail(nullptr, e, "cudaSetDevice"));
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(nullptr, e, "cudaStreamCreate"));
@@ -482,6 +495,8 @@ int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t 
     CK(cudaStreamSynchronize(ctx->stream));
     err = decode_tiff_level(file, L, ctx->tile.p, ctx->tpitch, ctx->device, threads);
     if (!err.empty()) { ctx->have_tile = false; return fail(ctx, NFX_ERR_UNSUPPORTED, "tiff: " + err); }
+    ctx->rules |= NFX_RULE_WINDOW_SLIDE;   // .svs / .tif input takes the reference's slide path (src/utils.rs:96-126)
+    ctx->have_geom = false;
     return NFX_OK;
 }
 
@@ -671,6 +686,8 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
         g.poly_xy = ctx->xy.p; g.poly_off = ctx->off.p; g.n = n; g.P = P; g.tile_ox = 0; g.tile_oy = 0;
         g.vmax = std::max(ctx->vmax, 1); g.centroid = ctx->centroid.p; g.info = ctx->info.p;
         g.bitmask = ctx->bitmask.p; g.out = ctx->out.p; g.out_stride = cols; g.col_shape = c.shape; g.ellipse_bits = nullptr;
+        g.sample_off = (ctx->rules & NFX_RULE_RASTER_PIXEL_CENTRE) ? 0.5f : 0.0f;
+        g.slide_window = 0;
         CK(timed(ctx, "k_geom<shape>", 1, [&] { return launch_geom(g, false, true, ctx->stream); }));
     }
     if (fs & NFX_FS_COLOR)

@@ -29,10 +29,9 @@ template <bool SHAPE> struct GeomCfg {
     static constexpr int kNpc = SHAPE ? 1 : 4;         // nuclei per CTA
 };
 
-// first index k in [0,P] such that (k - P/2) >= v   (exact; v may be any double)
-__device__ __forceinline__ int first_index_geq(double v, int P) {
+// first index k in [0,P] such that (k - half) >= v   (exact; v may be any double). half = P/2 - sample offset.
+__device__ __forceinline__ int first_index_geq(double v, int P, double half) {
     if (!(v == v)) return P;
-    const double half = 0.5 * (double)P;
     const double t = v + half;
     int k = (t <= 0.0) ? 0 : (t >= (double)P ? P : (int)ceil(t));
     while (k > 0 && ((double)(k - 1) - half) >= v) --k;
@@ -71,9 +70,8 @@ struct EdgeRecs {               // per nucleus, in shared memory
     int off[kEdgeBlock + 1];    // exclusive scan of the row counts
 };
 
-__device__ __forceinline__ void raster_warp(const float2* pts, int V, int P, uint32_t* rows, EdgeRecs* er, int lane) {
+__device__ __forceinline__ void raster_warp(const float2* pts, int V, int P, double half, uint32_t* rows, EdgeRecs* er, int lane) {
     const int wpr = mask_wpr(P);
-    const double half = 0.5 * (double)P;
     for (int e0 = 0; e0 < V; e0 += kEdgeBlock) {
         int cnt[2];
 #pragma unroll
@@ -84,7 +82,7 @@ __device__ __forceinline__ void raster_warp(const float2* pts, int V, int P, uin
                 const float2 a = pts[k], b = pts[(k + 1 == V) ? 0 : k + 1];
                 if (!(a.y == b.y || !(a.y == a.y) || !(b.y == b.y))) {
                     const double ylo = fmin((double)a.y, (double)b.y), yhi = fmax((double)a.y, (double)b.y);
-                    const int r0 = first_index_geq(ylo, P), r1 = first_index_geq(yhi, P);
+                    const int r0 = first_index_geq(ylo, P, half), r1 = first_index_geq(yhi, P, half);
                     if (r1 > r0) {
                         const double dye = __dsub_rn((double)b.y, (double)a.y);
                         er->xi[j] = (double)a.x;
@@ -124,7 +122,7 @@ __device__ __forceinline__ void raster_warp(const float2* pts, int V, int P, uin
             if (!(fabs(fr) > 1e-9 * fmax(1.0, fabs(tt))))   // next to a pixel abscissa (or not finite): the rule's own division
                 X = __dadd_rn(xi, __ddiv_rn(num, er->dy[j]));
             if (!(X == X)) continue;                          // `x < NaN` is false for every pixel: nothing toggled
-            const int nb = first_index_geq(X, P);             // pixels c < nb satisfy (c - P/2) < X
+            const int nb = first_index_geq(X, P, half);       // pixels c < nb satisfy (c - half) < X
             for (int w = 0; w < wpr; ++w) {
                 const uint32_t m = prefix_bits(nb - 32 * w);
                 if (m) atomicXor(&rows[r * wpr + w], m);
@@ -197,10 +195,20 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
                 return (int)max(-(1ll << 30), min(1ll << 30, v));
             };
             NucInfo inf;
-            inf.left = clamp32(left - p.tile_ox);
-            inf.top = clamp32(top - p.tile_oy);
-            inf.nvc = (int)max(0ll, min((long long)P, right - left));
-            inf.nvr = (int)max(0ll, min((long long)P, bottom - top));
+            if (p.slide_window) {
+                // utils.rs:104-105 -- `as u32` saturates: negative and NaN origins read from 0 (the window is shifted, not
+                // padded); OpenSlide always returns P x P pixels, black beyond the slide (= TMA zero fill)
+                auto as_u32 = [](float v) -> long long { return (v == v && v > 0.f) ? min(__float2ll_rz(v), 4294967295ll) : 0ll; };
+                inf.left = clamp32(as_u32(__fsub_rn(cx, half)) - p.tile_ox);
+                inf.top = clamp32(as_u32(__fsub_rn(cy, half)) - p.tile_oy);
+                inf.nvc = P;
+                inf.nvr = P;
+            } else {
+                inf.left = clamp32(left - p.tile_ox);
+                inf.top = clamp32(top - p.tile_oy);
+                inf.nvc = (int)max(0ll, min((long long)P, right - left));
+                inf.nvr = (int)max(0ll, min((long long)P, bottom - top));
+            }
             p.info[i] = inf;
         }
         sync();
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
         sync();
 
         // ---- SPEC.md B1: scanline raster over flattened (edge, row) pairs, one warp ----
-        if (tid < 32) raster_warp(pts, V, P, rows, erecs, tid);
+        if (tid < 32) raster_warp(pts, V, P, 0.5 * (double)P - (double)p.sample_off, rows, erecs, tid);
         sync();
         for (int k = tid; k < P * wpr; k += kGeomThreads) p.bitmask[i * P * wpr + k] = rows[k];
     }
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
                           isfinite(ecx) && isfinite(ecy);
     double cs = 0.0, sn = 0.0;
     if (drawable) sincos(ang, &sn, &cs);
-    const double half = 0.5 * (double)P;
+    const double half = 0.5 * (double)P - (double)p.sample_off;   // pixel k samples k - half
     const double ia2 = 1.0 / (ea * ea), ib2 = 1.0 / (eb * eb);
     const double qa = cs * cs * ia2 + sn * sn * ib2;
     double diff[1] = {0.0};

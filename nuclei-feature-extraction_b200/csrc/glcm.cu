@@ -191,7 +191,7 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
             const float g = __fdiv_rn(
                 __fadd_rn(__fadd_rn(s_lut[patch[a]], s_lut[patch[a + 1]]), s_lut[patch[a + 2]]), 3.0f);
             q128[k] = (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
-            q254[k] = (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253);
+            q254[k] = (uint8_t)min((int)floorf(__fmul_rn(g, p.scale254)), 253);
         }
     }
     __syncthreads();   // patch is dead from here on: region A becomes the triangular histogram
@@ -545,7 +545,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         }
         const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
         q128[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
-        q254[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253);
+        q254[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, p.scale254)), 253);
     };
     if (dbg_all) {
         for (int k = tid; k < P * P; k += kG64Threads) quantise(k / P, k % P);
@@ -807,7 +807,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                     pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
                 }
                 const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
-                plane[r * PP + c] = round == 0 ? (uint8_t)min((int)floorf(__fmul_rn(g, 254.0f)), 253)
+                plane[r * PP + c] = round == 0 ? (uint8_t)min((int)floorf(__fmul_rn(g, p.scale254)), 253)
                                               : (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
             }
         }

@@ -33,6 +33,8 @@ struct GeomParams {
     int out_stride;
     int col_shape;             // first column of the geometry set in `out`, or -1
     uint32_t* ellipse_bits;    // optional debug tap [n][P][wpr], or nullptr
+    float sample_off;          // 0 (SPEC.md B1/B2) or 0.5 (NFX_RULE_RASTER_PIXEL_CENTRE): pixel k samples k + off - P/2
+    int slide_window;          // NFX_RULE_WINDOW_SLIDE: window origin saturates at 0, always P x P (utils.rs:96-109)
 };
 // raster=true : polygons are raw rings; computes centroid/info, rasterises, writes bitmask.
 // raster=false: polygons are already centred and bitmask is an input (trait-level path).
@@ -74,6 +76,7 @@ struct GlcmParams {
     uint32_t* dbg_counts;      // [n][L][L] symmetric counts for (dbg_levels, dbg_dy, dbg_dx)
     int dbg_levels, dbg_dy, dbg_dx;
     uint8_t* dbg_grey;         // [n][P][P] quantised grey for dbg_levels
+    float scale254;            // 254.0f, or 255.0f under NFX_RULE_GLCM_254_U8: q254 = min(floor(g * scale254), 253)
 };
 // map = whole-window map for P <= 128, the 64-row slab map (color_slab_rows) when glcm_uses_slab_map(P)
 cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s);

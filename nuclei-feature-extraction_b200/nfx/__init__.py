@@ -14,8 +14,9 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (FS_ALL, FS_COLOR, FS_GABOR, FS_GEOMETRY, FS_GLCM, FS_GLRLM, FS_TEXTURE, NFX_OK,
-                   NfxConfig, NfxError, NfxKernelTime, NfxTiffLevel, lib)
+from ._lib import (FS_ALL, FS_COLOR, FS_GABOR, FS_GEOMETRY, FS_GLCM, FS_GLRLM, FS_TEXTURE, NFX_OK, RULE_GABOR_HALF_TURN,
+                   RULE_GLCM_254_U8, RULE_RASTER_PIXEL_CENTRE, RULE_WINDOW_SLIDE, NfxConfig, NfxError, NfxKernelTime,
+                   NfxTiffLevel, lib)
 
 _FLAT_BITS = (FS_GEOMETRY, FS_COLOR, FS_GLCM, FS_GLRLM, FS_GABOR)
 
@@ -158,9 +159,9 @@ def _ptr(a):
 class Extractor:
     """One context per (host thread, GPU) -- the analogue of one rayon worker (src/utils.rs:215-221)."""
 
-    def __init__(self, device: int = 0, patch_size: int = 64, batch_size: int = 100):
+    def __init__(self, device: int = 0, patch_size: int = 64, batch_size: int = 100, rule_flags: int = 0):
         self._h = C.c_void_p()
-        cfg = NfxConfig(patch_size, batch_size)
+        cfg = NfxConfig(patch_size, batch_size, rule_flags)
         rc = lib().nfx_create(device, C.byref(cfg), C.byref(self._h))
         if rc != NFX_OK:
             raise NfxError(rc, (lib().nfx_last_error(None) or b"").decode())

@@ -15,7 +15,11 @@ FS_ALL = 0x1F
 
 
 class NfxConfig(C.Structure):
-    _fields_ = [("patch_size", C.c_int32), ("batch_size", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("patch_size", C.c_int32), ("batch_size", C.c_int32), ("rule_flags", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+# nfx_config.rule_flags (include/nfx.h): switches of the unpinned rules, mirrored by oracle.RULES
+RULE_RASTER_PIXEL_CENTRE, RULE_GABOR_HALF_TURN, RULE_GLCM_254_U8, RULE_WINDOW_SLIDE = 0x1, 0x2, 0x4, 0x8
 
 
 class NfxTiffLevel(C.Structure):

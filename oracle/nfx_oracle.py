@@ -31,6 +31,41 @@ GABOR_SIGMA = 0.45                                    # src/features/texture.rs:
 
 
 # --------------------------------------------------------------------------------------------
+# Switches of the highest-risk UNPINNED rules (SPEC.md section B): each has the adopted position (default) and
+# the most plausible alternative, so that a mismatch against reference vectors (tests/test_reference_golden.py,
+# tools/emit_reference_golden.rs) is a one-flag fix here and in the kernels (nfx_config.rule_flags, include/nfx.h).
+#   raster_offset : 0.0 = pixel (r, c) samples (c - w/2, r - h/2); 0.5 = the pixel centre (c + 0.5 - w/2, ...)   [B1, B2]
+#   gabor_span    : angles theta_i = i * span / 8 with span = 2 pi (default) or pi                                [B9]
+#   glcm_quant    : "floor" = min(floor(g * L), L - 1) for every level count; "u8" = the 254-level matrix quantises like an
+#                   8-bit image, q = min(floor(g * 255), 253) (the other level counts are unchanged: the kernels rely on
+#                   floor(g*32) = floor(g*128) >> 2, which a rounding rule would break)                            [B5]
+#   window        : "image" = src/utils.rs:159-192 (trunc toward zero, zero padding on every side);
+#                   "slide" = src/utils.rs:96-126 (OpenSlide read at `(c - P/2) as u32`: a negative origin saturates to 0,
+#                   the window is always P x P and pixels beyond the slide read as 0)                               [A2 / G3]
+# --------------------------------------------------------------------------------------------
+RULES = {"raster_offset": 0.0, "gabor_span": 2.0 * math.pi, "glcm_quant": "floor", "window": "image"}
+
+
+class rules:
+    """with rules(raster_offset=0.5): ...   -- temporarily switch rules (test infrastructure)."""
+
+    def __init__(self, **kw):
+        unknown = set(kw) - set(RULES)
+        if unknown:
+            raise KeyError(f"unknown rule(s) {sorted(unknown)}")
+        self.kw, self.old = kw, None
+
+    def __enter__(self):
+        self.old = dict(RULES)
+        RULES.update(self.kw)
+        return self
+
+    def __exit__(self, *a):
+        RULES.clear()
+        RULES.update(self.old)
+
+
+# --------------------------------------------------------------------------------------------
 # Schema (A14)
 # --------------------------------------------------------------------------------------------
 SHAPE_COLUMNS = [  # src/features/shape.rs:114-128
@@ -119,8 +154,8 @@ def preprocess_polygon(ring):
 def polygon_mask(w, h, pts):
     """[B1] tch_utils::shapes::polygon(w, h, &pts_f64, (Float, Cpu)) -> [h,w] bool. SPEC.md B1."""
     pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
-    X = (np.arange(w, dtype=np.float64) - w / 2.0)[None, :]
-    Y = (np.arange(h, dtype=np.float64) - h / 2.0)[:, None]
+    X = (np.arange(w, dtype=np.float64) + RULES["raster_offset"] - w / 2.0)[None, :]
+    Y = (np.arange(h, dtype=np.float64) + RULES["raster_offset"] - h / 2.0)[:, None]
     inside = np.zeros((h, w), dtype=bool)
     n = len(pts)
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -138,8 +173,8 @@ def ellipse_mask(w, h, center, radii, angle):
     cx, cy = np.float64(center[0]), np.float64(center[1])
     a, b = np.float64(radii[0]), np.float64(radii[1])
     ang = np.float64(angle)
-    X = (np.arange(w, dtype=np.float64) - w / 2.0)[None, :]
-    Y = (np.arange(h, dtype=np.float64) - h / 2.0)[:, None]
+    X = (np.arange(w, dtype=np.float64) + RULES["raster_offset"] - w / 2.0)[None, :]
+    Y = (np.arange(h, dtype=np.float64) + RULES["raster_offset"] - h / 2.0)[:, None]
     with np.errstate(divide="ignore", invalid="ignore"):
         cs, sn = np.cos(ang), np.sin(ang)
         dx, dy = X - cx, Y - cy
@@ -155,6 +190,14 @@ def patch_window(centroid, P):
     """[A2] src/utils.rs:159-162: f32 arithmetic, Rust `as i64` truncates toward zero."""
     half = F32(P) / F32(2.0)
     cx, cy = F32(centroid[0]), F32(centroid[1])
+    if RULES["window"] == "slide":
+        # src/utils.rs:96-109: Region { address: ((cx - P/2) as u32, (cy - P/2) as u32), size: P x P, level 0 }. Rust's
+        # float -> u32 cast saturates: negative and NaN give 0. OpenSlide returns a full P x P image (black outside the
+        # slide), so the top-left padding branch (utils.rs:113-122) never changes it.
+        def as_u32(v):
+            return 0 if not (v == v) or v <= 0 else int(min(np.trunc(v), 4294967295.0))
+        top, left = as_u32(cy - half), as_u32(cx - half)
+        return top, left, top + P, left + P
     top, left = int(np.trunc(cy - half)), int(np.trunc(cx - half))
     bottom, right = int(np.trunc(cy + half)), int(np.trunc(cx + half))
     return top, left, bottom, right
@@ -458,9 +501,11 @@ def grey_scale(patchs):
     return patchs.mean(dim=[-3], keepdim=True, dtype=torch.float32)
 
 
-def quantise(grey, levels):
-    """[B5] q = min(floor(grey*L), L-1) with an f32 multiply."""
-    q = torch.floor(grey * float(levels)).to(torch.int64)
+def quantise(grey, levels, rule="floor"):
+    """[B5] q = min(floor(grey*L), L-1) with an f32 multiply (rule "floor"); rule "u8" (GLCM only, see RULES) scales the
+    254-level case by 255 instead."""
+    scale = 255.0 if (rule == "u8" and int(levels) == 254) else float(levels)
+    q = torch.floor(grey * scale).to(torch.int64)
     return torch.clamp(q, max=int(levels) - 1)
 
 
@@ -469,7 +514,7 @@ def glcm_counts(grey, offset, levels, masks):
     N, _, H, W = grey.shape
     L = int(levels)
     dy, dx = offset
-    q = quantise(grey, L)[:, 0]
+    q = quantise(grey, L, RULES["glcm_quant"])[:, 0]
     m = masks[:, 0] != 0
     r0, r1 = max(0, -dy), min(H, H - dy)
     c0, c1 = max(0, -dx), min(W, W - dx)
@@ -667,7 +712,7 @@ def gabor_bank(angles=GABOR_ANGLES, ksize=GABOR_KERNEL, freqs=GABOR_FREQUENCIES,
     U, V = np.meshgrid(t, t)          # U varies along columns, V along rows
     bank = []
     for a in range(angles):
-        th = a * 2.0 * np.pi / angles
+        th = a * RULES["gabor_span"] / angles
         xr = U * np.cos(th) + V * np.sin(th)
         for f in freqs:
             bank.append(np.exp(-(U * U + V * V) / (2.0 * sigma * sigma)) * np.cos(2.0 * np.pi * f * xr))

