@@ -424,7 +424,7 @@ def roofline_of(run, workload, nuclei, P, F, peak, peak_kind, world=1):
     kern = run["kern"]
     if not kern:
         return None
-    R = max(1, min(P, 1024 // P))
+    R = max(1, min(P, 256 // ((P + 3) // 4)))      # hue_slab_rows(P) of color.cu
     slabs = (P + R - 1) // R
     for k, v in kern.items():
         v["gbs"] = kernel_bytes(k, P, slabs) * nuclei / (v["avg_ms"] * 1e-3) / 1e9 if v["avg_ms"] > 0 else 0.0

@@ -44,7 +44,7 @@ typedef struct nfx_ctx nfx_ctx;
 
 /* Mirrors the reference's operating-point flags (src/args.rs:93-108). */
 typedef struct nfx_config {
-    int32_t patch_size;   /* -p/--patch-size, default 64. A multiple of 4 in [16, 256]. */
+    int32_t patch_size;   /* -p/--patch-size, default 64. Any size in [16, 256] (odd sizes included). */
     int32_t batch_size;   /* -b/--batch-size, default 100. mean_h couples the nuclei of one chunk
                              [k*B,(k+1)*B) (src/features/color.rs:50-51, 144-155; src/main.rs:148). */
     int32_t rule_flags;   /* NFX_RULE_* bits below; 0 = the rules of oracle/SPEC.md */

@@ -552,7 +552,7 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     __shared__ int s_nact;
     __shared__ float s_rcp[256];   // (pi/3) / d
     for (int k = tid; k < 256; k += kThreads) s_rcp[k] = k ? __fdiv_rn(1.0471975511965976f, (float)k) : 0.f;
-    const int qpr = P >> 2, nquads = R * qpr;
+    const int qpr = (P + 3) >> 2, nquads = R * qpr;   // the last quad of a row may hang over (P % 4 != 0): never stored
     const int nrows_u = min(R, P - row0), words_u = nrows_u * wpr;
     if (tid < 64) s_union[tid] = 0u;
     for (int k = tid; k < R * ppitch; k += kThreads) pre[k] = make_int2(0, 0);
@@ -811,7 +811,8 @@ __global__ void k_hue_finalize(const ColorParams p) {
 
 }  // namespace
 
-int hue_slab_rows(int P) { return max(1, min(P, 1024 / P)); }
+// rows per (chunk, slab) CTA of k_hue_batch: at most kHueMaxQuads pixel quads (one per consumer thread)
+int hue_slab_rows(int P) { return max(1, min(P, kHueMaxQuads / ((P + 3) / 4))); }
 int color_slab_rows(int P) { return P < 64 ? P : 64; }
 int color_smem_bytes(int P) {
     const int cs = color_slab_rows(P);

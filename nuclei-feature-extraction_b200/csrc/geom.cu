@@ -143,6 +143,10 @@ __host__ __device__ __forceinline__ size_t geom_edge_offset(int P, int vmax, boo
     return (b + 15) & ~(size_t)15;
 }
 
+__host__ __device__ __forceinline__ size_t ring_bytes(int vmax) {
+    return (size_t)((vmax + 1) & ~1) * 8 + (size_t)vmax * 16 + (((size_t)vmax * 2 * 4 + 15) & ~(size_t)15);
+}
+
 template <bool RASTER, bool SHAPE>
 __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNpc) k_geom(const GeomParams p, const int nuc_smem) {
     constexpr int kGeomThreads = GeomCfg<SHAPE>::kThreads, kNpc = GeomCfg<SHAPE>::kNpc;
@@ -156,12 +160,18 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
     const int64_t o0 = p.poly_off[i];
     const int V = (int)(p.poly_off[i + 1] - o0);
 
-    // shared layout: rows[P*wpr] u32 | pts[vmax] float2 | sorted[vmax] double2 | stk[2*vmax] int
+    // shared layout: rows[P*wpr] u32 | pts[cap] float2 | sorted[cap] double2 | stk[2*cap] int | edge records.
+    // A ring longer than the shared-memory capacity (kGeomRingSmem vertices) keeps pts / sorted / stk in its HBM slot.
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw);
+    int cap = p.vsmem;
     float2* pts = reinterpret_cast<float2*>(rows + ((P * wpr + 3) & ~3));
-    double2* sorted = reinterpret_cast<double2*>(pts + ((p.vmax + 1) & ~1));   // 16-byte aligned
-    int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? p.vmax : 0));
-    EdgeRecs* erecs = reinterpret_cast<EdgeRecs*>(smem_raw + geom_edge_offset(P, p.vmax, SHAPE));   // RASTER only
+    if (V > p.vsmem) {
+        cap = p.vmax;
+        pts = reinterpret_cast<float2*>(p.ring_scratch + (size_t)p.giant_slot[i] * ring_bytes(p.vmax));
+    }
+    double2* sorted = reinterpret_cast<double2*>(pts + ((cap + 1) & ~1));   // 16-byte aligned
+    int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? cap : 0));
+    EdgeRecs* erecs = reinterpret_cast<EdgeRecs*>(smem_raw + geom_edge_offset(P, p.vsmem, SHAPE));   // RASTER only
     __shared__ double s_red[16];
     __shared__ float s_c_all[kNpc][2];
     __shared__ int s_hull[2];
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
     }
     __syncthreads();
     if (tid == 0 || tid == 32) {
-        int* S = stk + (tid == 0 ? 0 : p.vmax);
+        int* S = stk + (tid == 0 ? 0 : cap);
         int sz = 0;
         for (int t = 0; t < V; ++t) {
             const int idx = (tid == 0) ? t : V - 1 - t;
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
     __syncthreads();
     if (tid == 0) {
         const int nl = max(s_hull[0] - 1, 0), nu = max(s_hull[1] - 1, 0), h = nl + nu;
-        auto hp = [&](int k) -> double2 { return sorted[k < nl ? stk[k] : stk[p.vmax + (k - nl)]]; };
+        auto hp = [&](int k) -> double2 { return sorted[k < nl ? stk[k] : stk[cap + (k - nl)]]; };
         double sh = 0.0, per = 0.0;
         for (int k = 0; k < h; ++k) {
             const double2 a = hp(k), b = hp(k + 1 == h ? 0 : k + 1);
@@ -399,9 +409,13 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
 
 }  // namespace
 
+size_t geom_ring_bytes(int vmax) {   // pts | sorted | stk, every part 16-byte aligned (= ring_bytes below)
+    return (size_t)((vmax + 1) & ~1) * 8 + (size_t)vmax * 16 + (((size_t)vmax * 2 * 4 + 15) & ~(size_t)15);
+}
+
 cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s) {
     if (p.n <= 0) return cudaSuccess;
-    size_t nuc = geom_edge_offset(p.P, p.vmax, shape);
+    size_t nuc = geom_edge_offset(p.P, p.vsmem, shape);
     if (raster) nuc += sizeof(EdgeRecs);
     nuc = (nuc + 15) & ~(size_t)15;
     auto go = [&](auto kern, int threads, int npc) -> cudaError_t {

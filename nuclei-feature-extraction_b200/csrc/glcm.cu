@@ -48,9 +48,10 @@ __host__ __device__ inline GlcmSmem glcm_layout(int P) {
     L.region_a = 0;
     L.rows = a;
     L.q128 = L.rows + ((P * mask_wpr(P) * 4 + 15) & ~15);
-    L.q254 = L.q128 + P * P;
-    L.pairs = L.q254 + P * P;                       // u32 per pair: a254 | b254<<8 | a128<<16 | b128<<24
-    L.hist = L.pairs + P * P * 4;
+    const int plane = (P * P + 15) & ~15;           // odd patch sizes: keep every array 16-byte aligned
+    L.q254 = L.q128 + plane;
+    L.pairs = L.q254 + plane;                       // u32 per pair: a254 | b254<<8 | a128<<16 | b128<<24
+    L.hist = L.pairs + ((P * P * 4 + 15) & ~15);
     L.part_i = L.hist + (256 + 512 + 256) * 4;
     L.part_f = L.part_i + kCombos * kNW * kNI * 8;  // u64
     L.total = L.part_f + kCombos * kNW * kNF * 4;
@@ -412,9 +413,10 @@ __host__ __device__ inline Glcm64Smem glcm64_layout(int P) {
     L.marg = kRegionA64;
     L.rows = L.marg + kMargWords * 4;
     L.q128 = L.rows + ((P * mask_wpr(P) * 4 + 15) & ~15);
-    L.q254 = L.q128 + P * P;
-    L.list = L.q254 + P * P;
-    L.parts = L.list + P * P * 2;
+    const int plane = (P * P + 15) & ~15;           // odd patch sizes: keep every array 16-byte aligned
+    L.q254 = L.q128 + plane;
+    L.list = L.q254 + plane;
+    L.parts = L.list + ((P * P * 2 + 15) & ~15);
     L.total = L.parts + kCombos * kG64NW * kNP * 4;
     return L;
 }
@@ -744,7 +746,7 @@ __host__ __device__ inline GlcmLargeSmem glcm_large_layout(int P) {
     L.region_t = (P * (P + 4) + 127) & ~127;   // plane rows are P + 4 bytes apart: a 256-byte pitch would put every row on the same banks
     int t = window_smem_bytes(P, 64) > kTriBytes ? window_smem_bytes(P, 64) : kTriBytes;
     L.rows = L.region_t + ((t + 127) & ~127);
-    L.hist = L.rows + P * mask_wpr(P) * 4;
+    L.hist = L.rows + ((P * mask_wpr(P) * 4 + 15) & ~15);
     L.part_i = L.hist + 3 * 1024 * 4;   // hx[256] hs[512] hd[256] for each of the (up to) three levels of a round
     L.part_f = L.part_i + kCombos * kLNW * kNI * 8;
     L.total = L.part_f + kCombos * kLNW * kNF * 4;

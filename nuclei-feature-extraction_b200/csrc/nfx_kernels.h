@@ -25,7 +25,10 @@ struct GeomParams {
     int64_t n;
     int P;
     int tile_ox, tile_oy;      // slide coordinates of tile pixel (0,0)
-    int vmax;                  // max ring length in this launch (sizes dynamic shared memory)
+    int vmax;                  // max ring length in this launch
+    int vsmem;                 // ring capacity of the shared-memory layout = min(vmax, kGeomRingSmem); longer rings work in HBM:
+    const int* giant_slot;     // [n] slot of nucleus i in ring_scratch, -1 for rings that fit (nullptr: none is longer)
+    unsigned char* ring_scratch;   // [slots][geom_ring_bytes(vmax)] pts | sorted | stk of the long rings
     float2* centroid;          // [n] out (RASTER) / unused
     NucInfo* info;             // [n] out (RASTER) / unused
     uint32_t* bitmask;         // [n][P][wpr]: out when RASTER, in otherwise
@@ -39,6 +42,8 @@ struct GeomParams {
 // raster=true : polygons are raw rings; computes centroid/info, rasterises, writes bitmask.
 // raster=false: polygons are already centred and bitmask is an input (trait-level path).
 cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s);
+constexpr int kGeomRingSmem = 4000;   // vertices of a ring kept in shared memory (32 B each with the hull's work arrays)
+size_t geom_ring_bytes(int vmax);     // bytes of one ring_scratch slot
 
 // ---- color.cu ---------------------------------------------------------------------------------
 struct ColorParams {

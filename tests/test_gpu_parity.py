@@ -283,9 +283,10 @@ def test_mid_p128_all_sets(libnfx):
     check_all_columns(got, names, rings, tile, 128, 5, sets=["geometry", "color", "glcm"])      # every column, not a selection
 
 
-@pytest.mark.parametrize("P,scale", [(16, 0.05), (20, 0.07), (48, 0.17), (80, 0.28), (96, 0.34), (200, 0.75)])
+@pytest.mark.parametrize("P,scale", [(16, 0.05), (20, 0.07), (48, 0.17), (80, 0.28), (96, 0.34), (200, 0.75),
+                                     (17, 0.05), (50, 0.18), (63, 0.22), (101, 0.36), (255, 0.9)])   # not multiples of 4, odd
 def test_odd_patch_sizes_all_sets(libnfx, P, scale):
-    """patch_size is any multiple of 4 in [16, 256]: sizes that are not powers of two leave partial mask words, partial
+    """patch_size is any size in [16, 256]: sizes that are not powers of two leave partial mask words, partial pixel quads,
     hue slabs (1024 / P rows), partial Gabor tiles (P = 80, 96, 200) and take each of the three GLCM kernels."""
     tile, rings = stress_case(n=10, size=640, seed=P, patch=256)
     rings = [((r - r.mean(0)) * scale + r.mean(0)).astype(np.float32) for r in rings]
@@ -689,3 +690,25 @@ def test_rule_gabor_half_turn_is_oracle_only(case):
             e.compute(nfx.FS_GABOR)
     with pytest.raises(nfx.NfxError):
         nfx.Extractor(0, 64, 100, rule_flags=0x100)  # unknown bit
+
+
+def test_rings_longer_than_the_shared_memory_capacity(libnfx):
+    """A 10 000-vertex ring (and a 4 001-vertex one) among ordinary nuclei: rings beyond k_geom's shared-memory capacity
+    (4 000 vertices) keep their work arrays in HBM; masks bit-exact, every column in parity."""
+    tile = synth.synth_tile(400, 400, 21)
+    xy, off = synth.synth_polygons(12, 400, 400, 21)
+    rings = synth.rings_of(xy, off)
+    rng = np.random.default_rng(21)
+    for V, c in ((10_000, (150.3, 160.7)), (4_001, (260.5, 240.25))):
+        t = 2 * np.pi * np.arange(V + 1) / V
+        t[-1] = 0.0
+        r = 22.0 * (1 + 0.2 * np.cos(5 * t) + 0.03 * np.cos(131 * t)) + rng.uniform(-0.2, 0.2, V + 1)
+        r[-1] = r[0]
+        rings.insert(len(rings) // 2, np.stack([c[0] + r * np.cos(t), c[1] + r * np.sin(t)], 1).astype(np.float32))
+    xy, off = nfx.pack_polygons(rings)
+    with nfx.Extractor(0, 64, 5) as e:
+        e.upload_tile(tile)
+        keys, cents, got, names = e.extract(xy, off, ["all"])
+        masks = e.rasterize()
+    pm = check_all_columns(got, names, rings, tile, 64, 5)
+    assert np.array_equal(masks != 0, pm[:, 0].numpy() != 0)
