@@ -146,6 +146,22 @@ int nfx_extract(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int64_t* po
 
 int nfx_sync(nfx_ctx* ctx);
 
+/* ---- extension outputs ----------------------------------------------------------------------------
+ * Quantities BASELINE.json's north_star lists that the REFERENCE does not compute: masked skewness /
+ * kurtosis, raw / central / Hu moments of the mask, a contour perimeter, and the GLCM at distance 2 (BASELINE config 3's
+ * "32 grey levels, distances 1/2, 4 angles"). They have no reference counterpart -- oracle/SPEC.md section C defines
+ * them -- and are NEVER part of the 418-column drop-in schema: their own bit mask, matrix and column names.
+ * Needs a staged tile and polygons like nfx_compute; rows in input order, columns in the order of the bits below. */
+#define NFX_EXT_COLOR_MOMENTS 0x1u   /* skew_<c>, kurtosis_<c> for c in r g b grey s v haematoxylin eosin dab   (18 columns) */
+#define NFX_EXT_MASK_MOMENTS  0x2u   /* m00 m10 m01 m20 m11 m02 m30 m21 m12 m03 mu20 mu11 mu02 mu30 mu21 mu12 mu03 hu1..hu7 (24) */
+#define NFX_EXT_CONTOUR       0x4u   /* contour_crack_length, contour_perimeter                                     (2) */
+#define NFX_EXT_GLCM_D2       0x8u   /* <haralick>_<dy>_<dx>_32 for (dy,dx) in (0,1) (1,1) (1,0) (1,-1) (0,2) (2,2) (2,0) (2,-2) (112) */
+#define NFX_EXT_ALL           0xFu
+int nfx_ext_feature_count(uint32_t ext_mask);
+const char* nfx_ext_feature_name(uint32_t ext_mask, int idx);
+int nfx_compute_ext(nfx_ctx* ctx, uint32_t ext_mask);
+int nfx_download_ext(nfx_ctx* ctx, float* out /* [n][nfx_ext_feature_count(ext_mask)] */);
+
 /* ---- trait-level drop-in -------------------------------------------------------------------- */
 /* FeatureSet::compute_features_batched(centroids, polygons, patchs, masks) (src/features/mod.rs:
  * 12-28) for ONE batch built by the reference's own loader: patchs [n,3,P,P] f32 with values k/255

@@ -82,6 +82,8 @@ struct nfx_ctx {
     DevBuf<NucInfo> info;
     DevBuf<uint32_t> bitmask;
     DevBuf<float> out;
+    DevBuf<float> ext_out;
+    uint32_t ext_mask = 0;
     DevBuf<float> hue;
     DevBuf<uint32_t> ellipse;
     DevBuf<double> gabor_part;
@@ -383,7 +385,7 @@ int nfx_destroy(nfx_ctx* ctx) {
     for (auto& pr : ctx->peers) cudaIpcCloseMemHandle(pr.second);
     ctx->peers.clear();
     ctx->tile.release(); ctx->xy.release(); ctx->off.release(); ctx->centroid.release(); ctx->info.release();
-    ctx->giant_slot.release(); ctx->ring_scratch.release(); ctx->bitmask.release(); ctx->out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->gabor_part.release(); ctx->patches.release();
+    ctx->giant_slot.release(); ctx->ring_scratch.release(); ctx->bitmask.release(); ctx->out.release(); ctx->ext_out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->gabor_part.release(); ctx->patches.release();
     ctx->scratch8.release(); ctx->scratchf.release(); ctx->scratch32.release(); ctx->flush.release();
     ctx->csv_len.release(); ctx->csv_off.release(); ctx->csv_tmp.release(); ctx->csv_text.release(); ctx->csv_in.release();
     if (ctx->d_bad) cudaFree(ctx->d_bad);
@@ -557,6 +559,7 @@ int nfx_polygons_upload(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int
     ctx->have_poly = true;
     ctx->have_geom = false;
     ctx->computed_mask = 0;
+    ctx->ext_mask = 0;
     return NFX_OK;
 }
 
@@ -579,6 +582,81 @@ int nfx_compute(nfx_ctx* ctx, uint32_t mask) {
     if (mask & (NFX_FS_GLRLM | NFX_FS_GABOR))
         if ((rc = run_tex2(ctx, n, mask, &ctx->map_tile_cslab, &ctx->map_tile_patch, &ctx->map_tile_gabor, ctx->out.p, c.total, c.glrlm, c.gabor))) return rc;
     ctx->computed_mask = mask;
+    return NFX_OK;
+}
+
+// ---- extension outputs (ext.cu) ---------------------------------------------------------------------
+namespace {
+const char* const kExtChan[9] = {"r", "g", "b", "grey", "s", "v", "haematoxylin", "eosin", "dab"};
+const char* const kExtMask[24] = {"m00", "m10", "m01", "m20", "m11", "m02", "m30", "m21", "m12", "m03", "mu20", "mu11", "mu02", "mu30",
+                                  "mu21", "mu12", "mu03", "hu1", "hu2", "hu3", "hu4", "hu5", "hu6", "hu7"};
+const char* const kExtHaralick[14] = {"correlation", "contrast", "dissimilarity", "entropy", "angular_second_moment", "sum_average",
+                                      "sum_variance", "sum_entropy", "sum_of_squares", "inverse_difference_moment", "difference_average",
+                                      "difference_variance", "information_measure_correlation1", "information_measure_correlation2"};
+const int kExtOff[8][2] = {{0, 1}, {1, 1}, {1, 0}, {1, -1}, {0, 2}, {2, 2}, {2, 0}, {2, -2}};
+thread_local std::string g_ext_name;
+}  // namespace
+
+int nfx_ext_feature_count(uint32_t m) {
+    if (m & ~NFX_EXT_ALL) return -1;
+    return ((m & NFX_EXT_COLOR_MOMENTS) ? kExtColorCols : 0) + ((m & NFX_EXT_MASK_MOMENTS) ? kExtMaskCols : 0) +
+           ((m & NFX_EXT_CONTOUR) ? kExtContourCols : 0) + ((m & NFX_EXT_GLCM_D2) ? kExtGlcmCols : 0);
+}
+
+const char* nfx_ext_feature_name(uint32_t m, int idx) {
+    if (idx < 0 || idx >= nfx_ext_feature_count(m)) return nullptr;
+    if (m & NFX_EXT_COLOR_MOMENTS) {
+        if (idx < kExtColorCols) { g_ext_name = std::string((idx & 1) ? "kurtosis_" : "skew_") + kExtChan[idx / 2]; return g_ext_name.c_str(); }
+        idx -= kExtColorCols;
+    }
+    if (m & NFX_EXT_MASK_MOMENTS) {
+        if (idx < kExtMaskCols) return kExtMask[idx];
+        idx -= kExtMaskCols;
+    }
+    if (m & NFX_EXT_CONTOUR) {
+        if (idx < kExtContourCols) return idx == 0 ? "contour_crack_length" : "contour_perimeter";
+        idx -= kExtContourCols;
+    }
+    const int o = idx / 14;
+    g_ext_name = std::string(kExtHaralick[idx % 14]) + "_" + std::to_string(kExtOff[o][0]) + "_" + std::to_string(kExtOff[o][1]) + "_32";
+    return g_ext_name.c_str();
+}
+
+int nfx_compute_ext(nfx_ctx* ctx, uint32_t m) {
+    int rc = need_inputs(ctx, true);
+    if (rc) return rc;
+    if (m == 0 || (m & ~NFX_EXT_ALL)) return fail(ctx, NFX_ERR_INVALID, "empty or unknown extension mask");
+    if ((rc = set_device(ctx))) return rc;
+    const int cols = nfx_ext_feature_count(m);
+    const int64_t n = ctx->n;
+    CK(ctx->ext_out.ensure((size_t)std::max<int64_t>(n, 1) * cols));
+    ctx->ext_mask = 0;
+    if (n == 0) { ctx->ext_mask = m; return NFX_OK; }
+    if (!ctx->have_geom)
+        if ((rc = run_geom(ctx, false, nullptr, 0, -1, nullptr))) return rc;
+    ExtParams e;
+    e.n = n; e.P = ctx->P; e.info = ctx->info.p; e.bitmask = ctx->bitmask.p;
+    e.tile = ctx->tile.p; e.tpitch = ctx->tpitch; e.tw = ctx->tw; e.th = ctx->th;
+    e.out = ctx->ext_out.p; e.out_stride = cols;
+    int c = 0;
+    e.col_color = (m & NFX_EXT_COLOR_MOMENTS) ? c : -1;  c += (m & NFX_EXT_COLOR_MOMENTS) ? kExtColorCols : 0;
+    e.col_mask = (m & NFX_EXT_MASK_MOMENTS) ? c : -1;    c += (m & NFX_EXT_MASK_MOMENTS) ? kExtMaskCols : 0;
+    e.col_contour = (m & NFX_EXT_CONTOUR) ? c : -1;      c += (m & NFX_EXT_CONTOUR) ? kExtContourCols : 0;
+    e.col_glcm = (m & NFX_EXT_GLCM_D2) ? c : -1;
+    CK(timed(ctx, "k_ext", 2, [&] { return launch_ext(e, ctx->stream); }));
+    ctx->ext_mask = m;
+    return NFX_OK;
+}
+
+int nfx_download_ext(nfx_ctx* ctx, float* out) {
+    if (!ctx) return NFX_ERR_INVALID;
+    if (!ctx->ext_mask) return fail(ctx, NFX_ERR_STATE, "nothing computed: call nfx_compute_ext first");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    if (ctx->n > 0 && out)
+        CK(cudaMemcpyAsync(out, ctx->ext_out.p, (size_t)ctx->n * nfx_ext_feature_count(ctx->ext_mask) * sizeof(float),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return NFX_OK;
 }
 

@@ -118,6 +118,21 @@ cudaError_t launch_pack_batch(int64_t n, int P, const float* patchs, const float
                               uint8_t* patches_u8, int64_t pitch, uint32_t* bitmask, NucInfo* info,
                               int* bad_count, cudaStream_t s);
 
+// ---- ext.cu: extension outputs (north_star items the reference does not compute; never part of the drop-in schema) ----
+constexpr int kExtColorCols = 18, kExtMaskCols = 24, kExtContourCols = 2, kExtGlcmCols = 112;
+struct ExtParams {
+    int64_t n;
+    int P;
+    const NucInfo* info;
+    const uint32_t* bitmask;
+    const uint8_t* tile;       // the resident slide (u8 interleaved RGB)
+    int64_t tpitch, tw, th;
+    float* out;                // [n][out_stride]
+    int out_stride;
+    int col_color, col_mask, col_contour, col_glcm;   // first column of each extension set, or -1
+};
+cudaError_t launch_ext(const ExtParams& p, cudaStream_t s);
+
 // ---- csv.cu: output assembly -----------------------------------------------
 struct CsvParams {
     const float2* centroids;   // [n] all rows of the context

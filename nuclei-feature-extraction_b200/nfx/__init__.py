@@ -17,6 +17,7 @@ import numpy as np
 from ._lib import (FS_ALL, FS_COLOR, FS_GABOR, FS_GEOMETRY, FS_GLCM, FS_GLRLM, FS_TEXTURE, NFX_OK, RULE_GABOR_HALF_TURN,
                    RULE_GLCM_254_U8, RULE_RASTER_PIXEL_CENTRE, RULE_WINDOW_SLIDE, NfxConfig, NfxError, NfxKernelTime,
                    NfxTiffLevel, lib)
+from ._lib import EXT_ALL, EXT_COLOR_MOMENTS, EXT_CONTOUR, EXT_GLCM_D2, EXT_MASK_MOMENTS  # noqa: F401
 
 _FLAT_BITS = (FS_GEOMETRY, FS_COLOR, FS_GLCM, FS_GLRLM, FS_GABOR)
 
@@ -247,6 +248,15 @@ class Extractor:
 
     def sync(self):
         self._ck(lib().nfx_sync(self._h))
+
+    def compute_ext(self, ext_mask: int = EXT_ALL):
+        """Extension outputs (include/nfx.h NFX_EXT_*: skew / kurtosis, mask moments, contour length, GLCM at distance 2) for
+        the staged tile + polygons: (names, [n, F] f32). Never part of the drop-in schema."""
+        self._ck(lib().nfx_compute_ext(self._h, ext_mask))
+        F = lib().nfx_ext_feature_count(ext_mask)
+        out = np.empty((self.n, F), dtype=np.float32)
+        self._ck(lib().nfx_download_ext(self._h, _ptr(out)))
+        return [lib().nfx_ext_feature_name(ext_mask, i).decode() for i in range(F)], out
 
     def download(self, centroids=None, features=None):
         F = lib().nfx_feature_count(self._mask)

@@ -20,6 +20,8 @@ class NfxConfig(C.Structure):
 
 # nfx_config.rule_flags (include/nfx.h): switches of the unpinned rules, mirrored by oracle.RULES
 RULE_RASTER_PIXEL_CENTRE, RULE_GABOR_HALF_TURN, RULE_GLCM_254_U8, RULE_WINDOW_SLIDE = 0x1, 0x2, 0x4, 0x8
+# extension outputs (never part of the drop-in schema)
+EXT_COLOR_MOMENTS, EXT_MASK_MOMENTS, EXT_CONTOUR, EXT_GLCM_D2, EXT_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 
 
 class NfxTiffLevel(C.Structure):
@@ -45,6 +47,10 @@ SYMBOLS = {
     "nfx_slide_import_rows": (_i, [_vp, _vp, _i64, _i64]),
     "nfx_slide_copy_rows": (_i, [_vp, _vp, _i64, _i64]),
     "nfx_polygons_upload": (_i, [_vp, _i64, _vp, _vp]),
+    "nfx_ext_feature_count": (_i, [_u32]),
+    "nfx_ext_feature_name": (C.c_char_p, [_u32, _i]),
+    "nfx_compute_ext": (_i, [_vp, _u32]),
+    "nfx_download_ext": (_i, [_vp, _vp]),
     "nfx_compute": (_i, [_vp, _u32]),
     "nfx_download": (_i, [_vp, _vp, _vp]),
     "nfx_extract": (_i, [_vp, _i64, _vp, _vp, _u32, _vp, _vp]),

@@ -775,3 +775,101 @@ def extract(rings, image_hwc, feature_sets, patch_size=64, batch_size=100):
         cents.append(c)
         keys += [centroid_key(x) for x in c]
     return keys, np.concatenate(cents, 0), np.concatenate(rows, 0), names
+
+
+# --------------------------------------------------------------------------------------------
+# EXTENSION outputs (BASELINE.json north_star items the REFERENCE does not compute: skew / kurtosis, raw / central /
+# Hu moments, a contour perimeter, GLCM at distance 2). They have no reference counterpart -- the definitions below
+# ARE the specification (SPEC.md section C) -- and are never mixed into the 418-column drop-in schema:
+# separate NFX_EXT_* bits, separate matrix (include/nfx.h nfx_compute_ext).
+# --------------------------------------------------------------------------------------------
+EXT_COLOR_CHANNELS = ("r", "g", "b", "grey", "s", "v", "haematoxylin", "eosin", "dab")
+EXT_COLOR_COLUMNS = [f"{m}_{c}" for c in EXT_COLOR_CHANNELS for m in ("skew", "kurtosis")]
+EXT_MASK_COLUMNS = ["m00", "m10", "m01", "m20", "m11", "m02", "m30", "m21", "m12", "m03",
+                    "mu20", "mu11", "mu02", "mu30", "mu21", "mu12", "mu03"] + [f"hu{k}" for k in range(1, 8)]
+EXT_CONTOUR_COLUMNS = ["contour_crack_length", "contour_perimeter"]
+EXT_GLCM_OFFSETS = ((0, 1), (1, 1), (1, 0), (1, -1), (0, 2), (2, 2), (2, 0), (2, -2))   # BASELINE config 3: 32 levels, d in {1, 2}
+EXT_GLCM_COLUMNS = [f"{f}_{o[0]}_{o[1]}_32" for o in EXT_GLCM_OFFSETS for f in GLCM_FEATURES]
+EXT_COLUMNS = {"color_moments": EXT_COLOR_COLUMNS, "mask_moments": EXT_MASK_COLUMNS, "contour": EXT_CONTOUR_COLUMNS,
+               "glcm_d2": EXT_GLCM_COLUMNS}
+EXT_ORDER = ("color_moments", "mask_moments", "contour", "glcm_d2")
+
+
+def ext_color_moments(patchs, masks):
+    """[C1] masked population skewness m3 / m2^1.5 and excess kurtosis m4 / m2^2 - 3 (scipy.stats.skew / kurtosis with
+    their defaults) of r, g, b, grey = ((r+g)+b)/3, s, v, haematoxylin, eosin, dab; float64; m2 == 0 -> NaN. [N,18]."""
+    hsv, hed = hsv_from_rgb(patchs), hed_from_rgb(patchs)
+    chans = torch.cat([patchs, grey_scale(patchs), hsv[:, 1:3], hed], dim=1).to(torch.float64)   # [N,9,P,P]
+    m = masks.to(torch.float64)
+    K = m.sum(dim=[1, 2, 3]).view(-1, 1, 1, 1)
+    mean = (chans * m).sum(dim=[2, 3], keepdim=True) / K
+    d = (chans - mean) * m
+    m2, m3, m4 = [(d ** k).sum(dim=[2, 3]) / K.view(-1, 1) for k in (2, 3, 4)]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        skew, kurt = (m3 / m2 ** 1.5).numpy(), (m4 / (m2 * m2) - 3.0).numpy()
+    bad = ~(m2.numpy() > 0)
+    skew[bad], kurt[bad] = np.nan, np.nan
+    return np.stack([skew, kurt], axis=2).reshape(len(patchs), 18).astype(F32)
+
+
+def ext_mask_moments(masks):
+    """[C2] cv2.moments(mask, binaryImage=True) + cv2.HuMoments on the raster mask: x = column, y = row, float64.
+    Raw m_pq = sum x^p y^q (exact integers), central mu_pq about (m10/m00, m01/m00), nu_pq = mu_pq / m00^((p+q)/2+1),
+    Hu's seven invariants. Empty mask -> m00 = 0 and NaN for everything that divides by it. [N,24]."""
+    out = []
+    for m in masks[:, 0].numpy() != 0:
+        ys, xs = np.nonzero(m)
+        x, y = xs.astype(np.float64), ys.astype(np.float64)
+        raw = [float(len(x)), x.sum(), y.sum(), (x * x).sum(), (x * y).sum(), (y * y).sum(), (x ** 3).sum(), (x * x * y).sum(),
+               (x * y * y).sum(), (y ** 3).sum()]
+        if len(x) == 0:
+            out.append(raw + [np.nan] * 14)
+            continue
+        cx, cy = raw[1] / raw[0], raw[2] / raw[0]
+        dx, dy = x - cx, y - cy
+        mu = {"20": (dx * dx).sum(), "11": (dx * dy).sum(), "02": (dy * dy).sum(), "30": (dx ** 3).sum(), "21": (dx * dx * dy).sum(),
+              "12": (dx * dy * dy).sum(), "03": (dy ** 3).sum()}
+        n = {k: v / raw[0] ** ((int(k[0]) + int(k[1])) / 2.0 + 1.0) for k, v in mu.items()}
+        a, b = n["30"] + n["12"], n["21"] + n["03"]
+        c, d = n["30"] - 3 * n["12"], 3 * n["21"] - n["03"]
+        hu = [n["20"] + n["02"],
+              (n["20"] - n["02"]) ** 2 + 4 * n["11"] ** 2,
+              c * c + d * d,
+              a * a + b * b,
+              c * a * (a * a - 3 * b * b) + d * b * (3 * a * a - b * b),
+              (n["20"] - n["02"]) * (a * a - b * b) + 4 * n["11"] * a * b,
+              d * a * (a * a - 3 * b * b) - c * b * (3 * a * a - b * b)]
+        out.append(raw + [mu[k] for k in ("20", "11", "02", "30", "21", "12", "03")] + hu)
+    return np.array(out, dtype=np.float64).astype(F32)
+
+
+def ext_contour(masks):
+    """[C3] boundary length of the raster mask, two local definitions (pixels outside the window count as background):
+    contour_crack_length = number of pixel edges between a set and an unset 4-neighbour (the exact length of the
+    boundary cracks); contour_perimeter = Pratt's bit-quad estimate n(Q2) + (n(Q1) + n(Q3) + 2 n(QD)) / sqrt(2) over all
+    2 x 2 windows of the zero-padded mask (Q_k = k set pixels, QD = the two diagonal ones). [N,2]."""
+    out = []
+    for m in masks[:, 0].numpy() != 0:
+        p = np.pad(m.astype(np.int64), 1)
+        crack = (np.abs(np.diff(p, axis=0)).sum() + np.abs(np.diff(p, axis=1)).sum())
+        q = p[:-1, :-1] + p[:-1, 1:] + p[1:, :-1] + p[1:, 1:]
+        diag = (q == 2) & (p[:-1, :-1] == p[1:, 1:])
+        n1, n2, n3, nd = (q == 1).sum(), ((q == 2) & ~diag).sum(), (q == 3).sum(), diag.sum()
+        out.append([float(crack), n2 + (n1 + n3 + 2 * nd) / math.sqrt(2.0)])
+    return np.array(out, dtype=np.float64).astype(F32)
+
+
+def ext_glcm_d2(patchs, masks):
+    """[C4] BASELINE config 3's literal variant: 32 grey levels, distances 1 and 2, 4 angles = 8 symmetric masked matrices
+    (rules B5 / B6 unchanged, offsets EXT_GLCM_OFFSETS) x 14 Haralick features. [N,112]."""
+    grey = grey_scale(patchs)
+    return np.concatenate([glcm_features(glcm(grey, off, 32, masks)) for off in EXT_GLCM_OFFSETS], axis=1).astype(F32)
+
+
+def extract_ext(rings, image_hwc, ext_sets, patch_size=64):
+    """Extension matrix for the given sets (EXT_ORDER order): (names, [N,F] f32)."""
+    cents, polys, patches, masks = load_image_dataset(rings, image_hwc, patch_size)
+    fn = {"color_moments": lambda: ext_color_moments(patches, masks), "mask_moments": lambda: ext_mask_moments(masks),
+          "contour": lambda: ext_contour(masks), "glcm_d2": lambda: ext_glcm_d2(patches, masks)}
+    sets = [s for s in EXT_ORDER if s in ext_sets]
+    return [c for s in sets for c in EXT_COLUMNS[s]], np.concatenate([fn[s]() for s in sets], axis=1)

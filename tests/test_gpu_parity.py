@@ -712,3 +712,63 @@ def test_rings_longer_than_the_shared_memory_capacity(libnfx):
         masks = e.rasterize()
     pm = check_all_columns(got, names, rings, tile, 64, 5)
     assert np.array_equal(masks != 0, pm[:, 0].numpy() != 0)
+
+
+# ---- extension outputs (include/nfx.h NFX_EXT_*, SPEC.md section C): no reference counterpart, oracle = definition --------
+def _check_ext(got, names, rings, tile, P):
+    wnames, want = o.extract_ext(rings, tile, list(o.EXT_ORDER), P)
+    assert names == wnames
+    got, want = got.astype(np.float64), want.astype(np.float64)
+    nan_ok = np.isnan(got) & np.isnan(want)
+    # moments span 1 .. 1e12 (relative tolerance); Hu invariants down to 1e-12 (their own scale: hu1^k); skew / kurtosis and the
+    # Haralick features on the scales tolerances.py uses for the drop-in GLCM
+    floor = np.full(len(names), 1e-2)
+    for j, nm in enumerate(names):
+        if nm.startswith(("m", "mu")) and nm[1:2].isdigit() or nm.startswith("mu"):
+            floor[j] = 0.0
+        if nm.startswith("hu"):
+            floor[j] = 0.0
+        if nm.startswith(("correlation_", "information_measure_")):
+            floor[j] = 1.0
+    tol = 1e-4 * np.maximum(np.abs(want), floor)
+    hu = [j for j, nm in enumerate(names) if nm.startswith("hu")]
+    k = np.array([1, 2, 3, 3, 6, 4, 6], dtype=np.float64)      # degree of each invariant in the normalised moments
+    tol[:, hu] = 1e-4 * np.maximum(np.abs(want[:, hu]), np.abs(want[:, [hu[0]]]) ** k * 1e-3)
+    mu3 = [names.index(c) for c in ("mu30", "mu21", "mu12", "mu03")]
+    tol[:, mu3] = 1e-4 * np.maximum(np.abs(want[:, mu3]), np.abs(want[:, [names.index("mu20")]]) ** 1.5 * 1e-3)   # ~0 for symmetric masks
+    mu2 = [names.index(c) for c in ("mu20", "mu11", "mu02")]
+    tol[:, mu2] = 1e-4 * np.maximum(np.abs(want[:, mu2]), (want[:, [mu2[0]]] + want[:, [mu2[2]]]) * 1e-3)   # mu11 ~ 0 for symmetric masks
+    bad = ~((np.abs(got - want) <= tol) | nan_ok)
+    assert not bad.any(), [(int(i), names[j], float(got[i, j]), float(want[i, j])) for i, j in np.argwhere(bad)[:8]]
+
+
+def test_extension_outputs(case):
+    with nfx.Extractor(0, 64, 100) as e:
+        e.upload_tile(case["tile"])
+        e.upload_polygons(case["xy"], case["off"])
+        names, got = e.compute_ext(nfx.EXT_ALL)
+        _check_ext(got, names, case["rings"], case["tile"], 64)
+        n2, g2 = e.compute_ext(nfx.EXT_CONTOUR | nfx.EXT_GLCM_D2)       # subsets keep their columns
+        assert n2 == names[42:] and g2.tobytes() == np.ascontiguousarray(got[:, 42:]).tobytes()
+        # the distance-1 columns of the extension GLCM are the drop-in schema's 32-level columns
+        keys, cents, feats, fnames = e.extract(case["xy"], case["off"], ["glcm"])
+        for nm in ("contrast_0_1_32", "entropy_1_-1_32", "correlation_1_1_32"):
+            a, b = got[:, names.index(nm)], feats[:, fnames.index(nm)]
+            assert np.allclose(a, b, rtol=1e-4, atol=1e-5, equal_nan=True), nm
+        with pytest.raises(nfx.NfxError):
+            e.compute_ext(0x40)
+
+
+def test_extension_outputs_other_patch_sizes(stress):
+    with nfx.Extractor(0, 256, 8) as e:
+        e.upload_tile(stress["tile"])
+        e.upload_polygons(stress["xy"][:stress["off"][6]], stress["off"][:7])
+        names, got = e.compute_ext(nfx.EXT_ALL)
+    _check_ext(got, names, stress["rings"][:6], stress["tile"], 256)
+    tile = synth.synth_tile(300, 300, 31)
+    xy, off = synth.synth_polygons(20, 300, 300, 31, patch=50, r0_range=(4.0, 20.0), border_frac=0.3)
+    with nfx.Extractor(0, 50, 7) as e:
+        e.upload_tile(tile)
+        e.upload_polygons(xy, off)
+        names, got = e.compute_ext(nfx.EXT_ALL)
+    _check_ext(got, names, synth.rings_of(xy, off), tile, 50)

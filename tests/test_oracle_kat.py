@@ -325,3 +325,42 @@ def test_rule_switches_of_the_unpinned_rules():
         assert o.patch_window((100.5, 200.25), 64) == (168, 68, 232, 132)
     with pytest.raises(KeyError):
         o.rules(nonsense=1)
+
+
+def test_extension_outputs_against_independent_implementations():
+    """SPEC.md section C (extension outputs, no reference counterpart): the oracle's definitions against scipy (skew /
+    kurtosis), cv2 (moments, Hu) and hand-countable boundaries."""
+    import cv2
+    from scipy import stats
+    rng = np.random.default_rng(3)
+    tile = (rng.integers(0, 256, size=(96, 96, 3))).astype(np.uint8)
+    t = np.linspace(0, 2 * np.pi, 25)
+    rings = [np.stack([48 + r * np.cos(t), 47.5 + 0.8 * r * np.sin(t) + 2 * np.cos(3 * t)], 1).astype(np.float32) for r in (9.0, 17.0, 24.5)]
+    cents, polys, patches, masks = o.load_image_dataset(rings, tile, 64)
+    cm = o.ext_color_moments(patches, masks)
+    for i in range(3):
+        sel = masks[i, 0].numpy() != 0
+        r = patches[i, 0].numpy()[sel].astype(np.float64)
+        assert np.isclose(cm[i, 0], stats.skew(r), rtol=1e-5) and np.isclose(cm[i, 1], stats.kurtosis(r), rtol=1e-5, atol=1e-6)
+        v = o.hsv_from_rgb(patches[i:i + 1])[0, 2].numpy()[sel].astype(np.float64)
+        assert np.isclose(cm[i, 10], stats.skew(v), rtol=1e-5) and np.isclose(cm[i, 11], stats.kurtosis(v), rtol=1e-5, atol=1e-6)
+    mm = o.ext_mask_moments(masks)
+    for i in range(3):
+        m8 = (masks[i, 0].numpy() != 0).astype(np.uint8)
+        M = cv2.moments(m8, binaryImage=True)
+        want = [M[k] for k in ("m00", "m10", "m01", "m20", "m11", "m02", "m30", "m21", "m12", "m03", "mu20", "mu11", "mu02", "mu30", "mu21", "mu12", "mu03")]
+        want += cv2.HuMoments(M).flatten().tolist()
+        assert np.allclose(mm[i], np.array(want, dtype=np.float32), rtol=2e-5, atol=1e-12), (mm[i], want)
+    sq = torch.zeros(1, 1, 8, 8)
+    sq[0, 0, 2:5, 1:6] = 1                      # 3 x 5 rectangle: 16 cracks; 4 corners (Q1), 2*(2+4) edge quads (Q2)
+    c = o.ext_contour(sq)[0]
+    assert c[0] == 16.0 and np.isclose(c[1], 12 + 4 / np.sqrt(2))
+    one = torch.zeros(1, 1, 8, 8)
+    one[0, 0, 0, 0] = 1                          # a corner pixel: the window border counts as background
+    assert o.ext_contour(one)[0].tolist() == [4.0, np.float32(4 / np.sqrt(2))]
+    g = o.ext_glcm_d2(patches, masks)
+    assert g.shape == (3, 112) and np.array_equal(np.nan_to_num(g[:, :14]), np.nan_to_num(o.glcm_features(o.glcm(o.grey_scale(patches), (0, 1), 32, masks))))
+    names, allx = o.extract_ext(rings, tile, list(o.EXT_ORDER))
+    assert allx.shape == (3, 18 + 24 + 2 + 112) and names[:2] == ["skew_r", "kurtosis_r"] and names[-1] == "information_measure_correlation2_2_-2_32"
+    empty = torch.zeros(1, 1, 8, 8)
+    assert o.ext_contour(empty)[0].tolist() == [0.0, 0.0] and o.ext_mask_moments(empty)[0, 0] == 0 and np.isnan(o.ext_mask_moments(empty)[0, 10])

@@ -102,3 +102,23 @@ def test_pack_polygons_roundtrip():
     rings = [np.arange(8, dtype=np.float32).reshape(4, 2), np.ones((3, 2), np.float32)]
     xy, off = nfx.pack_polygons(rings)
     assert off.tolist() == [0, 4, 7] and xy.dtype == np.float32 and xy.shape == (7, 2)
+
+
+def test_extension_schema_is_separate_from_the_drop_in_schema():
+    """NFX_EXT_*: north_star items the reference does not compute. Their names come from nfx_ext_feature_name, match the
+    oracle's EXT_COLUMNS, and never appear among the 418 drop-in columns (except the distance-1 GLCM columns at 32 levels,
+    which BASELINE config 3's literal variant repeats)."""
+    import nfx
+    import nfx_oracle as o
+    from nfx._lib import lib
+    L = lib()
+    assert L.nfx_ext_feature_count(nfx.EXT_ALL) == 18 + 24 + 2 + 112
+    assert L.nfx_ext_feature_count(0x10) == -1 and L.nfx_ext_feature_name(nfx.EXT_ALL, 156) is None
+    names = [L.nfx_ext_feature_name(nfx.EXT_ALL, i).decode() for i in range(156)]
+    assert names == [c for s in o.EXT_ORDER for c in o.EXT_COLUMNS[s]]
+    bits = {"color_moments": nfx.EXT_COLOR_MOMENTS, "mask_moments": nfx.EXT_MASK_MOMENTS, "contour": nfx.EXT_CONTOUR, "glcm_d2": nfx.EXT_GLCM_D2}
+    for s, b in bits.items():
+        assert [L.nfx_ext_feature_name(b, i).decode() for i in range(L.nfx_ext_feature_count(b))] == o.EXT_COLUMNS[s]
+    drop_in = set(nfx.feature_names(nfx.FS_ALL))
+    shared = [n for n in names if n in drop_in]
+    assert len(shared) == 56 and all(n.endswith("_32") for n in shared)
