@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libnfx.so")
+# NFX_LIB selects another build of the same library (e.g. the CMake build: NFX_LIB=$PWD/b/libnfx.so)
+LIB_PATH = os.environ.get("NFX_LIB") or os.path.join(os.path.dirname(_HERE), "libnfx.so")
 
 NFX_OK = 0
 FS_GEOMETRY, FS_COLOR, FS_GLCM, FS_GLRLM, FS_GABOR = 0x01, 0x02, 0x04, 0x08, 0x10
