@@ -119,10 +119,16 @@ __device__ __forceinline__ void raster_warp(const float2* pts, int V, int P, dou
             const double num = __dmul_rn(__dsub_rn(y, er->yi[j]), er->dx[j]);
             double X = __dadd_rn(xi, __dmul_rn(num, er->rdy[j]));
             const double tt = X + half, fr = tt - rint(tt);
-            if (!(fabs(fr) > 1e-9 * fmax(1.0, fabs(tt))))   // next to a pixel abscissa (or not finite): the rule's own division
+            int nb;                                           // pixels c < nb satisfy (c - half) < X
+            if (fabs(fr) > 1e-9 * fmax(1.0, fabs(tt))) {
+                // X' is further than its own error from every pixel abscissa, and so is the rounding of X' + half: the first
+                // index at or above X is ceil(X' + half), clamped to the row
+                nb = tt <= 0.0 ? 0 : (tt >= (double)P ? P : (int)ceil(tt));
+            } else {   // next to a pixel abscissa (or not finite): the rule's own division and the exact search
                 X = __dadd_rn(xi, __ddiv_rn(num, er->dy[j]));
-            if (!(X == X)) continue;                          // `x < NaN` is false for every pixel: nothing toggled
-            const int nb = first_index_geq(X, P, half);       // pixels c < nb satisfy (c - half) < X
+                if (!(X == X)) continue;                      // `x < NaN` is false for every pixel: nothing toggled
+                nb = first_index_geq(X, P, half);
+            }
             for (int w = 0; w < wpr; ++w) {
                 const uint32_t m = prefix_bits(nb - 32 * w);
                 if (m) atomicXor(&rows[r * wpr + w], m);
