@@ -72,7 +72,7 @@ struct nfx_ctx {
     DevBuf<int64_t> off;
     int64_t n = 0, nverts = 0;
     int vmax = 0;
-    DevBuf<int> giant_slot;            // rings longer than kGeomRingSmem vertices work in HBM (geom.cu)
+    DevBuf<int> giant_list;            // nuclei whose ring is longer than kGeomRingSmem vertices: they work in HBM (geom.cu)
     DevBuf<unsigned char> ring_scratch;
     int64_t n_giant = 0;
     bool have_poly = false;
@@ -222,7 +222,8 @@ int run_geom(nfx_ctx* ctx, bool shape, float* out, int stride, int col, uint32_t
     g.tile_oy = (int)ctx->toy;
     g.vmax = std::max(ctx->vmax, 1);
     g.vsmem = std::min(g.vmax, kGeomRingSmem);
-    g.giant_slot = ctx->n_giant ? ctx->giant_slot.p : nullptr;
+    g.n_giant = ctx->n_giant;
+    g.giant_list = ctx->n_giant ? ctx->giant_list.p : nullptr;
     g.ring_scratch = ctx->n_giant ? ctx->ring_scratch.p : nullptr;
     g.centroid = ctx->centroid.p;
     g.info = ctx->info.p;
@@ -385,7 +386,7 @@ int nfx_destroy(nfx_ctx* ctx) {
     for (auto& pr : ctx->peers) cudaIpcCloseMemHandle(pr.second);
     ctx->peers.clear();
     ctx->tile.release(); ctx->xy.release(); ctx->off.release(); ctx->centroid.release(); ctx->info.release();
-    ctx->giant_slot.release(); ctx->ring_scratch.release(); ctx->bitmask.release(); ctx->out.release(); ctx->ext_out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->gabor_part.release(); ctx->patches.release();
+    ctx->giant_list.release(); ctx->ring_scratch.release(); ctx->bitmask.release(); ctx->out.release(); ctx->ext_out.release(); ctx->hue.release(); ctx->ellipse.release(); ctx->gabor_part.release(); ctx->patches.release();
     ctx->scratch8.release(); ctx->scratchf.release(); ctx->scratch32.release(); ctx->flush.release();
     ctx->csv_len.release(); ctx->csv_off.release(); ctx->csv_tmp.release(); ctx->csv_text.release(); ctx->csv_in.release();
     if (ctx->d_bad) cudaFree(ctx->d_bad);
@@ -541,13 +542,14 @@ int nfx_polygons_upload(nfx_ctx* ctx, int64_t n, const float* poly_xy, const int
     // rings that do not fit the shared-memory layout of k_geom get a work slot in HBM
     ctx->n_giant = 0;
     if (vmax > kGeomRingSmem) {
-        std::vector<int> slot((size_t)n, -1);
+        std::vector<int> list;
         for (int64_t i = 0; i < n; ++i)
-            if (poly_off[i + 1] - poly_off[i] > kGeomRingSmem) slot[i] = (int)ctx->n_giant++;
-        CK(ctx->giant_slot.ensure((size_t)n));
+            if (poly_off[i + 1] - poly_off[i] > kGeomRingSmem) list.push_back((int)i);
+        ctx->n_giant = (int64_t)list.size();
+        CK(ctx->giant_list.ensure(list.size()));
         CK(ctx->ring_scratch.ensure((size_t)ctx->n_giant * geom_ring_bytes(vmax)));
-        CK(cudaMemcpyAsync(ctx->giant_slot.p, slot.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // `slot` is a local
+        CK(cudaMemcpyAsync(ctx->giant_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // `list` is a local
     }
     CK(ctx->xy.ensure((size_t)total + 1));
     CK(ctx->off.ensure((size_t)n + 1));
@@ -780,7 +782,7 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
         GeomParams g;
         g.poly_xy = ctx->xy.p; g.poly_off = ctx->off.p; g.n = n; g.P = P; g.tile_ox = 0; g.tile_oy = 0;
         g.vmax = std::max(ctx->vmax, 1); g.vsmem = std::min(g.vmax, kGeomRingSmem);
-        g.giant_slot = ctx->n_giant ? ctx->giant_slot.p : nullptr; g.ring_scratch = ctx->n_giant ? ctx->ring_scratch.p : nullptr;
+        g.n_giant = ctx->n_giant; g.giant_list = ctx->n_giant ? ctx->giant_list.p : nullptr; g.ring_scratch = ctx->n_giant ? ctx->ring_scratch.p : nullptr;
         g.centroid = ctx->centroid.p; g.info = ctx->info.p;
         g.bitmask = ctx->bitmask.p; g.out = ctx->out.p; g.out_stride = cols; g.col_shape = c.shape; g.ellipse_bits = nullptr;
         g.sample_off = (ctx->rules & NFX_RULE_RASTER_PIXEL_CENTRE) ? 0.5f : 0.0f;

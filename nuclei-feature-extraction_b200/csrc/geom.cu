@@ -153,28 +153,31 @@ __host__ __device__ __forceinline__ size_t ring_bytes(int vmax) {
     return (size_t)((vmax + 1) & ~1) * 8 + (size_t)vmax * 16 + (((size_t)vmax * 2 * 4 + 15) & ~(size_t)15);
 }
 
-template <bool RASTER, bool SHAPE>
+// GIANT = false: every ring of the launch lives in shared memory (nuclei whose ring is longer are skipped: the second launch
+// takes them). GIANT = true: grid = the long rings only (p.giant_list[slot] = nucleus), work arrays in the HBM slot. Two
+// instantiations instead of one pointer that may be either: ring accesses stay LDS on the common path (generic loads on the
+// hull's serial chain had cost the shape kernel 6 %).
+template <bool RASTER, bool SHAPE, bool GIANT>
 __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNpc) k_geom(const GeomParams p, const int nuc_smem) {
     constexpr int kGeomThreads = GeomCfg<SHAPE>::kThreads, kNpc = GeomCfg<SHAPE>::kNpc;
     extern __shared__ __align__(16) unsigned char smem_all[];
     const int sub = kNpc > 1 ? (int)(threadIdx.x / kGeomThreads) : 0;            // which nucleus of the CTA
     unsigned char* smem_raw = smem_all + (size_t)sub * nuc_smem;
     const int P = p.P, wpr = mask_wpr(P), tid = kNpc > 1 ? (int)(threadIdx.x % kGeomThreads) : (int)threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.x * kNpc + sub;
-    if (kNpc > 1 && i >= p.n) return;   // whole warp; the multi-nucleus variant only uses warp-level barriers
+    const int64_t slot = (int64_t)blockIdx.x * kNpc + sub;
+    if (kNpc > 1 && slot >= (GIANT ? p.n_giant : p.n)) return;   // whole warp; the multi-nucleus variant only uses warp-level barriers
+    const int64_t i = GIANT ? (int64_t)p.giant_list[slot] : slot;
     auto sync = [] { if (kNpc > 1) __syncwarp(); else __syncthreads(); };
     const int64_t o0 = p.poly_off[i];
     const int V = (int)(p.poly_off[i + 1] - o0);
+    if (!GIANT && V > p.vsmem) return;   // whole nucleus (warp or CTA): the GIANT launch computes it
 
     // shared layout: rows[P*wpr] u32 | pts[cap] float2 | sorted[cap] double2 | stk[2*cap] int | edge records.
     // A ring longer than the shared-memory capacity (kGeomRingSmem vertices) keeps pts / sorted / stk in its HBM slot.
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw);
-    int cap = p.vsmem;
-    float2* pts = reinterpret_cast<float2*>(rows + ((P * wpr + 3) & ~3));
-    if (V > p.vsmem) {
-        cap = p.vmax;
-        pts = reinterpret_cast<float2*>(p.ring_scratch + (size_t)p.giant_slot[i] * ring_bytes(p.vmax));
-    }
+    const int cap = GIANT ? p.vmax : p.vsmem;
+    float2* pts = GIANT ? reinterpret_cast<float2*>(p.ring_scratch + (size_t)slot * ring_bytes(p.vmax))
+                        : reinterpret_cast<float2*>(rows + ((P * wpr + 3) & ~3));
     double2* sorted = reinterpret_cast<double2*>(pts + ((cap + 1) & ~1));   // 16-byte aligned
     int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? cap : 0));
     EdgeRecs* erecs = reinterpret_cast<EdgeRecs*>(smem_raw + geom_edge_offset(P, p.vsmem, SHAPE));   // RASTER only
@@ -424,19 +427,28 @@ cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream
     size_t nuc = geom_edge_offset(p.P, p.vsmem, shape);
     if (raster) nuc += sizeof(EdgeRecs);
     nuc = (nuc + 15) & ~(size_t)15;
-    auto go = [&](auto kern, int threads, int npc) -> cudaError_t {
+    auto go = [&](auto kern, int threads, int npc, int64_t count) -> cudaError_t {
+        if (count <= 0) return cudaSuccess;
         const size_t smem = nuc * npc;
         if (smem > 32 * 1024) {   // static shared memory counts towards the 48 KB default limit too
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<(unsigned)((p.n + npc - 1) / npc), threads * npc, smem, s>>>(p, (int)nuc);
+        kern<<<(unsigned)((count + npc - 1) / npc), threads * npc, smem, s>>>(p, (int)nuc);
         return cudaGetLastError();
     };
-    if (raster)
-        return shape ? go(k_geom<true, true>, GeomCfg<true>::kThreads, GeomCfg<true>::kNpc)
-                     : go(k_geom<true, false>, GeomCfg<false>::kThreads, GeomCfg<false>::kNpc);
-    return shape ? go(k_geom<false, true>, GeomCfg<true>::kThreads, GeomCfg<true>::kNpc) : cudaSuccess;
+    constexpr int T1 = GeomCfg<true>::kThreads, N1 = GeomCfg<true>::kNpc, T0 = GeomCfg<false>::kThreads, N0 = GeomCfg<false>::kNpc;
+    cudaError_t e;
+    if (raster) {
+        e = shape ? go(k_geom<true, true, false>, T1, N1, p.n) : go(k_geom<true, false, false>, T0, N0, p.n);
+        if (e == cudaSuccess && p.n_giant > 0)
+            e = shape ? go(k_geom<true, true, true>, T1, N1, p.n_giant) : go(k_geom<true, false, true>, T0, N0, p.n_giant);
+        return e;
+    }
+    if (!shape) return cudaSuccess;
+    e = go(k_geom<false, true, false>, T1, N1, p.n);
+    if (e == cudaSuccess && p.n_giant > 0) e = go(k_geom<false, true, true>, T1, N1, p.n_giant);
+    return e;
 }
 
 }  // namespace nfx

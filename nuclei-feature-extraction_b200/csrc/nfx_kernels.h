@@ -27,8 +27,9 @@ struct GeomParams {
     int tile_ox, tile_oy;      // slide coordinates of tile pixel (0,0)
     int vmax;                  // max ring length in this launch
     int vsmem;                 // ring capacity of the shared-memory layout = min(vmax, kGeomRingSmem); longer rings work in HBM:
-    const int* giant_slot;     // [n] slot of nucleus i in ring_scratch, -1 for rings that fit (nullptr: none is longer)
-    unsigned char* ring_scratch;   // [slots][geom_ring_bytes(vmax)] pts | sorted | stk of the long rings
+    int64_t n_giant;           // rings longer than vsmem: computed by a second launch over giant_list
+    const int* giant_list;     // [n_giant] nucleus index of every long ring (slot s works in ring_scratch slot s)
+    unsigned char* ring_scratch;   // [n_giant][geom_ring_bytes(vmax)] pts | sorted | stk of the long rings
     float2* centroid;          // [n] out (RASTER) / unused
     NucInfo* info;             // [n] out (RASTER) / unused
     uint32_t* bitmask;         // [n][P][wpr]: out when RASTER, in otherwise
