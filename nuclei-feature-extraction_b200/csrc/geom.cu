@@ -20,13 +20,14 @@ namespace nfx {
 
 namespace {
 
-// The raster-only variant runs one warp per nucleus (a ring has ~30 edges: a second warp only doubles the
-// issue slots of the serial parts); the shape variant keeps two warps for its two hull chains.
-// A raster-only CTA carries four independent nuclei (one warp each, warp-level synchronisation only): one-warp CTAs are
-// capped at 32 resident warps per SM by the CTA limit, and the kernel is latency bound (serial centroid fold, f64 divides).
+// One WARP per nucleus, four nuclei per CTA, warp-level synchronisation only -- for the raster-only and the shape variant
+// alike: a ring has ~30 edges (a second warp only doubles the issue slots of the serial parts), one-warp CTAs are capped at
+// 32 resident warps per SM by the CTA limit, and the kernel is latency bound (serial centroid fold, f64 divides, the hull's
+// monotone chains). The shape variant ran two warps per nucleus with block barriers in round 1: its two hull chains now run
+// on lanes 0 and 1 of the one warp (one instruction stream instead of two), every block reduction is a shuffle tree.
 template <bool SHAPE> struct GeomCfg {
-    static constexpr int kThreads = SHAPE ? 64 : 32;   // threads per nucleus
-    static constexpr int kNpc = SHAPE ? 1 : 4;         // nuclei per CTA
+    static constexpr int kThreads = 32;   // threads per nucleus
+    static constexpr int kNpc = 4;        // nuclei per CTA
 };
 
 // first index k in [0,P] such that (k - half) >= v   (exact; v may be any double). half = P/2 - sample offset.
@@ -181,9 +182,9 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
     double2* sorted = reinterpret_cast<double2*>(pts + ((cap + 1) & ~1));   // 16-byte aligned
     int* stk = reinterpret_cast<int*>(sorted + (SHAPE ? cap : 0));
     EdgeRecs* erecs = reinterpret_cast<EdgeRecs*>(smem_raw + geom_edge_offset(P, p.vsmem, SHAPE));   // RASTER only
-    __shared__ double s_red[16];
     __shared__ float s_c_all[kNpc][2];
-    __shared__ int s_hull[2];
+    __shared__ int s_hull_all[kNpc][2];
+    int* s_hull = s_hull_all[sub];
     float* s_c = s_c_all[sub];
 
     for (int k = tid; k < V; k += kGeomThreads) pts[k] = p.poly_xy[o0 + k];
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
     float* out = p.out + i * (int64_t)p.out_stride + p.col_shape;
 
     // ---- polygon scalars, SPEC.md B7 (float64 on the centred ring) ----
+    double poly_area = 0.0;   // lane 0 keeps it for the hull's deviation
     {
         double v2[2] = {0.0, 0.0};   // shoelace sum, perimeter
         for (int k = tid; k < V; k += kGeomThreads) {
@@ -258,14 +260,15 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
             const double ex = (double)b.x - (double)a.x, ey = (double)b.y - (double)a.y;
             v2[1] += sqrt(ex * ex + ey * ey);
         }
-        block_sum<2>(v2, s_red);
+        v2[0] = warp_sum(v2[0]);
+        v2[1] = warp_sum(v2[1]);
         if (tid == 0) {
             const double area = 0.5 * fabs(v2[0]), per = v2[1];
             out[0] = (float)area;
             out[5] = (float)per;
             out[6] = (float)(2.0 * sqrt(CUDART_PI * area));
             out[7] = (float)((4.0 * CUDART_PI * area) / (per * per));
-            s_red[8] = area;
+            poly_area = area;
         }
     }
     // ---- convex hull, SPEC.md B8: rank sort + two monotone chains (threads 0 and 32) ----
@@ -278,8 +281,8 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
         }
         sorted[rank] = make_double2((double)a.x, (double)a.y);   // converted once: the chain is latency bound
     }
-    __syncthreads();
-    if (tid == 0 || tid == 32) {
+    sync();
+    if (tid < 2) {   // lower chain on lane 0, upper chain on lane 1
         int* S = stk + (tid == 0 ? 0 : cap);
         int sz = 0;
         for (int t = 0; t < V; ++t) {
@@ -288,9 +291,9 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
             while (sz >= 2 && cross3(sorted[S[sz - 2]], sorted[S[sz - 1]], q) <= 0.0) --sz;
             S[sz++] = idx;
         }
-        s_hull[tid == 0 ? 0 : 1] = sz;
+        s_hull[tid] = sz;
     }
-    __syncthreads();
+    sync();
     if (tid == 0) {
         const int nl = max(s_hull[0] - 1, 0), nu = max(s_hull[1] - 1, 0), h = nl + nu;
         auto hp = [&](int k) -> double2 { return sorted[k < nl ? stk[k] : stk[cap + (k - nl)]]; };
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
         const double harea = (h >= 3) ? 0.5 * fabs(sh) : 0.0;
         if (h < 2) per = 0.0;
         out[9] = (float)harea;
-        out[10] = (float)((harea - s_red[8]) / harea);
+        out[10] = (float)((harea - poly_area) / harea);
         out[11] = (float)per;
     }
 
@@ -329,7 +332,8 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
         mom[4] += (double)(sc * r);
         mom[5] += (double)scc;
     }
-    block_sum<6>(mom, s_red);   // sums of integers < 2^53: exact in any order
+#pragma unroll
+    for (int k = 0; k < 6; ++k) mom[k] = warp_sum(mom[k]);   // sums of integers < 2^53: exact in any order
 
     // every thread derives the same scalars (cheap) so no extra broadcast is needed
     const double K = mom[0];
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
             if (p.ellipse_bits) p.ellipse_bits[i * P * wpr + r * wpr + w] = e;
         }
     }
-    block_sum<1>(diff, s_red);
+    diff[0] = warp_sum(diff[0]);
     if (tid == 0) out[8] = __fdiv_rn((float)diff[0], (float)K);   // shape.rs:209-217 (f32 tensor / scalar)
 }
 

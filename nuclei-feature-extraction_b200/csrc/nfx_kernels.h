@@ -43,7 +43,7 @@ struct GeomParams {
 // raster=true : polygons are raw rings; computes centroid/info, rasterises, writes bitmask.
 // raster=false: polygons are already centred and bitmask is an input (trait-level path).
 cudaError_t launch_geom(const GeomParams& p, bool raster, bool shape, cudaStream_t s);
-constexpr int kGeomRingSmem = 4000;   // vertices of a ring kept in shared memory (32 B each with the hull's work arrays)
+constexpr int kGeomRingSmem = 1400;   // vertices of a ring kept in shared memory (32 B each with the hull's work arrays, four nuclei per CTA)
 size_t geom_ring_bytes(int vmax);     // bytes of one ring_scratch slot
 
 // ---- color.cu ---------------------------------------------------------------------------------

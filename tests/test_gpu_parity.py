@@ -694,12 +694,12 @@ def test_rule_gabor_half_turn_is_oracle_only(case):
 
 def test_rings_longer_than_the_shared_memory_capacity(libnfx):
     """A 10 000-vertex ring (and a 4 001-vertex one) among ordinary nuclei: rings beyond k_geom's shared-memory capacity
-    (4 000 vertices) keep their work arrays in HBM; masks bit-exact, every column in parity."""
+    (1 400 vertices) keep their work arrays in HBM; masks bit-exact, every column in parity."""
     tile = synth.synth_tile(400, 400, 21)
     xy, off = synth.synth_polygons(12, 400, 400, 21)
     rings = synth.rings_of(xy, off)
     rng = np.random.default_rng(21)
-    for V, c in ((10_000, (150.3, 160.7)), (4_001, (260.5, 240.25))):
+    for V, c in ((10_000, (150.3, 160.7)), (1_401, (260.5, 240.25))):
         t = 2 * np.pi * np.arange(V + 1) / V
         t[-1] = 0.0
         r = 22.0 * (1 + 0.2 * np.cos(5 * t) + 0.03 * np.cos(131 * t)) + rng.uniform(-0.2, 0.2, V + 1)
