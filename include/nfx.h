@@ -57,9 +57,8 @@ typedef struct nfx_config {
  * position the reference takes once someone can run it. */
 #define NFX_RULE_RASTER_PIXEL_CENTRE 0x1  /* polygon / ellipse rasters sample the pixel CENTRE (c + 0.5 - P/2, r + 0.5 - P/2)
                                              instead of (c - P/2, r - P/2)          (src/utils.rs:152-157, shape.rs:80-87) */
-#define NFX_RULE_GABOR_HALF_TURN     0x2  /* Gabor angles i * pi / 8 instead of i * 2 pi / 8 (texture.rs:333-334). The oracle has
-                                             both positions; the kernel bank is built for the full turn (24 distinct filters)
-                                             and nfx_compute refuses the Gabor set under this flag (NFX_ERR_UNSUPPORTED) */
+#define NFX_RULE_GABOR_HALF_TURN     0x2  /* Gabor angles i * pi / 8 (48 distinct filters, three oblique angle pairs per frequency) instead of
+                                             i * 2 pi / 8 (24 distinct filters, theta and theta + pi coincide)   (texture.rs:333-334) */
 #define NFX_RULE_GLCM_254_U8         0x4  /* the 254-level GLCM quantises like an 8-bit image, q = min(floor(g * 255), 253), instead of
                                              min(floor(g * 254), 253) (src/features/texture.rs:19, 40-46). The power-of-two level
                                              counts keep floor(g * L): the kernels use floor(g*32) = floor(g*128) >> 2 */

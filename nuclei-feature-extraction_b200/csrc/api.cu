@@ -2,6 +2,7 @@
 // measurement. No torch, no CPU fallback: every compute entry point fails if CUDA fails.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 #include <stdio.h>
 #include <string.h>
 
@@ -152,7 +153,9 @@ cudaError_t timed(nfx_ctx* c, const char* name, int nlaunch, F&& f) {
         r.kid = kernel_id(c, name);
         cudaEventRecord(r.a, c->stream);
     }
+    nvtxRangePushA(name);   // the reference logs wall-clock per feature set (src/main.rs:55-70); here every kernel is a range
     cudaError_t e = f();
+    nvtxRangePop();
     c->launches += nlaunch;
     if (prof) {
         cudaEventRecord(r.b, c->stream);
@@ -201,8 +204,6 @@ Cols columns(uint32_t mask) {
 
 int check_patch_size(nfx_ctx* ctx, uint32_t mask) {
     if (mask == 0 || (mask & ~NFX_FS_ALL)) return fail(ctx, NFX_ERR_INVALID, "empty or unknown feature mask");
-    if ((mask & NFX_FS_GABOR) && (ctx->rules & NFX_RULE_GABOR_HALF_TURN))
-        return fail(ctx, NFX_ERR_UNSUPPORTED, "NFX_RULE_GABOR_HALF_TURN: the kernel bank is built for angles i * 2 pi / 8 (24 distinct filters); only the oracle has the half-turn bank");
     return NFX_OK;
 }
 
@@ -297,9 +298,10 @@ int run_tex2(nfx_ctx* ctx, int64_t n, uint32_t mask, const CUtensorMap* map_csla
     t.col_glrlm = col_glrlm;
     t.col_gabor = col_gabor;
     t.gabor_partial = nullptr;
+    t.gabor_half_turn = (ctx->rules & NFX_RULE_GABOR_HALF_TURN) ? 1 : 0;
     const bool gabor_tiled = gabor_tiles(ctx->P) > 1;
     if ((mask & NFX_FS_GABOR) && gabor_tiled) {
-        CK(ctx->gabor_part.ensure((size_t)n * gabor_tiles(ctx->P) * 49));
+        CK(ctx->gabor_part.ensure((size_t)n * gabor_tiles(ctx->P) * 97));
         t.gabor_partial = ctx->gabor_part.p;
     }
     if (mask & NFX_FS_GLRLM) CK(timed(ctx, "k_glrlm", 1, [&] { return launch_glrlm(t, map_cslab, ctx->stream); }));

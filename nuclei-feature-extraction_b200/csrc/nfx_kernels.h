@@ -98,7 +98,8 @@ struct TexParams {
     float* out;
     int out_stride;
     int col_glrlm, col_gabor;  // first column of each set (or -1)
-    double* gabor_partial;     // [n][gabor_tiles(P)][49] scratch when P > 64, else nullptr
+    double* gabor_partial;     // [n][gabor_tiles(P)][97] scratch when P > 64, else nullptr
+    int gabor_half_turn;       // NFX_RULE_GABOR_HALF_TURN: angles i * pi / 8 (48 distinct filters) instead of i * 2 pi / 8
 };
 cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaStream_t s);
 cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map, cudaStream_t s);   // map: see texture2.cu

@@ -38,6 +38,11 @@ constexpr int kGaborFilters = 48, kGaborK = 30, kGaborLo = 14;   // 'same' paddi
 // and the bare Gaussian envelope G(t). Rows and columns share them (the tap grid is symmetric).
 __device__ __constant__ float c_gtap[6][4][kGaborK];
 __device__ __constant__ float c_genv[kGaborK];
+// Oblique angle pairs (theta, pi - theta): cos(a u +- b v) = [G cos au][G cos bv] -+ [G sin au][G sin bv] with a = w cos(theta),
+// b = w sin(theta). [pair][q] = {G cos(a t), G sin(a t) (row pass), G cos(b t), G sin(b t) (column pass)}.
+// pair 0: theta = 45 (a = b); pairs 1, 2: theta = 22.5 and 67.5 degrees -- only under NFX_RULE_GABOR_HALF_TURN, where the
+// eight angles are i * pi / 8 (48 distinct filters) instead of i * 2 pi / 8 (24 distinct ones, theta and theta + pi coincide).
+__device__ __constant__ float c_gobl[3][6][4][kGaborK];
 
 __device__ __forceinline__ float grey_of(const float* lut, uint32_t r, uint32_t g, uint32_t b) {
     // texture.rs:189/332: mean_dim(-3) of u8/255 values = ((r+g)+b)/3 with IEEE f32 operations
@@ -236,9 +241,10 @@ __host__ __device__ constexpr int gabor_ps(int P) { return ((P + 27) & ~31) + 4;
 // window, zeros outside), runs the same passes with the planes sized for a 64-pixel tile, and writes
 // per-tile partial sums (sum v, sum v^2 per distinct filter, tile pixel count) that k_gabor_finalize folds.
 constexpr int kGaborTile = 64, kGaborFetch = kGaborTile + kGaborK - 1;   // 93 rows/cols fetched per tile
-constexpr int kGaborPartial = 49;                                        // 24 filters x (sum, sum^2) + pixel count
+constexpr int kGaborDistinct = 48;                                       // distinct filters: 24 (full turn) or 48 (half turn)
+constexpr int kGaborPartial = 2 * kGaborDistinct + 1;                    // (sum, sum^2) per distinct filter + pixel count
 
-template <int kP, bool TILED>   // kP = 64: compile-time plane strides (immediate LDS offsets); 0: runtime
+template <int kP, bool TILED, bool HALF>   // kP = 64: compile-time plane strides (immediate LDS offsets); 0: runtime; HALF: NFX_RULE_GABOR_HALF_TURN
 __global__ void __launch_bounds__(kTexThreads, 2)
 k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, P rows} or {208, 93 rows} */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -260,7 +266,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
     __shared__ int s_box[5];
-    __shared__ double s_part[NW][2 * 24];   // per warp: (sum, sum of squares) of the 24 distinct filters
+    __shared__ double s_part[NW][2 * kGaborDistinct];   // per warp: (sum, sum of squares) of the distinct filters
+    // slot of angle index k (x 6 frequencies): full turn 0, 45, 90, 135 -> 0, 6, 12, 18; half turn i * 22.5 degrees -> 6 i
+    constexpr bool half_turn = HALF;   // its own instantiation: the default bank keeps compile-time table and slot indices
+    const int nf = half_turn ? 48 : 24, slot0 = 0, slot90 = half_turn ? 24 : 12;
 
     const NucInfo inf = p.info[i];
     // fetched region: rows/cols [f0, f0 + fetch) of the window, f0 = -14 relative to the tile when TILED
@@ -352,7 +361,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 
     // Horizontal FIR, 4 outputs per thread from 9 float4 loads (row index fastest across the lanes):
     //   dA[pr][c0+m] = sum_t src[pr][c0+m+t] * ta[t]   (and dB with tb when TWO), pr = row_lo .. row_lo+nr-1.
-    auto h_store = [&](const float* src, int ss, float* dA, float* dB, int ds, bool env, int q, int row_lo, int nr, float inv_nr) {
+    auto h_store = [&](const float* src, int ss, float* dA, float* dB, int ds, bool env, int pair, int q, int row_lo, int nr, float inv_nr) {
         const bool two = !env;
         for (int k = tid; k < nr * nquad; k += kTexThreads) {
             const int kq = fdiv(k, inv_nr), pr = row_lo + (k - kq * nr), c0 = cq0 + 4 * kq;
@@ -366,7 +375,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int t = 0; t < kGaborK; ++t) {
-                const float wa = env ? c_genv[t] : c_gtap[q][2][t], wb = c_gtap[q][3][t];
+                const float wa = env ? c_genv[t] : c_gobl[pair][q][0][t], wb = c_gobl[pair][q][1][t];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     a[m] = fmaf(x[m + t], wa, a[m]);
@@ -381,7 +390,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     // ======== theta = 90 (filters 12..17): rows with the envelope (ONE plane), then a vertical pass with the six
     // cos(w v) profiles. The profiles are even (tap[t] = tap[29-t]): the 15 pair sums x[t] + x[29-t] are shared by
     // the six filters (15 adds + 6 x 15 FMAs instead of 180 FMAs). SH output rows per thread share their loads. ====
-    h_store(G, GS, B, B, PS, true, 0, rmin, nrow, inv_nrow);
+    h_store(G, GS, B, B, PS, true, 0, 0, rmin, nrow, inv_nrow);
     __syncthreads();
     auto v_six = [&](auto sh_tag) {
         constexpr int SH = decltype(sh_tag)::value;
@@ -415,7 +424,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             }
         }
 #pragma unroll
-        for (int q = 0; q < 6; ++q) stash2(s[2 * q], s[2 * q + 1], 2 * (12 + q));
+        for (int q = 0; q < 6; ++q) stash2(s[2 * q], s[2 * q + 1], 2 * (slot90 + q));
     };
     // strip height: 4 rows halve the shared-memory traffic, 2 rows fill the 256 threads better on small boxes
     const auto rounds = [&](int sh) { return (((rh + sh - 1) / sh) * ncol + kTexThreads - 1) / kTexThreads; };
@@ -481,13 +490,13 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             }
         }
 #pragma unroll
-        for (int q = 0; q < 6; ++q) stash2(s[2 * q], s[2 * q + 1], 2 * q);
+        for (int q = 0; q < 6; ++q) stash2(s[2 * q], s[2 * q + 1], 2 * (slot0 + q));
     }
     __syncthreads();
 
     // ======== theta = 45 (filter 6+q) and 135 (filter 18+q): rows with cos(w'u) -> A and sin(w'u) -> B in one pass,
     // then p = (A columns, cos w'v), q = (B columns, sin w'v): the two filters are p - q and p + q. ========
-    auto v_diag = [&](auto sh_tag, int q) {
+    auto v_diag = [&](auto sh_tag, int pair, int q, int slot_minus, int slot_plus) {
         constexpr int SH = decltype(sh_tag)::value;
         double s[4] = {0.0, 0.0, 0.0, 0.0};
         const int nstrip = (rh + SH - 1) / SH;
@@ -504,8 +513,8 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
                     for (int t = 0; t < kGaborK; ++t) {
-                        if (t & 1) v1 = fmaf(x[m + t], c_gtap[q][2][t], v1);
-                        else v0 = fmaf(x[m + t], c_gtap[q][2][t], v0);
+                        if (t & 1) v1 = fmaf(x[m + t], c_gobl[pair][q][2][t], v1);
+                        else v0 = fmaf(x[m + t], c_gobl[pair][q][2][t], v0);
                     }
                     pp[m] = v0 + v1;
                 }
@@ -520,8 +529,8 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
                     for (int t = 0; t < kGaborK; ++t) {
-                        if (t & 1) v1 = fmaf(x[m + t], c_gtap[q][3][t], v1);
-                        else v0 = fmaf(x[m + t], c_gtap[q][3][t], v0);
+                        if (t & 1) v1 = fmaf(x[m + t], c_gobl[pair][q][3][t], v1);
+                        else v0 = fmaf(x[m + t], c_gobl[pair][q][3][t], v0);
                     }
                     qq[m] = v0 + v1;
                 }
@@ -534,18 +543,25 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                 s[2] += v135; s[3] += v135 * v135;
             }
         }
-        stash2(s[0], s[1], 2 * (6 + q));
-        stash2(s[2], s[3], 2 * (18 + q));
+        stash2(s[0], s[1], 2 * (slot_minus + q));
+        stash2(s[2], s[3], 2 * (slot_plus + q));
     };
-    for (int q = 0; q < 6; ++q) {
-        h_store(G, GS, A, B, PS, false, q, rmin, nrow, inv_nrow);
-        __syncthreads();
-        if (tall) v_diag(std::integral_constant<int, 4>{}, q); else v_diag(std::integral_constant<int, 2>{}, q);
-        __syncthreads();
+    // full turn: the one oblique pair (45, 135) -> slots 6, 18. Half turn: (22.5, 157.5), (45, 135), (67.5, 112.5) -> 6 i.
+    constexpr int npair = half_turn ? 3 : 1;
+    for (int pi = 0; pi < npair; ++pi) {
+        const int pair = half_turn ? (pi == 0 ? 1 : (pi == 1 ? 0 : 2)) : 0;
+        const int sm = half_turn ? (pair == 1 ? 6 : (pair == 0 ? 12 : 18)) : 6;     // theta      : p - q
+        const int sp = half_turn ? (pair == 1 ? 42 : (pair == 0 ? 36 : 30)) : 18;   // pi - theta : p + q
+        for (int q = 0; q < 6; ++q) {
+            h_store(G, GS, A, B, PS, false, pair, q, rmin, nrow, inv_nrow);
+            __syncthreads();
+            if (tall) v_diag(std::integral_constant<int, 4>{}, pair, q, sm, sp); else v_diag(std::integral_constant<int, 2>{}, pair, q, sm, sp);
+            __syncthreads();
+        }
     }
 
     // ---- fold the warp partials in a fixed order: one thread per distinct filter ----
-    if (tid < 24) {
+    if (tid < nf) {
         const int f = tid;
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -557,7 +573,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             const double Kd = (double)K, mean = s0 / Kd;
             const float mf = (float)mean, vf = (float)fmax(s1 / Kd - mean * mean, 0.0);
             out[2 * f] = mf; out[2 * f + 1] = vf;
-            out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf;   // theta + 180 degrees: same kernel
+            if (!half_turn) { out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf; }   // theta + 180 degrees: same kernel
         }
     }
 }
@@ -565,9 +581,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 // one thread per (nucleus, distinct filter): fold the tiles, write theta and theta + 180 degrees
 __global__ void k_gabor_finalize(const TexParams p, const int ntiles) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.n * 24) return;
-    const int64_t i = g / 24;
-    const int f = (int)(g - i * 24);
+    const int nf = p.gabor_half_turn ? 48 : 24;
+    if (g >= p.n * nf) return;
+    const int64_t i = g / nf;
+    const int f = (int)(g - i * nf);
     const double* part = p.gabor_partial + i * (int64_t)ntiles * kGaborPartial;
     double s0 = 0.0, s1 = 0.0, K = 0.0;
     for (int t = 0; t < ntiles; ++t) {
@@ -583,7 +600,7 @@ __global__ void k_gabor_finalize(const TexParams p, const int ntiles) {
         vf = (float)fmax(s1 / K - mean * mean, 0.0);
     }
     out[2 * f] = mf; out[2 * f + 1] = vf;
-    out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf;
+    if (!p.gabor_half_turn) { out[2 * (f + 24)] = mf; out[2 * (f + 24) + 1] = vf; }
 }
 
 }  // namespace
@@ -616,7 +633,20 @@ static cudaError_t ensure_gabor_taps() {
             h[q][3][t] = (float)(ge * sin(w2 * u));
         }
     }
+    static float ho[3][6][4][kGaborK];
+    const double th[3] = {pi / 4.0, pi / 8.0, 3.0 * pi / 8.0};
+    for (int a = 0; a < 3; ++a)
+        for (int q = 0; q < 6; ++q)
+            for (int t = 0; t < kGaborK; ++t) {
+                const double u = -1.0 + 2.0 * t / (kGaborK - 1), ge = exp(-u * u / (2.0 * sigma * sigma));
+                const double w = 2.0 * pi * freqs[q], wa = w * cos(th[a]), wb = w * sin(th[a]);
+                ho[a][q][0][t] = (float)(ge * cos(wa * u));
+                ho[a][q][1][t] = (float)(ge * sin(wa * u));
+                ho[a][q][2][t] = (float)(ge * cos(wb * u));
+                ho[a][q][3][t] = (float)(ge * sin(wb * u));
+            }
     e = cudaMemcpyToSymbol(c_gtap, h, sizeof(h));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_gobl, ho, sizeof(ho));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_genv, env, sizeof(env));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess && dev < 64) g_taps_ready[dev] = true;
@@ -657,10 +687,14 @@ cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map, cudaStream_
         kern<<<dim3((unsigned)p.n, (unsigned)ntiles), kTexThreads, smem, s>>>(p, *map);
         return cudaGetLastError();
     };
-    if (!tiled) return p.P == 64 ? go(k_gabor<64, false>) : go(k_gabor<0, false>);
-    e = go(k_gabor<64, true>);
+    const bool half = p.gabor_half_turn != 0;
+    if (!tiled) {
+        if (half) return p.P == 64 ? go(k_gabor<64, false, true>) : go(k_gabor<0, false, true>);
+        return p.P == 64 ? go(k_gabor<64, false, false>) : go(k_gabor<0, false, false>);
+    }
+    e = half ? go(k_gabor<64, true, true>) : go(k_gabor<64, true, false>);
     if (e != cudaSuccess) return e;
-    k_gabor_finalize<<<(unsigned)((p.n * 24 + 255) / 256), 256, 0, s>>>(p, ntiles);
+    k_gabor_finalize<<<(unsigned)((p.n * (p.gabor_half_turn ? 48 : 24) + 255) / 256), 256, 0, s>>>(p, ntiles);
     return cudaGetLastError();
 }
 

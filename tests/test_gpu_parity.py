@@ -681,13 +681,27 @@ def test_rule_window_slide(case):
         assert not bad, _report(bad)
 
 
-def test_rule_gabor_half_turn_is_oracle_only(case):
+def test_rule_gabor_half_turn(case, stress):
+    """NFX_RULE_GABOR_HALF_TURN: angles i * pi / 8 -- 48 distinct filters (three oblique angle pairs per frequency) instead of
+    24. All 96 columns against the oracle's gabor_span = pi, single-tile (P = 64) and tiled (P = 256) kernels; the default
+    position differs from it in the oblique columns and agrees at 0 and 90 degrees."""
+    with o.rules(gabor_span=np.pi):
+        want = o.gabor_feature_set(case["patches"], case["masks"])
+        want256 = o.gabor_feature_set(stress["patches"][:4], stress["masks"][:4])
+    default = o.gabor_feature_set(case["patches"], case["masks"])
     with nfx.Extractor(0, 64, 100, rule_flags=nfx.RULE_GABOR_HALF_TURN) as e:
         e.upload_tile(case["tile"])
-        e.upload_polygons(case["xy"], case["off"])
-        e.compute(nfx.FS_GLCM)                       # other sets are unaffected
-        with pytest.raises(nfx.NfxError, match="HALF_TURN"):
-            e.compute(nfx.FS_GABOR)
+        keys, cents, got, names = e.extract(case["xy"], case["off"], ["gabor"])
+    bad = mismatches(got, want, names, "gabor")
+    assert not bad, _report(bad)
+    ok = np.isfinite(want[:, 0])
+    assert np.allclose(want[ok, :12], default[ok, :12], atol=1e-5) and np.allclose(want[ok, 48:60], default[ok, 24:36], atol=1e-5)   # 0 and 90 degrees
+    assert not np.allclose(want[ok, 12:24], default[ok, 12:24], atol=1e-3)                                                     # 22.5 vs 45 degrees
+    with nfx.Extractor(0, 256, 8, rule_flags=nfx.RULE_GABOR_HALF_TURN) as e:
+        e.upload_tile(stress["tile"])
+        keys, cents, got, names = e.extract(stress["xy"][:stress["off"][4]], stress["off"][:5], ["gabor"])
+    bad = mismatches(got, want256, names, "gabor")
+    assert not bad, _report(bad)
     with pytest.raises(nfx.NfxError):
         nfx.Extractor(0, 64, 100, rule_flags=0x100)  # unknown bit
 
