@@ -455,6 +455,20 @@ def e2e_double_buffered(ctxs, outs, submit, n_steps):
 
 SET_NAMES = {"geometry": "shape", "color": "color", "glcm": "glcm", "glrlm": "glrlm", "gabor": "gabor", "all": "all"}
 
+# Shared-memory atomics of the GLCM kernel (BASELINE north_star: "shared-memory atomic throughput against its peak for GLCM").
+# Lane-atomics per nucleus of k_glcm64 on the bench's synthetic nuclei: ncu smsp__inst_executed_op_shared_atom.sum = 32.24 M
+# warp-instructions per 20 000 nuclei x 28.55 active lanes (profiles/r2_all_base_ncu.txt); peaks from scripts/atoms_probe.cu
+# (profiles/r1_smem_atomics_probe.txt): 3.5e12 random-address, 9.1e12 conflict-free shared-memory atomics per second and B200.
+GLCM_LANE_ATOMICS_PER_NUCLEUS = 32243500 * 28.55 / 20000
+SMEM_ATOMICS_PEAK_RANDOM, SMEM_ATOMICS_PEAK_CONFLICT_FREE = 3.5e12, 9.1e12
+
+
+def glcm_atomics(nuclei, kernel_ms):
+    rate = GLCM_LANE_ATOMICS_PER_NUCLEUS * nuclei / (kernel_ms * 1e-3)
+    return {"lane_atomics_per_nucleus": GLCM_LANE_ATOMICS_PER_NUCLEUS, "source": "ncu capture of k_glcm64, P = 64 (profiles/r2_all_base_ncu.txt)",
+            "achieved_per_s": rate, "peak_random_address_per_s": SMEM_ATOMICS_PEAK_RANDOM,
+            "peak_conflict_free_per_s": SMEM_ATOMICS_PEAK_CONFLICT_FREE, "frac_of_random_address_peak": rate / SMEM_ATOMICS_PEAK_RANDOM}
+
 
 def per_set_block(args, ex, ex2, tile, xy, off, nuclei, P, peak, peak_kind, cpu):
     """BASELINE metric "nuclei/sec per feature set": every set on the headline's resident inputs (100 000 nuclei, 64 x 64
@@ -470,6 +484,8 @@ def per_set_block(args, ex, ex2, tile, xy, off, nuclei, P, peak, peak_kind, cpu)
         rec = {"columns": F, "ms_per_step": run["ms"], "value": nuclei / (run["ms"] * 1e-3), "unit": "nuclei/s",
                "dominant_kernel": roof["kernel"], "frac": roof["frac"], "pipeline_frac": roof["pipeline_frac"],
                "kernels_ms": {k: v["avg_ms"] for k, v in run["kern"].items()}, "gpu_launches": run["launches"]}
+        if "k_glcm" in run["kern"] and P <= 64:
+            rec["smem_atomics"] = glcm_atomics(nuclei, run["kern"]["k_glcm"]["avg_ms"])
         if not args.no_e2e:
             outs = [(nfx.pinned_empty((nuclei, 2), np.float32), nfx.pinned_empty((nuclei, F), np.float32)) for _ in range(2)]
 
@@ -590,6 +606,11 @@ def slide_job(args, sets, nuclei, side, P, rank, local_rank, world, dist, seed, 
     if run["kern"]:
         dom = max(run["kern"], key=lambda k: run["kern"][k]["avg_ms"])
         rec["dominant_kernel"] = dom
+        R = max(1, min(P, 256 // ((P + 3) // 4)))
+        peak, _ = hbm_peak()
+        rec["frac"] = kernel_bytes(dom, P, (P + R - 1) // R) * n / (run["kern"][dom]["avg_ms"] * 1e-3) / 1e9 / peak
+        if "k_glcm" in run["kern"] and P <= 64:
+            rec["smem_atomics"] = glcm_atomics(n, run["kern"]["k_glcm"]["avg_ms"])
     ex.close()
     return rec
 
