@@ -317,12 +317,16 @@ __global__ void __launch_bounds__(GeomCfg<SHAPE>::kThreads * GeomCfg<SHAPE>::kNp
         unsigned long long n = 0, sc = 0, scc = 0;
         for (int w = 0; w < wpr; ++w) {
             uint32_t bits = rows[r * wpr + w];
-            while (bits) {
-                const int c = 32 * w + __ffs(bits) - 1;
-                bits &= bits - 1;
-                ++n;
-                sc += c;
-                scc += (unsigned)(c * c);
+            while (bits) {   // one step per RUN of set bits [c0, c1): closed-form sums of c and c^2 (a blob row is one run)
+                const int s0 = __ffs(bits) - 1;
+                const uint32_t nt = ~(bits >> s0);
+                const int e0 = s0 + (nt ? __ffs(nt) - 1 : 32);
+                const unsigned c0 = 32u * w + s0, c1 = 32u * w + e0, len = c1 - c0;
+                n += len;
+                sc += (unsigned long long)(c0 + c1 - 1u) * len / 2u;
+                // sum_{c < k} c^2 = (k - 1) k (2k - 1) / 6
+                scc += ((unsigned long long)(c1 - 1u) * c1 * (2u * c1 - 1u) - (unsigned long long)(c0 ? (c0 - 1u) : 0u) * c0 * (2u * c0 - 1u)) / 6u;
+                bits = (e0 >= 32) ? 0u : (bits & (0xffffffffu << e0));
             }
         }
         mom[0] += (double)n;
