@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-NAMES = {"k_geom<1, 0>": "k_geom<raster>", "k_geom<1, 1>": "k_geom<raster,shape>", "k_hue_batch": "k_hue_batch", "k_color_warp": "k_color_warp",
+NAMES = {"k_geom<1, 0": "k_geom<raster>", "k_geom<1, 1": "k_geom<raster,shape>", "k_hue_batch": "k_hue_batch", "k_color_warp": "k_color_warp",
          "k_color(": "k_color", "k_glcm": "k_glcm", "k_glrlm": "k_glrlm", "k_gabor": "k_gabor", "k_gather": "k_gather"}
 out = {"csrc_sha16": bench.source_hash(), "unit": "bytes per launch", "source": "ncu --set full --clock-control none (scripts/refresh_r2.sh)"}
 a = sys.argv[1:]

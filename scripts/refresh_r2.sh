@@ -12,4 +12,4 @@ NFX_BENCH_EXACT_WARMUP=1 ncu --set full --clock-control none --import-source on 
     -o $O/r2_color_final -f python bench.py $Q > $O/ncu_c.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_gather|k_geom" -s 4 -c 2 \
     -o $O/r2_staged -f python bench.py --workload staged --steps 3 > $O/ncu_s.log 2>&1
-tail -2 $O/ncu_c.log $O/ncu_s.log
+tail -n 2 $O/ncu_c.log; tail -n 2 $O/ncu_s.log
