@@ -267,6 +267,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     __shared__ float s_lut[256];
     __shared__ int s_box[5];
     __shared__ double s_part[NW][2 * kGaborDistinct];   // per warp: (sum, sum of squares) of the distinct filters
+    // The oblique taps of the pair being filtered, [q][profile][t] (32 floats per profile: float4 loads). A phase keeps its 60
+    // taps in registers; fetching them from constant memory (30 LDC.64 + 32 MOV per warp and phase, right after a barrier
+    // when no other warp of the CTA can issue) drew 10 % of the kernel's stall samples (profiles/r2_tex_ncu.txt).
+    __shared__ __align__(16) float s_tap[6][4][32];
     // slot of angle index k (x 6 frequencies): full turn 0, 45, 90, 135 -> 0, 6, 12, 18; half turn i * 22.5 degrees -> 6 i
     constexpr bool half_turn = HALF;   // its own instantiation: the default bank keeps compile-time table and slot indices
     const int nf = half_turn ? 48 : 24, slot0 = 0, slot90 = half_turn ? 24 : 12;
@@ -285,6 +289,13 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         s_box[0] = P; s_box[1] = -1; s_box[2] = P; s_box[3] = -1; s_box[4] = 0;
     }
     s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    auto stage_taps = [&](int pair) {
+        for (int k = tid; k < 6 * 4 * 32; k += kTexThreads) {
+            const int t = k & 31;
+            (&s_tap[0][0][0])[k] = t < kGaborK ? c_gobl[pair][k >> 7][(k >> 5) & 3][t] : 0.f;
+        }
+    };
+    stage_taps(half_turn ? 1 : 0);
     for (int k = tid; k < PH * GS; k += kTexThreads) G[k] = 0.f;
     __syncthreads();
     // ---- mask rows of the tile, bounding box, pixel count (tile-local coordinates) ----
@@ -361,8 +372,19 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 
     // Horizontal FIR, 4 outputs per thread from 9 float4 loads (row index fastest across the lanes):
     //   dA[pr][c0+m] = sum_t src[pr][c0+m+t] * ta[t]   (and dB with tb when TWO), pr = row_lo .. row_lo+nr-1.
-    auto h_store = [&](const float* src, int ss, float* dA, float* dB, int ds, bool env, int pair, int q, int row_lo, int nr, float inv_nr) {
+    auto h_store = [&](const float* src, int ss, float* dA, float* dB, int ds, bool env, int q, int row_lo, int nr, float inv_nr) {
         const bool two = !env;
+        float wa[32], wb[32];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const float4 u = reinterpret_cast<const float4*>(s_tap[q][0])[m], v = reinterpret_cast<const float4*>(s_tap[q][1])[m];
+            wa[4 * m] = u.x; wa[4 * m + 1] = u.y; wa[4 * m + 2] = u.z; wa[4 * m + 3] = u.w;
+            wb[4 * m] = v.x; wb[4 * m + 1] = v.y; wb[4 * m + 2] = v.z; wb[4 * m + 3] = v.w;
+        }
+        if (env) {
+#pragma unroll
+            for (int t = 0; t < kGaborK; ++t) wa[t] = c_genv[t];
+        }
         for (int k = tid; k < nr * nquad; k += kTexThreads) {
             const int kq = fdiv(k, inv_nr), pr = row_lo + (k - kq * nr), c0 = cq0 + 4 * kq;
             const float4* g4 = reinterpret_cast<const float4*>(src + pr * ss + c0);
@@ -375,11 +397,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int t = 0; t < kGaborK; ++t) {
-                const float wa = env ? c_genv[t] : c_gobl[pair][q][0][t], wb = c_gobl[pair][q][1][t];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    a[m] = fmaf(x[m + t], wa, a[m]);
-                    if (two) b[m] = fmaf(x[m + t], wb, b[m]);
+                    a[m] = fmaf(x[m + t], wa[t], a[m]);
+                    if (two) b[m] = fmaf(x[m + t], wb[t], b[m]);
                 }
             }
             *reinterpret_cast<float4*>(dA + pr * ds + c0) = make_float4(a[0], a[1], a[2], a[3]);
@@ -390,7 +411,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     // ======== theta = 90 (filters 12..17): rows with the envelope (ONE plane), then a vertical pass with the six
     // cos(w v) profiles. The profiles are even (tap[t] = tap[29-t]): the 15 pair sums x[t] + x[29-t] are shared by
     // the six filters (15 adds + 6 x 15 FMAs instead of 180 FMAs). SH output rows per thread share their loads. ====
-    h_store(G, GS, B, B, PS, true, 0, 0, rmin, nrow, inv_nrow);
+    h_store(G, GS, B, B, PS, true, 0, rmin, nrow, inv_nrow);
     __syncthreads();
     auto v_six = [&](auto sh_tag) {
         constexpr int SH = decltype(sh_tag)::value;
@@ -496,8 +517,15 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 
     // ======== theta = 45 (filter 6+q) and 135 (filter 18+q): rows with cos(w'u) -> A and sin(w'u) -> B in one pass,
     // then p = (A columns, cos w'v), q = (B columns, sin w'v): the two filters are p - q and p + q. ========
-    auto v_diag = [&](auto sh_tag, int pair, int q, int slot_minus, int slot_plus) {
+    auto v_diag = [&](auto sh_tag, int q, int slot_minus, int slot_plus) {
         constexpr int SH = decltype(sh_tag)::value;
+        float wc[32], ws[32];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const float4 u = reinterpret_cast<const float4*>(s_tap[q][2])[m], v = reinterpret_cast<const float4*>(s_tap[q][3])[m];
+            wc[4 * m] = u.x; wc[4 * m + 1] = u.y; wc[4 * m + 2] = u.z; wc[4 * m + 3] = u.w;
+            ws[4 * m] = v.x; ws[4 * m + 1] = v.y; ws[4 * m + 2] = v.z; ws[4 * m + 3] = v.w;
+        }
         double s[4] = {0.0, 0.0, 0.0, 0.0};
         const int nstrip = (rh + SH - 1) / SH;
         for (int k = tid; k < nstrip * ncol; k += kTexThreads) {
@@ -513,8 +541,8 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
                     for (int t = 0; t < kGaborK; ++t) {
-                        if (t & 1) v1 = fmaf(x[m + t], c_gobl[pair][q][2][t], v1);
-                        else v0 = fmaf(x[m + t], c_gobl[pair][q][2][t], v0);
+                        if (t & 1) v1 = fmaf(x[m + t], wc[t], v1);
+                        else v0 = fmaf(x[m + t], wc[t], v0);
                     }
                     pp[m] = v0 + v1;
                 }
@@ -529,8 +557,8 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
                     for (int t = 0; t < kGaborK; ++t) {
-                        if (t & 1) v1 = fmaf(x[m + t], c_gobl[pair][q][3][t], v1);
-                        else v0 = fmaf(x[m + t], c_gobl[pair][q][3][t], v0);
+                        if (t & 1) v1 = fmaf(x[m + t], ws[t], v1);
+                        else v0 = fmaf(x[m + t], ws[t], v0);
                     }
                     qq[m] = v0 + v1;
                 }
@@ -552,10 +580,11 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         const int pair = half_turn ? (pi == 0 ? 1 : (pi == 1 ? 0 : 2)) : 0;
         const int sm = half_turn ? (pair == 1 ? 6 : (pair == 0 ? 12 : 18)) : 6;     // theta      : p - q
         const int sp = half_turn ? (pair == 1 ? 42 : (pair == 0 ? 36 : 30)) : 18;   // pi - theta : p + q
+        if (pi > 0) { stage_taps(pair); __syncthreads(); }   // (the previous pair's last phase ended with a barrier)
         for (int q = 0; q < 6; ++q) {
-            h_store(G, GS, A, B, PS, false, pair, q, rmin, nrow, inv_nrow);
+            h_store(G, GS, A, B, PS, false, q, rmin, nrow, inv_nrow);
             __syncthreads();
-            if (tall) v_diag(std::integral_constant<int, 4>{}, pair, q, sm, sp); else v_diag(std::integral_constant<int, 2>{}, pair, q, sm, sp);
+            if (tall) v_diag(std::integral_constant<int, 4>{}, q, sm, sp); else v_diag(std::integral_constant<int, 2>{}, q, sm, sp);
             __syncthreads();
         }
     }
