@@ -449,7 +449,11 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     };
     // strip height: 4 rows halve the shared-memory traffic, 2 rows fill the 256 threads better on small boxes
     const auto rounds = [&](int sh) { return (((rh + sh - 1) / sh) * ncol + kTexThreads - 1) / kTexThreads; };
-    const bool tall = rounds(4) * (kGaborK + 3 + 4 * kGaborK) <= rounds(2) * (kGaborK + 1 + 2 * kGaborK);
+    // cost per item from the ncu source view (profiles/r2_tex_ncu.txt): v_six issues 673 / 366 instructions per strip of 4 / 2
+    // rows; v_diag issues 362 / 222, but its 2-row form is bound by the shared-memory pipe (63 loads per 120 FMAs: four
+    // schedulers x 63 wavefronts = 252 cycles per item), which the old load + FMA count under-estimated
+    const bool tall = rounds(4) * 673 <= rounds(2) * 366;
+    const bool tall_d = rounds(4) * 362 <= rounds(2) * 252;
     if (tall) v_six(std::integral_constant<int, 4>{}); else v_six(std::integral_constant<int, 2>{});
     __syncthreads();
 
@@ -584,7 +588,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         for (int q = 0; q < 6; ++q) {
             h_store(G, GS, A, B, PS, false, q, rmin, nrow, inv_nrow);
             __syncthreads();
-            if (tall) v_diag(std::integral_constant<int, 4>{}, q, sm, sp); else v_diag(std::integral_constant<int, 2>{}, q, sm, sp);
+            if (tall_d) v_diag(std::integral_constant<int, 4>{}, q, sm, sp); else v_diag(std::integral_constant<int, 2>{}, q, sm, sp);
             __syncthreads();
         }
     }
