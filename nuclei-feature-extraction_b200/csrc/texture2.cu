@@ -447,14 +447,10 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
 #pragma unroll
         for (int q = 0; q < 6; ++q) stash2(s[2 * q], s[2 * q + 1], 2 * (slot90 + q));
     };
-    // strip height: 4 rows halve the shared-memory traffic, 2 rows fill the 256 threads better on small boxes
-    const auto rounds = [&](int sh) { return (((rh + sh - 1) / sh) * ncol + kTexThreads - 1) / kTexThreads; };
-    // cost per item from the ncu source view (profiles/r2_tex_ncu.txt): v_six issues 673 / 366 instructions per strip of 4 / 2
-    // rows; v_diag issues 362 / 222, but its 2-row form is bound by the shared-memory pipe (63 loads per 120 FMAs: four
-    // schedulers x 63 wavefronts = 252 cycles per item), which the old load + FMA count under-estimated
-    const bool tall = rounds(4) * 673 <= rounds(2) * 366;
-    const bool tall_d = rounds(4) * 362 <= rounds(2) * 252;
-    if (tall) v_six(std::integral_constant<int, 4>{}); else v_six(std::integral_constant<int, 2>{});
+    // Strips of 4 rows for every box size. Round 2 measured 2-row strips (better thread fill on small boxes, but v_diag's
+    // 2-row form is bound by the shared-memory pipe: 63 loads per 120 FMAs) and 8-row strips (37 loads per 480 FMAs, half
+    // as many items): choosing per nucleus by a cost model was slower than always 4 (12.70 / 12.54 against 12.39 ms per 100k).
+    v_six(std::integral_constant<int, 4>{});
     __syncthreads();
 
     // ======== theta = 0 (filters 0..5): columns with the envelope first (one plane over the padded columns the box
@@ -588,7 +584,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         for (int q = 0; q < 6; ++q) {
             h_store(G, GS, A, B, PS, false, q, rmin, nrow, inv_nrow);
             __syncthreads();
-            if (tall_d) v_diag(std::integral_constant<int, 4>{}, q, sm, sp); else v_diag(std::integral_constant<int, 2>{}, q, sm, sp);
+            v_diag(std::integral_constant<int, 4>{}, q, sm, sp);
             __syncthreads();
         }
     }
