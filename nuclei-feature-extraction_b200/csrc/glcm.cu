@@ -478,8 +478,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     uint32_t* hx128 = marg, *hx254 = marg + 128, *hs128 = marg + 384, *hs254 = marg + 640, *hs64r = marg + 1152, *hs32r = marg + 1536;
     const int rep3 = lane % 3, rep8 = lane & 7;
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + L.rows);
-    uint8_t* q128 = smem_raw + L.q128;
-    uint8_t* q254 = smem_raw + L.q254;
+    uint16_t* qq = reinterpret_cast<uint16_t*>(smem_raw + L.q128);   // per pixel: q254 | q128 << 8 (spans the q128 and q254 slots of the layout)
     uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + L.list);
     uint32_t* parts = reinterpret_cast<uint32_t*>(smem_raw + L.parts);   // [combo][warp][kNP]
     __shared__ __align__(8) uint64_t bar;
@@ -546,13 +545,27 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
             pr = patch[a]; pg = patch[a + 1]; pb = patch[a + 2];
         }
         const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
-        q128[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
-        q254[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(g, p.scale254)), 253);
+        const int a128 = min((int)floorf(__fmul_rn(g, 128.0f)), 127), a254 = min((int)floorf(__fmul_rn(g, p.scale254)), 253);
+        qq[r * P + c] = (uint16_t)(a254 | (a128 << 8));
     };
     if (dbg_all) {
         for (int k = tid; k < P * P; k += kG64Threads) quantise(k / P, k % P);
-    } else {
-        for (int j = tid; j < K; j += kG64Threads) { const uint32_t rc = list[j]; quantise(rc >> 8, rc & 255); }
+    }
+    // The list entry becomes (position, neighbour flags): bit 12 + oi is set when the pixel's neighbour at offset oi is
+    // inside the window and masked. The sweeps then cost three 16-bit loads per pixel (entry, own levels, neighbour's
+    // levels) instead of a mask-word load with its bit arithmetic and four byte loads (ncu round 2: 11 % of the kernel's
+    // shared-memory wavefronts and a fifth of the two sweeps' instructions went into finding the pair).
+    for (int j = tid; j < K; j += kG64Threads) {
+        const uint32_t rc = list[j];
+        const int r = rc >> 8, c = rc & 255;
+        if (!dbg_all) quantise(r, c);
+        uint32_t fl = 0u;
+#pragma unroll
+        for (int oi = 0; oi < kGlcmOffsets; ++oi) {
+            const int r2 = r + c_off[oi][0], c2 = c + c_off[oi][1];
+            if ((r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u)) fl |= 1u << oi;
+        }
+        list[j] = (uint16_t)((r * P + c) | (fl << 12));
     }
     __syncthreads();   // the window is dead from here on: region A becomes the histograms
     {
@@ -566,7 +579,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         for (int t = 0; t < 4; ++t)
             if (c_levels[t] == p.dbg_levels) lv = t;
         for (int k = tid; k < P * P; k += kG64Threads)
-            p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)((lv == 3) ? q254[k] : (q128[k] >> (2 - lv)));
+            p.dbg_grey[i * (int64_t)P * P + k] = (uint8_t)((lv == 3) ? (qq[k] & 0xff) : ((qq[k] >> 8) >> (2 - lv)));
     }
     __syncthreads();
 
@@ -581,12 +594,12 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         uint32_t d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
         float fi[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = tid; j < K; j += kG64Threads) {
-            const uint32_t rc = list[j];
-            const int r = rc >> 8, c = rc & 255, r2 = r + dy, c2 = c + dx;
-            if (!((r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u))) continue;
+            const uint32_t e = list[j];
+            if (!((e >> (12 + oi)) & 1u)) continue;
             ++np_local;
-            const int src = r * P + c;
-            const int a3 = q254[src], b3 = q254[src + dpos], a2 = q128[src], b2 = q128[src + dpos];
+            const int src = e & 0xfff;
+            const uint32_t qa = qq[src], qb = qq[src + dpos];
+            const int a3 = qa & 0xff, b3 = qb & 0xff, a2 = qa >> 8, b2 = qb >> 8;
             // 254 levels
             hash_add(hash, lg, (uint32_t)(min(a3, b3) * 256 + max(a3, b3)));
             atomicAdd(&hx254[a3], 1u);
@@ -627,11 +640,11 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         // ---- pass 2: per-pair cell counts (entropy, ASM) for the four levels ----
         uint32_t sg[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0};
         for (int j = tid; j < K; j += kG64Threads) {
-            const uint32_t rc = list[j];
-            const int r = rc >> 8, c = rc & 255, r2 = r + dy, c2 = c + dx;
-            if (!((r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u))) continue;
-            const int src = r * P + c;
-            const int a3 = q254[src], b3 = q254[src + dpos], a2 = q128[src], b2 = q128[src + dpos];
+            const uint32_t e = list[j];
+            if (!((e >> (12 + oi)) & 1u)) continue;
+            const int src = e & 0xfff;
+            const uint32_t qa = qq[src], qb = qq[src + dpos];
+            const int a3 = qa & 0xff, b3 = qb & 0xff, a2 = qa >> 8, b2 = qb >> 8;
             const int a1 = a2 >> 1, b1 = b2 >> 1, a0 = a2 >> 2, b0 = b2 >> 2;
             uint32_t g[4];
             g[3] = hash_get(hash, lg, (uint32_t)(min(a3, b3) * 256 + max(a3, b3))) << (a3 == b3 ? 1 : 0);
