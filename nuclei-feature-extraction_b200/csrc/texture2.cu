@@ -67,9 +67,14 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     // region X = slab buffer while the window streams in, pixel list afterwards
     const int region_x = max(window_smem_bytes(P, CS), (P * P * 2 + 127) & ~127);
     uint8_t* slab = smem_raw;
-    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw);   // (one-slab windows: moved below)
     uint8_t* plane = smem_raw + region_x;
     uint32_t* rows = reinterpret_cast<uint32_t*>(plane + ((P * P + 15) & ~15));
+    // One-slab windows (P <= 64) keep the pixel list in its own region: it is built while the window is in flight and only
+    // the MASKED pixels are quantised (a run never leaves the mask). Quantising every pixel of the rows that hold mask bits
+    // was a fifth of the kernel's instructions (ncu round 2) for 900 of 4096 pixels that matter.
+    const bool early = nslab == 1;
+    if (early) list = reinterpret_cast<uint16_t*>(rows + ((P * wpr + 3) & ~3));
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_lut[256];
     __shared__ uint32_t s_R[4 * kRlCells];   // one 24 x 16 histogram per direction
@@ -88,60 +93,79 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
     for (int k = tid; k < P * wpr; k += THREADS) rows[k] = gm[k];
     __syncthreads();
-    // ---- 24-level plane (texture.rs:189 + SPEC.md B9), rows that hold mask bits only ----
-    for (int sidx = 0; sidx < nslab; ++sidx) {
-        const int row0 = sidx * CS, nrows = min(CS, P - row0);
-        mbar_wait(&bar, sidx & 1);
-        for (int k = tid; k < nrows * P; k += THREADS) {
-            const int lr = k / P, c = k - lr * P, r = row0 + lr;
-            uint32_t any = 0;
-            for (int w = 0; w < wpr; ++w) any |= rows[r * wpr + w];
-            if (!any) continue;
+    // ---- compacted list of the masked pixels ----
+    int K = 0;
+    auto build_list = [&]() {
+        for (int base = 0; base < P * wpr; base += THREADS) {
+            const int k = base + tid;
+            uint32_t bits = (k < P * wpr) ? rows[k] : 0u;
+            const int cnt = __popc(bits);
+            int incl = cnt;
+    #pragma unroll
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+                if (lane >= o2) incl += t;
+            }
+            __syncthreads();
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            int wbase = 0, total = 0;
+    #pragma unroll
+            for (int t = 0; t < NW; ++t) {
+                const int v = s_scan[t];
+                wbase += (t < warp) ? v : 0;
+                total += v;
+            }
+            int pos = K + wbase + incl - cnt;
+            const int r = k / wpr, cb = (k - r * wpr) * 32;
+            while (bits) {
+                const int c = cb + __ffs(bits) - 1;
+                bits &= bits - 1;
+                list[pos++] = (uint16_t)((r << 8) | c);
+            }
+            K += total;
+        }
+        __syncthreads();
+    };
+    if (early) {
+        build_list();
+        mbar_wait(&bar, 0);
+        for (int j = tid; j < K; j += THREADS) {
+            const uint32_t rc = list[j];
+            const int r = rc >> 8, c = rc & 255;
             uint32_t pr = 0, pg = 0, pb = 0;
             if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
-                const int a = patch_addr(CS, o, lr, c);
+                const int a = patch_addr(CS, o, r, c);
                 pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
             }
             plane[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
         }
         __syncthreads();
-        if (tid == 0 && sidx + 1 < nslab) {
-            mbar_expect_tx(&bar, slab_tx);
-            tma_load_window(slab, &map, inf.left, inf.top + row0 + CS, P, CS, &bar);
+    } else {
+        // ---- 24-level plane (texture.rs:189 + SPEC.md B9), rows that hold mask bits only ----
+        for (int sidx = 0; sidx < nslab; ++sidx) {
+            const int row0 = sidx * CS, nrows = min(CS, P - row0);
+            mbar_wait(&bar, sidx & 1);
+            for (int k = tid; k < nrows * P; k += THREADS) {
+                const int lr = k / P, c = k - lr * P, r = row0 + lr;
+                uint32_t any = 0;
+                for (int w = 0; w < wpr; ++w) any |= rows[r * wpr + w];
+                if (!any) continue;
+                uint32_t pr = 0, pg = 0, pb = 0;
+                if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
+                    const int a = patch_addr(CS, o, lr, c);
+                    pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
+                }
+                plane[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
+            }
+            __syncthreads();
+            if (tid == 0 && sidx + 1 < nslab) {
+                mbar_expect_tx(&bar, slab_tx);
+                tma_load_window(slab, &map, inf.left, inf.top + row0 + CS, P, CS, &bar);
+            }
         }
+        build_list();
     }
-    // ---- compacted list of the masked pixels (overwrites the slab buffer) ----
-    int K = 0;
-    for (int base = 0; base < P * wpr; base += THREADS) {
-        const int k = base + tid;
-        uint32_t bits = (k < P * wpr) ? rows[k] : 0u;
-        const int cnt = __popc(bits);
-        int incl = cnt;
-#pragma unroll
-        for (int o2 = 1; o2 < 32; o2 <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o2);
-            if (lane >= o2) incl += t;
-        }
-        __syncthreads();
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        int wbase = 0, total = 0;
-#pragma unroll
-        for (int t = 0; t < NW; ++t) {
-            const int v = s_scan[t];
-            wbase += (t < warp) ? v : 0;
-            total += v;
-        }
-        int pos = K + wbase + incl - cnt;
-        const int r = k / wpr, cb = (k - r * wpr) * 32;
-        while (bits) {
-            const int c = cb + __ffs(bits) - 1;
-            bits &= bits - 1;
-            list[pos++] = (uint16_t)((r << 8) | c);
-        }
-        K += total;
-    }
-    __syncthreads();
     float* out = p.out + i * (int64_t)p.out_stride + p.col_glrlm;
     auto masked = [&](int r, int c) -> bool {
         return (unsigned)r < (unsigned)P && (unsigned)c < (unsigned)P && ((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u);
@@ -686,7 +710,7 @@ cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaS
     if (p.n <= 0) return cudaSuccess;
     cudaError_t e;
     const int rx = window_smem_bytes(p.P, p.slab_rows) > ((p.P * p.P * 2 + 127) & ~127) ? window_smem_bytes(p.P, p.slab_rows) : ((p.P * p.P * 2 + 127) & ~127);
-    const int smem = rx + ((p.P * p.P + 15) & ~15) + p.P * mask_wpr(p.P) * 4;
+    const int smem = rx + ((p.P * p.P + 15) & ~15) + ((p.P * mask_wpr(p.P) + 3) & ~3) * 4 + (p.P <= p.slab_rows ? p.P * p.P * 2 : 0);   // one-slab windows: + the list
     if (p.P > 128) {
         e = cudaFuncSetAttribute(k_glrlm<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
