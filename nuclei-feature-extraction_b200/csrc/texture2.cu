@@ -53,7 +53,7 @@ __device__ __forceinline__ float grey_of(const float* lut, uint32_t r, uint32_t 
 constexpr int kRlCells = kRlLevels * kRlMax;
 static_assert(kRlLevels == 24, "u = (i - 12.5)/11.5 below assumes 24 levels");
 
-// Dynamic smem: region X (slab, later the pixel list u16 (row << 8) | col) | plane[P*P] u8 | rows[P*wpr] u32
+// Dynamic smem: region X (slab; windows of several slabs reuse it for the pixel list u16 (row << 8) | col) | plane[(P+2)^2] u8 | rows[P*wpr] u32 | list (one-slab windows)
 // THREADS = 256 for P <= 128 (several CTAs per SM); 1024 for larger windows, whose 204 KB of shared memory leave
 // room for one CTA per SM only (8 warps per SM measured 25 % issue-active at P = 256).
 template <int THREADS>
@@ -69,7 +69,10 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     uint8_t* slab = smem_raw;
     uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw);   // (one-slab windows: moved below)
     uint8_t* plane = smem_raw + region_x;
-    uint32_t* rows = reinterpret_cast<uint32_t*>(plane + ((P * P + 15) & ~15));
+    // plane[(r + 1) * PP + c + 1] = level of a masked pixel, 0xFF everywhere else (one-pixel border included): the run
+    // walk compares ONE byte per step instead of a bounds check, a mask-word test and a level load.
+    const int PP = P + 2;
+    uint32_t* rows = reinterpret_cast<uint32_t*>(plane + ((PP * PP + 15) & ~15));
     // One-slab windows (P <= 64) keep the pixel list in its own region: it is built while the window is in flight and only
     // the MASKED pixels are quantised (a run never leaves the mask). Quantising every pixel of the rows that hold mask bits
     // was a fifth of the kernel's instructions (ncu round 2) for 900 of 4096 pixels that matter.
@@ -92,6 +95,7 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     if (tid < 256) s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
     const uint32_t* gm = p.bitmask + i * (int64_t)P * wpr;
     for (int k = tid; k < P * wpr; k += THREADS) rows[k] = gm[k];
+    for (int k = tid; k < ((PP * PP + 15) >> 4); k += THREADS) reinterpret_cast<uint4*>(plane)[k] = make_uint4(~0u, ~0u, ~0u, ~0u);
     __syncthreads();
     // ---- compacted list of the masked pixels ----
     int K = 0;
@@ -138,7 +142,7 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
                 const int a = patch_addr(CS, o, r, c);
                 pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
             }
-            plane[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
+            plane[(r + 1) * PP + c + 1] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
         }
         __syncthreads();
     } else {
@@ -148,15 +152,13 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
             mbar_wait(&bar, sidx & 1);
             for (int k = tid; k < nrows * P; k += THREADS) {
                 const int lr = k / P, c = k - lr * P, r = row0 + lr;
-                uint32_t any = 0;
-                for (int w = 0; w < wpr; ++w) any |= rows[r * wpr + w];
-                if (!any) continue;
+                if (!((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u)) continue;
                 uint32_t pr = 0, pg = 0, pb = 0;
                 if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
                     const int a = patch_addr(CS, o, lr, c);
                     pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
                 }
-                plane[r * P + c] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
+                plane[(r + 1) * PP + c + 1] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
             }
             __syncthreads();
             if (tid == 0 && sidx + 1 < nslab) {
@@ -167,22 +169,19 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
         build_list();
     }
     float* out = p.out + i * (int64_t)p.out_stride + p.col_glrlm;
-    auto masked = [&](int r, int c) -> bool {
-        return (unsigned)r < (unsigned)P && (unsigned)c < (unsigned)P && ((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u);
-    };
     // ---- run detection for the four directions: one sweep per direction, four histograms ----
     for (int k = tid; k < 4 * kRlCells; k += THREADS) s_R[k] = 0u;
     __syncthreads();
     for (int j = tid; j < K; j += THREADS) {
         const uint32_t rc = list[j];
-        const int r = rc >> 8, c = rc & 255;
-        const int lv = plane[r * P + c];
+        const int at = ((rc >> 8) + 1) * PP + (rc & 255) + 1;
+        const uint32_t lv = plane[at];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            const int dx = c_dirs[d][0], dy = c_dirs[d][1];
-            if (masked(r - dy, c - dx) && plane[(r - dy) * P + (c - dx)] == lv) continue;   // not a run start
-            int len = 1, r2 = r + dy, c2 = c + dx;
-            while (masked(r2, c2) && plane[r2 * P + c2] == lv) { ++len; r2 += dy; c2 += dx; }
+            const int step = c_dirs[d][1] * PP + c_dirs[d][0];
+            if (plane[at - step] == lv) continue;   // not a run start
+            int len = 1, q = at + step;
+            while (plane[q] == lv) { ++len; q += step; }
             atomicAdd(&s_R[d * kRlCells + lv * kRlMax + min(len, kRlMax) - 1], 1u);
         }
     }
@@ -710,7 +709,7 @@ cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaS
     if (p.n <= 0) return cudaSuccess;
     cudaError_t e;
     const int rx = window_smem_bytes(p.P, p.slab_rows) > ((p.P * p.P * 2 + 127) & ~127) ? window_smem_bytes(p.P, p.slab_rows) : ((p.P * p.P * 2 + 127) & ~127);
-    const int smem = rx + ((p.P * p.P + 15) & ~15) + ((p.P * mask_wpr(p.P) + 3) & ~3) * 4 + (p.P <= p.slab_rows ? p.P * p.P * 2 : 0);   // one-slab windows: + the list
+    const int smem = rx + (((p.P + 2) * (p.P + 2) + 15) & ~15) + ((p.P * mask_wpr(p.P) + 3) & ~3) * 4 + (p.P <= p.slab_rows ? p.P * p.P * 2 : 0);   // one-slab windows: + the list
     if (p.P > 128) {
         e = cudaFuncSetAttribute(k_glrlm<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
