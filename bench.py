@@ -456,18 +456,28 @@ def e2e_double_buffered(ctxs, outs, submit, n_steps):
 SET_NAMES = {"geometry": "shape", "color": "color", "glcm": "glcm", "glrlm": "glrlm", "gabor": "gabor", "all": "all"}
 
 # Shared-memory atomics of the GLCM kernel (BASELINE north_star: "shared-memory atomic throughput against its peak for GLCM").
-# Lane-atomics per nucleus of k_glcm64 on the bench's synthetic nuclei: ncu smsp__inst_executed_op_shared_atom.sum = 32.24 M
-# warp-instructions per 20 000 nuclei x 28.55 active lanes (profiles/r2_all_base_ncu.txt); peaks from scripts/atoms_probe.cu
-# (profiles/r1_smem_atomics_probe.txt): 3.5e12 random-address, 9.1e12 conflict-free shared-memory atomics per second and B200.
-GLCM_LANE_ATOMICS_PER_NUCLEUS = 32243500 * 28.55 / 20000
+# Per nucleus of the bench's synthetic set, from the ncu capture of k_glcm64 in profiles/r2_tex_ncu.txt (20 000 nuclei):
+#   smsp__inst_executed_op_shared_atom.sum = 32.23 M warp-instructions x 28.49 active lanes  -> lane-atomics
+#   l1tex__data_pipe_lsu_wavefronts_mem_shared.sum = 276.8 M                                 -> shared-memory wavefronts
+# Peaks: scripts/atoms_probe.cu (profiles/r1_smem_atomics_probe.txt): 3.5e12 random-address, 9.1e12 conflict-free
+# shared-memory atomics per second and B200; the shared-memory data pipe moves one 128-byte wavefront per clock and SM.
+GLCM_LANE_ATOMICS_PER_NUCLEUS = 32230563 * 28.49 / 20000
+GLCM_SMEM_WAVEFRONTS_PER_NUCLEUS = 276781036 / 20000
 SMEM_ATOMICS_PEAK_RANDOM, SMEM_ATOMICS_PEAK_CONFLICT_FREE = 3.5e12, 9.1e12
+B200_SMS = 148
 
 
-def glcm_atomics(nuclei, kernel_ms):
+def glcm_atomics(nuclei, kernel_ms, sm_mhz=1965.0):
     rate = GLCM_LANE_ATOMICS_PER_NUCLEUS * nuclei / (kernel_ms * 1e-3)
-    return {"lane_atomics_per_nucleus": GLCM_LANE_ATOMICS_PER_NUCLEUS, "source": "ncu capture of k_glcm64, P = 64 (profiles/r2_all_base_ncu.txt)",
+    wf = GLCM_SMEM_WAVEFRONTS_PER_NUCLEUS * nuclei / (kernel_ms * 1e-3)
+    wf_peak = B200_SMS * sm_mhz * 1e6
+    return {"lane_atomics_per_nucleus": GLCM_LANE_ATOMICS_PER_NUCLEUS, "source": "ncu capture of k_glcm64, P = 64 (profiles/r2_tex_ncu.txt)",
             "achieved_per_s": rate, "peak_random_address_per_s": SMEM_ATOMICS_PEAK_RANDOM,
-            "peak_conflict_free_per_s": SMEM_ATOMICS_PEAK_CONFLICT_FREE, "frac_of_random_address_peak": rate / SMEM_ATOMICS_PEAK_RANDOM}
+            "peak_conflict_free_per_s": SMEM_ATOMICS_PEAK_CONFLICT_FREE, "frac_of_random_address_peak": rate / SMEM_ATOMICS_PEAK_RANDOM,
+            "smem_pipe": {"wavefronts_per_nucleus": GLCM_SMEM_WAVEFRONTS_PER_NUCLEUS, "achieved_per_s": wf,
+                          "peak_per_s": wf_peak, "frac": wf / wf_peak,
+                          "note": "all shared-memory wavefronts of the kernel (atomics, their bank-conflict replays, loads, clears) "
+                                  "against one wavefront per clock and SM at the maximum SM clock"}}
 
 
 def per_set_block(args, ex, ex2, tile, xy, off, nuclei, P, peak, peak_kind, cpu):

@@ -34,3 +34,4 @@ def test_roofline_helpers():
     assert (t is None) == (tj["csrc_sha16"] != h)           # stale captures read as null, never as a number
     a = bench.glcm_atomics(100000, 7.3)
     assert 0.0 < a["frac_of_random_address_peak"] < 1.0
+    assert 0.0 < a["smem_pipe"]["frac"] < 1.0 and abs(a["smem_pipe"]["peak_per_s"] - 148 * 1.965e9) < 1e6
