@@ -816,6 +816,8 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
             phase ^= 1u;
             for (int k = tid; k < nrows * P; k += kLargeThreads) {
                 const int lr = k / P, c = k - lr * P, r = row0 + lr;
+                // only pixels under the mask ever enter a pair (the debug dump wants the whole plane)
+                if (!p.dbg_grey && !((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u)) continue;
                 uint32_t pr = 0, pg = 0, pb = 0;
                 if (r < inf.nvr && c < inf.nvc) {
                     const int a = patch_addr(64, o, lr, c);
