@@ -363,14 +363,20 @@ def hbm_peak():
         return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
-def source_hash():
-    """sha256 (16 hex digits) over the kernel sources: ties the ncu-derived DRAM traffic in profiles/r2_traffic.json to the
-    kernels it was captured from (a stale entry reads as null, never as a number)."""
+# kernel sources behind the captured kernels of each workload in profiles/r2_traffic.json (shared headers included)
+TRAFFIC_SOURCES = {"color": ("color.cu", "geom.cu", "nfx_device.cuh", "nfx_kernels.h"),
+                   "staged": ("staged.cu", "geom.cu", "nfx_device.cuh", "nfx_kernels.h")}
+
+
+def source_hash(files=None):
+    """sha256 (16 hex digits) over kernel sources (all of csrc/ by default): ties the ncu-derived DRAM traffic in
+    profiles/r2_traffic.json to the kernels it was captured from (a stale entry reads as null, never as a number)."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "nuclei-feature-extraction_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in sorted(files if files is not None else os.listdir(d)):
         if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -378,9 +384,10 @@ def source_hash():
 def measured_traffic(workload, kernel, nuclei, P):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-        if tj.get("csrc_sha16") != source_hash():
+        wl = tj.get(workload, {})
+        if wl.get("src_sha16") != source_hash(TRAFFIC_SOURCES[workload]):
             return None
-        ent = tj.get(workload, {}).get(kernel)
+        ent = wl.get(kernel)
         if ent and ent["nuclei"] == nuclei and ent["patch"] == P:
             return ent["dram_bytes_per_launch"]
     except Exception:

@@ -31,7 +31,8 @@ def test_roofline_helpers():
     assert len(h) == 16 and h == bench.source_hash()
     t = bench.measured_traffic("color", "k_hue_batch", 100000, 64)
     tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-    assert (t is None) == (tj["csrc_sha16"] != h)           # stale captures read as null, never as a number
+    hc = bench.source_hash(bench.TRAFFIC_SOURCES["color"])
+    assert (t is None) == (tj["color"]["src_sha16"] != hc)  # stale captures read as null, never as a number
     a = bench.glcm_atomics(100000, 7.3)
     assert 0.0 < a["frac_of_random_address_peak"] < 1.0
     assert 0.0 < a["smem_pipe"]["frac"] < 1.0 and abs(a["smem_pipe"]["peak_per_s"] - 148 * 1.965e9) < 1e6
