@@ -859,17 +859,29 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
             uint32_t d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};        // <= 128 pairs per thread: 128 * 253^2 < 2^32
             float fi[3] = {0.f, 0.f, 0.f};
             for (int pass = 0; pass < 2; ++pass) {
-                for (int k = tid; k < P * wpr; k += kLargeThreads) {
-                    const int r = k / wpr, w = k - r * wpr, r2 = r + dy;
-                    if (r2 >= P) continue;
-                    const uint32_t* nr = rows + r2 * wpr;
-                    uint32_t nb = nr[w];
-                    if (dx == 1) nb = (nb >> 1) | ((w + 1 < wpr) ? (nr[w + 1] << 31) : 0u);
-                    else if (dx == -1) nb = (nb << 1) | ((w > 0) ? (nr[w - 1] >> 31) : 0u);
-                    uint32_t pb = rows[k] & nb;
-                    while (pb) {
-                        const int c = 32 * w + __ffs(pb) - 1;
-                        pb &= pb - 1;
+                // Every lane prepares the pair bits of ONE mask word; the warp then walks its 32 words together, lane l taking
+                // bit l of the word in turn (empty words are skipped warp-uniformly). Lanes that walked the bits of their own
+                // word ran 15 of 32 at a time (words inside the nucleus are full, words outside are empty).
+                for (int base = 0; base < P * wpr; base += kLargeThreads) {
+                    const int k = base + tid;
+                    uint32_t pbw = 0u;
+                    if (k < P * wpr) {
+                        const int r = k / wpr, w = k - r * wpr, r2 = r + dy;
+                        if (r2 < P) {
+                            const uint32_t* nr = rows + r2 * wpr;
+                            uint32_t nb = nr[w];
+                            if (dx == 1) nb = (nb >> 1) | ((w + 1 < wpr) ? (nr[w + 1] << 31) : 0u);
+                            else if (dx == -1) nb = (nb << 1) | ((w > 0) ? (nr[w - 1] >> 31) : 0u);
+                            pbw = rows[k] & nb;
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, pbw != 0u)) continue;
+                    for (int t = 0; t < 32; ++t) {
+                        const uint32_t pbt = __shfl_sync(0xffffffffu, pbw, t);
+                        if (pbt == 0u) continue;                      // warp-uniform
+                        if (!((pbt >> lane) & 1u)) continue;
+                        const int kt = base + (warp << 5) + t, r = kt / wpr, w = kt - r * wpr;
+                        const int c = 32 * w + lane;
                         const int src = r * PP + c;
                         const int a0 = plane[src], b0 = plane[src + dpos];
                         if (pass == 0) ++np_local;
