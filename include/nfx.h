@@ -163,8 +163,10 @@ int nfx_download_ext(nfx_ctx* ctx, float* out /* [n][nfx_ext_feature_count(ext_m
 
 /* ---- trait-level drop-in -------------------------------------------------------------------- */
 /* FeatureSet::compute_features_batched(centroids, polygons, patchs, masks) (src/features/mod.rs:
- * 12-28) for ONE batch built by the reference's own loader: patchs [n,3,P,P] f32 with values k/255
- * (utils.rs:172), masks [n,1,P,P] f32 in {0,1}, polygons = CENTRED rings (utils.rs:65-72) in CSR.
+ * 12-28) for ONE batch: patchs [n,3,P,P] f32 in [0,1], masks [n,1,P,P] f32 (non-zero = inside), polygons = CENTRED
+ * rings (utils.rs:65-72) in CSR. A batch built by the reference's own loader holds values k/255 (utils.rs:172) and runs
+ * on the u8 kernels; any other f32 values are accepted too: the texture sets then read an f32 grey plane and the colour
+ * set is evaluated from the f32 patches (csrc/f32batch.cu; written for correctness, not speed).
  * `feature_set` is one NFX_FS_* bit (the trait call), or a union of bits: the batch is then uploaded
  * once and the columns of the sets follow each other in flat() order (src/args.rs:38-45), which saves
  * the 65 KB per nucleus of PCIe traffic each further per-set call would repeat. All pointers are HOST

@@ -100,6 +100,7 @@ struct nfx_ctx {
     // scratch
     DevBuf<uint8_t> scratch8;
     DevBuf<float> scratchf;
+    const float* grey_f32 = nullptr;   // set while a trait-level batch of arbitrary f32 patches is computed (f32batch.cu)
     DevBuf<uint32_t> scratch32;
     DevBuf<uint8_t> flush;
     int* d_bad = nullptr;
@@ -281,6 +282,7 @@ int run_glcm(nfx_ctx* ctx, int64_t n, const CUtensorMap* mp, float* out, int str
     g.dbg_dx = ddx;
     g.dbg_grey = dbg_grey;
     g.scale254 = (ctx->rules & NFX_RULE_GLCM_254_U8) ? 255.0f : 254.0f;
+    g.grey = ctx->grey_f32;
     CK(timed(ctx, "k_glcm", 1, [&] { return launch_glcm(g, mp, ctx->stream); }));
     return NFX_OK;
 }
@@ -299,6 +301,7 @@ int run_tex2(nfx_ctx* ctx, int64_t n, uint32_t mask, const CUtensorMap* map_csla
     t.col_gabor = col_gabor;
     t.gabor_partial = nullptr;
     t.gabor_half_turn = (ctx->rules & NFX_RULE_GABOR_HALF_TURN) ? 1 : 0;
+    t.grey = ctx->grey_f32;
     const bool gabor_tiled = gabor_tiles(ctx->P) > 1;
     if ((mask & NFX_FS_GABOR) && gabor_tiled) {
         CK(ctx->gabor_part.ensure((size_t)n * gabor_tiles(ctx->P) * 97));
@@ -777,6 +780,12 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
         return launch_pack_batch(n, P, d_patchs, d_masks, ctx->patches.p, ctx->ppitch, ctx->bitmask.p,
                                  ctx->info.p, ctx->d_bad, ctx->stream);
     }));
+    // Values that are not k/255 (no loader of the reference produces them, utils.rs:172, but the trait accepts any tensor):
+    // the texture sets then read an f32 grey plane and the colour set is evaluated from the f32 patches (f32batch.cu).
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const bool f32path = bad != 0;
     const Cols c = columns(fs);
     const int cols = c.total;
     CK(ctx->out.ensure((size_t)n * cols));
@@ -791,20 +800,34 @@ int nfx_compute_features_batched(nfx_ctx* ctx, uint32_t fs, int64_t n, const flo
         g.slide_window = 0;
         CK(timed(ctx, "k_geom<shape>", 1, [&] { return launch_geom(g, false, true, ctx->stream); }));
     }
-    if (fs & NFX_FS_COLOR)
-        if ((rc = run_color(ctx, n, (int)std::min<int64_t>(n, 1 << 30), &ctx->map_pat_cslab, &ctx->map_pat_slab, ctx->out.p, cols, c.color))) return rc;
+    const int batch = (int)std::min<int64_t>(n, 1 << 30);   // the trait call IS one batch
+    if (f32path) {
+        if (fs & (NFX_FS_GLCM | NFX_FS_GLRLM | NFX_FS_GABOR)) {
+            // the f32 masks are packed into the bitmask by now: their region of the scratch buffer takes the grey planes
+            CK(timed(ctx, "k_grey_f32", 1, [&] { return launch_grey_f32(n, P, d_patchs, d_masks, ctx->stream); }));
+            ctx->grey_f32 = d_masks;
+        }
+        if (fs & NFX_FS_COLOR) {
+            const int64_t chunks = (n + batch - 1) / batch;
+            CK(ctx->hue.ensure((size_t)chunks * plane * 2));
+            CK(timed(ctx, "k_color_f32", 3, [&] {
+                return launch_color_f32(n, P, batch, d_patchs, ctx->bitmask.p, ctx->hue.p, ctx->out.p, cols, c.color, ctx->stream);
+            }));
+        }
+    } else if (fs & NFX_FS_COLOR) {
+        if ((rc = run_color(ctx, n, batch, &ctx->map_pat_cslab, &ctx->map_pat_slab, ctx->out.p, cols, c.color))) return rc;
+    }
     if (fs & NFX_FS_GLCM)
-        if ((rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_pat_cslab : &ctx->map_pat_patch, ctx->out.p, cols, c.glcm, nullptr, 0, 0, 0, nullptr))) return rc;
-    if (fs & (NFX_FS_GLRLM | NFX_FS_GABOR))
-        if ((rc = run_tex2(ctx, n, fs, &ctx->map_pat_cslab, &ctx->map_pat_patch, &ctx->map_pat_gabor, ctx->out.p, cols, c.glrlm, c.gabor))) return rc;
-    int bad = 0;
-    CK(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        rc = run_glcm(ctx, n, glcm_uses_slab_map(ctx->P) ? &ctx->map_pat_cslab : &ctx->map_pat_patch, ctx->out.p, cols, c.glcm, nullptr, 0, 0, 0, nullptr);
+    if (!rc && (fs & (NFX_FS_GLRLM | NFX_FS_GABOR)))
+        rc = run_tex2(ctx, n, fs, &ctx->map_pat_cslab, &ctx->map_pat_patch, &ctx->map_pat_gabor, ctx->out.p, cols, c.glrlm, c.gabor);
+    ctx->grey_f32 = nullptr;
+    if (rc) return rc;
     CK(cudaMemcpyAsync(out, ctx->out.p, (size_t)n * cols * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_geom = false;
     ctx->have_poly = false;   // the staged rings were centred ones: force a fresh upload for nfx_compute
     ctx->computed_mask = 0;
-    if (bad) return fail(ctx, NFX_ERR_UNSUPPORTED, "patchs holds values that are not k/255 (only image-derived batches, utils.rs:172, are supported)");
     return NFX_OK;
 }
 

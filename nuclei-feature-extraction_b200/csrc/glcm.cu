@@ -19,6 +19,8 @@
 //     each combination are computed once at the end by one thread per combination.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "nfx_kernels.h"
 
 namespace nfx {
@@ -142,7 +144,8 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         s_box[1] = -1;
     }
     __syncthreads();
-    if (tid == 0) {
+    const float* greyp = p.grey ? p.grey + i * (int64_t)P * P : nullptr;   // f32 grey plane instead of the u8 window
+    if (tid == 0 && !greyp) {
         mbar_expect_tx(&bar, (uint32_t)(patch_panels(P) * kPanelBytes * P));
         tma_load_patch(patch, &map, inf.left, inf.top, P, &bar);
     }
@@ -169,8 +172,8 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     __syncthreads();
     const int rmin = s_box[0], rmax = s_box[1];
     const int o = patch_byte_offset(inf.left);
-    mbar_wait(&bar, 0);
-    if (inf.nvc < P || inf.nvr < P) {
+    if (!greyp) mbar_wait(&bar, 0);
+    if (!greyp && (inf.nvc < P || inf.nvr < P)) {
         for (int k = tid; k < P * P; k += kGlcmThreads) {
             const int r = k / P, c = k - r * P;
             if (r >= inf.nvr || c >= inf.nvc) {
@@ -189,7 +192,7 @@ k_glcm_generic(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         for (int k = r0 * P + tid; k < (r1 + 1) * P; k += kGlcmThreads) {
             const int r = k / P, c = k - r * P;
             const int a = patch_addr(P, o, r, c);
-            const float g = __fdiv_rn(
+            const float g = greyp ? greyp[k] : __fdiv_rn(
                 __fadd_rn(__fadd_rn(s_lut[patch[a]], s_lut[patch[a + 1]]), s_lut[patch[a + 2]]), 3.0f);
             q128[k] = (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
             q254[k] = (uint8_t)min((int)floorf(__fmul_rn(g, p.scale254)), 253);
@@ -488,7 +491,8 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     __shared__ float s_idm[256];   // 2 / (1 + k^2): a pair adds 2 to G at distance k from the diagonal
 
     const NucInfo inf = p.info[i];
-    if (tid == 0) {
+    const float* greyp = p.grey ? p.grey + i * (int64_t)P * P : nullptr;   // f32 grey plane instead of the u8 window
+    if (tid == 0 && !greyp) {
         mbar_init(&bar, 1);
         mbar_fence_init();
         mbar_expect_tx(&bar, (uint32_t)(patch_panels(P) * kPanelBytes * P));
@@ -535,7 +539,7 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
     constexpr int lg = kHashLg;
     const int o = patch_byte_offset(inf.left);
     __syncthreads();
-    mbar_wait(&bar, 0);
+    if (!greyp) mbar_wait(&bar, 0);
     // ---- grey quantisation (texture.rs:36 + SPEC.md B5), bit-exact, masked pixels only ----
     const bool dbg_all = (p.dbg_grey != nullptr);
     auto quantise = [&](int r, int c) {
@@ -548,25 +552,33 @@ k_glcm64(const GlcmParams p, const __grid_constant__ CUtensorMap map) {
         const int a128 = min((int)floorf(__fmul_rn(g, 128.0f)), 127), a254 = min((int)floorf(__fmul_rn(g, p.scale254)), 253);
         qq[r * P + c] = (uint16_t)(a254 | (a128 << 8));
     };
+    auto quantise_grey = [&](int r, int c) {   // f32 batch (f32batch.cu): the grey plane is given
+        const float g = greyp[r * P + c];
+        const int a128 = min((int)floorf(__fmul_rn(g, 128.0f)), 127), a254 = min((int)floorf(__fmul_rn(g, p.scale254)), 253);
+        qq[r * P + c] = (uint16_t)(a254 | (a128 << 8));
+    };
     if (dbg_all) {
-        for (int k = tid; k < P * P; k += kG64Threads) quantise(k / P, k % P);
+        for (int k = tid; k < P * P; k += kG64Threads) { if (greyp) quantise_grey(k / P, k % P); else quantise(k / P, k % P); }
     }
     // The list entry becomes (position, neighbour flags): bit 12 + oi is set when the pixel's neighbour at offset oi is
     // inside the window and masked. The sweeps then cost three 16-bit loads per pixel (entry, own levels, neighbour's
     // levels) instead of a mask-word load with its bit arithmetic and four byte loads (ncu round 2: 11 % of the kernel's
     // shared-memory wavefronts and a fifth of the two sweeps' instructions went into finding the pair).
-    for (int j = tid; j < K; j += kG64Threads) {
-        const uint32_t rc = list[j];
-        const int r = rc >> 8, c = rc & 255;
-        if (!dbg_all) quantise(r, c);
-        uint32_t fl = 0u;
+    auto list_loop = [&](auto grey_tag) {
+        for (int j = tid; j < K; j += kG64Threads) {
+            const uint32_t rc = list[j];
+            const int r = rc >> 8, c = rc & 255;
+            if (!dbg_all) { if constexpr (decltype(grey_tag)::value) quantise_grey(r, c); else quantise(r, c); }
+            uint32_t fl = 0u;
 #pragma unroll
-        for (int oi = 0; oi < kGlcmOffsets; ++oi) {
-            const int r2 = r + c_off[oi][0], c2 = c + c_off[oi][1];
-            if ((r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u)) fl |= 1u << oi;
+            for (int oi = 0; oi < kGlcmOffsets; ++oi) {
+                const int r2 = r + c_off[oi][0], c2 = c + c_off[oi][1];
+                if ((r2 < P) && ((unsigned)c2 < (unsigned)P) && ((rows[r2 * wpr + (c2 >> 5)] >> (c2 & 31)) & 1u)) fl |= 1u << oi;
+            }
+            list[j] = (uint16_t)((r * P + c) | (fl << 12));
         }
-        list[j] = (uint16_t)((r * P + c) | (fl << 12));
-    }
+    };
+    if (greyp) list_loop(std::true_type{}); else list_loop(std::false_type{});
     __syncthreads();   // the window is dead from here on: region A becomes the histograms
     {
         uint4* z = reinterpret_cast<uint4*>(smem_raw);
@@ -788,6 +800,7 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
 
     const NucInfo inf = p.info[i];
     const int o = patch_byte_offset(inf.left);
+    const float* greyp = p.grey ? p.grey + i * (int64_t)P * P : nullptr;   // f32 grey plane instead of the u8 window
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
@@ -808,22 +821,24 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
         for (int sidx = 0; sidx < nslab; ++sidx) {
             const int row0 = sidx * 64, nrows = min(64, P - row0);
             __syncthreads();   // slab buffer (aliased with the histograms) is free
-            if (tid == 0) {
-                mbar_expect_tx(&bar, slab_tx);
-                tma_load_window(slab, &map, inf.left, inf.top + row0, P, 64, &bar);
+            if (!greyp) {
+                if (tid == 0) {
+                    mbar_expect_tx(&bar, slab_tx);
+                    tma_load_window(slab, &map, inf.left, inf.top + row0, P, 64, &bar);
+                }
+                mbar_wait(&bar, phase);
+                phase ^= 1u;
             }
-            mbar_wait(&bar, phase);
-            phase ^= 1u;
             for (int k = tid; k < nrows * P; k += kLargeThreads) {
                 const int lr = k / P, c = k - lr * P, r = row0 + lr;
                 // only pixels under the mask ever enter a pair (the debug dump wants the whole plane)
                 if (!p.dbg_grey && !((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u)) continue;
                 uint32_t pr = 0, pg = 0, pb = 0;
-                if (r < inf.nvr && c < inf.nvc) {
+                if (!greyp && r < inf.nvr && c < inf.nvc) {
                     const int a = patch_addr(64, o, lr, c);
                     pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
                 }
-                const float g = __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
+                const float g = greyp ? greyp[r * P + c] : __fdiv_rn(__fadd_rn(__fadd_rn(s_lut[pr], s_lut[pg]), s_lut[pb]), 3.0f);
                 plane[r * PP + c] = round == 0 ? (uint8_t)min((int)floorf(__fmul_rn(g, p.scale254)), 253)
                                               : (uint8_t)min((int)floorf(__fmul_rn(g, 128.0f)), 127);
             }

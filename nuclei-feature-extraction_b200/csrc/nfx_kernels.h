@@ -83,6 +83,7 @@ struct GlcmParams {
     int dbg_levels, dbg_dy, dbg_dx;
     uint8_t* dbg_grey;         // [n][P][P] quantised grey for dbg_levels
     float scale254;            // 254.0f, or 255.0f under NFX_RULE_GLCM_254_U8: q254 = min(floor(g * scale254), 253)
+    const float* grey;         // nullptr, or [n][P][P] f32 grey planes (f32batch.cu): the window is then neither fetched nor looked up
 };
 // map = whole-window map for P <= 128, the 64-row slab map (color_slab_rows) when glcm_uses_slab_map(P)
 cudaError_t launch_glcm(const GlcmParams& p, const CUtensorMap* map, cudaStream_t s);
@@ -100,6 +101,7 @@ struct TexParams {
     int col_glrlm, col_gabor;  // first column of each set (or -1)
     double* gabor_partial;     // [n][gabor_tiles(P)][97] scratch when P > 64, else nullptr
     int gabor_half_turn;       // NFX_RULE_GABOR_HALF_TURN: angles i * pi / 8 (48 distinct filters) instead of i * 2 pi / 8
+    const float* grey;         // nullptr, or [n][P][P] f32 grey planes (f32batch.cu): the window is then neither fetched nor looked up
 };
 cudaError_t launch_glrlm(const TexParams& p, const CUtensorMap* map_cslab, cudaStream_t s);
 cudaError_t launch_gabor(const TexParams& p, const CUtensorMap* map, cudaStream_t s);   // map: see texture2.cu
@@ -119,6 +121,14 @@ cudaError_t launch_expand_mask(int64_t n, int P, const uint32_t* bitmask, uint8_
 cudaError_t launch_pack_batch(int64_t n, int P, const float* patchs, const float* masks,
                               uint8_t* patches_u8, int64_t pitch, uint32_t* bitmask, NucInfo* info,
                               int* bad_count, cudaStream_t s);
+
+// ---- f32batch.cu: trait-level batches whose patch values are NOT k/255 (arbitrary f32 in [0,1]) ----
+// grey = ((r + g) + b) / 3 with IEEE f32 operations (texture.rs:36 / 189 / 332) for the texture kernels' `grey` input
+cudaError_t launch_grey_f32(int64_t n, int P, const float* patchs, float* grey, cudaStream_t s);
+// the colour set (color.rs:10-102) straight from f32 patches: 17 columns per nucleus + the batch-coupled mean_h;
+// hue_images = [ceil(n / batch_size)][P*P][2] f32 scratch
+cudaError_t launch_color_f32(int64_t n, int P, int batch_size, const float* patchs, const uint32_t* bitmask, float* hue_images,
+                             float* out, int out_stride, int col_color, cudaStream_t s);
 
 // ---- ext.cu: extension outputs (north_star items the reference does not compute; never part of the drop-in schema) ----
 constexpr int kExtColorCols = 18, kExtMaskCols = 24, kExtContourCols = 2, kExtGlcmCols = 112;

@@ -86,7 +86,8 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const NucInfo inf = p.info[i];
     const int o = patch_byte_offset(inf.left);
     const uint32_t slab_tx = (uint32_t)(patch_panels(P) * kPanelBytes * CS);
-    if (tid == 0) {
+    const float* greyp = p.grey ? p.grey + i * (int64_t)P * P : nullptr;   // f32 grey plane instead of the u8 window
+    if (tid == 0 && !greyp) {
         mbar_init(&bar, 1);
         mbar_fence_init();
         mbar_expect_tx(&bar, slab_tx);
@@ -133,35 +134,44 @@ k_glrlm(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     };
     if (early) {
         build_list();
-        mbar_wait(&bar, 0);
-        for (int j = tid; j < K; j += THREADS) {
-            const uint32_t rc = list[j];
-            const int r = rc >> 8, c = rc & 255;
-            uint32_t pr = 0, pg = 0, pb = 0;
-            if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
-                const int a = patch_addr(CS, o, r, c);
-                pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
+        if (!greyp) mbar_wait(&bar, 0);
+        if (!greyp) {
+            for (int j = tid; j < K; j += THREADS) {
+                const uint32_t rc = list[j];
+                const int r = rc >> 8, c = rc & 255;
+                uint32_t pr = 0, pg = 0, pb = 0;
+                if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
+                    const int a = patch_addr(CS, o, r, c);
+                    pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
+                }
+                plane[(r + 1) * PP + c + 1] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
             }
-            plane[(r + 1) * PP + c + 1] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
+        } else {   // f32 batch (f32batch.cu): the grey plane is given
+            for (int j = tid; j < K; j += THREADS) {
+                const uint32_t rc = list[j];
+                const int r = rc >> 8, c = rc & 255;
+                plane[(r + 1) * PP + c + 1] = (uint8_t)min((int)floorf(__fmul_rn(greyp[r * P + c], (float)kRlLevels)), kRlLevels - 1);
+            }
         }
         __syncthreads();
     } else {
         // ---- 24-level plane (texture.rs:189 + SPEC.md B9), rows that hold mask bits only ----
         for (int sidx = 0; sidx < nslab; ++sidx) {
             const int row0 = sidx * CS, nrows = min(CS, P - row0);
-            mbar_wait(&bar, sidx & 1);
+            if (!greyp) mbar_wait(&bar, sidx & 1);
             for (int k = tid; k < nrows * P; k += THREADS) {
                 const int lr = k / P, c = k - lr * P, r = row0 + lr;
                 if (!((rows[r * wpr + (c >> 5)] >> (c & 31)) & 1u)) continue;
                 uint32_t pr = 0, pg = 0, pb = 0;
-                if (r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
+                if (!greyp && r < inf.nvr && c < inf.nvc) {   // utils.rs:161-192: the rest of the window is zero
                     const int a = patch_addr(CS, o, lr, c);
                     pr = slab[a]; pg = slab[a + 1]; pb = slab[a + 2];
                 }
-                plane[(r + 1) * PP + c + 1] = (uint8_t)min((int)floorf(__fmul_rn(grey_of(s_lut, pr, pg, pb), (float)kRlLevels)), kRlLevels - 1);
+                const float g = greyp ? greyp[r * P + c] : grey_of(s_lut, pr, pg, pb);
+                plane[(r + 1) * PP + c + 1] = (uint8_t)min((int)floorf(__fmul_rn(g, (float)kRlLevels)), kRlLevels - 1);
             }
             __syncthreads();
-            if (tid == 0 && sidx + 1 < nslab) {
+            if (tid == 0 && !greyp && sidx + 1 < nslab) {
                 mbar_expect_tx(&bar, slab_tx);
                 tma_load_window(slab, &map, inf.left, inf.top + row0 + CS, P, CS, &bar);
             }
@@ -303,12 +313,15 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const int fy = TILED ? oy - kGaborLo : 0, fx = TILED ? ox - kGaborLo : 0;
     const int frows = TILED ? kGaborFetch : P;            // rows per panel of the fetched region
     const int o = patch_byte_offset(inf.left + fx);
+    const float* greyp = p.grey ? p.grey + i * (int64_t)WP * WP : nullptr;   // f32 grey plane instead of the u8 window
     if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-        const int fw = TILED ? kGaborFetch : P;
-        mbar_expect_tx(&bar, (uint32_t)(patch_panels(fw) * kPanelBytes * frows));
-        tma_load_window(patch, &map, inf.left + fx, inf.top + fy, fw, frows, &bar);
+        if (!greyp) {
+            mbar_init(&bar, 1);
+            mbar_fence_init();
+            const int fw = TILED ? kGaborFetch : P;
+            mbar_expect_tx(&bar, (uint32_t)(patch_panels(fw) * kPanelBytes * frows));
+            tma_load_window(patch, &map, inf.left + fx, inf.top + fy, fw, frows, &bar);
+        }
         s_box[0] = P; s_box[1] = -1; s_box[2] = P; s_box[3] = -1; s_box[4] = 0;
     }
     s_lut[tid] = __fdiv_rn((float)tid, 255.0f);
@@ -349,7 +362,7 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const int rmin = s_box[0], rmax = s_box[1], cmin = s_box[2], cmax = s_box[3], K = s_box[4];
     float* out = p.out + i * (int64_t)p.out_stride + p.col_gabor;
     double* part = TILED ? p.gabor_partial + (i * (int64_t)gridDim.y + blockIdx.y) * kGaborPartial : nullptr;
-    mbar_wait(&bar, 0);   // never leave the CTA with a TMA still writing its shared memory
+    if (!greyp) mbar_wait(&bar, 0);   // never leave the CTA with a TMA still writing its shared memory
     if (K == 0) {
         if (TILED) {        // empty tile: contributes nothing
             for (int k = tid; k < kGaborPartial; k += kTexThreads) part[k] = 0.0;
@@ -366,13 +379,21 @@ k_gabor(const TexParams p, const __grid_constant__ CUtensorMap map /* box {208, 
     const int gw = gc1 - gc0 + 1;
     const float inv_gw = 1.0f / (float)gw;
     const int wr_lim = min(WP, inf.nvr), wc_lim = min(WP, inf.nvc);
-    for (int k = tid; k < (gr1 - gr0 + 1) * gw; k += kTexThreads) {
-        const int kr = __float2int_rz(((float)k + 0.5f) * inv_gw);   // = k / gw exactly (see fdiv below)
-        const int r = gr0 + kr, c = gc0 + (k - kr * gw);       // tile-local
-        const int wr = oy + r, wc = ox + c;                    // window coordinates
-        if (wr >= 0 && wr < wr_lim && wc >= 0 && wc < wc_lim) {
-            const int a = patch_addr(frows, o, wr - fy, wc - fx);
-            G[(r + kGaborLo) * GS + c + kGaborLo] = grey_of(s_lut, patch[a], patch[a + 1], patch[a + 2]);
+    if (!greyp) {
+        for (int k = tid; k < (gr1 - gr0 + 1) * gw; k += kTexThreads) {
+            const int kr = __float2int_rz(((float)k + 0.5f) * inv_gw);   // = k / gw exactly (see fdiv below)
+            const int r = gr0 + kr, c = gc0 + (k - kr * gw);       // tile-local
+            const int wr = oy + r, wc = ox + c;                    // window coordinates
+            if (wr >= 0 && wr < wr_lim && wc >= 0 && wc < wc_lim) {
+                const int a = patch_addr(frows, o, wr - fy, wc - fx);
+                G[(r + kGaborLo) * GS + c + kGaborLo] = grey_of(s_lut, patch[a], patch[a + 1], patch[a + 2]);
+            }
+        }
+    } else {   // f32 batch (f32batch.cu): the grey plane is given
+        for (int k = tid; k < (gr1 - gr0 + 1) * gw; k += kTexThreads) {
+            const int kr = __float2int_rz(((float)k + 0.5f) * inv_gw);
+            const int r = gr0 + kr, c = gc0 + (k - kr * gw), wr = oy + r, wc = ox + c;
+            if (wr >= 0 && wr < wr_lim && wc >= 0 && wc < wc_lim) G[(r + kGaborLo) * GS + c + kGaborLo] = greyp[wr * WP + wc];
         }
     }
     __syncthreads();   // the fetched pixels (aliased with A) are dead from here on

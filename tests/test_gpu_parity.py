@@ -183,6 +183,35 @@ def test_trait_level_compute_features_batched(case, ex):
     ex.upload_tile(case["tile"])
 
 
+def test_trait_level_arbitrary_f32_patches(case, ex):
+    """A Batch whose patch values are NOT k/255 (nothing in the reference produces one, but the trait takes any tensor):
+    the texture sets run on an f32 grey plane, the colour set on the f32 patches (f32batch.cu). Every column of the four
+    patch-based sets against the oracle on the very same tensors."""
+    n = 60
+    rng = np.random.default_rng(11)
+    cents, polys = case["cents"][:n], case["polys"][:n]
+    base, masks_t = case["patches"][:n], case["masks"][:n]
+    pf = torch.from_numpy((base.numpy() * 0.93 + 0.06 * rng.random(base.shape, dtype=np.float32)).astype(np.float32))
+    pf[3] = 0.0                      # a black patch (grey 0, hue 0, optical density clamp)
+    pf[4, :, :, :] = 0.5             # a flat grey patch (saturation 0, one GLCM cell)
+    assert not np.allclose(pf.numpy() * 255.0, np.rint(pf.numpy() * 255.0), atol=1e-3)
+    got = ex.compute_features_batched(nfx.FS_COLOR | nfx.FS_GLCM | nfx.FS_GLRLM | nfx.FS_GABOR, cents, polys, pf.numpy(), masks_t.numpy())
+    assert got.shape == (n, 18 + 224 + 68 + 96)
+    want = o.color_features(pf.clone(), masks_t)
+    check_color(got[:, :18], want, list(o.COLOR_COLUMNS), pf, masks_t, n)
+    col = 18
+    for sname, fn in (("glcm", o.glcm_feature_set), ("glrlm", o.glrlm_feature_set), ("gabor", o.gabor_feature_set)):
+        cols = o.SET_COLUMNS[sname]
+        bad = mismatches(got[:, col:col + len(cols)], fn(pf, masks_t), cols, sname)
+        assert not bad, f"{sname}: {bad[:8]} ({len(bad)} mismatches)"
+        col += len(cols)
+    # the same call with k/255 values still takes the u8 kernels and gives the same bits as before
+    a = ex.compute_features_batched(nfx.FS_COLOR, cents, polys, base.numpy(), masks_t.numpy())
+    b = ex.compute_features_batched(nfx.FS_COLOR, cents, polys, base.numpy(), masks_t.numpy())
+    assert a.tobytes() == b.tobytes()
+    ex.upload_tile(case["tile"])
+
+
 def test_errors_do_not_abort(case):
     with nfx.Extractor(0, 64, 100) as e:
         with pytest.raises(nfx.NfxError):
