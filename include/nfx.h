@@ -228,7 +228,18 @@ typedef struct nfx_tiff_level {
     int32_t jpeg_tables_bytes;           /* tag 347 */
 } nfx_tiff_level;
 int nfx_tiff_info(const uint8_t* file, int64_t len, nfx_tiff_level* out);   /* host only: no GPU needed */
-int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads);
+int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads);   /* = _ex with flags 0 */
+/* Decoder choice. Default (flags = 0): every JPEG block is decoded on the host threads by csrc/jpeg_exact.cpp, a restatement
+ * of the IJG / libjpeg-turbo default path (integer "islow" IDCT, triangle-filter chroma upsampling, fixed-point YCbCr -> RGB)
+ * whose pixels equal libjpeg's bit for bit -- the pixels OpenSlide hands the reference -- and uploaded from pinned staging;
+ * streams outside its scope (progressive, 1x2 sampling, several scans) go through nvJPEG. NFX_DECODE_FAST: nvJPEG for every
+ * block (only compressed bytes cross PCIe, about twice the tile rate, pixels within a few grey levels of libjpeg's). */
+#define NFX_DECODE_FAST 0x1u
+int nfx_slide_load_tiff_ex(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads, uint32_t flags);
+/* The exact decoder on its own (host only: no GPU needed): one baseline JPEG stream -> interleaved u8 RGB.
+ * colourspace: 0 = the components are R,G,B (TIFF Photometric = RGB), 1 = YCbCr, -1 = libjpeg's rule (JFIF / Adobe marker /
+ * component ids). rgb may be NULL to query the size; capacity in bytes. NFX_ERR_UNSUPPORTED for streams outside its scope. */
+int nfx_jpeg_decode(const uint8_t* data, int64_t len, int32_t colourspace, uint8_t* rgb, int64_t capacity, int32_t* width, int32_t* height);
 /* parity tap: a region of the resident slide back to the host, interleaved u8 RGB [h][w][3] */
 int nfx_debug_slide_read(nfx_ctx* ctx, int64_t x0, int64_t y0, int64_t w, int64_t h, uint8_t* rgb);
 

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnfx.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "geom.cu", "color.cu", "glcm.cu", "texture2.cu", "staged.cu", "csv.cu", "slide_decode.cu", "ext.cu", "f32batch.cu", "schema.cpp", "geojson.cpp", "tiff.cpp"]
+SOURCES = ["api.cu", "geom.cu", "color.cu", "glcm.cu", "texture2.cu", "staged.cu", "csv.cu", "slide_decode.cu", "ext.cu", "f32batch.cu", "schema.cpp", "geojson.cpp", "tiff.cpp", "jpeg_exact.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]

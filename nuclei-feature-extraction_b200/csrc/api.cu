@@ -499,7 +499,27 @@ int nfx_slide_copy_rows(nfx_ctx* ctx, nfx_ctx* src, int64_t y0, int64_t rows) {
 }
 
 int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads) {
+    return nfx_slide_load_tiff_ex(ctx, file, len, threads, 0);
+}
+
+int nfx_jpeg_decode(const uint8_t* data, int64_t len, int32_t colourspace, uint8_t* rgb, int64_t capacity, int32_t* width, int32_t* height) {
+    if (!data || len <= 0 || !width || !height || colourspace < -1 || colourspace > 1) return fail(nullptr, NFX_ERR_INVALID, "nfx_jpeg_decode: bad arguments");
+    std::vector<uint8_t> out;
+    int w = 0, h = 0;
+    std::string err;
+    if (!jpeg_decode_exact(data, (size_t)len, colourspace, out, w, h, err)) return fail(nullptr, NFX_ERR_UNSUPPORTED, "jpeg: " + err);
+    *width = w;
+    *height = h;
+    if (rgb) {
+        if ((int64_t)out.size() > capacity) return fail(nullptr, NFX_ERR_INVALID, "nfx_jpeg_decode: output buffer too small");
+        memcpy(rgb, out.data(), out.size());
+    }
+    return NFX_OK;
+}
+
+int nfx_slide_load_tiff_ex(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t threads, uint32_t flags) {
     if (!ctx) return NFX_ERR_INVALID;
+    if (flags & ~(uint32_t)NFX_DECODE_FAST) return fail(ctx, NFX_ERR_INVALID, "unknown nfx_slide_load_tiff_ex flag");
     TiffLevel L;
     std::string err;
     if (!tiff_parse(file, len, L, err)) return fail(ctx, NFX_ERR_INVALID, "tiff: " + err);
@@ -507,7 +527,7 @@ int nfx_slide_load_tiff(nfx_ctx* ctx, const uint8_t* file, int64_t len, int32_t 
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->tile.p, 0, (size_t)ctx->tpitch * L.height, ctx->stream));   // sparse blocks stay black
     CK(cudaStreamSynchronize(ctx->stream));
-    err = decode_tiff_level(file, L, ctx->tile.p, ctx->tpitch, ctx->device, threads);
+    err = decode_tiff_level(file, L, ctx->tile.p, ctx->tpitch, ctx->device, threads, (flags & NFX_DECODE_FAST) != 0);
     if (!err.empty()) { ctx->have_tile = false; return fail(ctx, NFX_ERR_UNSUPPORTED, "tiff: " + err); }
     ctx->rules |= NFX_RULE_WINDOW_SLIDE;   // .svs / .tif input takes the reference's slide path (src/utils.rs:96-126)
     ctx->have_geom = false;

@@ -21,6 +21,10 @@ struct TiffLevel {
     std::vector<uint8_t> jpeg_tables;        // tag 347: SOI DQT DHT EOI shared by abbreviated block streams (may be empty)
 };
 bool tiff_parse(const uint8_t* file, int64_t len, TiffLevel& out, std::string& err);
-// slide_decode.cu: every block of L through nvJPEG into the slide (device pointer); "" on success
-std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* slide, int64_t pitch, int device, int threads);
+// slide_decode.cu: every block of L into the slide (device pointer); "" on success. fast = false: the host decoder of
+// jpeg_exact.cpp (libjpeg's pixels), nvJPEG only for streams it does not cover; fast = true: nvJPEG for every block.
+std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* slide, int64_t pitch, int device, int threads, bool fast);
+// jpeg_exact.cpp: baseline JPEG -> interleaved u8 RGB with libjpeg / libjpeg-turbo's default arithmetic, bit for bit.
+// colourspace: 0 = components are R,G,B; 1 = YCbCr; -1 = libjpeg's own rule (JFIF / Adobe marker / component ids)
+bool jpeg_decode_exact(const uint8_t* data, size_t len, int colourspace, std::vector<uint8_t>& out, int& W, int& H, std::string& err);
 }  // namespace nfx

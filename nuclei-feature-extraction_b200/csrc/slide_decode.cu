@@ -1,6 +1,8 @@
 // slide_decode.cu -- SURVEY.md 8f row 4: the slide decode path. The reference opens `.svs` files with OpenSlide and
 // reads one region per nucleus under a Mutex (src/utils.rs:79-139); here level 0 of the TIFF container (tiff.cpp) is
-// decoded block by block with nvJPEG and lands directly in the slide that is resident in HBM (nfx_slide_alloc), so
+// decoded block by block into the slide that is resident in HBM (nfx_slide_alloc). Default: the host decoder of
+// jpeg_exact.cpp, whose pixels are libjpeg's bit for bit (what OpenSlide hands the reference), one block per host thread
+// at a time, uploaded from pinned staging. NFX_DECODE_FAST (and streams the exact decoder does not cover): nvJPEG, so
 // that the compressed bytes are all that crosses PCIe. Host threads feed nvJPEG (its Huffman stage runs on the CPU),
 // each with its own decoder state, CUDA stream and device scratch; k_block_store moves a decoded block into the
 // slide, clipped at the right / bottom edge (TIFF blocks are always full size) and interleaved when nvJPEG returns
@@ -43,6 +45,9 @@ struct Worker {
     uint8_t* scratch = nullptr;
     size_t scratch_bytes = 0;
     std::vector<uint8_t> merged;
+    std::vector<uint8_t> rgb;        // exact path: decoded block
+    uint8_t* pinned = nullptr;       // exact path: staging of the block on its way to the slide
+    size_t pinned_bytes = 0;
     std::string err;
 };
 
@@ -65,7 +70,7 @@ const char* nvjpeg_str(nvjpegStatus_t s) {
 
 // Decodes every block of L into the slide at `slide` (pitch bytes per row, L.width x L.height pixels).
 // Returns an empty string on success.
-std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* slide, int64_t pitch, int device, int threads) {
+std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* slide, int64_t pitch, int device, int threads, bool fast) {
     if (L.compression != 7) return "only JPEG-compressed TIFF blocks (compression 7) are supported, found compression " + std::to_string(L.compression);
     if (L.photometric != 2 && L.photometric != 6) return "unsupported photometric interpretation " + std::to_string(L.photometric);
     nvjpegHandle_t handle = nullptr;
@@ -96,6 +101,30 @@ std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* 
                 data = w.merged.data();
                 n = w.merged.size();
             }
+            const int64_t bx = b % L.across, by = b / L.across;
+            const int64_t x0 = bx * L.block_w, y0 = by * L.block_h;
+            if (!fast) {   // libjpeg's pixels (jpeg_exact.cpp); nvJPEG below only when the stream is outside its scope
+                int ew = 0, eh = 0;
+                std::string why;
+                if (jpeg_decode_exact(data, n, rgb_components ? 0 : 1, w.rgb, ew, eh, why)) {
+                    const int vw = (int)std::min<int64_t>(std::min<int64_t>(ew, L.block_w), L.width - x0);
+                    const int vh = (int)std::min<int64_t>(std::min<int64_t>(eh, L.block_h), L.height - y0);
+                    if (vw > 0 && vh > 0) {
+                        // the staging buffer is reused by the next block of this worker: wait for the previous upload
+                        if (cudaStreamSynchronize(w.stream) != cudaSuccess) { w.err = "decode stream failed"; failed = true; break; }
+                        if (w.rgb.size() > w.pinned_bytes) {
+                            if (w.pinned) cudaFreeHost(w.pinned);
+                            w.pinned = nullptr;
+                            if (cudaMallocHost((void**)&w.pinned, w.rgb.size()) != cudaSuccess) { w.err = "out of pinned memory"; failed = true; break; }
+                            w.pinned_bytes = w.rgb.size();
+                        }
+                        memcpy(w.pinned, w.rgb.data(), w.rgb.size());
+                        if (cudaMemcpy2DAsync(slide + (size_t)y0 * pitch + 3 * (size_t)x0, (size_t)pitch, w.pinned, (size_t)3 * ew, (size_t)3 * vw,
+                                              (size_t)vh, cudaMemcpyHostToDevice, w.stream) != cudaSuccess) { w.err = "block upload failed"; failed = true; break; }
+                    }
+                    continue;
+                }
+            }
             int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
             nvjpegChromaSubsampling_t sub;
             nvjpegStatus_t s = nvjpegGetImageInfo(handle, data, n, &nc, &sub, ws, hs);
@@ -125,8 +154,6 @@ std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* 
             }
             s = nvjpegDecode(handle, w.state, data, n, planes ? NVJPEG_OUTPUT_UNCHANGED : NVJPEG_OUTPUT_RGBI, &img, w.stream);
             if (s != NVJPEG_STATUS_SUCCESS) { w.err = std::string("block ") + std::to_string(b) + ": " + nvjpeg_str(s); failed = true; break; }
-            const int64_t bx = b % L.across, by = b / L.across;
-            const int64_t x0 = bx * L.block_w, y0 = by * L.block_h;
             const int vw = (int)std::min<int64_t>(std::min<int64_t>(bw, L.block_w), L.width - x0);
             const int vh = (int)std::min<int64_t>(std::min<int64_t>(bh, L.block_h), L.height - y0);
             if (vw > 0 && vh > 0) {
@@ -149,6 +176,7 @@ std::string decode_tiff_level(const uint8_t* file, const TiffLevel& L, uint8_t* 
     for (auto& w : workers) {
         if (err.empty() && !w.err.empty()) err = w.err;
         if (w.scratch) cudaFree(w.scratch);
+        if (w.pinned) cudaFreeHost(w.pinned);
         if (w.stream) cudaStreamDestroy(w.stream);
         if (w.state) nvjpegJpegStateDestroy(w.state);
     }

@@ -100,6 +100,22 @@ def tiff_info(data) -> dict:
     return {f: getattr(lv, f) for f, _ in NfxTiffLevel._fields_}
 
 
+DECODE_FAST = 0x1
+
+
+def jpeg_decode(data, colourspace: int = -1) -> np.ndarray:
+    """One baseline JPEG stream -> [h, w, 3] u8 with libjpeg's pixels bit for bit (nfx_jpeg_decode, host only).
+    colourspace: 0 = components are R,G,B; 1 = YCbCr; -1 = libjpeg's own rule."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    w, h = C.c_int32(), C.c_int32()
+    if lib().nfx_jpeg_decode(buf.ctypes.data, buf.size, colourspace, None, 0, C.byref(w), C.byref(h)) != NFX_OK:
+        raise NfxError(-1, (lib().nfx_last_error(None) or b"").decode())
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    if lib().nfx_jpeg_decode(buf.ctypes.data, buf.size, colourspace, out.ctypes.data, out.size, C.byref(w), C.byref(h)) != NFX_OK:
+        raise NfxError(-1, (lib().nfx_last_error(None) or b"").decode())
+    return out
+
+
 def parse_f32(token: str) -> np.float32:
     """One JSON number token as the reference's serde_json hands it to an f32 field (nfx_parse_f32)."""
     o = C.c_float()
@@ -198,10 +214,11 @@ class Extractor:
         self._ck(lib().nfx_tile_upload(self._h, _ptr(rgb), rgb.shape[1], rgb.shape[0], rgb.strides[0],
                                        int(origin[0]), int(origin[1])))
 
-    def load_tiff(self, data, threads: int = 0):
-        """Level 0 of a JPEG-compressed TIFF / .svs held in memory -> the resident slide, decoded by nvJPEG."""
+    def load_tiff(self, data, threads: int = 0, fast: bool = False):
+        """Level 0 of a JPEG-compressed TIFF / .svs held in memory -> the resident slide. Default: libjpeg's pixels bit for
+        bit (host decoder, csrc/jpeg_exact.cpp); fast=True: nvJPEG (a few grey levels off, about twice the tile rate)."""
         buf = np.frombuffer(data, dtype=np.uint8)
-        self._ck(lib().nfx_slide_load_tiff(self._h, buf.ctypes.data, buf.size, threads))
+        self._ck(lib().nfx_slide_load_tiff_ex(self._h, buf.ctypes.data, buf.size, threads, DECODE_FAST if fast else 0))
 
     def slide_read(self, x0, y0, w, h):
         out = np.empty((h, w, 3), dtype=np.uint8)

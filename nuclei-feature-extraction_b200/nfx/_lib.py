@@ -70,6 +70,8 @@ SYMBOLS = {
     "nfx_format_f32": (_i, [_f, C.c_char_p, _i]),
     "nfx_tiff_info": (_i, [_vp, _i64, _vp]),
     "nfx_slide_load_tiff": (_i, [_vp, _vp, _i64, C.c_int32]),
+    "nfx_slide_load_tiff_ex": (_i, [_vp, _vp, _i64, C.c_int32, C.c_uint32]),
+    "nfx_jpeg_decode": (_i, [_vp, _i64, C.c_int32, _vp, _i64, _vp, _vp]),
     "nfx_debug_slide_read": (_i, [_vp, _i64, _i64, _i64, _i64, _vp]),
     "nfx_geojson_parse": (_i, [C.c_char_p, _i64, C.c_int32, C.POINTER(_vp)]),
     "nfx_geojson_count": (_i64, [_vp]),

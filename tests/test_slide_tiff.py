@@ -1,8 +1,8 @@
-"""Slide decode: the TIFF / BigTIFF container parser (host) and the nvJPEG decode of its blocks
-into the resident slide (GPU), on synthetic files: strips written by libtiff through PIL (shared JPEGTables, RGB
-components) and tiles written by the helper below (stand-alone YCbCr JPEG streams, classic and BigTIFF, both byte
-orders). The decode is compared with libjpeg-turbo (PIL): IDCT / upsampling implementations differ by a few grey
-levels, which is the tolerance OpenSlide's own libjpeg path would have against any other decoder."""
+"""Slide decode: the TIFF / BigTIFF container parser (host) and the decode of its JPEG blocks into the
+resident slide (GPU), on synthetic files: strips written by libtiff through PIL (shared JPEGTables, RGB components) and
+tiles written by the helper below (stand-alone YCbCr JPEG streams, classic and BigTIFF, both byte orders). The default
+decoder (csrc/jpeg_exact.cpp) must give libjpeg-turbo's pixels (PIL) bit for bit -- what OpenSlide hands the reference;
+the nvJPEG path (fast=True) differs by a few grey levels (its IDCT / upsampling are not libjpeg's)."""
 import io
 import struct
 
@@ -123,8 +123,11 @@ def test_decode_tiles_matches_libjpeg(libnfx, image, big, be, subsampling):
     with nfx.Extractor(0) as ex:
         ex.load_tiff(data, 3)
         got = ex.slide_read(0, 0, 600, 450)
-        # 4:4:4: only the IDCT differs; 4:2:0: chroma upsampling differs too (libjpeg-turbo's "fancy" filter)
-        _close(got, want, 6 if subsampling == 0 else 48, 0.8 if subsampling == 0 else 3.0)
+        assert np.array_equal(got, want)                         # the default decoder: libjpeg's pixels, bit for bit
+        ex.load_tiff(data, 3, fast=True)
+        fast = ex.slide_read(0, 0, 600, 450)
+        # nvJPEG, 4:4:4: only the IDCT differs; 4:2:0: chroma upsampling differs too (libjpeg-turbo's "fancy" filter)
+        _close(fast, want, 6 if subsampling == 0 else 48, 0.8 if subsampling == 0 else 3.0)
         _close(got, image, 60 if subsampling == 0 else 200, 6.0 if subsampling == 0 else 12.0)   # the picture, not garbage (JPEG loss)
         # the decoded slide feeds the feature kernels like an uploaded tile does
         xy, off = synth.synth_polygons(40, 450, 600, 3, border_frac=0.1)
@@ -143,7 +146,9 @@ def test_decode_libtiff_strips_rgb_components(libnfx, image, tmp_path):
     with nfx.Extractor(0) as ex:
         ex.load_tiff(p.read_bytes(), 2)
         got = ex.slide_read(0, 0, 600, 450)
-    _close(got, want, 6, 0.8)
+        assert np.array_equal(got, want)
+        ex.load_tiff(p.read_bytes(), 2, fast=True)
+        _close(ex.slide_read(0, 0, 600, 450), want, 6, 0.8)
     with nfx.Extractor(0) as ex:
         q = tmp_path / "raw.tif"
         Image.fromarray(image).save(q)
