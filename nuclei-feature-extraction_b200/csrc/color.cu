@@ -558,13 +558,23 @@ k_hue_batch(const ColorParams p, const __grid_constant__ CUtensorMap map, const 
     for (int k = tid; k < R * ppitch; k += kThreads) pre[k] = make_int2(0, 0);
     __syncthreads();
     {   // union of the chunk's masks over this slab (thread t walks words t, t + T, ... of the [nb][words_u] block)
+        // four independent loads per round: one load per round left every CTA waiting ~11 L2 latencies before its first
+        // TMA (ncu: 10 % of the kernel's stall samples sat in this loop for 3 % of its instructions)
         int j = tid / words_u, w = tid - j * words_u;
         const int dj = kThreads / words_u, dw = kThreads - dj * words_u;
         while (j < nb) {
-            const uint32_t v = p.bitmask[((b0 + j) * (int64_t)P + row0) * wpr + w];
-            if (v) atomicOr(&s_union[w], v);
-            j += dj; w += dw;
-            if (w >= words_u) { w -= words_u; ++j; }
+            uint32_t v[4];
+            int ww[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ww[u] = w;
+                v[u] = (j < nb) ? p.bitmask[((b0 + j) * (int64_t)P + row0) * wpr + w] : 0u;
+                j += dj; w += dw;
+                if (w >= words_u) { w -= words_u; ++j; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (v[u]) atomicOr(&s_union[ww[u]], v[u]);
         }
     }
     __syncthreads();
