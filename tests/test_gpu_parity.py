@@ -212,6 +212,28 @@ def test_trait_level_arbitrary_f32_patches(case, ex):
     ex.upload_tile(case["tile"])
 
 
+@pytest.mark.parametrize("P", [256, 100])
+def test_trait_level_arbitrary_f32_patches_other_sizes(stress, P):
+    """The same f32 path through the kernels of the other window sizes (k_glcm_large / k_glcm_generic, tiled k_gabor,
+    multi-slab k_glrlm): P = 256 and P = 100 (the centre crop of the stress patches), all four patch-based sets."""
+    n = 6
+    rng = np.random.default_rng(P)
+    lo = (256 - P) // 2
+    base = stress["patches"][:n, :, lo:lo + P, lo:lo + P].contiguous()
+    masks_t = stress["masks"][:n, :, lo:lo + P, lo:lo + P].contiguous()
+    pf = torch.from_numpy((base.numpy() * 0.93 + 0.06 * rng.random(base.shape, dtype=np.float32)).astype(np.float32))
+    cents, polys = stress["cents"][:n], stress["polys"][:n]
+    with nfx.Extractor(0, P, 8) as e:
+        got = e.compute_features_batched(nfx.FS_COLOR | nfx.FS_GLCM | nfx.FS_GLRLM | nfx.FS_GABOR, cents, polys, pf.numpy(), masks_t.numpy())
+    check_color(got[:, :18], o.color_features(pf.clone(), masks_t), list(o.COLOR_COLUMNS), pf, masks_t, n)
+    col = 18
+    for sname, fn in (("glcm", o.glcm_feature_set), ("glrlm", o.glrlm_feature_set), ("gabor", o.gabor_feature_set)):
+        cols = o.SET_COLUMNS[sname]
+        bad = mismatches(got[:, col:col + len(cols)], fn(pf, masks_t), cols, sname)
+        assert not bad, f"{sname} at P={P}: {bad[:8]} ({len(bad)} mismatches)"
+        col += len(cols)
+
+
 def test_errors_do_not_abort(case):
     with nfx.Extractor(0, 64, 100) as e:
         with pytest.raises(nfx.NfxError):
