@@ -403,7 +403,7 @@ constexpr int kOffTri64 = kOffTri128 + kTri128 * 2;            // 16512
 constexpr int kOffTri32 = kOffTri64 + kTri64 * 2;              // 20672
 constexpr int kOffHash = ((kOffTri32 + kTri32 * 2 + 127) / 128) * 128;   // 21760
 constexpr int kHashMax = 4096, kHashLg = 12;
-constexpr int kRegionA64 = kOffHash + kHashMax * 4;            // 54528
+constexpr int kRegionA64 = kOffHash + kHashMax * 4;            // 38144
 constexpr int kMargWords = 2048;                               // hx128 @0, hx254 @128, hs128 @384, hs254 @640, hs64 x3 @1152, hs32 x8 @1536
 constexpr int kNP = 11;                                        // partial sums per (level, offset)
 constexpr float kLnFix = 0.6931471805599453f * 65536.0f;      // log2 -> ln, 16 fractional bits
