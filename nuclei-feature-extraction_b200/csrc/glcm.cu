@@ -908,15 +908,17 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                             const int cell = ((hi * (hi + 1)) >> 1) + lo;
                             uint32_t* hxs = hx + s * 1024;
                             if (pass == 0) {
-                                atomicAdd(&tri32[tri_off[s] + (cell >> 1)], 1u << ((cell & 1) * 16));
-                                atomicAdd(&hxs[a], 1u);
-                                atomicAdd(&hxs[b], 1u);
-                                atomicAdd(&hxs[256 + a + b], 2u);
+                                if (s == 0) {   // slots 1, 2 (64 / 32 levels) are POOLED from the 128-level tables below
+                                    atomicAdd(&tri32[tri_off[s] + (cell >> 1)], 1u << ((cell & 1) * 16));
+                                    atomicAdd(&hxs[a], 1u);
+                                    atomicAdd(&hxs[b], 1u);
+                                    atomicAdd(&hxs[256 + a + b], 2u);
+                                }
                                 const uint32_t kd = (uint32_t)(hi - lo);
                                 d1[s] += kd;
                                 d2[s] += kd * kd;
                                 fi[s] += s_idm[kd];
-                            } else {
+                            } else if (s == 0) {
                                 const uint32_t g = (uint32_t)tri16[2 * tri_off[s] + cell] << (a == b ? 1 : 0);
                                 g2[s] += g;
                                 glg[s] += __logf((float)g);
@@ -931,6 +933,65 @@ k_glcm_large(const GlcmParams p, const __grid_constant__ CUtensorMap map /* box 
                     }
                 }
                 __syncthreads();
+                if (pass == 0 && nlev == 3) {
+                    // q64 = q128 >> 1 and q32 = q128 >> 2 exactly, so the 64- and 32-level matrices are 2 x 2 poolings of the
+                    // 128-level one: at 256 x 256 a nucleus has ~25 000 pairs per offset against 8 256 + 2 080 + 528 cells, and
+                    // pooling replaces 8 of the 12 atomics per pair and two of the three cell look-ups of the second sweep.
+                    const uint16_t* T128 = tri16 + 2 * tri_off[0];
+                    uint16_t* T64 = tri16 + 2 * tri_off[1];
+                    uint16_t* T32 = tri16 + 2 * tri_off[2];
+                    uint32_t* hx64 = hx + 1024, *hx32 = hx + 2048;
+                    auto tc = [](int hi, int lo) { return ((hi * (hi + 1)) >> 1) + lo; };
+                    for (int t = tid; t < 64 * 64; t += kLargeThreads) {
+                        const int A = t >> 6, B = t & 63;
+                        if (B > A) continue;
+                        uint32_t c = (uint32_t)T128[tc(2 * A, 2 * B)] + T128[tc(2 * A + 1, 2 * B + 1)] + T128[tc(2 * A + 1, 2 * B)];
+                        if (A > B) c += T128[tc(2 * A, 2 * B + 1)];
+                        T64[tc(A, B)] = (uint16_t)c;   // <= 65 280 pairs per offset in total
+                    }
+                    if (tid < 64) hx64[tid] = hx[2 * tid] + hx[2 * tid + 1];
+                    if (tid >= 64 && tid < 96) { const int k = tid - 64; hx32[k] = hx[4 * k] + hx[4 * k + 1] + hx[4 * k + 2] + hx[4 * k + 3]; }
+                    __syncthreads();
+                    {
+                        const int A = tid >> 5, B = tid & 31;   // 1024 threads = 32 x 32
+                        if (B <= A) {
+                            uint32_t c = (uint32_t)T64[tc(2 * A, 2 * B)] + T64[tc(2 * A + 1, 2 * B + 1)] + T64[tc(2 * A + 1, 2 * B)];
+                            if (A > B) c += T64[tc(2 * A, 2 * B + 1)];
+                            T32[tc(A, B)] = (uint16_t)c;
+                        }
+                    }
+                    __syncthreads();
+                    // p_{x+y}: a pair adds 2 at a + b; sums over the anti-diagonals of the pooled matrices
+                    if (tid < 127) {
+                        uint32_t c = 0;
+                        for (int B = max(0, tid - 63); 2 * B <= tid; ++B) c += T64[tc(tid - B, B)];
+                        hx64[256 + tid] = 2u * c;
+                    } else if (tid >= 128 && tid < 128 + 63) {
+                        const int k = tid - 128;
+                        uint32_t c = 0;
+                        for (int B = max(0, k - 31); 2 * B <= k; ++B) c += T32[tc(k - B, B)];
+                        hx32[256 + k] = 2u * c;
+                    }
+                    // entropy / ASM sums of the pooled matrices, cell by cell: sum_pairs G = sum_cells c G, sum_pairs ln G = sum_cells c ln G
+                    for (int t = tid; t < 64 * 64 + 32 * 32; t += kLargeThreads) {
+                        const bool l64 = t < 64 * 64;
+                        const int u = l64 ? t : t - 64 * 64, NLq = l64 ? 64 : 32, A = l64 ? (u >> 6) : (u >> 5), B = u & (NLq - 1);
+                        if (B > A) continue;
+                        const uint32_t c = l64 ? T64[tc(A, B)] : T32[tc(A, B)];
+                        const uint32_t g = c << (A == B ? 1 : 0);
+                        if (c) {
+                            const unsigned long long cg = (unsigned long long)c * g;
+                            const float cl = (float)c * __logf((float)g);
+                            if (l64) { g2[1] += cg; glg[1] += cl; } else { g2[2] += cg; glg[2] += cl; }
+                        }
+                        if (p.dbg_counts && p.dbg_levels == NLq && p.dbg_dy == dy && p.dbg_dx == dx) {
+                            uint32_t* dc = p.dbg_counts + i * (int64_t)NLq * NLq;
+                            dc[A * NLq + B] = g;
+                            dc[B * NLq + A] = g;
+                        }
+                    }
+                    __syncthreads();
+                }
             }
             np_local = warp_sum(np_local);
             if (tid == 0) s_npairs[oi] = 0ull;
